@@ -1,0 +1,86 @@
+"""ctypes binding of libbzk.so — the only way Python reaches the kernels.
+
+There is deliberately no fallback: if the shared library is missing, or no CUDA device is present,
+every compute entry point raises.  (The CPU oracle under oracle/ is test infrastructure and is never
+imported from this package.)"""
+import ctypes as ct
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libbzk.so")
+HEADER_PATH = os.path.join(HERE, "..", "include", "bzk.h")
+PARAMS_PATH = os.path.join(HERE, "data", "poseidon_params.bin")
+
+BZK_OK = 0
+ERRORS = {
+    -1: "BZK_ERR_BAD_ARG", -2: "BZK_ERR_CUDA", -3: "BZK_ERR_OOM", -4: "BZK_ERR_NOT_ON_CURVE",
+    -5: "BZK_ERR_NO_PARAMS", -6: "BZK_ERR_NO_DEVICE", -7: "BZK_ERR_UNSAT",
+}
+
+
+class BzkError(RuntimeError):
+    def __init__(self, status, detail=""):
+        self.status = status
+        super().__init__(f"{ERRORS.get(status, status)}: {detail}")
+
+
+_lib = None
+
+_vp, _sz, _i32, _u32, _u64 = ct.c_void_p, ct.c_size_t, ct.c_int32, ct.c_uint32, ct.c_uint64
+# name -> (restype, argtypes); every symbol include/bzk.h declares
+SIGNATURES = {
+    "bzk_strerror": (ct.c_char_p, [_i32]),
+    "bzk_last_error": (ct.c_char_p, [_vp]),
+    "bzk_abi_version": (_u32, []),
+    "bzk_ctx_create": (_i32, [_i32, ct.POINTER(_vp)]),
+    "bzk_ctx_destroy": (_i32, [_vp]),
+    "bzk_ctx_set_stream": (_i32, [_vp, _vp]),
+    "bzk_ctx_synchronize": (_i32, [_vp]),
+    "bzk_ctx_launch_count": (_u64, [_vp]),
+    "bzk_poseidon_load_params": (_i32, [_vp, _vp, _sz]),
+    "bzk_poseidon_hash": (_i32, [_vp, _u32, _vp, _sz, _vp]),
+    "bzk_poseidon_hash_dev": (_i32, [_vp, _u32, _vp, _sz, _vp]),
+    "bzk_ntt": (_i32, [_vp, _vp, _u32, _i32]),
+    "bzk_ntt_dev": (_i32, [_vp, _vp, _u32, _i32]),
+    "bzk_divide_by_z_on_coset_dev": (_i32, [_vp, _vp, _u32]),
+    "bzk_groth16_h_dev": (_i32, [_vp, _vp, _vp, _vp, _u32]),
+    "bzk_msm_g1": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "bzk_msm_g2": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "bzk_g1_bases_upload": (_i32, [_vp, _vp, _sz, _i32, ct.POINTER(_vp)]),
+    "bzk_g2_bases_upload": (_i32, [_vp, _vp, _sz, _i32, ct.POINTER(_vp)]),
+    "bzk_g1_bases_from_dev": (_i32, [_vp, _vp, _sz, ct.POINTER(_vp)]),
+    "bzk_g2_bases_from_dev": (_i32, [_vp, _vp, _sz, ct.POINTER(_vp)]),
+    "bzk_g1_bases_free": (_i32, [_vp, _vp]),
+    "bzk_g2_bases_free": (_i32, [_vp, _vp]),
+    "bzk_g1_bases_len": (_sz, [_vp]),
+    "bzk_g2_bases_len": (_sz, [_vp]),
+    "bzk_msm_g1_resident": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "bzk_msm_g2_resident": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "bzk_msm_g1_resident_dev": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "bzk_msm_g2_resident_dev": (_i32, [_vp, _vp, _sz, _vp, _sz, _vp]),
+    "bzk_g1_add": (_i32, [_vp, _vp, _vp]),
+    "bzk_g2_add": (_i32, [_vp, _vp, _vp]),
+    "bzk_g1_random_bases_dev": (_i32, [_vp, _u64, _sz, _vp]),
+    "bzk_g2_random_bases_dev": (_i32, [_vp, _u64, _sz, _vp]),
+    "bzk_fr_random_dev": (_i32, [_vp, _u64, _sz, _vp]),
+    "bzk_fr_binop_dev": (_i32, [_vp, _i32, _vp, _vp, _vp, _sz]),
+    "bzk_fp_mul_dev": (_i32, [_vp, _vp, _vp, _vp, _sz]),
+}
+
+
+def load():
+    """dlopen libbzk.so and type every entry point; raises if the extension is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(
+            f"{SO_PATH} is missing: build it with `python -m bazuka_b200.build` "
+            "(bazuka_b200 has no CPU fallback)")
+    lib = ct.CDLL(SO_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

@@ -1,0 +1,332 @@
+// bazuka_b200 — Montgomery prime-field arithmetic for sm_100a (and a bit-identical host path).
+//
+// Replaces, on the GPU, what the reference obtains from un-vendored crates:
+//   Fr  = `ZkScalar([u64;4])`            /root/reference/src/zk/mod.rs:202-206   (ff 0.13 derive)
+//   Fp  = `groth16::Fp([u64;6])`         /root/reference/src/zk/groth16/mod.rs:19-20 (bls12_381 0.8.0)
+// Memory image = the reference's: little-endian 64-bit limbs in Montgomery form (R = 2^256 / 2^384),
+// always fully reduced, so device results can be memcmp'd against the CPU prover's.
+//
+// Blackwell has no 64-bit integer multiplier; the native wide op is IMAD.WIDE.U32 (32x32+64 with
+// carry-in/out predicates).  The product is therefore organised on 32-bit limbs as two interleaved
+// accumulators — one holding the 64-bit partial products that start on even columns, one those
+// that start on odd columns — so that every 32x32 product is ONE `mad.lo.cc/madc.hi.cc` pair
+// (fused by ptxas into one IMAD.WIDE) in a gap-free carry chain, and Montgomery reduction is
+// interleaved row by row (CIOS).  ~2N^2+6N integer instructions per N-limb product.
+//
+// The same algorithm text compiles for the host with an explicit carry variable standing in for
+// the PTX condition code; tests run it on the CPU against the oracle, so the carry-chain logic is
+// verified without a GPU.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BZK_HD __host__ __device__ __forceinline__
+#define BZK_D __device__ __forceinline__
+#else
+#define BZK_HD inline
+#define BZK_D inline
+#endif
+
+#if defined(__CUDACC__)
+#define BZK_HD_POW __host__ __device__ __noinline__
+#else
+#define BZK_HD_POW
+#endif
+
+namespace bzk {
+
+// ---------------------------------------------------------------------------------------------
+// carry-chain primitives.  Device: PTX condition code (the CC argument is dead).  Host: explicit.
+// ---------------------------------------------------------------------------------------------
+struct CC {
+    uint32_t c;
+};
+
+#if defined(__CUDA_ARCH__)
+#define BZK_ASM asm volatile
+BZK_D uint32_t add_cc(uint32_t a, uint32_t b, CC &) { uint32_t r; BZK_ASM("add.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+BZK_D uint32_t addc_cc(uint32_t a, uint32_t b, CC &) { uint32_t r; BZK_ASM("addc.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+BZK_D uint32_t addc(uint32_t a, uint32_t b, CC &) { uint32_t r; BZK_ASM("addc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+BZK_D uint32_t sub_cc(uint32_t a, uint32_t b, CC &) { uint32_t r; BZK_ASM("sub.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+BZK_D uint32_t subc_cc(uint32_t a, uint32_t b, CC &) { uint32_t r; BZK_ASM("subc.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+BZK_D uint32_t subc(uint32_t a, uint32_t b, CC &) { uint32_t r; BZK_ASM("subc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+BZK_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c, CC &) { uint32_t r; BZK_ASM("mad.lo.cc.u32 %0,%1,%2,%3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+BZK_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c, CC &) { uint32_t r; BZK_ASM("madc.lo.cc.u32 %0,%1,%2,%3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+BZK_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c, CC &) { uint32_t r; BZK_ASM("madc.hi.cc.u32 %0,%1,%2,%3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+BZK_D uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+BZK_D uint32_t mul_hi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+#else
+BZK_HD uint32_t add_cc(uint32_t a, uint32_t b, CC &cc) { uint64_t t = (uint64_t)a + b; cc.c = (uint32_t)(t >> 32); return (uint32_t)t; }
+BZK_HD uint32_t addc_cc(uint32_t a, uint32_t b, CC &cc) { uint64_t t = (uint64_t)a + b + cc.c; cc.c = (uint32_t)(t >> 32); return (uint32_t)t; }
+BZK_HD uint32_t addc(uint32_t a, uint32_t b, CC &cc) { return a + b + cc.c; }
+BZK_HD uint32_t sub_cc(uint32_t a, uint32_t b, CC &cc) { uint64_t t = (uint64_t)a - b; cc.c = (uint32_t)(t >> 63); return (uint32_t)t; }
+BZK_HD uint32_t subc_cc(uint32_t a, uint32_t b, CC &cc) { uint64_t t = (uint64_t)a - b - cc.c; cc.c = (uint32_t)(t >> 63); return (uint32_t)t; }
+BZK_HD uint32_t subc(uint32_t a, uint32_t b, CC &cc) { return a - b - cc.c; }
+BZK_HD uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c, CC &cc) { uint64_t t = (uint64_t)(uint32_t)((uint64_t)a * b) + c; cc.c = (uint32_t)(t >> 32); return (uint32_t)t; }
+BZK_HD uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c, CC &cc) { uint64_t t = (uint64_t)(uint32_t)((uint64_t)a * b) + c + cc.c; cc.c = (uint32_t)(t >> 32); return (uint32_t)t; }
+BZK_HD uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c, CC &cc) { uint64_t t = (((uint64_t)a * b) >> 32) + c + cc.c; cc.c = (uint32_t)(t >> 32); return (uint32_t)t; }
+BZK_HD uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+BZK_HD uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// Field element: N 32-bit limbs, little-endian (identical bytes to N/2 little-endian u64 limbs).
+// P supplies: static constexpr int N; modulus p[N]; inv = -p^-1 mod 2^32; one[N] = R mod p;
+//             r2[N] = R^2 mod p   (as functions returning the k-th limb so that they constant-fold)
+// ---------------------------------------------------------------------------------------------
+template <class P>
+struct Fe {
+    static constexpr int N = P::N;
+    uint32_t l[N];
+
+    BZK_HD static Fe zero() {
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = 0;
+        return r;
+    }
+    BZK_HD static Fe one() {
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = P::one(i);
+        return r;
+    }
+    BZK_HD static Fe r2() {
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = P::r2(i);
+        return r;
+    }
+    BZK_HD bool is_zero() const {
+        uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) t |= l[i];
+        return t == 0;
+    }
+    BZK_HD bool operator==(const Fe &o) const {
+        uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) t |= l[i] ^ o.l[i];
+        return t == 0;
+    }
+    BZK_HD bool operator!=(const Fe &o) const { return !(*this == o); }
+
+    // r = a - p if a >= p else a        (a < 2p)
+    BZK_HD static Fe reduce_once(const Fe &a) {
+        Fe t;
+        CC cc{0};
+        t.l[0] = sub_cc(a.l[0], P::p(0), cc);
+#pragma unroll
+        for (int i = 1; i < N; i++) t.l[i] = subc_cc(a.l[i], P::p(i), cc);
+        uint32_t borrow = subc(0, 0, cc);  // 0 or 0xffffffff
+        Fe r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = borrow ? a.l[i] : t.l[i];
+        return r;
+    }
+    BZK_HD friend Fe operator+(const Fe &a, const Fe &b) {
+        Fe t;
+        CC cc{0};
+        t.l[0] = add_cc(a.l[0], b.l[0], cc);
+#pragma unroll
+        for (int i = 1; i < N; i++) t.l[i] = addc_cc(a.l[i], b.l[i], cc);
+        return reduce_once(t);  // both moduli leave a spare top bit: no carry out of limb N-1
+    }
+    BZK_HD friend Fe operator-(const Fe &a, const Fe &b) {
+        Fe t;
+        CC cc{0};
+        t.l[0] = sub_cc(a.l[0], b.l[0], cc);
+#pragma unroll
+        for (int i = 1; i < N; i++) t.l[i] = subc_cc(a.l[i], b.l[i], cc);
+        uint32_t borrow = subc(0, 0, cc);
+        CC c2{0};
+        t.l[0] = add_cc(t.l[0], borrow & P::p(0), c2);
+#pragma unroll
+        for (int i = 1; i < N; i++) t.l[i] = addc_cc(t.l[i], borrow & P::p(i), c2);
+        return t;
+    }
+    BZK_HD Fe neg() const { return zero() - *this; }
+    BZK_HD Fe dbl() const { return *this + *this; }
+
+    // Montgomery product a*b/R mod p, fully reduced.  See the header comment for the layout:
+    // E holds 64-bit partial products starting on even absolute columns, O those starting on odd
+    // columns; row i adds a*b[i] and m_i*p and retires column i.
+    BZK_HD friend Fe operator*(const Fe &a, const Fe &b) {
+#if defined(__CUDA_ARCH__)
+        return mul_evenodd(a, b);
+#else
+        return mul_host64(a, b);
+#endif
+    }
+    // host fast path: plain CIOS on 64-bit limbs (unsigned __int128 products); same result
+    static inline Fe mul_host64(const Fe &a, const Fe &b) {
+        constexpr int M = N / 2;
+        uint64_t A[M], B[M], Pm[M], t[M + 2];
+        for (int i = 0; i < M; i++) {
+            A[i] = (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32);
+            B[i] = (uint64_t)b.l[2 * i] | ((uint64_t)b.l[2 * i + 1] << 32);
+            Pm[i] = (uint64_t)P::p(2 * i) | ((uint64_t)P::p(2 * i + 1) << 32);
+        }
+        // -p^-1 mod 2^64 from the 32-bit constant by one Newton step
+        uint64_t x = (uint64_t)(0u - P::inv());           // p^-1 mod 2^32
+        x *= 2 - Pm[0] * x;                                // p^-1 mod 2^64
+        const uint64_t inv64 = (uint64_t)0 - x;
+        for (int i = 0; i < M + 2; i++) t[i] = 0;
+        for (int i = 0; i < M; i++) {
+            unsigned __int128 cur;
+            uint64_t carry = 0;
+            for (int j = 0; j < M; j++) {
+                cur = (unsigned __int128)A[j] * B[i] + t[j] + carry;
+                t[j] = (uint64_t)cur;
+                carry = (uint64_t)(cur >> 64);
+            }
+            cur = (unsigned __int128)t[M] + carry;
+            t[M] = (uint64_t)cur;
+            t[M + 1] = (uint64_t)(cur >> 64);
+            const uint64_t m = t[0] * inv64;
+            cur = (unsigned __int128)m * Pm[0] + t[0];
+            carry = (uint64_t)(cur >> 64);
+            for (int j = 1; j < M; j++) {
+                cur = (unsigned __int128)m * Pm[j] + t[j] + carry;
+                t[j - 1] = (uint64_t)cur;
+                carry = (uint64_t)(cur >> 64);
+            }
+            cur = (unsigned __int128)t[M] + carry;
+            t[M - 1] = (uint64_t)cur;
+            t[M] = t[M + 1] + (uint64_t)(cur >> 64);
+        }
+        Fe r;
+        for (int i = 0; i < M; i++) {
+            r.l[2 * i] = (uint32_t)t[i];
+            r.l[2 * i + 1] = (uint32_t)(t[i] >> 32);
+        }
+        return reduce_once(r);  // t < 2p and 2p < 2^(32N): t[M] == 0
+    }
+    // the device algorithm (also compiled for the host so tests can check its carry logic)
+    BZK_HD static Fe mul_evenodd(const Fe &a, const Fe &b) {
+        uint32_t E[2 * N + 2], O[2 * N + 2];
+#pragma unroll
+        for (int i = 0; i < 2 * N + 2; i++) E[i] = O[i] = 0;
+        CC cc{0};
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            uint32_t *Pp = (i & 1) ? O : E;  // pairs start on column i's parity
+            uint32_t *Q = (i & 1) ? E : O;
+            const uint32_t bi = b.l[i];
+            if (i == 0) {
+#pragma unroll
+                for (int j = 0; j < N; j += 2) {
+                    Pp[j] = mul_lo(a.l[j], bi);
+                    Pp[j + 1] = mul_hi(a.l[j], bi);
+                    Q[j + 1] = mul_lo(a.l[j + 1], bi);
+                    Q[j + 2] = mul_hi(a.l[j + 1], bi);
+                }
+            } else {
+                // retire the high half Q[i] of Q's pair (i-1,i) into column i; its carry enters
+                // Q's chain at column i+1
+                Pp[i] = add_cc(Pp[i], Q[i], cc);
+#pragma unroll
+                for (int j = 1; j < N; j += 2) {
+                    Q[i + j] = madc_lo_cc(a.l[j], bi, Q[i + j], cc);
+                    Q[i + j + 1] = madc_hi_cc(a.l[j], bi, Q[i + j + 1], cc);
+                }
+                Q[i + N + 1] = addc(0, 0, cc);
+                Pp[i] = mad_lo_cc(a.l[0], bi, Pp[i], cc);
+                Pp[i + 1] = madc_hi_cc(a.l[0], bi, Pp[i + 1], cc);
+#pragma unroll
+                for (int j = 2; j < N; j += 2) {
+                    Pp[i + j] = madc_lo_cc(a.l[j], bi, Pp[i + j], cc);
+                    Pp[i + j + 1] = madc_hi_cc(a.l[j], bi, Pp[i + j + 1], cc);
+                }
+                Pp[i + N] = addc(Pp[i + N], 0, cc);
+            }
+            const uint32_t m = mul_lo(Pp[i], P::inv());
+            Pp[i] = mad_lo_cc(m, P::p(0), Pp[i], cc);
+            Pp[i + 1] = madc_hi_cc(m, P::p(0), Pp[i + 1], cc);
+#pragma unroll
+            for (int j = 2; j < N; j += 2) {
+                Pp[i + j] = madc_lo_cc(m, P::p(j), Pp[i + j], cc);
+                Pp[i + j + 1] = madc_hi_cc(m, P::p(j), Pp[i + j + 1], cc);
+            }
+            Pp[i + N] = addc(Pp[i + N], 0, cc);
+            Q[i + 1] = mad_lo_cc(m, P::p(1), Q[i + 1], cc);
+            Q[i + 2] = madc_hi_cc(m, P::p(1), Q[i + 2], cc);
+#pragma unroll
+            for (int j = 3; j < N; j += 2) {
+                Q[i + j] = madc_lo_cc(m, P::p(j), Q[i + j], cc);
+                Q[i + j + 1] = madc_hi_cc(m, P::p(j), Q[i + j + 1], cc);
+            }
+            Q[i + N + 1] = addc(Q[i + N + 1], 0, cc);
+        }
+        // columns N .. 2N-1 of E + O  (column 2N is provably zero: the result is < 2p < 2^(32N))
+        Fe r;
+        r.l[0] = add_cc(E[N], O[N], cc);
+#pragma unroll
+        for (int k = 1; k < N; k++) r.l[k] = addc_cc(E[N + k], O[N + k], cc);
+        return reduce_once(r);
+    }
+    BZK_HD Fe sqr() const { return (*this) * (*this); }
+
+    BZK_HD Fe to_mont() const { return (*this) * r2(); }
+    BZK_HD Fe from_mont() const {
+        Fe o = zero();
+        o.l[0] = 1;
+        return (*this) * o;
+    }
+    BZK_HD static Fe from_u32(uint32_t v) {
+        Fe o = zero();
+        o.l[0] = v;
+        return o.to_mont();
+    }
+    // a^e for a plain little-endian exponent of `nw` 32-bit words (not constant time; not needed)
+    BZK_HD_POW Fe pow(const uint32_t *e, int nw) const {
+        Fe acc = one();
+        for (int i = nw * 32 - 1; i >= 0; i--) {
+            acc = acc.sqr();
+            if ((e[i >> 5] >> (i & 31)) & 1) acc = acc * (*this);
+        }
+        return acc;
+    }
+    // Fermat inverse (0 -> 0)
+    BZK_HD Fe inv() const {
+        uint32_t e[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) e[i] = P::p(i);
+        e[0] -= 2;  // both moduli are odd with low limb >= 2
+        return pow(e, N);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// BLS12-381 parameter packs.  Limbs as constexpr switch tables so that they fold to immediates.
+// (R, R^2, inv are checked against big-integer arithmetic in tests/test_host_arith.py.)
+// ---------------------------------------------------------------------------------------------
+#define BZK_TABLE(name, ...)                                   \
+    BZK_HD static constexpr uint32_t name(int i) {             \
+        constexpr uint32_t t[] = {__VA_ARGS__};                \
+        return t[i];                                           \
+    }
+
+struct FrParams {  // r = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    static constexpr int N = 8;
+    BZK_TABLE(p, 0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u)
+    BZK_TABLE(one, 0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau, 0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u)
+    BZK_TABLE(r2, 0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u)
+    BZK_HD static constexpr uint32_t inv() { return 0xffffffffu; }
+};
+
+struct FpParams {  // p = 0x1a0111ea...ffffaaab
+    static constexpr int N = 12;
+    BZK_TABLE(p, 0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, 0x64774b84u,
+              0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau)
+    BZK_TABLE(one, 0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u, 0x70525745u, 0x77ce5853u,
+              0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u)
+    BZK_TABLE(r2, 0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu, 0x939d83c0u, 0x67eb88a9u,
+              0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u)
+    BZK_HD static constexpr uint32_t inv() { return 0xfffcfffdu; }
+};
+
+typedef Fe<FrParams> Fr;
+typedef Fe<FpParams> Fp;
+
+}  // namespace bzk

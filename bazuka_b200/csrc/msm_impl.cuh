@@ -1,0 +1,528 @@
+// bazuka_b200 — Pippenger multi-scalar multiplication over BLS12-381 G1 / G2 on sm_100a.
+//
+// GPU replacement for bellman 0.14.0 `multiexp::multiexp` (un-vendored crate), the eight sums
+// h, l, a_inputs, a_aux, b_g1_inputs, b_g1_aux, b_g2_inputs, b_g2_aux of `create_proof`
+// (reference call sites /root/reference/src/mpn/circuits/test.rs:135,175,215 and every gadget test).
+// The result is the same group element bellman computes; the algorithm is re-designed for the GPU:
+//
+//   1. digits     signed-digit (Booth) recoding of every scalar with window c: W = ceil(256/c)
+//                 digits in [-2^(c-1), 2^(c-1)], halving the bucket count.  Scalars arrive as
+//                 Montgomery images and are converted in-register.  Histogram by (window, |digit|)
+//                 with global REDs.                        [bellman: unsigned windows, c = ceil(ln n)]
+//   2. scan       exclusive prefix sum of the W * 2^(c-1) counters -> bucket offsets.
+//   3. scatter    counting sort: entry = base index | sign bit, grouped by (window, bucket).
+//   4. accumulate the sorted entry list is cut into equal chunks, one per thread, INDEPENDENT of
+//                 bucket boundaries, so the work per thread is identical whatever the scalar
+//                 distribution (witness vectors are full of 0/1 and small values; bellman special-
+//                 cases them, here they are just long runs).  A thread walks its chunk, gathers the
+//                 96-byte packed affine base with 6 LDG.128, mixed-adds into an XYZZ accumulator
+//                 and flushes at bucket boundaries: runs wholly inside the chunk go straight to the
+//                 bucket array, the (at most two) runs cut by a chunk edge go to a side list.
+//   5. fixup      side-list runs of the same bucket are folded and stored.
+//   6. reduce     per window sum_b (b+1) * B_b: slices of buckets -> running-sum trick per thread
+//                 (+ [slice offset] * slice-sum), then a shared-memory tree per window.
+//   7. combine    the W window sums (W * 192 B) go to the host, which does the Horner chain of
+//                 c*(W-1) doublings and the affine conversion: 255 dependent doublings are a serial
+//                 chain no GPU thread runs faster than a CPU core, and it is < 2 % of the job.
+//
+// Algorithmic traffic: 128 B per term (32 B scalar + 96 B base) for G1, 224 B for G2; the kernel is
+// integer-ALU bound (≈ W * 10 Fp products per term), see DESIGN.md for both rooflines.
+#pragma once
+#include "common.cuh"
+
+namespace bzk {
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+struct MsmPlan {
+    uint32_t c = 0;        // window bits
+    uint32_t W = 0;        // windows
+    uint32_t NB = 0;       // buckets per window = 2^(c-1)
+    uint32_t TB = 0;       // total buckets = W * NB
+};
+
+static MsmPlan make_plan(size_t n, int force_c = 0) {
+    // cost model: n*W mixed adds + ~3*W*NB add-equivalents for the reduction
+    uint32_t best_c = 1;
+    double best = 1e300;
+    for (uint32_t c = 2; c <= 18; c++) {
+        uint32_t W = (256 + c - 1) / c;
+        double cost = (double)n * W + 3.0 * W * (double)(1u << (c - 1));
+        if (cost < best) { best = cost; best_c = c; }
+    }
+    MsmPlan p;
+    p.c = force_c ? (uint32_t)force_c : best_c;
+    // W*c >= 256 guarantees the recoding carry never leaves the top window (scalars < 2^255)
+    p.W = (256 + p.c - 1) / p.c;
+    p.NB = 1u << (p.c - 1);
+    p.TB = p.W * p.NB;
+    return p;
+}
+
+// signed digit w of canonical scalar k (8 LE 32-bit limbs): value in [-2^(c-1), 2^(c-1)]
+__host__ __device__ __forceinline__ int32_t signed_digit(const uint32_t k[8], uint32_t c, uint32_t w, uint32_t &carry) {
+    const uint32_t pos = w * c;
+    uint32_t raw = 0;
+    if (pos < 256) {
+        const uint32_t limb = pos >> 5, sh = pos & 31;
+        uint64_t two = k[limb];
+        if (limb + 1 < 8) two |= (uint64_t)k[limb + 1] << 32;
+        raw = (uint32_t)(two >> sh) & ((1u << c) - 1);
+    }
+    raw += carry;
+    if (raw > (1u << (c - 1))) {
+        carry = 1;
+        return (int32_t)raw - (int32_t)(1u << c);
+    }
+    carry = 0;
+    return (int32_t)raw;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1. digits + histogram          3. scatter
+// ---------------------------------------------------------------------------------------------
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_digits(const Fr *__restrict__ scalars, size_t n, uint32_t c, uint32_t W, uint32_t NB,
+                                                uint32_t *__restrict__ counts_or_cursor, uint32_t *__restrict__ sorted) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr k = load_vec(scalars + i).from_mont();
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < W; w++) {
+        int32_t d = signed_digit(k.l, c, w, carry);
+        if (d == 0) continue;
+        uint32_t neg = d < 0;
+        uint32_t b = (uint32_t)(neg ? -d : d) - 1;
+        uint32_t slot = w * NB + b;
+        if (SCATTER) {
+            uint32_t pos = atomicAdd(&counts_or_cursor[slot], 1u);
+            sorted[pos] = (uint32_t)i | (neg << 31);
+        } else {
+            atomicAdd(&counts_or_cursor[slot], 1u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. exclusive scan of uint32 counters (three small kernels)
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanBlock = 256, kScanItems = 4, kScanTile = kScanBlock * kScanItems;
+
+static __global__ void __launch_bounds__(kScanBlock) k_scan_tile_sums(const uint32_t *__restrict__ in, uint32_t count, uint32_t *__restrict__ tile_sums) {
+    __shared__ uint32_t sh[kScanBlock / 32];
+    uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++)
+        if (base + k < count) s += in[base + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int k = 0; k < kScanBlock / 32; k++) t += sh[k];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+// single block: exclusive scan of tile sums in place; writes grand total to tile_sums[ntiles]
+static __global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t *__restrict__ tile_sums, uint32_t ntiles) {
+    __shared__ uint32_t sh[1024];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < ntiles; base += 1024) {
+        uint32_t idx = base + threadIdx.x;
+        uint32_t v = idx < ntiles ? tile_sums[idx] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (uint32_t o = 1; o < 1024; o <<= 1) {
+            uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        uint32_t incl = sh[threadIdx.x];
+        if (idx < ntiles) tile_sums[idx] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_sums[ntiles] = carry;
+}
+// offsets[i] = exclusive prefix; offsets[count] = total; cursor = copy of offsets
+static __global__ void __launch_bounds__(kScanBlock) k_scan_apply(const uint32_t *__restrict__ in, uint32_t count, const uint32_t *__restrict__ tile_sums,
+                                                           uint32_t ntiles, uint32_t *__restrict__ offsets, uint32_t *__restrict__ cursor) {
+    __shared__ uint32_t sh[kScanBlock];
+    uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    uint32_t v[kScanItems], s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) { v[k] = (base + k < count) ? in[base + k] : 0; s += v[k]; }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (uint32_t o = 1; o < kScanBlock; o <<= 1) {
+        uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    uint32_t run = tile_sums[blockIdx.x] + sh[threadIdx.x] - s;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (base + k < count) { offsets[base + k] = run; cursor[base + k] = run; }
+        run += v[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) offsets[count] = tile_sums[ntiles];
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. accumulate (chunked, bucket-boundary agnostic)
+// ---------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
+                                                    const uint32_t *__restrict__ offsets, uint32_t TB, uint32_t chunk,
+                                                    Xyzz<F> *__restrict__ buckets, Xyzz<F> *__restrict__ part_pts,
+                                                    int32_t *__restrict__ part_bucket) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t M = offsets[TB];
+    const uint64_t start64 = (uint64_t)t * chunk;
+    part_bucket[2 * t] = -1;
+    part_bucket[2 * t + 1] = -1;
+    if (start64 >= M) return;
+    const uint32_t start = (uint32_t)start64;
+    const uint32_t end = (uint32_t)(start64 + chunk < M ? start64 + chunk : M);
+    // largest b with offsets[b] <= start
+    uint32_t lo = 0, hi = TB;  // invariant: offsets[lo] <= start < offsets[hi] (offsets[TB] = M > start)
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= start) lo = mid; else hi = mid;
+    }
+    uint32_t b = lo;
+    uint32_t bend = offsets[b + 1];
+    while (bend <= start) { b++; bend = offsets[b + 1]; }  // skip empty buckets sharing the offset
+    uint32_t run_start = start;
+    bool run_from_bucket_start = (offsets[b] == start);
+    Xyzz<F> acc = Xyzz<F>::inf();
+    for (uint32_t pos = start; pos < end; pos++) {
+        if (pos == bend) {
+            // bucket b ended exactly here: flush
+            if (run_from_bucket_start) {
+                store_vec(buckets + b, acc);
+            } else {
+                const uint32_t slot = 2 * t + (run_start == start ? 0 : 1);
+                store_vec(part_pts + slot, acc);
+                part_bucket[slot] = (int32_t)b;
+            }
+            acc = Xyzz<F>::inf();
+            do { b++; bend = offsets[b + 1]; } while (bend <= pos);
+            run_start = pos;
+            run_from_bucket_start = true;
+        }
+        const uint32_t e = sorted[pos];
+        Affine<F> p = load_vec(bases + (e & 0x7fffffffu));
+        if (e >> 31) p.y = p.y.neg();
+        acc.madd(p);
+    }
+    // final run: complete only if it started at the bucket start and the bucket ends at `end`
+    if (run_from_bucket_start && bend == end) {
+        store_vec(buckets + b, acc);
+    } else {
+        const uint32_t slot = 2 * t + (run_start == start ? 0 : 1);
+        store_vec(part_pts + slot, acc);
+        part_bucket[slot] = (int32_t)b;
+    }
+}
+
+// 5. fold the side list: the first slot of each bucket's run of partials sums the run and stores it
+template <class F>
+__global__ void __launch_bounds__(128) k_fixup(const Xyzz<F> *__restrict__ part_pts, const int32_t *__restrict__ part_bucket,
+                                               uint32_t nslots, Xyzz<F> *__restrict__ buckets) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nslots) return;
+    const int32_t b = part_bucket[e];
+    if (b < 0) return;
+    for (uint32_t q = e; q-- > 0;) {
+        int32_t pb = part_bucket[q];
+        if (pb < 0) continue;
+        if (pb == b) return;  // not the head of the run
+        break;
+    }
+    Xyzz<F> acc = load_vec(part_pts + e);
+    for (uint32_t q = e + 1; q < nslots; q++) {
+        int32_t nb = part_bucket[q];
+        if (nb < 0) continue;
+        if (nb != b) break;
+        acc.add(load_vec(part_pts + q));
+    }
+    store_vec(buckets + b, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 6. bucket reduction: per window  sum_b (b+1) * B_b
+// ---------------------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ Xyzz<F> small_mul(const Xyzz<F> &p, uint32_t k) {
+    Xyzz<F> acc = Xyzz<F>::inf();
+    if (k == 0) return acc;
+    for (int i = 31 - __clz(k); i >= 0; i--) {
+        acc = acc.dbl();
+        if ((k >> i) & 1) acc.add(p);
+    }
+    return acc;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_bucket_slices(const Xyzz<F> *__restrict__ buckets, uint32_t NB, uint32_t slice, uint32_t nslices_total,
+                                                       Xyzz<F> *__restrict__ slice_out) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nslices_total) return;
+    const uint32_t per_win = NB / slice;
+    const uint32_t w = g / per_win, sidx = g % per_win;
+    const uint32_t lo = sidx * slice;
+    const Xyzz<F> *B = buckets + (size_t)w * NB;
+    Xyzz<F> run = Xyzz<F>::inf(), acc = Xyzz<F>::inf();
+    for (uint32_t k = slice; k-- > 0;) {
+        run.add(load_vec(B + lo + k));
+        acc.add(run);
+    }
+    if (lo) acc.add(small_mul(run, lo));
+    store_vec(slice_out + g, acc);
+}
+
+// one CTA per window: sum `per_win` slice results
+template <class F>
+__global__ void __launch_bounds__(128) k_window_sum(const Xyzz<F> *__restrict__ slice_out, uint32_t per_win, Xyzz<F> *__restrict__ win_out) {
+    extern __shared__ uint4 smem_raw[];
+    Xyzz<F> *sh = (Xyzz<F> *)smem_raw;
+    const uint32_t w = blockIdx.x;
+    Xyzz<F> acc = Xyzz<F>::inf();
+    for (uint32_t k = threadIdx.x; k < per_win; k += blockDim.x) acc.add(load_vec(slice_out + (size_t)w * per_win + k));
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            Xyzz<F> a = sh[threadIdx.x];
+            a.add(sh[threadIdx.x + o]);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) store_vec(win_out + w, sh[0]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// wire image <-> packed, synthetic inputs
+// ---------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256) k_pack_g1(const uint8_t *__restrict__ images, size_t n, G1Affine *__restrict__ out, uint32_t *bad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine p = load_g1_image(images + i * 104);
+    if (bad && !p.is_inf()) {
+        Fp rhs = p.x.sqr() * p.x + Fp::from_u32(4);
+        if (p.y.sqr() != rhs) atomicAdd(bad, 1u);
+    }
+    store_vec(out + i, p);
+}
+static __global__ void __launch_bounds__(128) k_pack_g2(const uint8_t *__restrict__ images, size_t n, G2Affine *__restrict__ out, uint32_t *bad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G2Affine p = load_g2_image(images + i * 200);
+    if (bad && !p.is_inf()) {
+        Fp four = Fp::from_u32(4);
+        Fp2 rhs = p.x.sqr() * p.x + Fp2{four, four};
+        if (p.y.sqr() != rhs) atomicAdd(bad, 1u);
+    }
+    store_vec(out + i, p);
+}
+
+static __global__ void __launch_bounds__(128) k_random_g1(uint64_t seed, size_t n, G1Affine gen, uint8_t *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr k = splitmix_fr_canonical(seed, i);
+    store_g1_image(out + i * 104, scalar_mul(gen, k.l).to_affine());
+}
+static __global__ void __launch_bounds__(64) k_random_g2(uint64_t seed, size_t n, G2Affine gen, uint8_t *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr k = splitmix_fr_canonical(seed, i);
+    store_g2_image(out + i * 200, scalar_mul(gen, k.l).to_affine());
+}
+static __global__ void __launch_bounds__(256) k_random_fr(uint64_t seed, size_t n, Fr *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    store_vec(out + i, splitmix_fr_canonical(seed, i).to_mont());
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: generator constants (canonical big-endian hex -> Montgomery)
+// ---------------------------------------------------------------------------------------------
+static Fp fp_from_hex(const char *hex96) {
+    Fp v;
+    for (int i = 0; i < 12; i++) {
+        uint32_t x = 0;
+        for (int k = 0; k < 8; k++) {
+            char ch = hex96[(11 - i) * 8 + k];
+            x = (x << 4) | (uint32_t)(ch <= '9' ? ch - '0' : (ch | 32) - 'a' + 10);
+        }
+        v.l[i] = x;
+    }
+    return v.to_mont();
+}
+static G1Affine g1_generator() {
+    return G1Affine{
+        fp_from_hex("17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"),
+        fp_from_hex("08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1")};
+}
+static G2Affine g2_generator() {
+    return G2Affine{
+        Fp2{fp_from_hex("024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8"),
+            fp_from_hex("13e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e")},
+        Fp2{fp_from_hex("0ce5d527727d6e118cc9cdc6da2e351aadfd9baa8cbdd3a76d429a695160d12c923ac9cc3baca289e193548608b82801"),
+            fp_from_hex("0606c4a02ea734cc32acd2b02bc28b99cb3e287e85a763af267492ab572e99ab3f370d275cec1da1aaa9075ff05f79be")}};
+}
+
+// wire image (host) <-> Affine<F>
+static G1Affine g1_from_image(const bzk_g1_affine *img) {
+    if (img->infinity) return G1Affine::inf();
+    G1Affine p;
+    memcpy(p.x.l, img->x, 48);
+    memcpy(p.y.l, img->y, 48);
+    return p;
+}
+static void g1_to_image(bzk_g1_affine *img, const G1Affine &p) {
+    memset(img, 0, sizeof *img);
+    if (p.is_inf()) {
+        Fp one = Fp::one();
+        memcpy(img->y, one.l, 48);
+        img->infinity = 1;
+        return;
+    }
+    memcpy(img->x, p.x.l, 48);
+    memcpy(img->y, p.y.l, 48);
+}
+static G2Affine g2_from_image(const bzk_g2_affine *img) {
+    if (img->infinity) return G2Affine::inf();
+    G2Affine p;
+    memcpy(p.x.c0.l, img->x, 48);
+    memcpy(p.x.c1.l, img->x + 6, 48);
+    memcpy(p.y.c0.l, img->y, 48);
+    memcpy(p.y.c1.l, img->y + 6, 48);
+    return p;
+}
+static void g2_to_image(bzk_g2_affine *img, const G2Affine &p) {
+    memset(img, 0, sizeof *img);
+    if (p.is_inf()) {
+        Fp one = Fp::one();
+        memcpy(img->y, one.l, 48);
+        img->infinity = 1;
+        return;
+    }
+    memcpy(img->x, p.x.c0.l, 48);
+    memcpy(img->x + 6, p.x.c1.l, 48);
+    memcpy(img->y, p.y.c0.l, 48);
+    memcpy(img->y + 6, p.y.c1.l, 48);
+}
+template <class F> struct Wire;
+template <> struct Wire<Fp> {
+    typedef bzk_g1_affine image;
+    static void to_image(image *i, const Affine<Fp> &p) { g1_to_image(i, p); }
+    static Affine<Fp> from_image(const image *i) { return g1_from_image(i); }
+};
+template <> struct Wire<Fp2> {
+    typedef bzk_g2_affine image;
+    static void to_image(image *i, const Affine<Fp2> &p) { g2_to_image(i, p); }
+    static Affine<Fp2> from_image(const image *i) { return g2_from_image(i); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------------
+template <class F>
+static int32_t msm_run(bzk_ctx *ctx, const Affine<F> *d_bases, const Fr *d_scalars, size_t n, typename Wire<F>::image *out) {
+    if (!out) return BZK_ERR_BAD_ARG;
+    if (n == 0) { Wire<F>::to_image(out, Affine<F>::inf()); return BZK_OK; }
+    if (n >= ((size_t)1 << 31)) return BZK_ERR_BAD_ARG;
+    const MsmPlan pl = make_plan(n);
+    if ((double)n * pl.W >= 4294967295.0) return BZK_ERR_BAD_ARG;
+    const uint64_t max_entries = (uint64_t)n * pl.W;
+
+    // thread geometry of the accumulate kernel
+    const uint32_t acc_threads_target = (uint32_t)ctx->sm_count * 384;
+    uint32_t chunk = (uint32_t)((max_entries + acc_threads_target - 1) / acc_threads_target);
+    if (chunk < 16) chunk = 16;
+    const uint32_t acc_threads = (uint32_t)((max_entries + chunk - 1) / chunk);
+    const uint32_t acc_blocks = div_up(acc_threads, 128);
+    const uint32_t nslots = 2 * acc_blocks * 128;
+
+    uint32_t slice = pl.NB >= 32 ? 32 : pl.NB;
+    if (pl.NB >= 4096) slice = 16;
+    const uint32_t per_win = pl.NB / slice;
+    const uint32_t nslices = per_win * pl.W;
+    const uint32_t ntiles = div_up(pl.TB, kScanTile);
+
+    // workspace
+    size_t need = 0;
+    {
+        Carver cv(nullptr);
+        cv.take<uint32_t>(pl.TB + 1); cv.take<uint32_t>(pl.TB + 1); cv.take<uint32_t>(pl.TB + 1);
+        cv.take<uint32_t>(ntiles + 1);
+        cv.take<uint32_t>(max_entries);
+        cv.take<Xyzz<F>>(pl.TB);
+        cv.take<Xyzz<F>>(nslots); cv.take<int32_t>(nslots);
+        cv.take<Xyzz<F>>(nslices);
+        cv.take<Xyzz<F>>(pl.W);
+        need = cv.used();
+    }
+    BZK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, need));
+    Carver cv(ctx->ws);
+    uint32_t *counts = cv.take<uint32_t>(pl.TB + 1);
+    uint32_t *offsets = cv.take<uint32_t>(pl.TB + 1);
+    uint32_t *cursor = cv.take<uint32_t>(pl.TB + 1);
+    uint32_t *tile_sums = cv.take<uint32_t>(ntiles + 1);
+    uint32_t *sorted = cv.take<uint32_t>(max_entries);
+    Xyzz<F> *buckets = cv.take<Xyzz<F>>(pl.TB);
+    Xyzz<F> *part_pts = cv.take<Xyzz<F>>(nslots);
+    int32_t *part_bucket = cv.take<int32_t>(nslots);
+    Xyzz<F> *slice_out = cv.take<Xyzz<F>>(nslices);
+    Xyzz<F> *win_out = cv.take<Xyzz<F>>(pl.W);
+
+    cudaStream_t st = ctx->stream;
+    BZK_CUDA(ctx, cudaMemsetAsync(counts, 0, (pl.TB + 1) * sizeof(uint32_t), st));
+    BZK_CUDA(ctx, cudaMemsetAsync(buckets, 0, (size_t)pl.TB * sizeof(Xyzz<F>), st));  // all-zero = identity
+
+    k_digits<false><<<div_up(n, 256), 256, 0, st>>>(d_scalars, n, pl.c, pl.W, pl.NB, counts, nullptr);
+    BZK_LAUNCHED(ctx);
+    k_scan_tile_sums<<<ntiles, kScanBlock, 0, st>>>(counts, pl.TB, tile_sums);
+    BZK_LAUNCHED(ctx);
+    k_scan_tiles<<<1, 1024, 0, st>>>(tile_sums, ntiles);
+    BZK_LAUNCHED(ctx);
+    k_scan_apply<<<ntiles, kScanBlock, 0, st>>>(counts, pl.TB, tile_sums, ntiles, offsets, cursor);
+    BZK_LAUNCHED(ctx);
+    k_digits<true><<<div_up(n, 256), 256, 0, st>>>(d_scalars, n, pl.c, pl.W, pl.NB, cursor, sorted);
+    BZK_LAUNCHED(ctx);
+    k_accumulate<F><<<acc_blocks, 128, 0, st>>>(d_bases, sorted, offsets, pl.TB, chunk, buckets, part_pts, part_bucket);
+    BZK_LAUNCHED(ctx);
+    k_fixup<F><<<div_up(nslots, 128), 128, 0, st>>>(part_pts, part_bucket, nslots, buckets);
+    BZK_LAUNCHED(ctx);
+    k_bucket_slices<F><<<div_up(nslices, 128), 128, 0, st>>>(buckets, pl.NB, slice, nslices, slice_out);
+    BZK_LAUNCHED(ctx);
+    const size_t smem = 128 * sizeof(Xyzz<F>);
+    BZK_CUDA(ctx, cudaFuncSetAttribute(k_window_sum<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_window_sum<F><<<pl.W, 128, smem, st>>>(slice_out, per_win, win_out);
+    BZK_LAUNCHED(ctx);
+
+    // 7. host Horner over the W window sums
+    std::vector<Xyzz<F>> h(pl.W);
+    BZK_CUDA(ctx, cudaMemcpyAsync(h.data(), win_out, pl.W * sizeof(Xyzz<F>), cudaMemcpyDeviceToHost, st));
+    BZK_CUDA(ctx, cudaStreamSynchronize(st));
+    Xyzz<F> acc = h[pl.W - 1];
+    for (int w = (int)pl.W - 2; w >= 0; w--) {
+        for (uint32_t k = 0; k < pl.c; k++) acc = acc.dbl();
+        acc.add(h[w]);
+    }
+    Wire<F>::to_image(out, acc.to_affine());
+    return BZK_OK;
+}
+
+}  // namespace bzk

@@ -1,0 +1,156 @@
+// bazuka_b200 — batched Poseidon (x^5, t = 2..17) over BLS12-381 Fr.
+//
+// GPU replacement for `poseidon::poseidon` / `PoseidonState::hash`
+// (/root/reference/src/zk/poseidon/mod.rs:24-84): state = [0] ++ inputs, R_F/2 full rounds,
+// R_P partial rounds (S-box on lane 0), R_F/2 full rounds, each round = add t round constants
+// (consumed sequentially), S-box, dense t x t MDS product; digest = lane 1.  The reference
+// serialises all hashing behind a process-global Mutex<LruCache> (/root/reference/src/zk/mod.rs:491-511);
+// here one thread owns one hash and a launch processes the whole batch.
+//
+// Layout: in[n][arity] / out[n] are Montgomery Fr images (32 B = one DRAM sector per element, so
+// the strided per-thread reads are sector-exact).  The per-width constant table (round constants,
+// then MDS rows) is staged into shared memory once per CTA and read as warp-uniform broadcasts.
+// Bound: integer ALU (t=5: 1 888 Fr products per 160 B of traffic) — see DESIGN.md.
+#include "common.cuh"
+
+namespace bzk {
+
+__device__ __forceinline__ Fr lds_fr(const Fr *s) {
+    Fr r;
+    const uint4 *p = (const uint4 *)s;
+    uint4 a = p[0], b = p[1];
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+
+__device__ __forceinline__ Fr pow5(const Fr &x) {
+    Fr x2 = x.sqr();
+    Fr x4 = x2.sqr();
+    return x * x4;
+}
+
+// Register-resident state, fully unrolled lanes (T <= 9).
+template <int T>
+__global__ void __launch_bounds__(128) k_poseidon_reg(const Fr *__restrict__ consts, uint32_t rf, uint32_t rp,
+                                                      const Fr *__restrict__ in, size_t n, Fr *__restrict__ out) {
+    extern __shared__ uint4 smem_raw[];
+    Fr *sc = (Fr *)smem_raw;
+    const uint32_t nconst = T * (rf + rp) + T * T;
+    {
+        const uint4 *src = (const uint4 *)consts;
+        uint4 *dst = (uint4 *)sc;
+        for (uint32_t i = threadIdx.x; i < nconst * 2; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const Fr *mds = sc + T * (rf + rp);
+    size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n) return;
+    Fr s[T];
+    s[0] = Fr::zero();
+#pragma unroll
+    for (int i = 1; i < T; i++) s[i] = load_vec(in + h * (T - 1) + (i - 1));
+    const uint32_t half = rf / 2;
+    const Fr *rc = sc;
+#pragma unroll 1
+    for (uint32_t rnd = 0; rnd < rf + rp; rnd++) {
+#pragma unroll
+        for (int i = 0; i < T; i++) s[i] = s[i] + lds_fr(rc + i);
+        rc += T;
+        if (rnd < half || rnd >= half + rp) {
+#pragma unroll
+            for (int i = 0; i < T; i++) s[i] = pow5(s[i]);
+        } else {
+            s[0] = pow5(s[0]);
+        }
+        Fr o[T];
+#pragma unroll
+        for (int j = 0; j < T; j++) {
+            Fr acc = lds_fr(mds + j * T) * s[0];
+#pragma unroll
+            for (int k = 1; k < T; k++) acc = acc + lds_fr(mds + j * T + k) * s[k];
+            o[j] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < T; i++) s[i] = o[i];
+    }
+    store_vec(out + h, s[1]);
+}
+
+// Generic width (T up to 17): state in shared memory, one thread per hash, rolled loops.
+__global__ void __launch_bounds__(64) k_poseidon_gen(const Fr *__restrict__ consts, uint32_t T, uint32_t rf, uint32_t rp,
+                                                     const Fr *__restrict__ in, size_t n, Fr *__restrict__ out) {
+    extern __shared__ uint4 smem_raw[];
+    Fr *sc = (Fr *)smem_raw;
+    const uint32_t nconst = T * (rf + rp) + T * T;
+    {
+        const uint4 *src = (const uint4 *)consts;
+        uint4 *dst = (uint4 *)sc;
+        for (uint32_t i = threadIdx.x; i < nconst * 2; i += blockDim.x) dst[i] = src[i];
+    }
+    // per-thread state and scratch rows, interleaved by thread to avoid bank conflicts on
+    // 16-byte accesses: element i of thread x lives at st[(i * blockDim + x)]
+    Fr *st = sc + nconst;
+    Fr *tmp = st + (size_t)T * blockDim.x;
+    __syncthreads();
+    const Fr *mds = sc + T * (rf + rp);
+    size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n) return;
+    const uint32_t x = threadIdx.x, bd = blockDim.x;
+    st[x] = Fr::zero();
+    for (uint32_t i = 1; i < T; i++) st[i * bd + x] = load_vec(in + h * (T - 1) + (i - 1));
+    const uint32_t half = rf / 2;
+    const Fr *rc = sc;
+    for (uint32_t rnd = 0; rnd < rf + rp; rnd++) {
+        const bool full = (rnd < half || rnd >= half + rp);
+        for (uint32_t i = 0; i < T; i++) {
+            Fr v = lds_fr(&st[i * bd + x]) + lds_fr(rc + i);
+            if (full || i == 0) v = pow5(v);
+            st[i * bd + x] = v;
+        }
+        rc += T;
+        for (uint32_t j = 0; j < T; j++) {
+            Fr acc = lds_fr(mds + j * T) * lds_fr(&st[x]);
+            for (uint32_t k = 1; k < T; k++) acc = acc + lds_fr(mds + j * T + k) * lds_fr(&st[k * bd + x]);
+            tmp[j * bd + x] = acc;
+        }
+        for (uint32_t i = 0; i < T; i++) st[i * bd + x] = tmp[i * bd + x];
+    }
+    store_vec(out + h, lds_fr(&st[bd + x]));
+}
+
+template <int T>
+static int32_t launch_reg(bzk_ctx *ctx, const PoseidonTable &pt, const Fr *d_in, size_t n, Fr *d_out) {
+    const int threads = 128;
+    size_t smem = (size_t)(pt.nrc + T * T) * sizeof(Fr);
+    BZK_CUDA(ctx, cudaFuncSetAttribute(k_poseidon_reg<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_poseidon_reg<T><<<div_up(n, threads), threads, smem, ctx->stream>>>(pt.d_consts, pt.rf, pt.rp, d_in, n, d_out);
+    BZK_LAUNCHED(ctx);
+    return BZK_OK;
+}
+
+int32_t poseidon_launch(bzk_ctx *ctx, uint32_t arity, const Fr *d_in, size_t n, Fr *d_out) {
+    if (!ctx->pos_loaded) return BZK_ERR_NO_PARAMS;
+    if (arity < 1 || arity > 16) return BZK_ERR_BAD_ARG;
+    if (n == 0) return BZK_OK;
+    const PoseidonTable &pt = ctx->pos[arity + 1];
+    switch (arity + 1) {
+        case 2: return launch_reg<2>(ctx, pt, d_in, n, d_out);
+        case 3: return launch_reg<3>(ctx, pt, d_in, n, d_out);
+        case 4: return launch_reg<4>(ctx, pt, d_in, n, d_out);
+        case 5: return launch_reg<5>(ctx, pt, d_in, n, d_out);
+        case 6: return launch_reg<6>(ctx, pt, d_in, n, d_out);
+        case 7: return launch_reg<7>(ctx, pt, d_in, n, d_out);
+        case 8: return launch_reg<8>(ctx, pt, d_in, n, d_out);
+        default: break;
+    }
+    const uint32_t T = arity + 1;
+    const int threads = 64;
+    size_t smem = ((size_t)(pt.nrc + T * T) + (size_t)2 * T * threads) * sizeof(Fr);
+    BZK_CUDA(ctx, cudaFuncSetAttribute(k_poseidon_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_poseidon_gen<<<div_up(n, threads), threads, smem, ctx->stream>>>(pt.d_consts, T, pt.rf, pt.rp, d_in, n, d_out);
+    BZK_LAUNCHED(ctx);
+    return BZK_OK;
+}
+
+}  // namespace bzk

@@ -1,0 +1,145 @@
+/* libbzk — B200-native prover kernels for Bazuka's MPN Groth16 path.  C ABI (drop-in boundary).
+ *
+ * Everything here is plain C: opaque handles, raw pointers and sizes, int32 status codes.  No
+ * exception, abort or global mutable state crosses this boundary.  One `bzk_ctx` per GPU; calls
+ * on one ctx are serialised by the caller, distinct ctxs may be used from different threads.
+ *
+ * Data images are the reference's own in-memory images, so a Rust caller passes `&[T]` pointers
+ * without conversion:
+ *   bzk_fr        = `ZkScalar([u64;4])`                      /root/reference/src/zk/mod.rs:202-206
+ *                   = bls12_381::Scalar (transmute)          /root/reference/src/zk/groth16/mod.rs:7-17
+ *                   4 little-endian u64 limbs, Montgomery form (R = 2^256), fully reduced.
+ *   bzk_g1_affine = `(Fp, Fp, bool)` = bls12_381::G1Affine   /root/reference/src/zk/groth16/mod.rs:21-23,44-60
+ *                   x, y: 6 LE u64 limbs each, Montgomery (R = 2^384); `infinity` byte; 7 pad bytes.
+ *   bzk_g2_affine = `((Fp,Fp),(Fp,Fp),bool)` = G2Affine      /root/reference/src/zk/groth16/mod.rs:25-27
+ *
+ * Which reference interface each entry point replaces is stated on the entry point.  The
+ * arithmetic the reference calls lives in un-vendored crates (bellman 0.14.0, bls12_381 0.8.0,
+ * ff 0.13 — /root/reference/Cargo.toml:19,27-28); "replaces" therefore names the crate function
+ * and the reference call site that reaches it.
+ */
+#ifndef BZK_H
+#define BZK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ types */
+typedef struct { uint64_t l[4]; } bzk_fr;                                          /* 32 B */
+typedef struct { uint64_t x[6]; uint64_t y[6]; uint8_t infinity; uint8_t pad[7]; } bzk_g1_affine; /* 104 B */
+typedef struct { uint64_t x[12]; uint64_t y[12]; uint8_t infinity; uint8_t pad[7]; } bzk_g2_affine; /* 200 B */
+
+typedef struct bzk_ctx bzk_ctx;            /* one per GPU */
+typedef struct bzk_g1_bases bzk_g1_bases;  /* device-resident, packed base vector (a proving-key column) */
+typedef struct bzk_g2_bases bzk_g2_bases;
+
+/* ------------------------------------------------------------------ status */
+#define BZK_OK 0
+#define BZK_ERR_BAD_ARG (-1)       /* null pointer, size out of range, unknown op */
+#define BZK_ERR_CUDA (-2)          /* a CUDA call failed; bzk_last_error(ctx) has the text */
+#define BZK_ERR_OOM (-3)           /* device or host allocation failed */
+#define BZK_ERR_NOT_ON_CURVE (-4)  /* a base failed the curve equation (only when checking is requested) */
+#define BZK_ERR_NO_PARAMS (-5)     /* Poseidon parameter table not loaded */
+#define BZK_ERR_NO_DEVICE (-6)     /* no CUDA device: the library never falls back to the CPU */
+#define BZK_ERR_UNSAT (-7)         /* witness does not satisfy the constraint system */
+
+const char *bzk_strerror(int32_t status);
+const char *bzk_last_error(const bzk_ctx *ctx);
+/* ABI version of this header: (major << 16) | minor */
+uint32_t bzk_abi_version(void);
+
+/* ------------------------------------------------------------------ context */
+/* Binds to CUDA device `device`, creates the ctx-owned stream and workspace.
+ * Fails with BZK_ERR_NO_DEVICE when no GPU is present — there is no CPU path. */
+int32_t bzk_ctx_create(int32_t device, bzk_ctx **out);
+int32_t bzk_ctx_destroy(bzk_ctx *ctx);
+/* Run subsequent work on a caller-owned CUDA stream (a `cudaStream_t` cast to void*, e.g. torch's
+ * current stream); NULL restores the ctx-owned stream. */
+int32_t bzk_ctx_set_stream(bzk_ctx *ctx, void *cuda_stream);
+int32_t bzk_ctx_synchronize(bzk_ctx *ctx);
+/* kernels launched through this ctx since creation (bench.py's `gpu_launches`) */
+uint64_t bzk_ctx_launch_count(const bzk_ctx *ctx);
+
+/* ------------------------------------------------------------------ Poseidon
+ * Replaces `poseidon::poseidon(vals)` / `PoseidonHasher::hash`
+ *   /root/reference/src/zk/poseidon/mod.rs:81-84 , /root/reference/src/zk/mod.rs:496-511
+ * arity 1..16 (state width arity+1, zero capacity lane 0, digest = lane 1). */
+/* `blob` = the BZKPOSv1 constant table (bazuka_b200/data/poseidon_params.bin). */
+int32_t bzk_poseidon_load_params(bzk_ctx *ctx, const uint8_t *blob, size_t len);
+/* host buffers: in[n][arity] -> out[n] */
+int32_t bzk_poseidon_hash(bzk_ctx *ctx, uint32_t arity, const bzk_fr *in, size_t n, bzk_fr *out);
+/* device buffers (same layout), asynchronous on the ctx stream */
+int32_t bzk_poseidon_hash_dev(bzk_ctx *ctx, uint32_t arity, const void *d_in, size_t n, void *d_out);
+
+/* ------------------------------------------------------------------ NTT over Fr
+ * Replaces bellman 0.14.0 `domain::EvaluationDomain::{fft, ifft, coset_fft, icoset_fft,
+ * divide_by_z_on_coset}` reached from `create_proof` (reference call sites
+ * /root/reference/src/mpn/circuits/test.rs:135,175,215).  Natural order in, natural order out,
+ * in place; n = 2^log_n, log_n <= 28. */
+#define BZK_NTT_FFT 0
+#define BZK_NTT_IFFT 1
+#define BZK_NTT_COSET_FFT 2
+#define BZK_NTT_ICOSET_FFT 3
+int32_t bzk_ntt(bzk_ctx *ctx, bzk_fr *data, uint32_t log_n, int32_t op);         /* host buffer */
+int32_t bzk_ntt_dev(bzk_ctx *ctx, void *d_data, uint32_t log_n, int32_t op);      /* device buffer, async */
+/* d[i] *= (7^n - 1)^-1 */
+int32_t bzk_divide_by_z_on_coset_dev(bzk_ctx *ctx, void *d_data, uint32_t log_n);
+/* Groth16 quotient: given the A, B, C evaluation vectors (each n = 2^log_n, overwritten), leaves
+ * the coefficients of H = (A*B - C)/Z in d_a (bellman prover.rs: 3x ifft, 3x coset_fft, pointwise
+ * a*b-c, divide_by_z_on_coset, icoset_fft). */
+int32_t bzk_groth16_h_dev(bzk_ctx *ctx, void *d_a, void *d_b, void *d_c, uint32_t log_n);
+
+/* ------------------------------------------------------------------ MSM
+ * Replaces bellman 0.14.0 `multiexp::multiexp(pool, (bases, 0), FullDensity, exponents)`
+ * (the h / l / a / b_g1 / b_g2 sums of `create_proof`; reference call sites as above).
+ * Scalars are Montgomery `bzk_fr` images (the prover's assignment vectors as they sit in memory);
+ * the result is the affine sum  sum_i [s_i] P_i  as a wire image. */
+int32_t bzk_msm_g1(bzk_ctx *ctx, const bzk_g1_affine *bases, const bzk_fr *scalars, size_t n, bzk_g1_affine *out);
+int32_t bzk_msm_g2(bzk_ctx *ctx, const bzk_g2_affine *bases, const bzk_fr *scalars, size_t n, bzk_g2_affine *out);
+
+/* Resident bases (`Parameters<Bls12>` columns stay on the GPU between proofs, as `Arc<Vec<_>>`
+ * stays in RAM in the reference).  `check_on_curve` != 0 validates every base. */
+int32_t bzk_g1_bases_upload(bzk_ctx *ctx, const bzk_g1_affine *bases, size_t n, int32_t check_on_curve, bzk_g1_bases **out);
+int32_t bzk_g2_bases_upload(bzk_ctx *ctx, const bzk_g2_affine *bases, size_t n, int32_t check_on_curve, bzk_g2_bases **out);
+/* adopt n wire images already in device memory (104 / 200 B each) */
+int32_t bzk_g1_bases_from_dev(bzk_ctx *ctx, const void *d_images, size_t n, bzk_g1_bases **out);
+int32_t bzk_g2_bases_from_dev(bzk_ctx *ctx, const void *d_images, size_t n, bzk_g2_bases **out);
+int32_t bzk_g1_bases_free(bzk_ctx *ctx, bzk_g1_bases *b);
+int32_t bzk_g2_bases_free(bzk_ctx *ctx, bzk_g2_bases *b);
+size_t bzk_g1_bases_len(const bzk_g1_bases *b);
+size_t bzk_g2_bases_len(const bzk_g2_bases *b);
+/* sum over bases[offset .. offset+n) with host scalars (copied in) or device scalars */
+int32_t bzk_msm_g1_resident(bzk_ctx *ctx, const bzk_g1_bases *b, size_t offset, const bzk_fr *scalars, size_t n, bzk_g1_affine *out);
+int32_t bzk_msm_g2_resident(bzk_ctx *ctx, const bzk_g2_bases *b, size_t offset, const bzk_fr *scalars, size_t n, bzk_g2_affine *out);
+int32_t bzk_msm_g1_resident_dev(bzk_ctx *ctx, const bzk_g1_bases *b, size_t offset, const void *d_scalars, size_t n, bzk_g1_affine *out);
+int32_t bzk_msm_g2_resident_dev(bzk_ctx *ctx, const bzk_g2_bases *b, size_t offset, const void *d_scalars, size_t n, bzk_g2_affine *out);
+
+/* Group helpers on wire images (host arithmetic, used to fold per-GPU partial sums after the
+ * all-gather and by tests): out = a + b ; out = [k] a. */
+int32_t bzk_g1_add(const bzk_g1_affine *a, const bzk_g1_affine *b, bzk_g1_affine *out);
+int32_t bzk_g2_add(const bzk_g2_affine *a, const bzk_g2_affine *b, bzk_g2_affine *out);
+
+/* Synthetic inputs generated on the GPU (bench / tests): P_i = [k_i] G with k_i the SplitMix64(seed)
+ * Fr stream of SURVEY.md §8(d); writes n wire images to device memory `d_out`. */
+int32_t bzk_g1_random_bases_dev(bzk_ctx *ctx, uint64_t seed, size_t n, void *d_out);
+int32_t bzk_g2_random_bases_dev(bzk_ctx *ctx, uint64_t seed, size_t n, void *d_out);
+/* n uniform Fr (Montgomery) from SplitMix64(seed), same stream rule */
+int32_t bzk_fr_random_dev(bzk_ctx *ctx, uint64_t seed, size_t n, void *d_out);
+
+/* ------------------------------------------------------------------ elementwise Fr (device)
+ * out[i] = a[i] (op) b[i]; used by the prover pipeline and the arithmetic parity tests. */
+#define BZK_FR_ADD 0
+#define BZK_FR_SUB 1
+#define BZK_FR_MUL 2
+int32_t bzk_fr_binop_dev(bzk_ctx *ctx, int32_t op, const void *d_a, const void *d_b, void *d_out, size_t n);
+/* Fp product, for the 384-bit arithmetic parity test: out[i] = a[i]*b[i] (Montgomery images, 48 B) */
+int32_t bzk_fp_mul_dev(bzk_ctx *ctx, const void *d_a, const void *d_b, void *d_out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BZK_H */

@@ -1,0 +1,47 @@
+// Host-side shim over bazuka_b200/csrc/ff.cuh + ec.cuh for the CPU ("not gpu") test tier:
+// runs the DEVICE multiplication algorithm (Fe::mul_evenodd, explicit-carry build) and the host
+// group law on the CPU so their logic is checked against the oracle without a GPU.
+#include <cstring>
+#include "ec.cuh"
+using namespace bzk;
+template <class T, int W> static void bin(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n, int op) {
+    for (size_t i = 0; i < n; i++) {
+        T x, y, z;
+        memcpy(x.l, a + W * i, 4 * W); memcpy(y.l, b + W * i, 4 * W);
+        switch (op) {
+            case 0: z = x + y; break;
+            case 1: z = x - y; break;
+            case 2: z = T::mul_evenodd(x, y); break;
+            default: z = x * y; break;  // host64 fast path
+        }
+        memcpy(r + W * i, z.l, 4 * W);
+    }
+}
+extern "C" {
+void shim_fr(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n, int op) { bin<Fr, 8>(a, b, r, n, op); }
+void shim_fp(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n, int op) { bin<Fp, 12>(a, b, r, n, op); }
+void shim_fp_inv(const uint32_t *a, uint32_t *r, size_t n) {
+    for (size_t i = 0; i < n; i++) { Fp x; memcpy(x.l, a + 12 * i, 48); Fp z = x.inv(); memcpy(r + 12 * i, z.l, 48); }
+}
+// packed affine (x|y, 96 B): out = [k] p via XYZZ double-and-add, k canonical 8x u32
+void shim_g1_mul(const uint32_t *p, const uint32_t *k, uint32_t *out) {
+    G1Affine a; memcpy(&a, p, 96);
+    G1Affine r = scalar_mul(a, k).to_affine();
+    memcpy(out, &r, 96);
+}
+void shim_g2_mul(const uint32_t *p, const uint32_t *k, uint32_t *out) {
+    G2Affine a; memcpy(&a, p, 192);
+    G2Affine r = scalar_mul(a, k).to_affine();
+    memcpy(out, &r, 192);
+}
+// acc (XYZZ from affine a) + b three ways: madd, add, and P+P / P-P exceptional cases
+void shim_g1_add(const uint32_t *pa, const uint32_t *pb, uint32_t *out_madd, uint32_t *out_add) {
+    G1Affine a, b; memcpy(&a, pa, 96); memcpy(&b, pb, 96);
+    G1Xyzz x = G1Xyzz::from_affine(a); x = x.dbl(); x.madd(a.neg());  // 2a - a = a, non-trivial ZZ
+    G1Xyzz y = x; y.madd(b);
+    G1Affine r1 = y.to_affine(); memcpy(out_madd, &r1, 96);
+    G1Xyzz z = G1Xyzz::from_affine(b); z = z.dbl(); z.madd(b.neg());
+    G1Xyzz w = x; w.add(z);
+    G1Affine r2 = w.to_affine(); memcpy(out_add, &r2, 96);
+}
+}
