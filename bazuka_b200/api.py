@@ -107,7 +107,10 @@ class Context:
     def use_torch_stream(self):
         """run on torch's current CUDA stream (so torch.cuda.Event timing brackets our kernels)."""
         import torch
-        self._check(self._l.bzk_ctx_set_stream(self._h, ct.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        h = torch.cuda.current_stream(self.device).cuda_stream
+        # torch reports its default stream as 0; libbzk reserves NULL for "ctx-owned stream", so
+        # name the legacy default stream explicitly (cudaStreamLegacy == (cudaStream_t)0x1)
+        self._check(self._l.bzk_ctx_set_stream(self._h, ct.c_void_p(h if h else 1)))
 
     def synchronize(self):
         self._check(self._l.bzk_ctx_synchronize(self._h))

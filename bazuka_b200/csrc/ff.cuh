@@ -292,7 +292,13 @@ struct Fe {
         uint32_t e[N];
 #pragma unroll
         for (int i = 0; i < N; i++) e[i] = P::p(i);
-        e[0] -= 2;  // both moduli are odd with low limb >= 2
+        // e = p - 2 with borrow propagation (r's low 32-bit limb is 1)
+        uint32_t borrow = 2;
+        for (int i = 0; i < N && borrow; i++) {
+            uint32_t before = e[i];
+            e[i] = before - borrow;
+            borrow = before < borrow ? 1 : 0;
+        }
         return pow(e, N);
     }
 };

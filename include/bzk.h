@@ -58,7 +58,8 @@ uint32_t bzk_abi_version(void);
 int32_t bzk_ctx_create(int32_t device, bzk_ctx **out);
 int32_t bzk_ctx_destroy(bzk_ctx *ctx);
 /* Run subsequent work on a caller-owned CUDA stream (a `cudaStream_t` cast to void*, e.g. torch's
- * current stream); NULL restores the ctx-owned stream. */
+ * current stream); NULL restores the ctx-owned stream — to name CUDA's default stream pass
+ * cudaStreamLegacy ((cudaStream_t)0x1) or cudaStreamPerThread ((cudaStream_t)0x2). */
 int32_t bzk_ctx_set_stream(bzk_ctx *ctx, void *cuda_stream);
 int32_t bzk_ctx_synchronize(bzk_ctx *ctx);
 /* kernels launched through this ctx since creation (bench.py's `gpu_launches`) */

@@ -270,8 +270,8 @@ void bzko_g1_random_bases(u64 seed, uint8_t *out, size_t n, int threads) {
     }
     free(row);
     if (threads < 1) threads = 1;
-    if (threads > 64) threads = 64;
-    gen_job jobs[64]; pthread_t th[64];
+    if (threads > 256) threads = 256;
+    gen_job jobs[256]; pthread_t th[256];
     for (int t = 0; t < threads; t++) {
         jobs[t] = (gen_job){ seed, n * t / threads, n * (t + 1) / threads, out, table, 0 };
         pthread_create(&th[t], NULL, g1_gen_thread, &jobs[t]);
@@ -314,8 +314,8 @@ void bzko_g2_random_bases(u64 seed, uint8_t *out, size_t n, int threads) {
     }
     free(row);
     if (threads < 1) threads = 1;
-    if (threads > 64) threads = 64;
-    gen_job jobs[64]; pthread_t th[64];
+    if (threads > 256) threads = 256;
+    gen_job jobs[256]; pthread_t th[256];
     for (int t = 0; t < threads; t++) {
         jobs[t] = (gen_job){ seed, n * t / threads, n * (t + 1) / threads, out, table, 1 };
         pthread_create(&th[t], NULL, g2_gen_thread, &jobs[t]);
@@ -430,8 +430,8 @@ int bzko_poseidon(const u64 *in, size_t n, uint32_t arity, u64 *out, int threads
     if (!g_pos_loaded) return -1;
     if (arity < 1 || arity > 16) return -2;
     if (threads < 1) threads = 1;
-    if (threads > 64) threads = 64;
-    pos_job jobs[64]; pthread_t th[64];
+    if (threads > 256) threads = 256;
+    pos_job jobs[256]; pthread_t th[256];
     for (int t = 0; t < threads; t++) {
         jobs[t] = (pos_job){ in, out, n * t / threads, n * (t + 1) / threads, arity };
         pthread_create(&th[t], NULL, pos_thread, &jobs[t]);
@@ -482,9 +482,9 @@ static void ntt_core(u64 *a, unsigned log_n, const u64 *omega, int threads) {
     memcpy(tw, fr_R1, 32);
     for (size_t i = 1; i < n / 2; i++) fr_mul(tw + 4 * i, tw + 4 * (i - 1), omega);
     if (threads < 1) threads = 1;
-    if (threads > 64) threads = 64;
+    if (threads > 256) threads = 256;
     for (size_t m = 1; m < n; m *= 2) {
-        ntt_job jobs[64]; pthread_t th[64];
+        ntt_job jobs[256]; pthread_t th[256];
         int nt = (n / 2 < 4096) ? 1 : threads;
         for (int t = 0; t < nt; t++) {
             jobs[t] = (ntt_job){ a, log_n, m, tw, (n / 2) * t / nt, (n / 2) * (t + 1) / nt };

@@ -195,27 +195,40 @@ static void *EN(pool_thread)(void *arg_) {
 
 static unsigned bellman_window_c(size_t n);
 
-/* sum_i [e_i] B_i ; exps canonical; result Jacobian */
+/* sum_i [e_i] B_i ; exps canonical; result Jacobian.
+ * bellman runs one pool task per window; on hosts with more cores than windows the base range is
+ * additionally cut into chunks (window sums are linear in the bases), so the baseline can use
+ * every core it is given. */
 static void EN(multiexp)(EN(jac) *out, const uint8_t *bases, const u64 *exps, size_t n, int threads) {
     unsigned c = bellman_window_c(n);
     int nwin = (255 + c - 1) / c;
-    EN(win_job) *jobs = calloc(nwin, sizeof(*jobs));
-    for (int w = 0; w < nwin; w++) {
-        jobs[w].bases = bases; jobs[w].exps = exps; jobs[w].n = n;
-        jobs[w].c = c; jobs[w].skip = w * c; jobs[w].handle_trivial = (w == 0);
-    }
-    volatile int next = 0;
-    EN(pool_arg) arg = { jobs, nwin, &next };
     if (threads < 1) threads = 1;
-    pthread_t th[64];
-    if (threads > 64) threads = 64;
-    for (int t = 1; t < threads; t++) pthread_create(&th[t], NULL, EN(pool_thread), &arg);
+    if (threads > 256) threads = 256;
+    int nchunk = threads / nwin;
+    if (nchunk < 1) nchunk = 1;
+    if ((size_t)nchunk > n / 1024 + 1) nchunk = (int)(n / 1024 + 1);
+    int njobs = nwin * nchunk;
+    EN(win_job) *jobs = calloc(njobs, sizeof(*jobs));
+    for (int w = 0; w < nwin; w++)
+        for (int k = 0; k < nchunk; k++) {
+            size_t lo = n * (size_t)k / nchunk, hi = n * (size_t)(k + 1) / nchunk;
+            EN(win_job) *j = &jobs[w * nchunk + k];
+            j->bases = bases + lo * AFF_BYTES; j->exps = exps + 4 * lo; j->n = hi - lo;
+            j->c = c; j->skip = w * c; j->handle_trivial = (w == 0);
+        }
+    volatile int next = 0;
+    EN(pool_arg) arg = { jobs, njobs, &next };
+    pthread_t th[256];
+    int nth = threads < njobs ? threads : njobs;
+    for (int t = 1; t < nth; t++) pthread_create(&th[t], NULL, EN(pool_thread), &arg);
     EN(pool_thread)(&arg);
-    for (int t = 1; t < threads; t++) pthread_join(th[t], NULL);
-    EN(jac) acc = jobs[nwin - 1].result;
+    for (int t = 1; t < nth; t++) pthread_join(th[t], NULL);
+    for (int w = 0; w < nwin; w++)
+        for (int k = 1; k < nchunk; k++) EN(add)(&jobs[w * nchunk].result, &jobs[w * nchunk].result, &jobs[w * nchunk + k].result);
+    EN(jac) acc = jobs[(nwin - 1) * nchunk].result;
     for (int w = nwin - 2; w >= 0; w--) {
         for (unsigned k = 0; k < c; k++) EN(dbl)(&acc, &acc);
-        EN(add)(&acc, &acc, &jobs[w].result);
+        EN(add)(&acc, &acc, &jobs[w * nchunk].result);
     }
     free(jobs);
     *out = acc;

@@ -64,6 +64,8 @@ def test_host_build_of_device_multiplier(hostshim, cref):
     for op, f in ((0, cref.fr_add), (1, cref.fr_sub), (2, cref.fr_mul), (3, cref.fr_mul)):
         hostshim.shim_fr(a.ctypes.data_as(ct.c_void_p), b.ctypes.data_as(ct.c_void_p), r.ctypes.data_as(ct.c_void_p), ct.c_size_t(n), op)
         assert (r == f(a, b)).all(), op
+    hostshim.shim_fr_inv(a.ctypes.data_as(ct.c_void_p), r.ctypes.data_as(ct.c_void_p), ct.c_size_t(50))
+    assert (r[:50] == cref.fr_inv(a[:50])).all()
     rnd = random.Random(1)
     vals = [rnd.randrange(Fd.P_MOD) for _ in range(n - 6)] + [0, 1, 2, Fd.P_MOD - 1, Fd.P_MOD - 2, (1 << 380)]
     x = np.frombuffer(b"".join(v.to_bytes(48, "little") for v in vals), dtype=np.uint64).reshape(-1, 6).copy()
