@@ -37,6 +37,8 @@ SIGNATURES = {
     "bzk_ctx_set_stream": (_i32, [_vp, _vp]),
     "bzk_ctx_synchronize": (_i32, [_vp]),
     "bzk_ctx_launch_count": (_u64, [_vp]),
+    "bzk_ctx_set_timing": (_i32, [_vp, _i32]),
+    "bzk_ctx_stage_ms": (_u64, [_vp, _vp, _vp, _u32]),
     "bzk_poseidon_load_params": (_i32, [_vp, _vp, _sz]),
     "bzk_poseidon_hash": (_i32, [_vp, _u32, _vp, _sz, _vp]),
     "bzk_poseidon_hash_dev": (_i32, [_vp, _u32, _vp, _sz, _vp]),
@@ -63,6 +65,16 @@ SIGNATURES = {
     "bzk_g1_random_bases_dev": (_i32, [_vp, _u64, _sz, _vp]),
     "bzk_g2_random_bases_dev": (_i32, [_vp, _u64, _sz, _vp]),
     "bzk_fr_random_dev": (_i32, [_vp, _u64, _sz, _vp]),
+    "bzk_r1cs_upload": (_i32, [_vp, _u64, _u64, _u64] + [_vp] * 9 + [ct.POINTER(_vp)]),
+    "bzk_r1cs_free": (_i32, [_vp, _vp]),
+    "bzk_r1cs_shape": (_i32, [_vp, _vp]),
+    "bzk_groth16_params_create": (_i32, [_vp] * 11 + [ct.POINTER(_vp)]),
+    "bzk_groth16_params_free": (_i32, [_vp, _vp]),
+    "bzk_groth16_prove": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "bzk_groth16_proof_bytes": (_i32, [_vp, _vp, _vp, _vp]),
+    "bzk_csr_spmv_dev": (_i32, [_vp, _vp, _vp, _vp, _u64, _vp, _vp]),
+    "bzk_g1_fixed_base_mul_dev": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "bzk_g2_fixed_base_mul_dev": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "bzk_fr_binop_dev": (_i32, [_vp, _i32, _vp, _vp, _vp, _sz]),
     "bzk_fp_mul_dev": (_i32, [_vp, _vp, _vp, _vp, _sz]),
 }

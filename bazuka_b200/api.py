@@ -112,8 +112,25 @@ class Context:
         # name the legacy default stream explicitly (cudaStreamLegacy == (cudaStream_t)0x1)
         self._check(self._l.bzk_ctx_set_stream(self._h, ct.c_void_p(h if h else 1)))
 
+    def use_own_stream(self):
+        """back to the ctx-owned stream."""
+        self.synchronize()
+        self._check(self._l.bzk_ctx_set_stream(self._h, None))
+
     def synchronize(self):
         self._check(self._l.bzk_ctx_synchronize(self._h))
+
+    MSM_STAGES = ("digits_hist", "scan", "scatter", "accumulate", "fixup", "bucket_slices", "window_sum")
+
+    def set_timing(self, on=True):
+        self._check(self._l.bzk_ctx_set_timing(self._h, int(on)))
+
+    def stage_ms(self):
+        """-> (runs, last_ms[16], sum_ms[16]) from the CUDA events the MSM driver records between kernels."""
+        last = np.zeros(16, dtype=np.float32)
+        tot = np.zeros(16, dtype=np.float64)
+        runs = int(self._l.bzk_ctx_stage_ms(self._h, _host_ptr(last), _host_ptr(tot), 16))
+        return runs, last, tot
 
     @property
     def launch_count(self):

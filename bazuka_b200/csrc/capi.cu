@@ -131,6 +131,7 @@ int32_t bzk_ctx_destroy(bzk_ctx *ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return BZK_OK;
@@ -146,6 +147,21 @@ int32_t bzk_ctx_synchronize(bzk_ctx *ctx) {
     return BZK_OK;
 }
 uint64_t bzk_ctx_launch_count(const bzk_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int32_t bzk_ctx_set_timing(bzk_ctx *ctx, int32_t on) {
+    if (!ctx) return BZK_ERR_BAD_ARG;
+    ctx->timing = on != 0;
+    ctx->stage_runs = 0;
+    for (int i = 0; i < bzk_ctx::kMaxStages; i++) { ctx->stage_ms[i] = 0; ctx->stage_ms_sum[i] = 0; }
+    return BZK_OK;
+}
+uint64_t bzk_ctx_stage_ms(const bzk_ctx *ctx, float *last_ms, double *sum_ms, uint32_t cap) {
+    if (!ctx) return 0;
+    for (uint32_t i = 0; i < cap && i < (uint32_t)bzk_ctx::kMaxStages; i++) {
+        if (last_ms) last_ms[i] = ctx->stage_ms[i];
+        if (sum_ms) sum_ms[i] = ctx->stage_ms_sum[i];
+    }
+    return ctx->stage_runs;
+}
 
 #define BZK_ENTER(ctx)                                   \
     if (!(ctx)) return BZK_ERR_BAD_ARG;                  \

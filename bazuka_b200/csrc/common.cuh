@@ -44,6 +44,14 @@ struct bzk_ctx {
     bzk::NttTables ntt[29];
     bzk::Fr *d_gpow = nullptr;  // coset generator power tables, see ntt.cu
     int sm_count = bzk::kNumSMs;
+    // optional per-stage device timing (CUDA events on the launching stream), see bzk_ctx_set_timing
+    bool timing = false;
+    static constexpr int kMaxStages = 16;
+    cudaEvent_t ev[kMaxStages + 1] = {nullptr};
+    int n_marks = 0;
+    float stage_ms[kMaxStages] = {0};
+    double stage_ms_sum[kMaxStages] = {0};
+    uint64_t stage_runs = 0;
 };
 
 struct bzk_g1_bases {
@@ -115,6 +123,32 @@ struct Carver {
     }
     size_t used() const { return (off + 255) & ~(size_t)255; }
 };
+
+// stage marks: mark(ctx) records an event between kernels when timing is on; collect() after the
+// stream was synchronised turns consecutive marks into per-stage milliseconds.
+inline void timing_begin(bzk_ctx *ctx) {
+    ctx->n_marks = 0;
+    if (!ctx->timing) return;
+    for (int i = 0; i <= bzk_ctx::kMaxStages; i++)
+        if (!ctx->ev[i]) cudaEventCreate(&ctx->ev[i]);
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    ctx->n_marks = 1;
+}
+inline void timing_mark(bzk_ctx *ctx) {
+    if (!ctx->timing || ctx->n_marks == 0 || ctx->n_marks > bzk_ctx::kMaxStages) return;
+    cudaEventRecord(ctx->ev[ctx->n_marks++], ctx->stream);
+}
+inline void timing_collect(bzk_ctx *ctx) {
+    if (!ctx->timing || ctx->n_marks < 2) return;
+    for (int i = 0; i + 1 < ctx->n_marks; i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]);
+        ctx->stage_ms[i] = ms;
+        ctx->stage_ms_sum[i] += ms;
+    }
+    for (int i = ctx->n_marks - 1; i < bzk_ctx::kMaxStages; i++) ctx->stage_ms[i] = 0;
+    ctx->stage_runs++;
+}
 
 inline uint32_t div_up(size_t a, size_t b) { return (uint32_t)((a + b - 1) / b); }
 

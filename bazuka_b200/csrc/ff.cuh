@@ -55,6 +55,33 @@ BZK_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c, CC &) { uint32_t r
 BZK_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c, CC &) { uint32_t r; BZK_ASM("madc.hi.cc.u32 %0,%1,%2,%3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 BZK_D uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
 BZK_D uint32_t mul_hi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+// (hi:lo) += a*b with the carry chained through, as ONE asm statement so that ptxas emits a single
+// IMAD.WIDE.U32.X per product (as separate statements it splits register-register products into
+// IMAD + IMAD.HI + 2 IADD3.X).  Measured on B200 (tools/microbench/imad.cu, profiles/): IMAD,
+// IMAD.HI and carry-less IMAD.WIDE each hold the fmaheavy pipe 2 cycles per warp, IMAD.WIDE.U32.X
+// ~4.4 and a carry-in/carry-out IADD3.X ~3.2 on the ALU pipe.  Per 384-bit product that is
+//   fused (this)              301 heavy instr                    -> 1276 cycles/warp   <- used
+//   IMAD+IMAD.HI+2 IADD3.X    433 heavy + 295 IADD3.X            -> 1240
+//   IMAD.WIDE + 2 IADD3.X     310 heavy + 575 IADD3.X            -> 1864
+// i.e. carries, not multiplies, are what is expensive on this part; the carry-free way out
+// (unsaturated 28/30-bit limbs, plain IMAD.WIDE only) is the round-2 multiplier.
+#ifndef BZK_MUL_WIDE_ADD
+BZK_D void mad_pair_first(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b, CC &) {
+    BZK_ASM("mad.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+BZK_D void mad_pair_next(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b, CC &) {
+    BZK_ASM("madc.lo.cc.u32 %0,%2,%3,%0; madc.hi.cc.u32 %1,%2,%3,%1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+#else  // carry-less IMAD.WIDE.U32 into a temporary + two IADD3.X (microbenchmark comparison only)
+BZK_D void mad_pair_first(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b, CC &) {
+    BZK_ASM("{ .reg .u64 t; .reg .u32 tl, th; mul.wide.u32 t,%2,%3; mov.b64 {tl,th}, t; add.cc.u32 %0,%0,tl; addc.cc.u32 %1,%1,th; }"
+            : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+BZK_D void mad_pair_next(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b, CC &) {
+    BZK_ASM("{ .reg .u64 t; .reg .u32 tl, th; mul.wide.u32 t,%2,%3; mov.b64 {tl,th}, t; addc.cc.u32 %0,%0,tl; addc.cc.u32 %1,%1,th; }"
+            : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+#endif
 #else
 BZK_HD uint32_t add_cc(uint32_t a, uint32_t b, CC &cc) { uint64_t t = (uint64_t)a + b; cc.c = (uint32_t)(t >> 32); return (uint32_t)t; }
 BZK_HD uint32_t addc_cc(uint32_t a, uint32_t b, CC &cc) { uint64_t t = (uint64_t)a + b + cc.c; cc.c = (uint32_t)(t >> 32); return (uint32_t)t; }
@@ -67,6 +94,14 @@ BZK_HD uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c, CC &cc) { uint64_
 BZK_HD uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c, CC &cc) { uint64_t t = (((uint64_t)a * b) >> 32) + c + cc.c; cc.c = (uint32_t)(t >> 32); return (uint32_t)t; }
 BZK_HD uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
 BZK_HD uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+BZK_HD void mad_pair_first(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b, CC &cc) {
+    lo = mad_lo_cc(a, b, lo, cc);
+    hi = madc_hi_cc(a, b, hi, cc);
+}
+BZK_HD void mad_pair_next(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b, CC &cc) {
+    lo = madc_lo_cc(a, b, lo, cc);
+    hi = madc_hi_cc(a, b, hi, cc);
+}
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -226,36 +261,21 @@ struct Fe {
                 // Q's chain at column i+1
                 Pp[i] = add_cc(Pp[i], Q[i], cc);
 #pragma unroll
-                for (int j = 1; j < N; j += 2) {
-                    Q[i + j] = madc_lo_cc(a.l[j], bi, Q[i + j], cc);
-                    Q[i + j + 1] = madc_hi_cc(a.l[j], bi, Q[i + j + 1], cc);
-                }
+                for (int j = 1; j < N; j += 2) mad_pair_next(Q[i + j], Q[i + j + 1], a.l[j], bi, cc);
                 Q[i + N + 1] = addc(0, 0, cc);
-                Pp[i] = mad_lo_cc(a.l[0], bi, Pp[i], cc);
-                Pp[i + 1] = madc_hi_cc(a.l[0], bi, Pp[i + 1], cc);
+                mad_pair_first(Pp[i], Pp[i + 1], a.l[0], bi, cc);
 #pragma unroll
-                for (int j = 2; j < N; j += 2) {
-                    Pp[i + j] = madc_lo_cc(a.l[j], bi, Pp[i + j], cc);
-                    Pp[i + j + 1] = madc_hi_cc(a.l[j], bi, Pp[i + j + 1], cc);
-                }
+                for (int j = 2; j < N; j += 2) mad_pair_next(Pp[i + j], Pp[i + j + 1], a.l[j], bi, cc);
                 Pp[i + N] = addc(Pp[i + N], 0, cc);
             }
             const uint32_t m = mul_lo(Pp[i], P::inv());
-            Pp[i] = mad_lo_cc(m, P::p(0), Pp[i], cc);
-            Pp[i + 1] = madc_hi_cc(m, P::p(0), Pp[i + 1], cc);
+            mad_pair_first(Pp[i], Pp[i + 1], m, P::p(0), cc);
 #pragma unroll
-            for (int j = 2; j < N; j += 2) {
-                Pp[i + j] = madc_lo_cc(m, P::p(j), Pp[i + j], cc);
-                Pp[i + j + 1] = madc_hi_cc(m, P::p(j), Pp[i + j + 1], cc);
-            }
+            for (int j = 2; j < N; j += 2) mad_pair_next(Pp[i + j], Pp[i + j + 1], m, P::p(j), cc);
             Pp[i + N] = addc(Pp[i + N], 0, cc);
-            Q[i + 1] = mad_lo_cc(m, P::p(1), Q[i + 1], cc);
-            Q[i + 2] = madc_hi_cc(m, P::p(1), Q[i + 2], cc);
+            mad_pair_first(Q[i + 1], Q[i + 2], m, P::p(1), cc);
 #pragma unroll
-            for (int j = 3; j < N; j += 2) {
-                Q[i + j] = madc_lo_cc(m, P::p(j), Q[i + j], cc);
-                Q[i + j + 1] = madc_hi_cc(m, P::p(j), Q[i + j + 1], cc);
-            }
+            for (int j = 3; j < N; j += 2) mad_pair_next(Q[i + j], Q[i + j + 1], m, P::p(j), cc);
             Q[i + N + 1] = addc(Q[i + N + 1], 0, cc);
         }
         // columns N .. 2N-1 of E + O  (column 2N is provably zero: the result is < 2p < 2^(32N))

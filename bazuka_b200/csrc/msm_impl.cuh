@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(128) k_bucket_slices(const Xyzz<F> *__restrict
 
 // one CTA per window: sum `per_win` slice results
 template <class F>
-__global__ void __launch_bounds__(128) k_window_sum(const Xyzz<F> *__restrict__ slice_out, uint32_t per_win, Xyzz<F> *__restrict__ win_out) {
+__global__ void __launch_bounds__(1024) k_window_sum(const Xyzz<F> *__restrict__ slice_out, uint32_t per_win, Xyzz<F> *__restrict__ win_out) {
     extern __shared__ uint4 smem_raw[];
     Xyzz<F> *sh = (Xyzz<F> *)smem_raw;
     const uint32_t w = blockIdx.x;
@@ -455,8 +455,9 @@ static int32_t msm_run(bzk_ctx *ctx, const Affine<F> *d_bases, const Fr *d_scala
     const uint32_t acc_blocks = div_up(acc_threads, 128);
     const uint32_t nslots = 2 * acc_blocks * 128;
 
-    uint32_t slice = pl.NB >= 32 ? 32 : pl.NB;
-    if (pl.NB >= 4096) slice = 16;
+    // slice length trades the serial running-sum (2*slice adds) against the [offset]*sum
+    // double-and-add (~log2(NB/slice) doublings): short slices keep every SM busy
+    uint32_t slice = pl.NB >= 8 ? 8 : pl.NB;
     const uint32_t per_win = pl.NB / slice;
     const uint32_t nslices = per_win * pl.W;
     const uint32_t ntiles = div_up(pl.TB, kScanTile);
@@ -488,34 +489,48 @@ static int32_t msm_run(bzk_ctx *ctx, const Affine<F> *d_bases, const Fr *d_scala
     Xyzz<F> *win_out = cv.take<Xyzz<F>>(pl.W);
 
     cudaStream_t st = ctx->stream;
+    // stage marks: 0 clear+digits/histogram, 1 scan, 2 scatter, 3 accumulate, 4 fixup,
+    //              5 bucket slices, 6 window sums (+ D2H of W points)
+    timing_begin(ctx);
     BZK_CUDA(ctx, cudaMemsetAsync(counts, 0, (pl.TB + 1) * sizeof(uint32_t), st));
     BZK_CUDA(ctx, cudaMemsetAsync(buckets, 0, (size_t)pl.TB * sizeof(Xyzz<F>), st));  // all-zero = identity
 
     k_digits<false><<<div_up(n, 256), 256, 0, st>>>(d_scalars, n, pl.c, pl.W, pl.NB, counts, nullptr);
     BZK_LAUNCHED(ctx);
+    timing_mark(ctx);
     k_scan_tile_sums<<<ntiles, kScanBlock, 0, st>>>(counts, pl.TB, tile_sums);
     BZK_LAUNCHED(ctx);
     k_scan_tiles<<<1, 1024, 0, st>>>(tile_sums, ntiles);
     BZK_LAUNCHED(ctx);
     k_scan_apply<<<ntiles, kScanBlock, 0, st>>>(counts, pl.TB, tile_sums, ntiles, offsets, cursor);
     BZK_LAUNCHED(ctx);
+    timing_mark(ctx);
     k_digits<true><<<div_up(n, 256), 256, 0, st>>>(d_scalars, n, pl.c, pl.W, pl.NB, cursor, sorted);
     BZK_LAUNCHED(ctx);
+    timing_mark(ctx);
     k_accumulate<F><<<acc_blocks, 128, 0, st>>>(d_bases, sorted, offsets, pl.TB, chunk, buckets, part_pts, part_bucket);
     BZK_LAUNCHED(ctx);
+    timing_mark(ctx);
     k_fixup<F><<<div_up(nslots, 128), 128, 0, st>>>(part_pts, part_bucket, nslots, buckets);
     BZK_LAUNCHED(ctx);
+    timing_mark(ctx);
     k_bucket_slices<F><<<div_up(nslices, 128), 128, 0, st>>>(buckets, pl.NB, slice, nslices, slice_out);
     BZK_LAUNCHED(ctx);
-    const size_t smem = 128 * sizeof(Xyzz<F>);
+    timing_mark(ctx);
+    // one CTA per window; as many threads as 200 KB of shared memory holds accumulators for
+    uint32_t ws_threads = sizeof(Xyzz<F>) <= 192 ? 1024 : 512;
+    while (ws_threads > 32 && ws_threads / 2 >= per_win) ws_threads /= 2;
+    const size_t smem = (size_t)ws_threads * sizeof(Xyzz<F>);
     BZK_CUDA(ctx, cudaFuncSetAttribute(k_window_sum<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_window_sum<F><<<pl.W, 128, smem, st>>>(slice_out, per_win, win_out);
+    k_window_sum<F><<<pl.W, ws_threads, smem, st>>>(slice_out, per_win, win_out);
     BZK_LAUNCHED(ctx);
 
     // 7. host Horner over the W window sums
     std::vector<Xyzz<F>> h(pl.W);
     BZK_CUDA(ctx, cudaMemcpyAsync(h.data(), win_out, pl.W * sizeof(Xyzz<F>), cudaMemcpyDeviceToHost, st));
+    timing_mark(ctx);
     BZK_CUDA(ctx, cudaStreamSynchronize(st));
+    timing_collect(ctx);
     Xyzz<F> acc = h[pl.W - 1];
     for (int w = (int)pl.W - 2; w >= 0; w--) {
         for (uint32_t k = 0; k < pl.c; k++) acc = acc.dbl();

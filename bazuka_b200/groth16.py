@@ -1,0 +1,303 @@
+"""Groth16 prover front-end over libbzk — the host-side mirror of bellman's
+`groth16::{Parameters, create_proof}` as the reference uses them
+(/root/reference/src/mpn/circuits/test.rs:133-149: setup -> create_random_proof -> verify_proof;
+production boundary: `MpnWork` in, `ZkProof::Groth16` out, /root/reference/src/mpn/mod.rs:264-295).
+
+  R1CS          constraint system in CSR form (what `Circuit::synthesize` emits), numpy arrays
+  ProvingKey    `Parameters<Bls12>` resident on one GPU
+  setup_gpu     bellman `generate_parameters` with explicit toxic waste, computed with libbzk kernels
+                (iNTT for the Lagrange basis, transposed SpMV, fixed-base multiplications); used to
+                make keys for synthetic circuits — production keys come from the ceremony
+  Prover.prove  -> 387-byte `Groth16Proof` bincode image (bit-exact vs the CPU prover for equal
+                (params, r, s, witness))
+"""
+import ctypes as ct
+
+import numpy as np
+
+from .api import Context, G1_BYTES, G2_BYTES, _host_ptr, NTT_IFFT
+
+
+class R1CS:
+    """A, B, C as CSR (rowptr uint64[n+1], col uint32[nnz], val uint64[nnz,4] Montgomery)."""
+
+    def __init__(self, num_inputs, num_aux, a, b, c):
+        self.num_inputs, self.num_aux = int(num_inputs), int(num_aux)
+        self.mats = []
+        for rp, col, val in (a, b, c):
+            rp = np.ascontiguousarray(rp, dtype=np.uint64)
+            col = np.ascontiguousarray(col, dtype=np.uint32)
+            val = np.ascontiguousarray(val, dtype=np.uint64).reshape(-1, 4)
+            assert rp[0] == 0 and rp[-1] == len(col) == len(val)
+            self.mats.append((rp, col, val))
+        self.num_constraints = len(self.mats[0][0]) - 1
+        assert all(len(m[0]) - 1 == self.num_constraints for m in self.mats)
+
+    @property
+    def num_vars(self):
+        return self.num_inputs + self.num_aux
+
+    @property
+    def log_m(self):
+        rows, e = self.num_constraints + self.num_inputs, 0
+        while (1 << e) < rows:
+            e += 1
+        return e
+
+    def density(self):
+        """bellman's density trackers as index lists into z (zero coefficients skipped):
+        a_idx = all inputs ++ aux present in A;  b_idx = inputs present in B ++ aux present in B."""
+        nv = self.num_vars
+        pres = []
+        for rp, col, val in self.mats[:2]:
+            d = np.zeros(nv, dtype=bool)
+            nz = val.any(axis=1)
+            d[col[nz]] = True
+            pres.append(d)
+        a_idx = np.concatenate([np.arange(self.num_inputs), self.num_inputs + np.nonzero(pres[0][self.num_inputs:])[0]])
+        b_idx = np.nonzero(pres[1])[0]
+        return a_idx.astype(np.uint32), b_idx.astype(np.uint32)
+
+    def transposed(self, k):
+        """matrix k (0/1/2) as CSR over variables (rows = variables, cols = constraints)."""
+        rp, col, val = self.mats[k]
+        rows = np.repeat(np.arange(self.num_constraints, dtype=np.uint32), np.diff(rp).astype(np.int64))
+        order = np.argsort(col, kind="stable")
+        counts = np.bincount(col, minlength=self.num_vars).astype(np.uint64)
+        trp = np.zeros(self.num_vars + 1, dtype=np.uint64)
+        np.cumsum(counts, out=trp[1:])
+        return trp, rows[order].astype(np.uint32), val[order]
+
+
+class ProvingKey:
+    def __init__(self, ctx, handle, vk):
+        self._ctx, self._h, self.vk = ctx, handle, vk
+
+    def free(self):
+        if self._h:
+            self._ctx._check(self._ctx._l.bzk_groth16_params_free(self._ctx._h, self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def proving_key_from_host(ctx, vk, h, l, a, b_g1, b_g2):
+    """vk: dict of wire images (alpha_g1, beta_g1, beta_g2, gamma_g2, delta_g1, delta_g2, ic[]);
+    h/l/a/b_g1: [n,104] uint8, b_g2: [n,200] uint8 — bellman `Parameters` vectors."""
+    hb, lb, ab, b1b = (ctx.g1_bases(np.ascontiguousarray(x, dtype=np.uint8).reshape(-1, G1_BYTES)) for x in (h, l, a, b_g1))
+    b2b = ctx.g2_bases(np.ascontiguousarray(b_g2, dtype=np.uint8).reshape(-1, G2_BYTES))
+    return _make_pk(ctx, vk, hb, lb, ab, b1b, b2b)
+
+
+def _make_pk(ctx, vk, hb, lb, ab, b1b, b2b):
+    out = ct.c_void_p()
+    pts = [np.ascontiguousarray(vk[k], dtype=np.uint8) for k in ("alpha_g1", "beta_g1", "beta_g2", "delta_g1", "delta_g2")]
+    ctx._check(ctx._l.bzk_groth16_params_create(ctx._h, *[_host_ptr(p) for p in pts], hb._h, lb._h, ab._h, b1b._h, b2b._h, ct.byref(out)))
+    for b in (hb, lb, ab, b1b, b2b):
+        b._h = None  # adopted by the params handle
+    return ProvingKey(ctx, out, vk)
+
+
+class Prover:
+    """One circuit on one GPU: the R1CS and (optionally) its proving key resident in HBM."""
+
+    def __init__(self, ctx: Context, r1cs: R1CS):
+        self.ctx, self.r1cs = ctx, r1cs
+        h = ct.c_void_p()
+        args = []
+        for rp, col, val in r1cs.mats:
+            args += [_host_ptr(rp), _host_ptr(col), _host_ptr(val)]
+        ctx._check(ctx._l.bzk_r1cs_upload(ctx._h, r1cs.num_inputs, r1cs.num_aux, r1cs.num_constraints, *args, ct.byref(h)))
+        self._h = h
+        shp = np.zeros(5, dtype=np.uint64)
+        ctx._check(ctx._l.bzk_r1cs_shape(self._h, _host_ptr(shp)))
+        self.log_m, self.h_len, self.l_len, self.a_len, self.b_len = (int(x) for x in shp)
+
+    def free(self):
+        if self._h:
+            self.ctx._check(self.ctx._l.bzk_r1cs_free(self.ctx._h, self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def prove(self, pk: ProvingKey, inputs, aux, r, s, check_satisfied=True):
+        """inputs [num_inputs,4] (inputs[0] = R(1)), aux [num_aux,4], r/s [4] — Montgomery.
+        Returns (proof_bytes[387], (a[104], b[200], c[104]))."""
+        inputs = np.ascontiguousarray(inputs, dtype=np.uint64).reshape(-1, 4)
+        aux = np.ascontiguousarray(aux, dtype=np.uint64).reshape(-1, 4)
+        assert len(inputs) == self.r1cs.num_inputs and len(aux) == self.r1cs.num_aux
+        r = np.ascontiguousarray(r, dtype=np.uint64).reshape(4)
+        s = np.ascontiguousarray(s, dtype=np.uint64).reshape(4)
+        pa, pb, pc = np.zeros(G1_BYTES, np.uint8), np.zeros(G2_BYTES, np.uint8), np.zeros(G1_BYTES, np.uint8)
+        c = self.ctx
+        c._check(c._l.bzk_groth16_prove(c._h, pk._h, self._h, _host_ptr(inputs), _host_ptr(aux), _host_ptr(r), _host_ptr(s),
+                                         int(check_satisfied), _host_ptr(pa), _host_ptr(pb), _host_ptr(pc)))
+        blob = np.zeros(387, np.uint8)
+        c._check(c._l.bzk_groth16_proof_bytes(_host_ptr(pa), _host_ptr(pb), _host_ptr(pc), _host_ptr(blob)))
+        return blob, (pa, pb, pc)
+
+
+def zkproof_blob(proof_bytes):
+    """391-byte bincode of `ZkProof::Groth16(Box<Groth16Proof>)` — u32 tag 0 + 387 B
+    (/root/reference/src/zk/mod.rs:646-651)."""
+    return np.concatenate([np.zeros(4, np.uint8), np.asarray(proof_bytes, dtype=np.uint8)])
+
+
+# ------------------------------------------------------------------------------------------------
+# trusted setup on the GPU (bellman `generate_parameters`, explicit toxic waste)
+# ------------------------------------------------------------------------------------------------
+def setup_gpu(ctx: Context, r1cs: R1CS, toxic, g1_image, g2_image):
+    """toxic = [tau, alpha, beta, gamma, delta] as [5,4] Montgomery; g1/g2: generator wire images.
+    Returns (ProvingKey, vk dict).  All field/group work runs in libbzk kernels; numpy only moves
+    and reorders data."""
+    import torch
+    # torch slicing / indexing kernels and libbzk kernels interleave below: put both on one stream
+    ctx.use_torch_stream()
+    try:
+        return _setup_gpu(ctx, r1cs, toxic, g1_image, g2_image)
+    finally:
+        torch.cuda.synchronize()
+        ctx.use_own_stream()
+
+
+def _setup_gpu(ctx, r1cs, toxic, g1_image, g2_image):
+    import torch
+    t = torch
+    toxic = np.ascontiguousarray(toxic, dtype=np.uint64).reshape(5, 4)
+    ni, na, nc, nv = r1cs.num_inputs, r1cs.num_aux, r1cs.num_constraints, r1cs.num_vars
+    log_m = r1cs.log_m
+    m = 1 << log_m
+
+    def dev(a):
+        return t.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
+
+    def rep(x, n):  # n copies of one field element on the device
+        return dev(np.repeat(np.asarray(x, dtype=np.uint64).reshape(1, 4), n, axis=0))
+
+    def mul(a, b):
+        o = t.empty_like(a)
+        ctx.fr_binop_dev(2, a, b, o, a.shape[0])
+        return o
+
+    def add(a, b):
+        o = t.empty_like(a)
+        ctx.fr_binop_dev(0, a, b, o, a.shape[0])
+        return o
+
+    one = _fr_one()
+    # powers of tau by repeated squaring of index halves: pw[i] = tau^i
+    pw = np.zeros((m, 4), dtype=np.uint64)
+    pw[0] = one
+    d_pw = dev(pw)
+    cur, step = 1, rep(toxic[0], m)  # step holds tau^(cur) broadcast
+    while cur < m:
+        n = min(cur, m - cur)
+        seg = mul(d_pw[:n].contiguous(), step[:n].contiguous())
+        d_pw[cur:cur + n] = seg
+        step = mul(step, step)
+        cur *= 2
+    # scalar helpers on tiny vectors (1 element) — still libbzk arithmetic
+    def s_mul(x, y):
+        return mul(dev(x.reshape(1, 4)), dev(y.reshape(1, 4))).cpu().numpy().view(np.uint64).reshape(4)
+
+    tau_m = s_mul(d_pw[m - 1:m].cpu().numpy().view(np.uint64).reshape(4), toxic[0])
+    o1 = t.empty((1, 4), dtype=t.int64, device="cuda")
+    ctx.fr_binop_dev(1, dev(tau_m.reshape(1, 4)), dev(one.reshape(1, 4)), o1, 1)
+    zt = o1.cpu().numpy().view(np.uint64).reshape(4)                      # tau^m - 1
+    dinv, ginv = _fr_inv_gpu(ctx, toxic[4]), _fr_inv_gpu(ctx, toxic[3])
+    zd = s_mul(zt, dinv)
+    h_k = mul(d_pw[: m - 1].contiguous(), rep(zd, m - 1))                  # tau^i Z(tau)/delta
+    ctx.ntt_dev(d_pw, log_m, NTT_IFFT)                                     # d_pw <- L_j(tau)
+    lag = d_pw
+    cols = []
+    for k in range(3):
+        trp, tcol, tval = r1cs.transposed(k)
+        out = t.empty((nv, 4), dtype=t.int64, device="cuda")
+        d_trp, d_tcol, d_tval = dev(trp), dev_u32(t, tcol), dev(tval)
+        ctx._check(ctx._l.bzk_csr_spmv_dev(ctx._h, _p(d_trp), _p(d_tcol),
+                                            _p(d_tval), nv, _p(lag), _p(out)))
+        ctx.synchronize()
+        cols.append(out)
+    at, bt, ctv = cols
+    # Input(i) * 0 = 0 rows add L_{nc+i}(tau) to A_i
+    at[:ni] = add(at[:ni].contiguous(), lag[nc:nc + ni].contiguous())
+    ext = add(add(mul(at, rep(toxic[2], nv)), mul(bt, rep(toxic[1], nv))), ctv)
+    ext_ic = mul(ext[:ni].contiguous(), rep(ginv, ni))
+    ext_l = mul(ext[ni:].contiguous(), rep(dinv, na)) if na else ext[ni:]
+    a_idx, b_idx = r1cs.density()
+
+    def g1_mul(scal):
+        n = scal.shape[0]
+        out = t.empty((max(n, 1), G1_BYTES), dtype=t.uint8, device="cuda")
+        ctx._check(ctx._l.bzk_g1_fixed_base_mul_dev(ctx._h, _host_ptr(g1_image), _p(scal.contiguous()), n, _p(out)))
+        return out[:n]
+
+    def g2_mul(scal):
+        n = scal.shape[0]
+        out = t.empty((max(n, 1), G2_BYTES), dtype=t.uint8, device="cuda")
+        ctx._check(ctx._l.bzk_g2_fixed_base_mul_dev(ctx._h, _host_ptr(g2_image), _p(scal.contiguous()), n, _p(out)))
+        return out[:n]
+
+    g1_image = np.ascontiguousarray(g1_image, dtype=np.uint8)
+    g2_image = np.ascontiguousarray(g2_image, dtype=np.uint8)
+    ai = t.from_numpy(a_idx.astype(np.int64)).cuda()
+    bi = t.from_numpy(b_idx.astype(np.int64)).cuda()
+    h_pts, l_pts = g1_mul(h_k), g1_mul(ext_l)
+    a_pts, b1_pts, b2_pts = g1_mul(at[ai]), g1_mul(bt[bi]), g2_mul(bt[bi])
+    ic = g1_mul(ext_ic).cpu().numpy()
+    tox = dev(toxic)
+    vk_g1 = g1_mul(tox[[1, 2, 4]]).cpu().numpy()      # alpha, beta, delta
+    vk_g2 = g2_mul(tox[[2, 3, 4]]).cpu().numpy()      # beta, gamma, delta
+    ctx.synchronize()
+    vk = {"alpha_g1": vk_g1[0], "beta_g1": vk_g1[1], "delta_g1": vk_g1[2],
+          "beta_g2": vk_g2[0], "gamma_g2": vk_g2[1], "delta_g2": vk_g2[2], "ic": ic}
+    hb = ctx.g1_bases_from_dev(h_pts.contiguous(), m - 1)
+    lb = ctx.g1_bases_from_dev(l_pts.contiguous() if na else t.empty((1, G1_BYTES), dtype=t.uint8, device="cuda"), na)
+    ab = ctx.g1_bases_from_dev(a_pts.contiguous(), len(a_idx))
+    b1b = ctx.g1_bases_from_dev(b1_pts.contiguous() if len(b_idx) else t.empty((1, G1_BYTES), dtype=t.uint8, device="cuda"), len(b_idx))
+    b2b = ctx.g2_bases_from_dev(b2_pts.contiguous() if len(b_idx) else t.empty((1, G2_BYTES), dtype=t.uint8, device="cuda"), len(b_idx))
+    ctx.synchronize()
+    host = {"h": h_pts, "l": l_pts, "a": a_pts, "b_g1": b1_pts, "b_g2": b2_pts}
+    pk = _make_pk(ctx, vk, hb, lb, ab, b1b, b2b)
+    pk.device_images = host  # wire images kept for tests / export
+    return pk, vk
+
+
+def _p(tensor):
+    return ct.c_void_p(tensor.data_ptr())
+
+
+def dev_u32(t, a):
+    return t.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
+
+
+def _fr_one():
+    # R mod r (Montgomery one), little-endian u64 limbs
+    return np.array([0x00000001FFFFFFFE, 0x5884B7FA00034802, 0x998C4FEFECBC4FF5, 0x1824B159ACC5056F], dtype=np.uint64)
+
+
+def _fr_inv_gpu(ctx, x):
+    """x^(r-2) by square-and-multiply with libbzk's Fr product (setup only: two inversions)."""
+    import torch
+    t = torch
+    R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    e = R - 2
+    base = t.from_numpy(np.asarray(x, dtype=np.uint64).reshape(1, 4).view(np.int64)).cuda()
+    acc = t.from_numpy(_fr_one().reshape(1, 4).view(np.int64)).cuda()
+    out = t.empty_like(acc)
+    for bit in bin(e)[2:]:
+        ctx.fr_binop_dev(2, acc, acc, out, 1)
+        acc, out = out, acc
+        if bit == "1":
+            ctx.fr_binop_dev(2, acc, base, out, 1)
+            acc, out = out, acc
+    ctx.synchronize()
+    return acc.cpu().numpy().view(np.uint64).reshape(4)

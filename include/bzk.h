@@ -62,6 +62,12 @@ int32_t bzk_ctx_destroy(bzk_ctx *ctx);
  * cudaStreamLegacy ((cudaStream_t)0x1) or cudaStreamPerThread ((cudaStream_t)0x2). */
 int32_t bzk_ctx_set_stream(bzk_ctx *ctx, void *cuda_stream);
 int32_t bzk_ctx_synchronize(bzk_ctx *ctx);
+/* Per-stage device timing: when on, the MSM driver records CUDA events on the launching stream
+ * between its kernels (stage order: 0 digits+histogram, 1 scan, 2 scatter, 3 accumulate, 4 fixup,
+ * 5 bucket slices, 6 window sums).  bzk_ctx_stage_ms copies the last call's per-stage milliseconds
+ * (up to `cap` floats) and returns how many calls have been timed since timing was switched on. */
+int32_t bzk_ctx_set_timing(bzk_ctx *ctx, int32_t on);
+uint64_t bzk_ctx_stage_ms(const bzk_ctx *ctx, float *last_ms, double *sum_ms, uint32_t cap);
 /* kernels launched through this ctx since creation (bench.py's `gpu_launches`) */
 uint64_t bzk_ctx_launch_count(const bzk_ctx *ctx);
 
@@ -130,6 +136,49 @@ int32_t bzk_g1_random_bases_dev(bzk_ctx *ctx, uint64_t seed, size_t n, void *d_o
 int32_t bzk_g2_random_bases_dev(bzk_ctx *ctx, uint64_t seed, size_t n, void *d_out);
 /* n uniform Fr (Montgomery) from SplitMix64(seed), same stream rule */
 int32_t bzk_fr_random_dev(bzk_ctx *ctx, uint64_t seed, size_t n, void *d_out);
+
+/* ------------------------------------------------------------------ Groth16 prover
+ * Replaces bellman 0.14.0 `groth16::create_proof(circuit, &params, r, s)` — reference call sites
+ * /root/reference/src/mpn/circuits/test.rs:135,175,215 (`create_random_proof`), gadget tests, and in
+ * production the external prover behind `MpnWork` (/root/reference/src/mpn/mod.rs:264-295).
+ *
+ * The circuit arrives as its R1CS in CSR form (what `Circuit::synthesize` emits into bellman's
+ * `ProvingAssignment`), one matrix per side: rowptr[num_constraints+1], col[nnz] = index into
+ * z = inputs ++ aux (z[0] = ONE), val[nnz] = Montgomery coefficients.  Like bellman, the library
+ * appends the `Input(i) * 0 = 0` rows itself and derives the A/B density lists from the non-zero
+ * coefficients.  Parameters are bellman's `Parameters<Bls12>` vectors: h (m-1), l (num_aux),
+ * a (num_inputs + |A aux density|), b_g1 / b_g2 (|B input density| + |B aux density|), in
+ * bellman's order (inputs first), identity entries already filtered out. */
+typedef struct bzk_r1cs bzk_r1cs;
+typedef struct bzk_groth16_params bzk_groth16_params;
+int32_t bzk_r1cs_upload(bzk_ctx *ctx, uint64_t num_inputs, uint64_t num_aux, uint64_t num_constraints,
+                        const uint64_t *a_rowptr, const uint32_t *a_col, const bzk_fr *a_val,
+                        const uint64_t *b_rowptr, const uint32_t *b_col, const bzk_fr *b_val,
+                        const uint64_t *c_rowptr, const uint32_t *c_col, const bzk_fr *c_val, bzk_r1cs **out);
+int32_t bzk_r1cs_free(bzk_ctx *ctx, bzk_r1cs *r1cs);
+/* out = { log2 m, |h| = m-1, |l|, |a|, |b_g1| = |b_g2| } the parameter vectors must have */
+int32_t bzk_r1cs_shape(const bzk_r1cs *r1cs, uint64_t out[5]);
+/* adopts the five resident base vectors (freed with the handle) plus the vk points the tail needs */
+int32_t bzk_groth16_params_create(bzk_ctx *ctx, const bzk_g1_affine *alpha_g1, const bzk_g1_affine *beta_g1, const bzk_g2_affine *beta_g2,
+                                  const bzk_g1_affine *delta_g1, const bzk_g2_affine *delta_g2,
+                                  bzk_g1_bases *h, bzk_g1_bases *l, bzk_g1_bases *a, bzk_g1_bases *b_g1, bzk_g2_bases *b_g2,
+                                  bzk_groth16_params **out);
+int32_t bzk_groth16_params_free(bzk_ctx *ctx, bzk_groth16_params *params);
+/* inputs[num_inputs] (inputs[0] = ONE), aux[num_aux], r, s: host Montgomery images.  With
+ * check_satisfied != 0 returns BZK_ERR_UNSAT when a*b != c on some constraint (bellman proves
+ * garbage silently).  Outputs are the wire images of Proof {a, b, c}. */
+int32_t bzk_groth16_prove(bzk_ctx *ctx, const bzk_groth16_params *params, const bzk_r1cs *r1cs,
+                          const bzk_fr *inputs, const bzk_fr *aux, const bzk_fr *r, const bzk_fr *s, int32_t check_satisfied,
+                          bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c);
+/* 387-byte bincode image of `Groth16Proof {a,b,c}` (/root/reference/src/zk/groth16/mod.rs:33-38);
+ * prefix it with the u32 variant tag 0 for `ZkProof::Groth16` (391 B). */
+int32_t bzk_groth16_proof_bytes(const bzk_g1_affine *a, const bzk_g2_affine *b, const bzk_g1_affine *c, uint8_t out[387]);
+/* Building blocks also used by the GPU-side trusted-setup helper (bellman `generate_parameters`):
+ * CSR sparse matrix-vector product over Fr (out[row] = sum val*vec[col]) and fixed-base scalar
+ * multiplication out[i] = [k_i] base written as wire images. */
+int32_t bzk_csr_spmv_dev(bzk_ctx *ctx, const void *d_rowptr, const void *d_col, const void *d_val, uint64_t nrows, const void *d_vec, void *d_out);
+int32_t bzk_g1_fixed_base_mul_dev(bzk_ctx *ctx, const bzk_g1_affine *base, const void *d_scalars, size_t n, void *d_out);
+int32_t bzk_g2_fixed_base_mul_dev(bzk_ctx *ctx, const bzk_g2_affine *base, const void *d_scalars, size_t n, void *d_out);
 
 /* ------------------------------------------------------------------ elementwise Fr (device)
  * out[i] = a[i] (op) b[i]; used by the prover pipeline and the arithmetic parity tests. */

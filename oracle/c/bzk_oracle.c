@@ -527,3 +527,203 @@ void bzko_divide_by_z_on_coset(u64 *a, unsigned log_n) {
     fr_set_u64(g, 7); fr_pow_u64(z, g, (u64)1 << log_n); fr_sub(z, z, fr_R1); fr_inv(z, z);
     for (size_t i = 0; i < ((size_t)1 << log_n); i++) fr_mul(a + 4 * i, a + 4 * i, z);
 }
+
+/* ------------------------------------------------------------------ Groth16 (bellman 0.14.0 generator / prover)
+ * Restates `groth16::generator::generate_parameters` and `groth16::prover::create_proof`
+ * (un-vendored crate; reference call sites /root/reference/src/config/blockchain.rs:372-400 and
+ * /root/reference/src/mpn/circuits/test.rs:135,175,215).  PARITY UNPINNED by the reference (no
+ * proof bytes recorded anywhere); pinned against oracle/py/groth16.py and the pairing check.
+ *
+ * R1CS in CSR form, one matrix per side: rowptr[nrows+1] (u64), col[nnz] (u32 index into
+ * z = inputs ++ aux, z[0] = ONE), val[nnz] (Montgomery Fr).  Both functions append bellman's
+ * `Input(i) * 0 = 0` rows themselves. */
+typedef struct { const u64 *rowptr; const uint32_t *col; const u64 *val; } csr_t;
+
+static void csr_row_eval(u64 *out, const csr_t *m, size_t row, const u64 *z) {
+    u64 acc[4] = {0, 0, 0, 0}, t[4];
+    for (u64 k = m->rowptr[row]; k < m->rowptr[row + 1]; k++) {
+        fr_mul(t, m->val + 4 * k, z + 4 * (size_t)m->col[k]);
+        fr_add(acc, acc, t);
+    }
+    memcpy(out, acc, 32);
+}
+typedef struct { const csr_t *m; const u64 *z; u64 *out; size_t lo, hi; } eval_job;
+static void *eval_thread(void *arg_) {
+    eval_job *j = arg_;
+    for (size_t r = j->lo; r < j->hi; r++) csr_row_eval(j->out + 4 * r, j->m, r, j->z);
+    return NULL;
+}
+static void csr_eval(u64 *out, const csr_t *m, size_t nrows, const u64 *z, int threads) {
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    eval_job jobs[256]; pthread_t th[256];
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = (eval_job){ m, z, out, nrows * t / threads, nrows * (t + 1) / threads };
+        pthread_create(&th[t], NULL, eval_thread, &jobs[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+}
+
+/* out[i] = [k_i] base for Montgomery scalars k — fixed-base 8-bit windows, threaded */
+typedef struct { const u64 *k; size_t lo, hi; uint8_t *out; const void *table; } fb_job;
+static void *fb_g1_thread(void *arg_) {
+    fb_job *job = arg_;
+    const uint8_t (*table)[255][104] = job->table;
+    size_t cnt = job->hi - job->lo;
+    if (!cnt) return NULL;
+    g1_jac *pts = malloc(sizeof(g1_jac) * cnt);
+    for (size_t i = 0; i < cnt; i++) {
+        u64 v[4]; fr_from_mont(v, job->k + 4 * (job->lo + i));
+        g1_jac acc; g1_set_inf(&acc);
+        for (int w = 0; w < 32; w++) { unsigned d = (v[w / 8] >> ((w % 8) * 8)) & 0xff; if (d) g1_madd(&acc, &acc, table[w][d - 1]); }
+        pts[i] = acc;
+    }
+    g1_batch_to_affine(job->out + job->lo * 104, pts, cnt);
+    free(pts);
+    return NULL;
+}
+static void *fb_g2_thread(void *arg_) {
+    fb_job *job = arg_;
+    const uint8_t (*table)[255][200] = job->table;
+    size_t cnt = job->hi - job->lo;
+    if (!cnt) return NULL;
+    g2_jac *pts = malloc(sizeof(g2_jac) * cnt);
+    for (size_t i = 0; i < cnt; i++) {
+        u64 v[4]; fr_from_mont(v, job->k + 4 * (job->lo + i));
+        g2_jac acc; g2_set_inf(&acc);
+        for (int w = 0; w < 32; w++) { unsigned d = (v[w / 8] >> ((w % 8) * 8)) & 0xff; if (d) g2_madd(&acc, &acc, table[w][d - 1]); }
+        pts[i] = acc;
+    }
+    g2_batch_to_affine(job->out + job->lo * 200, pts, cnt);
+    free(pts);
+    return NULL;
+}
+void bzko_g1_fixed_base_mul(const uint8_t *base_img, const u64 *k_mont, size_t n, uint8_t *out, int threads) {
+    bzko_init();
+    uint8_t (*table)[255][104] = malloc(32 * 255 * 104);
+    g1_jac base; g1_from_affine(&base, base_img);
+    g1_jac *row = malloc(sizeof(g1_jac) * 255);
+    for (int w = 0; w < 32; w++) {
+        row[0] = base;
+        for (int d = 1; d < 255; d++) g1_add(&row[d], &row[d - 1], &base);
+        g1_batch_to_affine(&table[w][0][0], row, 255);
+        g1_add(&base, &row[254], &base);
+    }
+    free(row);
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    fb_job jobs[256]; pthread_t th[256];
+    for (int t = 0; t < threads; t++) { jobs[t] = (fb_job){ k_mont, n * t / threads, n * (t + 1) / threads, out, table }; pthread_create(&th[t], NULL, fb_g1_thread, &jobs[t]); }
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    free(table);
+}
+void bzko_g2_fixed_base_mul(const uint8_t *base_img, const u64 *k_mont, size_t n, uint8_t *out, int threads) {
+    bzko_init();
+    uint8_t (*table)[255][200] = malloc(32 * 255 * 200);
+    g2_jac base; g2_from_affine(&base, base_img);
+    g2_jac *row = malloc(sizeof(g2_jac) * 255);
+    for (int w = 0; w < 32; w++) {
+        row[0] = base;
+        for (int d = 1; d < 255; d++) g2_add(&row[d], &row[d - 1], &base);
+        g2_batch_to_affine(&table[w][0][0], row, 255);
+        g2_add(&base, &row[254], &base);
+    }
+    free(row);
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    fb_job jobs[256]; pthread_t th[256];
+    for (int t = 0; t < threads; t++) { jobs[t] = (fb_job){ k_mont, n * t / threads, n * (t + 1) / threads, out, table }; pthread_create(&th[t], NULL, fb_g2_thread, &jobs[t]); }
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    free(table);
+}
+
+static unsigned log2_ceil(size_t n) { unsigned e = 0; size_t m = 1; while (m < n) { m <<= 1; e++; } return e; }
+
+/* Setup scalars.  Outputs (Montgomery Fr): h_k[m-1], at[nv], bt[nv], ext_ic[num_inputs],
+ * ext_l[num_aux];  returns log2(m).  The caller turns them into points with the fixed-base muls. */
+int bzko_groth16_setup_scalars(u64 num_inputs, u64 num_aux, u64 ncons,
+                               const u64 *a_rp, const uint32_t *a_col, const u64 *a_val,
+                               const u64 *b_rp, const uint32_t *b_col, const u64 *b_val,
+                               const u64 *c_rp, const uint32_t *c_col, const u64 *c_val,
+                               const u64 *toxic /* tau, alpha, beta, gamma, delta */,
+                               u64 *h_k, u64 *at, u64 *bt, u64 *ext_ic, u64 *ext_l, int threads) {
+    bzko_init();
+    const u64 *tau = toxic, *alpha = toxic + 4, *beta = toxic + 8, *gamma = toxic + 12, *delta = toxic + 16;
+    size_t rows = ncons + num_inputs, nv = num_inputs + num_aux;
+    unsigned log_m = log2_ceil(rows);
+    size_t m = (size_t)1 << log_m;
+    u64 *lag = malloc(32 * m);
+    memcpy(lag, fr_R1, 32);
+    for (size_t i = 1; i < m; i++) fr_mul(lag + 4 * i, lag + 4 * (i - 1), tau);
+    u64 zt[4]; fr_mul(zt, lag + 4 * (m - 1), tau); fr_sub(zt, zt, fr_R1);       /* tau^m - 1 */
+    u64 dinv[4], ginv[4], zd[4];
+    fr_inv(dinv, delta); fr_inv(ginv, gamma); fr_mul(zd, zt, dinv);
+    for (size_t i = 0; i + 1 < m; i++) fr_mul(h_k + 4 * i, lag + 4 * i, zd);    /* tau^i Z(tau)/delta */
+    bzko_ntt(lag, log_m, 1, threads);                                             /* L_j(tau) */
+    u64 *ct = calloc(nv, 32);
+    memset(at, 0, 32 * nv); memset(bt, 0, 32 * nv);
+    const u64 *rp[3] = { a_rp, b_rp, c_rp }; const uint32_t *cl[3] = { a_col, b_col, c_col }; const u64 *vl[3] = { a_val, b_val, c_val };
+    u64 *dst[3] = { at, bt, ct };
+    for (int s = 0; s < 3; s++)
+        for (size_t j = 0; j < ncons; j++)
+            for (u64 k = rp[s][j]; k < rp[s][j + 1]; k++) {
+                u64 t[4]; fr_mul(t, vl[s] + 4 * k, lag + 4 * j);
+                fr_add(dst[s] + 4 * (size_t)cl[s][k], dst[s] + 4 * (size_t)cl[s][k], t);
+            }
+    for (size_t i = 0; i < num_inputs; i++) fr_add(at + 4 * i, at + 4 * i, lag + 4 * (ncons + i));  /* Input(i)*0=0 rows */
+    for (size_t v = 0; v < nv; v++) {
+        u64 e[4], t[4];
+        fr_mul(e, beta, at + 4 * v); fr_mul(t, alpha, bt + 4 * v); fr_add(e, e, t); fr_add(e, e, ct + 4 * v);
+        if (v < num_inputs) fr_mul(ext_ic + 4 * v, e, ginv); else fr_mul(ext_l + 4 * (v - num_inputs), e, dinv);
+    }
+    free(ct); free(lag);
+    return (int)log_m;
+}
+
+/* a/b/c evaluations (padded to m) and the h coefficient vector (m-1 scalars, Montgomery) */
+int bzko_groth16_h(u64 num_inputs, u64 num_aux, u64 ncons,
+                   const u64 *a_rp, const uint32_t *a_col, const u64 *a_val,
+                   const u64 *b_rp, const uint32_t *b_col, const u64 *b_val,
+                   const u64 *c_rp, const uint32_t *c_col, const u64 *c_val,
+                   const u64 *z, u64 *h_out, int threads) {
+    bzko_init();
+    size_t rows = ncons + num_inputs;
+    unsigned log_m = log2_ceil(rows);
+    size_t m = (size_t)1 << log_m;
+    u64 *ev[3];
+    csr_t mats[3] = { { a_rp, a_col, a_val }, { b_rp, b_col, b_val }, { c_rp, c_col, c_val } };
+    for (int s = 0; s < 3; s++) { ev[s] = calloc(m, 32); csr_eval(ev[s], &mats[s], ncons, z, threads); }
+    for (size_t i = 0; i < num_inputs; i++) memcpy(ev[0] + 4 * (ncons + i), z + 4 * i, 32);
+    for (int s = 0; s < 3; s++) { bzko_ntt(ev[s], log_m, 1, threads); bzko_ntt(ev[s], log_m, 2, threads); }
+    for (size_t i = 0; i < m; i++) { fr_mul(ev[0] + 4 * i, ev[0] + 4 * i, ev[1] + 4 * i); fr_sub(ev[0] + 4 * i, ev[0] + 4 * i, ev[2] + 4 * i); }
+    bzko_divide_by_z_on_coset(ev[0], log_m);
+    bzko_ntt(ev[0], log_m, 3, threads);
+    memcpy(h_out, ev[0], 32 * (m - 1));
+    for (int s = 0; s < 3; s++) free(ev[s]);
+    return (int)log_m;
+}
+
+/* final assembly from the five MSM answers (affine images) — tail of create_proof */
+void bzko_groth16_assemble(const uint8_t *alpha_g1, const uint8_t *beta_g1, const uint8_t *beta_g2,
+                           const uint8_t *delta_g1, const uint8_t *delta_g2,
+                           const uint8_t *a_ans, const uint8_t *b1_ans, const uint8_t *b2_ans,
+                           const uint8_t *h_ans, const uint8_t *l_ans, const u64 *r_mont, const u64 *s_mont,
+                           uint8_t *out_a, uint8_t *out_b, uint8_t *out_c) {
+    bzko_init();
+    u64 r[4], s[4], rs[4], rsm[4];
+    fr_from_mont(r, r_mont); fr_from_mont(s, s_mont); fr_mul(rsm, r_mont, s_mont); fr_from_mont(rs, rsm);
+    g1_jac ga, gc, t, aa, b1;
+    g2_jac gb, t2, b2;
+    g1_from_affine(&t, delta_g1); g1_mul_u256(&ga, &t, r); g1_from_affine(&t, alpha_g1); g1_add(&ga, &ga, &t);
+    g1_from_affine(&aa, a_ans); g1_add(&ga, &ga, &aa);
+    g2_from_affine(&t2, delta_g2); g2_mul_u256(&gb, &t2, s); g2_from_affine(&t2, beta_g2); g2_add(&gb, &gb, &t2);
+    g2_from_affine(&b2, b2_ans); g2_add(&gb, &gb, &b2);
+    g1_from_affine(&t, delta_g1); g1_mul_u256(&gc, &t, rs);
+    g1_from_affine(&t, alpha_g1); g1_mul_u256(&t, &t, s); g1_add(&gc, &gc, &t);
+    g1_from_affine(&t, beta_g1); g1_mul_u256(&t, &t, r); g1_add(&gc, &gc, &t);
+    g1_mul_u256(&t, &aa, s); g1_add(&gc, &gc, &t);
+    g1_from_affine(&b1, b1_ans); g1_mul_u256(&t, &b1, r); g1_add(&gc, &gc, &t);
+    g1_from_affine(&t, h_ans); g1_add(&gc, &gc, &t);
+    g1_from_affine(&t, l_ans); g1_add(&gc, &gc, &t);
+    g1_to_affine(out_a, &ga); g2_to_affine(out_b, &gb); g1_to_affine(out_c, &gc);
+}
