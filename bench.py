@@ -166,20 +166,13 @@ def run_ours(args, rank, local_rank, world):
     h_scalars = d_scalars.cpu().pin_memory()
     h_img = d_img.cpu().pin_memory() if rank == 0 else None
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    gathered = torch.empty((world, 104), dtype=torch.uint8, device="cuda") if world > 1 else None
     torch.cuda.synchronize()
 
+    from bazuka_b200 import dist as bd
+
     def fold(partial):
-        """N>1: all-gather the per-rank partial points (104 B each) and add them."""
-        if world == 1:
-            return partial
-        mine = torch.from_numpy(partial).cuda()
-        dist.all_gather_into_tensor(gathered.view(-1), mine)
-        pts = gathered.cpu().numpy()
-        acc = pts[0]
-        for k in range(1, world):
-            acc = ctx.g1_add(acc, pts[k])
-        return acc
+        """N>1: one NCCL all-gather of the per-rank partial points (104 B each), then local adds."""
+        return bd.allgather_fold(partial, "g1", device="cuda") if world > 1 else partial
 
     def step_resident():
         return fold(ctx.msm_g1_resident(bases, d_scalars))
