@@ -43,12 +43,14 @@ struct MsmPlan {
 };
 
 static MsmPlan make_plan(size_t n, int force_c = 0) {
-    // cost model: n*W mixed adds + ~3*W*NB add-equivalents for the reduction
+    // cost model calibrated on B200 at 2^20 (bench.py stage marks, c = 14 vs 16 measured): a bucket
+    // costs about 6 mixed additions in the reduction (2 full additions, the [slice offset]
+    // double-and-add, the latency-bound tree and the extra digit/scatter work of more windows).
     uint32_t best_c = 1;
     double best = 1e300;
     for (uint32_t c = 2; c <= 18; c++) {
         uint32_t W = (256 + c - 1) / c;
-        double cost = (double)n * W + 3.0 * W * (double)(1u << (c - 1));
+        double cost = (double)n * W + 6.0 * W * (double)(1u << (c - 1));
         if (cost < best) { best = cost; best_c = c; }
     }
     MsmPlan p;
@@ -179,13 +181,21 @@ static __global__ void __launch_bounds__(kScanBlock) k_scan_apply(const uint32_t
 // ---------------------------------------------------------------------------------------------
 // 4. accumulate (chunked, bucket-boundary agnostic)
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t effective_chunk(uint32_t M, uint32_t threads, uint32_t min_chunk) {
+    uint32_t c = (M + threads - 1) / threads;
+    return c < min_chunk ? min_chunk : c;
+}
+
 template <class F>
 __global__ void __launch_bounds__(128) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
-                                                    const uint32_t *__restrict__ offsets, uint32_t TB, uint32_t chunk,
+                                                    const uint32_t *__restrict__ offsets, uint32_t TB, uint32_t min_chunk,
                                                     Xyzz<F> *__restrict__ buckets, Xyzz<F> *__restrict__ part_pts,
                                                     int32_t *__restrict__ part_bucket) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t M = offsets[TB];
+    // the launch is sized for "every digit non-zero"; spread the entries that really exist over all
+    // launched threads (witness vectors are full of zeros: M is often half of n*W)
+    const uint32_t chunk = effective_chunk(M, gridDim.x * blockDim.x, min_chunk);
     const uint64_t start64 = (uint64_t)t * chunk;
     part_bucket[2 * t] = -1;
     part_bucket[2 * t + 1] = -1;
@@ -234,11 +244,27 @@ __global__ void __launch_bounds__(128) k_accumulate(const Affine<F> *__restrict_
     }
 }
 
-// 5. fold the side list: the first slot of each bucket's run of partials sums the run and stores it
+// 5. fold the side list.  The first slot of each bucket's run of partials owns the run: short runs
+// (the common case: a bucket cut by one or two chunk edges) are summed by that thread; long runs
+// — a bucket that swallows thousands of chunks, e.g. digit 1 of window 0 when a third of a Groth16
+// witness is boolean — are queued for k_fixup_long, where a whole CTA sums the run with a
+// shared-memory tree instead of one thread walking it serially.
+constexpr uint32_t kLongRun = 24;       // partials; longer runs go to the CTA-wide path
+constexpr uint32_t kLongQueueCap = 4096;
+struct LongRun { uint32_t first, last; int32_t bucket; uint32_t pad; };
+
 template <class F>
 __global__ void __launch_bounds__(128) k_fixup(const Xyzz<F> *__restrict__ part_pts, const int32_t *__restrict__ part_bucket,
-                                               uint32_t nslots, Xyzz<F> *__restrict__ buckets) {
+                                               uint32_t nslots_max, const uint32_t *__restrict__ offsets, uint32_t TB, uint32_t acc_threads, uint32_t min_chunk,
+                                               Xyzz<F> *__restrict__ buckets,
+                                               LongRun *__restrict__ queue, uint32_t *__restrict__ queue_len) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    // only the chunks that actually hold entries have slots (the launch is sized for the worst case
+    // "every digit non-zero"; witness vectors are far sparser)
+    const uint32_t M = offsets[TB];
+    const uint32_t chunk = effective_chunk(M, acc_threads, min_chunk);
+    uint32_t nslots = 2 * ((M + chunk - 1) / chunk);
+    if (nslots > nslots_max) nslots = nslots_max;
     if (e >= nslots) return;
     const int32_t b = part_bucket[e];
     if (b < 0) return;
@@ -248,14 +274,56 @@ __global__ void __launch_bounds__(128) k_fixup(const Xyzz<F> *__restrict__ part_
         if (pb == b) return;  // not the head of the run
         break;
     }
-    Xyzz<F> acc = load_vec(part_pts + e);
+    // measure the run (slot indices only)
+    uint32_t last = e, count = 1;
     for (uint32_t q = e + 1; q < nslots; q++) {
         int32_t nb = part_bucket[q];
         if (nb < 0) continue;
         if (nb != b) break;
-        acc.add(load_vec(part_pts + q));
+        last = q;
+        count++;
     }
+    if (count > kLongRun) {
+        uint32_t at = atomicAdd(queue_len, 1u);
+        if (at < kLongQueueCap) {
+            queue[at] = LongRun{e, last, b, 0};
+            return;
+        }
+        // queue full (cannot happen with <= kLongQueueCap long runs; fall through to the serial sum)
+    }
+    Xyzz<F> acc = load_vec(part_pts + e);
+    for (uint32_t q = e + 1; q <= last; q++)
+        if (part_bucket[q] == b) acc.add(load_vec(part_pts + q));
     store_vec(buckets + b, acc);
+}
+
+// one CTA per queued long run (grid-stride over the queue)
+template <class F>
+__global__ void __launch_bounds__(256) k_fixup_long(const Xyzz<F> *__restrict__ part_pts, const int32_t *__restrict__ part_bucket,
+                                                    Xyzz<F> *__restrict__ buckets, const LongRun *__restrict__ queue,
+                                                    const uint32_t *__restrict__ queue_len) {
+    extern __shared__ uint4 smem_raw[];
+    Xyzz<F> *sh = (Xyzz<F> *)smem_raw;
+    uint32_t nq = *queue_len;
+    if (nq > kLongQueueCap) nq = kLongQueueCap;
+    for (uint32_t r = blockIdx.x; r < nq; r += gridDim.x) {
+        const LongRun run = queue[r];
+        Xyzz<F> acc = Xyzz<F>::inf();
+        for (uint32_t q = run.first + threadIdx.x; q <= run.last; q += blockDim.x)
+            if (part_bucket[q] == run.bucket) acc.add(load_vec(part_pts + q));
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        for (uint32_t o = blockDim.x / 2; o > 0; o >>= 1) {
+            if (threadIdx.x < o) {
+                Xyzz<F> a = sh[threadIdx.x];
+                a.add(sh[threadIdx.x + o]);
+                sh[threadIdx.x] = a;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) store_vec(buckets + run.bucket, sh[0]);
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -277,12 +345,13 @@ __global__ void __launch_bounds__(128) k_bucket_slices(const Xyzz<F> *__restrict
                                                        Xyzz<F> *__restrict__ slice_out) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nslices_total) return;
-    const uint32_t per_win = NB / slice;
+    const uint32_t per_win = (NB + slice - 1) / slice;  // the last slice of a window may be short
     const uint32_t w = g / per_win, sidx = g % per_win;
     const uint32_t lo = sidx * slice;
+    const uint32_t len = (lo + slice <= NB) ? slice : NB - lo;
     const Xyzz<F> *B = buckets + (size_t)w * NB;
     Xyzz<F> run = Xyzz<F>::inf(), acc = Xyzz<F>::inf();
-    for (uint32_t k = slice; k-- > 0;) {
+    for (uint32_t k = len; k-- > 0;) {
         run.add(load_vec(B + lo + k));
         acc.add(run);
     }
@@ -457,8 +526,14 @@ static int32_t msm_run(bzk_ctx *ctx, const Affine<F> *d_bases, const Fr *d_scala
 
     // slice length trades the serial running-sum (2*slice adds) against the [offset]*sum
     // double-and-add (~log2(NB/slice) doublings): short slices keep every SM busy
-    uint32_t slice = pl.NB >= 8 ? 8 : pl.NB;
-    const uint32_t per_win = pl.NB / slice;
+    // Pick the shortest slice whose thread count still fits ONE wave of the reduce kernel (3 CTAs
+    // of 128 threads per SM at its register count) — a second, nearly empty wave costs a full
+    // slice time.
+    const uint32_t red_capacity = (uint32_t)ctx->sm_count * 3 * 128;
+    uint32_t slice = (uint32_t)(((uint64_t)pl.TB + red_capacity - 1) / red_capacity);
+    if (slice < 4) slice = pl.NB >= 4 ? 4 : pl.NB;
+    if (slice > pl.NB) slice = pl.NB;
+    const uint32_t per_win = (pl.NB + slice - 1) / slice;
     const uint32_t nslices = per_win * pl.W;
     const uint32_t ntiles = div_up(pl.TB, kScanTile);
 
@@ -471,6 +546,7 @@ static int32_t msm_run(bzk_ctx *ctx, const Affine<F> *d_bases, const Fr *d_scala
         cv.take<uint32_t>(max_entries);
         cv.take<Xyzz<F>>(pl.TB);
         cv.take<Xyzz<F>>(nslots); cv.take<int32_t>(nslots);
+        cv.take<LongRun>(kLongQueueCap); cv.take<uint32_t>(4);
         cv.take<Xyzz<F>>(nslices);
         cv.take<Xyzz<F>>(pl.W);
         need = cv.used();
@@ -485,6 +561,8 @@ static int32_t msm_run(bzk_ctx *ctx, const Affine<F> *d_bases, const Fr *d_scala
     Xyzz<F> *buckets = cv.take<Xyzz<F>>(pl.TB);
     Xyzz<F> *part_pts = cv.take<Xyzz<F>>(nslots);
     int32_t *part_bucket = cv.take<int32_t>(nslots);
+    LongRun *long_queue = cv.take<LongRun>(kLongQueueCap);
+    uint32_t *long_len = cv.take<uint32_t>(4);
     Xyzz<F> *slice_out = cv.take<Xyzz<F>>(nslices);
     Xyzz<F> *win_out = cv.take<Xyzz<F>>(pl.W);
 
@@ -508,11 +586,18 @@ static int32_t msm_run(bzk_ctx *ctx, const Affine<F> *d_bases, const Fr *d_scala
     k_digits<true><<<div_up(n, 256), 256, 0, st>>>(d_scalars, n, pl.c, pl.W, pl.NB, cursor, sorted);
     BZK_LAUNCHED(ctx);
     timing_mark(ctx);
-    k_accumulate<F><<<acc_blocks, 128, 0, st>>>(d_bases, sorted, offsets, pl.TB, chunk, buckets, part_pts, part_bucket);
+    k_accumulate<F><<<acc_blocks, 128, 0, st>>>(d_bases, sorted, offsets, pl.TB, 16u, buckets, part_pts, part_bucket);
     BZK_LAUNCHED(ctx);
     timing_mark(ctx);
-    k_fixup<F><<<div_up(nslots, 128), 128, 0, st>>>(part_pts, part_bucket, nslots, buckets);
+    BZK_CUDA(ctx, cudaMemsetAsync(long_len, 0, 16, st));
+    k_fixup<F><<<div_up(nslots, 128), 128, 0, st>>>(part_pts, part_bucket, nslots, offsets, pl.TB, acc_blocks * 128, 16u, buckets, long_queue, long_len);
     BZK_LAUNCHED(ctx);
+    {
+        const size_t fsmem = 256 * sizeof(Xyzz<F>);
+        BZK_CUDA(ctx, cudaFuncSetAttribute(k_fixup_long<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        k_fixup_long<F><<<ctx->sm_count, 256, fsmem, st>>>(part_pts, part_bucket, buckets, long_queue, long_len);
+        BZK_LAUNCHED(ctx);
+    }
     timing_mark(ctx);
     k_bucket_slices<F><<<div_up(nslices, 128), 128, 0, st>>>(buckets, pl.NB, slice, nslices, slice_out);
     BZK_LAUNCHED(ctx);

@@ -3,6 +3,7 @@
 // group law on the CPU so their logic is checked against the oracle without a GPU.
 #include <cstring>
 #include "ec.cuh"
+#include "ffu.cuh"
 using namespace bzk;
 template <class T, int W> static void bin(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n, int op) {
     for (size_t i = 0; i < n; i++) {
@@ -18,6 +19,15 @@ template <class T, int W> static void bin(const uint32_t *a, const uint32_t *b, 
     }
 }
 extern "C" {
+// carry-free 13x30-bit Fp (ffu.cuh): wire image -> internal -> op -> wire image
+void shim_fpu(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n, int op) {
+    for (size_t i = 0; i < n; i++) {
+        Fp x, y; memcpy(x.l, a + 12 * i, 48); memcpy(y.l, b + 12 * i, 48);
+        FpU u = FpU::from_fp(x), v = FpU::from_fp(y), w;
+        switch (op) { case 0: w = u + v; break; case 1: w = u - v; break; case 2: w = u * v; break; default: w = u; break; }
+        Fp z = w.to_fp(); memcpy(r + 12 * i, z.l, 48);
+    }
+}
 void shim_fr(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n, int op) { bin<Fr, 8>(a, b, r, n, op); }
 void shim_fp(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n, int op) { bin<Fp, 12>(a, b, r, n, op); }
 void shim_fr_inv(const uint32_t *a, uint32_t *r, size_t n) {

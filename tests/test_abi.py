@@ -74,6 +74,10 @@ def test_host_build_of_device_multiplier(hostshim, cref):
     for op, f in ((0, cref.fp_add), (1, cref.fp_sub), (2, cref.fp_mul), (3, cref.fp_mul)):
         hostshim.shim_fp(x.ctypes.data_as(ct.c_void_p), y.ctypes.data_as(ct.c_void_p), r.ctypes.data_as(ct.c_void_p), ct.c_size_t(n), op)
         assert (r == f(x, y)).all(), op
+    # the carry-free 13 x 30-bit representation used inside the MSM: same field, different limbs
+    for op, f in ((0, cref.fp_add), (1, cref.fp_sub), (2, cref.fp_mul), (3, lambda u, v: u)):
+        hostshim.shim_fpu(x.ctypes.data_as(ct.c_void_p), y.ctypes.data_as(ct.c_void_p), r.ctypes.data_as(ct.c_void_p), ct.c_size_t(n), op)
+        assert (r == f(x, y)).all(), ("fpu", op)
     hostshim.shim_fp_inv(x.ctypes.data_as(ct.c_void_p), r.ctypes.data_as(ct.c_void_p), ct.c_size_t(50))
     assert (r[:50] == cref.fp_inv(x[:50])).all()
 

@@ -3,7 +3,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
-#include "../../bazuka_b200/csrc/ff.cuh"
+#include "../../bazuka_b200/csrc/ffu.cuh"
 using namespace bzk;
 
 #define ITERS 4096
@@ -113,5 +113,7 @@ int main() {
     for (int b = 1; b <= 4; b *= 2) { runmul<Fp, 0>("Fp mul (even/odd)", b); }
     for (int b = 1; b <= 8; b *= 2) { runmul<Fr, 0>("Fr mul (even/odd)", b); }
     runmul<Fp, 1>("Fp add/sub", 4);
+    for (int b = 1; b <= 4; b *= 2) { runmul<FpU, 0>("FpU mul (13x30 carry-free)", b); }
+    runmul<FpU, 1>("FpU add/sub", 4);
     return 0;
 }
