@@ -1,0 +1,140 @@
+"""CPU tier: the MPN host layer (bazuka_b200/mpn) against the reference's own fixtures and test shapes:
+gadget truth tables (gadgets/common/test.rs:51-56,113-141,189-198), EdDSA accept / reject / disabled
+(gadgets/eddsa/test.rs:64-95), Poseidon / Merkle gadgets vs the native functions, the empty-MPN-root
+constant, JubJub constants, and UpdateCircuit satisfiability for the reference's tested shape
+(A=3,T=3,B=1, mpn/circuits/test.rs:117-149) with null and real transitions."""
+import copy
+import json
+import os
+
+import pytest
+
+from bazuka_b200.mpn import cs as C, gadgets as G, native as N, update as U
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def make_state(A, T, nacc, bal=10 ** 12):
+    st, keys = U.MpnState(A, T), []
+    for i in range(nacc):
+        pk, sk = N.eddsa_keys(b"acct%d" % i)
+        keys.append((pk, sk))
+        st.set(i, U.MpnAccount(0, 0, pk, {0: U.Money(U.ZIESHA, bal)}))
+    return st, keys
+
+
+def transfer(keys, s, d, nonce, amount=1000, fee=10):
+    tx = U.MpnTransaction(nonce, N.jj_compress(keys[s][0]), N.jj_compress(keys[d][0]), U.Money(U.ZIESHA, amount), U.Money(U.ZIESHA, fee))
+    tx.sign(keys[s][1])
+    return tx
+
+
+def test_native_poseidon_kats_and_empty_root():
+    kats = json.load(open(f"{GOLD}/poseidon_kats.json"))["expected_decimal"]
+    assert all(N.poseidon(list(range(n))) == int(k) for n, k in enumerate(kats, 1))
+    st = U.MpnState(30, 1)
+    want = [h for h in json.load(open(f"{GOLD}/empty_root.json"))["hex_scalars_in_vector"] if int(h, 16)][0]
+    assert st.root == int(want, 16)
+
+
+def test_jubjub_constants_and_eddsa():
+    assert N.jj_on_curve(N.JJ_BASE) and N.jj_mul(N.JJ_BASE, N.JJ_ORDER) == (0, 1)
+    assert N.JJ_BASE_COFACTOR == N.jj_mul(N.JJ_BASE, 8)
+    p = N.jj_mul(N.JJ_BASE, 12345)
+    assert N.jj_add(p, N.jj_mul(N.JJ_BASE, 55)) == N.jj_mul(N.JJ_BASE, 12400)
+    assert N.jj_decompress(N.jj_compress(p)) == p
+    assert N.jj_decompress((0, False)) == U.NULL_DST
+    pk, sk = N.eddsa_keys(b"ABC")
+    sig = N.eddsa_sign(sk, 777)
+    assert N.eddsa_verify(pk, 777, sig) and not N.eddsa_verify(pk, 778, sig)
+
+
+@pytest.mark.parametrize("a,b", [(0, 0), (1, 0), (0, 1), (5, 5), (2 ** 64 - 1, 2 ** 64 - 1), (7, 2 ** 63), (2 ** 64 - 1, 0)])
+def test_comparison_truth_tables(a, b):
+    cs = C.ConstraintSystem()
+    ua, ub = G.UnsignedInteger.alloc_64(cs, a), G.UnsignedInteger.alloc_64(cs, b)
+    got = (ua.lt(cs, ub).value, ua.lte(cs, ub).value, ua.gt(cs, ub).value, ua.gte(cs, ub).value,
+           G.Number.of(ua).is_equal(cs, G.Number.of(ub)).value)
+    assert got == (int(a < b), int(a <= b), int(a > b), int(a >= b), int(a == b))
+    assert cs.is_satisfied()[0]
+
+
+def test_boolean_gadgets_and_mux():
+    for x in (0, 1):
+        for y in (0, 1):
+            cs = C.ConstraintSystem()
+            bx, by = C.Boolean.is_(C.AllocatedBit.alloc(cs, x)), C.Boolean.is_(C.AllocatedBit.alloc(cs, y))
+            assert G.boolean_or(cs, bx, by).value == (x | y)
+            assert C.Boolean.and_(cs, bx, by.not_()).value == (x & (1 - y))
+            assert C.Boolean.and_(cs, bx.not_(), by.not_()).value == ((1 - x) & (1 - y))
+            m = G.mux(cs, bx, G.Number.constant(10), G.Number.constant(20))
+            assert m.value == (20 if x else 10)
+            assert cs.is_satisfied()[0]
+    # a non-boolean witness for a bit is rejected by the booleanity row
+    cs = C.ConstraintSystem()
+    bit = C.AllocatedBit.alloc(cs, 1)
+    cs.aux[bit.var >> 1] = 2
+    assert not cs.is_satisfied()[0]
+
+
+def test_strict_bit_decomposition():
+    for v in (0, 1, N.R - 1, N.R - 2, 2 ** 254, 123456789):
+        cs = C.ConstraintSystem()
+        bits = C.AllocatedNum.alloc(cs, v).to_bits_le_strict(cs)
+        assert len(bits) == 255 and sum(b.value << i for i, b in enumerate(bits)) == v
+        assert cs.is_satisfied()[0]
+    assert cs.num_constraints in range(380, 400)  # ~388
+
+
+def test_poseidon_and_merkle_gadgets_match_native():
+    for vals in ([1, 2], [3, 4, 5, 6], [1, 2, 3, 4, 5], [9, 8, 7, 6, 5, 4, 3]):
+        cs = C.ConstraintSystem()
+        out = G.poseidon(cs, [G.Number.of(C.AllocatedNum.alloc(cs, v)) for v in vals])
+        assert out.value == N.poseidon(vals) and cs.is_satisfied()[0]
+    assert cs.num_constraints == 762  # arity 7: 24t + R_P(t+2)
+    tree = N.SparseTree4(3, 0)
+    tree.set_leaf(37, 1234)
+    cs = C.ConstraintSystem()
+    idx = G.UnsignedInteger.alloc(cs, 37, 6)
+    root = G.calc_root_poseidon4(cs, idx, G.Number.of(C.AllocatedNum.alloc(cs, 1234)), G.alloc_proof(cs, tree.prove(37)))
+    assert root.value == tree.root and cs.is_satisfied()[0]
+
+
+def test_eddsa_gadget_accept_reject_disabled():
+    pk, sk = N.eddsa_keys(b"ABC")
+    sig = N.eddsa_sign(sk, 123456)
+
+    def run(enabled, m):
+        cs = C.ConstraintSystem()
+        en = C.Boolean.is_(C.AllocatedBit.alloc(cs, enabled))
+        G.verify_eddsa(cs, en, G.AllocatedPoint.alloc(cs, pk), G.Number.of(C.AllocatedNum.alloc(cs, m)),
+                       G.AllocatedPoint.alloc(cs, sig["r"]), C.AllocatedNum.alloc(cs, sig["s"]))
+        return cs
+    good = run(1, 123456)
+    assert good.is_satisfied()[0] and abs(good.num_constraints - 10057) < 5
+    assert not run(1, 123457).is_satisfied()[0]
+    assert run(0, 123457).is_satisfied()[0]
+
+
+def test_update_circuit_reference_shape_null_and_real():
+    circ = U.UpdateCircuit(3, 3, 1, state=5, next_state=5, aux_data=N.poseidon([U.ZIESHA, 0]))
+    cs = circ.synthesize(C.ConstraintSystem())
+    assert cs.is_satisfied()[0] and len(cs.inputs) == 6
+    n_null = cs.num_constraints
+    st, keys = make_state(3, 3, 3)
+    keys.append(N.eddsa_keys(b"newcomer"))
+    txs = [transfer(keys, 0, 1, 1), transfer(keys, 1, 2, 1, amount=5), transfer(keys, 0, 3, 2, amount=77, fee=3),
+           transfer(keys, 2, 0, 5)]  # the last one has a wrong nonce
+    pub, trans, rej = U.update(st, txs, 1)
+    assert len(trans) == 3 and len(rej) == 1
+    cs = U.UpdateCircuit(3, 3, 1, commitment=42, height=7, transitions=trans, **pub).synthesize(C.ConstraintSystem())
+    assert cs.is_satisfied()[0] and cs.num_constraints == n_null  # shape is witness-independent
+    assert cs.inputs[1:] == [42, 7, pub["state"], pub["aux_data"], pub["next_state"]]
+    bad = dict(pub, next_state=pub["next_state"] + 1)
+    assert not U.UpdateCircuit(3, 3, 1, transitions=trans, **bad).synthesize(C.ConstraintSystem()).is_satisfied()[0]
+    forged = copy.deepcopy(trans)
+    forged[0].tx.sig["s"] = (forged[0].tx.sig["s"] + 1) % N.JJ_ORDER
+    assert not U.UpdateCircuit(3, 3, 1, transitions=forged, **pub).synthesize(C.ConstraintSystem()).is_satisfied()[0]
+    over = copy.deepcopy(trans)
+    over[1].tx.amount.amount += 1  # amount no longer matches the signed hash / balances
+    assert not U.UpdateCircuit(3, 3, 1, transitions=over, **pub).synthesize(C.ConstraintSystem()).is_satisfied()[0]

@@ -1,0 +1,54 @@
+#!/usr/bin/env python3
+"""MPN update proofs on the GPU: real UpdateCircuit instances (signed transfers on a Poseidon state),
+prints one JSON line per shape with constraint count, witness/CSR build time (host, Python) and the
+GPU proving time.  usage: bench_mpn.py A,T,B[,ntx] ..."""
+import json, os, sys, time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np, torch
+import bazuka_b200 as B
+from bazuka_b200 import groth16 as BG
+from bazuka_b200.mpn import cs as C, native as N, update as U
+from bench_groth16 import G1_GEN, G2_GEN
+
+def main():
+    ctx = B.Context(0)
+    shapes = [tuple(int(v) for v in a.split(",")) for a in (sys.argv[1:] or ["3,3,1", "15,3,0", "15,3,1"])]
+    for shp in shapes:
+        A, T, Bb = shp[:3]
+        ntx = shp[3] if len(shp) > 3 else 1 << (2 * Bb)
+        t0 = time.time()
+        st, keys = U.MpnState(A, T), []
+        nacc = max(2, min(ntx + 1, 64))
+        for i in range(nacc):
+            pk, sk = N.eddsa_keys(b"acct%d" % i); keys.append((pk, sk))
+            st.set(i, U.MpnAccount(0, 0, pk, {0: U.Money(U.ZIESHA, 10 ** 12)}))
+        nonces = [0] * nacc
+        txs = []
+        for k in range(ntx):
+            s, d = k % nacc, (k + 1) % nacc
+            nonces[s] += 1
+            tx = U.MpnTransaction(nonces[s], N.jj_compress(keys[s][0]), N.jj_compress(keys[d][0]), U.Money(U.ZIESHA, 1000 + k), U.Money(U.ZIESHA, 10))
+            tx.sign(keys[s][1]); txs.append(tx)
+        pub, trans, rej = U.update(st, txs, Bb)
+        t_build = time.time() - t0
+        t0 = time.time()
+        cs = U.UpdateCircuit(A, T, Bb, commitment=1, height=0, transitions=trans, **pub).synthesize(C.ConstraintSystem())
+        ni, na, mats, inputs, aux = cs.to_csr()
+        t_syn = time.time() - t0
+        ones = sum(1 for v in cs.aux if v in (0, 1)) / len(cs.aux)
+        pr = BG.Prover(ctx, BG.R1CS(ni, na, *mats))
+        d = torch.empty((7, 4), dtype=torch.int64, device="cuda"); ctx.fr_random_dev(99, 7, d); ctx.synchronize(); rnd = d.cpu().numpy().view(np.uint64)
+        t0 = time.time(); pk, vk = BG.setup_gpu(ctx, pr.r1cs, rnd[:5], G1_GEN, G2_GEN); t_setup = time.time() - t0
+        blob, _ = pr.prove(pk, inputs, aux, rnd[5], rnd[6])
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter(); b2, _ = pr.prove(pk, inputs, aux, rnd[5], rnd[6], check_satisfied=False); ts.append(time.perf_counter() - t0)
+        assert (b2 == blob).all()
+        print(json.dumps({"circuit": "UpdateCircuit", "A": A, "T": T, "B": Bb, "tx_slots": 1 << (2 * Bb), "accepted": len(trans), "constraints": cs.num_constraints,
+                          "log_m": pr.log_m, "aux": na, "witness_0_1_fraction": round(ones, 3), "transition_build_s": round(t_build, 2),
+                          "synthesize_s": round(t_syn, 2), "gpu_setup_s": round(t_setup, 2), "prove_ms_best": round(min(ts) * 1e3, 2),
+                          "proofs_per_s": round(1 / min(ts), 2), "tx_per_s": round(len(trans) / min(ts), 1)}), flush=True)
+        pk.free(); pr.free()
+
+if __name__ == "__main__":
+    main()
