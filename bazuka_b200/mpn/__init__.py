@@ -6,6 +6,8 @@ this image — see DESIGN.md §0):
   gadgets.py   /root/reference/src/zk/groth16/gadgets/{common,poseidon,merkle,eddsa}
   native.py    Fr helpers, Poseidon (/root/reference/src/zk/poseidon/mod.rs), JubJub + EdDSA
                (/root/reference/src/crypto/jubjub), sparse 4-ary Merkle state (/root/reference/src/zk/state/mod.rs)
+  dw.py        deposit / withdraw transition builders, reveal gadget, DepositCircuit, WithdrawCircuit
+               (/root/reference/src/mpn/{deposit,withdraw}.rs, circuits/{deposit,withdraw}_circuit.rs, gadgets/reveal)
   update.py    UpdateTransition builder (/root/reference/src/mpn/update.rs) and UpdateCircuit
                (/root/reference/src/mpn/circuits/update_circuit.rs)
 

@@ -65,3 +65,16 @@ def test_null_witness_proves_with_same_key_shape(ctx, cref):
     ma, mb = a.to_csr()[2], b.to_csr()[2]
     for (rp1, c1, v1), (rp2, c2, v2) in zip(ma, mb):
         assert (rp1 == rp2).all() and (c1 == c2).all() and (v1 == v2).all()
+
+
+def test_deposit_and_withdraw_circuits_prove(ctx, cref):
+    from bazuka_b200.mpn import dw as D, native as N, update as U
+    st, keys = make_state(3, 3, 2)
+    deps = [D.MpnDeposit(N.jj_compress(keys[0][0]), U.ZIESHA, 500), D.MpnDeposit(N.jj_compress(N.eddsa_keys(b"dep-new")[0]), 77, 9)]
+    pub, tr = D.deposit(st, deps, 1)
+    _prove_and_check(ctx, cref, D.DepositCircuit(3, 3, 1, commitment=3, height=1, transitions=tr, **pub), 81)
+    w = D.MpnWithdraw(N.jj_compress(keys[1][0]), 1, amount=U.Money(U.ZIESHA, 100), fee=U.Money(U.ZIESHA, 2), fingerprint=4242)
+    w.sign(keys[1][1])
+    pub, tr = D.withdraw(st, [w], 1)
+    assert len(tr) == 1
+    _prove_and_check(ctx, cref, D.WithdrawCircuit(3, 3, 1, commitment=4, height=2, transitions=tr, **pub), 91)

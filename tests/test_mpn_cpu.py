@@ -138,3 +138,34 @@ def test_update_circuit_reference_shape_null_and_real():
     over = copy.deepcopy(trans)
     over[1].tx.amount.amount += 1  # amount no longer matches the signed hash / balances
     assert not U.UpdateCircuit(3, 3, 1, transitions=over, **pub).synthesize(C.ConstraintSystem()).is_satisfied()[0]
+
+
+def test_deposit_and_withdraw_circuits():
+    """same shape as the reference's circuit tests (A=3,T=3,B=1; mpn/circuits/test.rs:157-229) with
+    real transitions; aux_data is the revealed root of the batch (deposit.rs:178-218, withdraw.rs:190-245)."""
+    from bazuka_b200.mpn import dw as D
+    st, keys = make_state(3, 3, 2)
+    newpk, _ = N.eddsa_keys(b"dep-new")
+    deps = [D.MpnDeposit(N.jj_compress(keys[0][0]), U.ZIESHA, 500), D.MpnDeposit(N.jj_compress(newpk), 77, 9),
+            D.MpnDeposit(N.jj_compress(keys[1][0]), 77, 1)]
+    pub, tr = D.deposit(st, deps, 1)
+    assert len(tr) == 3
+    cs = D.DepositCircuit(3, 3, 1, commitment=3, height=1, transitions=tr, **pub).synthesize(C.ConstraintSystem())
+    assert cs.is_satisfied()[0]
+    assert D.DepositCircuit(3, 3, 1).synthesize(C.ConstraintSystem()).num_constraints == cs.num_constraints
+    assert not D.DepositCircuit(3, 3, 1, transitions=tr, **dict(pub, aux_data=pub["aux_data"] + 1)).synthesize(C.ConstraintSystem()).is_satisfied()[0]
+    null_pub = {"state": 5, "next_state": 5, "aux_data": D.native_list_root(1, [[0] * 4] * 4)}
+    assert D.DepositCircuit(3, 3, 1, **null_pub).synthesize(C.ConstraintSystem()).is_satisfied()[0]
+    ws = []
+    for i, amt in enumerate([100, 5]):
+        w = D.MpnWithdraw(N.jj_compress(keys[i][0]), 1, amount=U.Money(U.ZIESHA, amt), fee=U.Money(U.ZIESHA, 2), fingerprint=1000 + i)
+        w.sign(keys[i][1])
+        ws.append(w)
+    pub, tr = D.withdraw(st, ws, 1)
+    assert len(tr) == 2
+    assert D.WithdrawCircuit(3, 3, 1, transitions=tr, **pub).synthesize(C.ConstraintSystem()).is_satisfied()[0]
+    t2 = copy.deepcopy(tr)
+    t2[0].tx.fingerprint += 1  # signature no longer covers the payment
+    assert not D.WithdrawCircuit(3, 3, 1, transitions=t2, **pub).synthesize(C.ConstraintSystem()).is_satisfied()[0]
+    null_pub = {"state": 5, "next_state": 5, "aux_data": D.native_list_root(1, [[0] * 7] * 4)}
+    assert D.WithdrawCircuit(3, 3, 1, **null_pub).synthesize(C.ConstraintSystem()).is_satisfied()[0]
