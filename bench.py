@@ -295,9 +295,65 @@ def run_ours(args, rank, local_rank, world):
                                     "matches_gpu": bool((cpu_out == result).all())}
         except Exception as e:  # the oracle is test infrastructure; its absence must not break the bench
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
+        if not args.no_mpn:
+            line["mpn_groth16"] = mpn_groth16_section(ctx)
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
+
+
+def mpn_groth16_section(ctx):
+    """BASELINE configs[0]: one MPN state update (UpdateCircuit A=15,T=3,B=0: a signed transfer between two
+    funded accounts on the production tree shape) — Groth16 prove on the GPU, the same proof on the CPU
+    oracle (all host cores) and the pairing check of the GPU proof.  Secondary to the MSM headline; kept
+    small (about 57 k constraints) so the default bench stays within minutes."""
+    import numpy as np
+    import torch
+    from bazuka_b200 import groth16 as BG
+    from bazuka_b200.mpn import cs as C, native as N, update as U
+    out = {"circuit": "UpdateCircuit A=15 T=3 B=0 (1 tx), /root/reference/src/mpn/circuits/update_circuit.rs"}
+    try:
+        st, keys = U.MpnState(15, 3), []
+        for i in range(2):
+            pk, sk = N.eddsa_keys(b"ABC" if i == 0 else b"DEF")
+            keys.append((pk, sk))
+            st.set(i, U.MpnAccount(0, 0, pk, {0: U.Money(U.ZIESHA, 10 ** 12)}))
+        tx = U.MpnTransaction(1, N.jj_compress(keys[0][0]), N.jj_compress(keys[1][0]), U.Money(U.ZIESHA, 1000), U.Money(U.ZIESHA, 10))
+        tx.sign(keys[0][1])
+        pub, trans, _ = U.update(st, [tx], 0)
+        t0 = time.perf_counter()
+        cs = U.UpdateCircuit(15, 3, 0, commitment=1, height=0, transitions=trans, **pub).synthesize(C.ConstraintSystem())
+        ni, na, mats, inputs, aux = cs.to_csr()
+        out.update({"constraints": cs.num_constraints, "aux": na, "host_synthesize_s": time.perf_counter() - t0})
+        pr = BG.Prover(ctx, BG.R1CS(ni, na, *mats))
+        d = torch.empty((7, 4), dtype=torch.int64, device="cuda")
+        ctx.fr_random_dev(99, 7, d)
+        torch.cuda.synchronize()
+        rnd = d.cpu().numpy().view(np.uint64)
+        from oracle import cref, groth16_c as GC  # generators + CPU baseline + pairing check only
+        pk, vk = BG.setup_gpu(ctx, pr.r1cs, rnd[:5], cref.g1_generator(), cref.g2_generator())
+        blob, pts = pr.prove(pk, inputs, aux, rnd[5], rnd[6])
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            b2, _ = pr.prove(pk, inputs, aux, rnd[5], rnd[6], check_satisfied=False)
+            ts.append(time.perf_counter() - t0)
+        out.update({"log_m": pr.log_m, "gpu_prove_ms": min(ts) * 1e3, "gpu_proofs_per_s": 1 / min(ts),
+                    "timing": "host wall clock around bzk_groth16_prove (host witness in, 387-byte proof out), best of 5"})
+        a_idx, b_idx = GC.density(ni, na, mats)
+        cpk = {"log_m": pr.log_m, "vk": vk, "a_idx": a_idx, "b_idx": b_idx}
+        for k in ("h", "l", "a", "b_g1", "b_g2"):
+            cpk[k] = pk.device_images[k].cpu().numpy()
+        GC.prove(ni, na, mats, cpk, inputs, aux, rnd[5], rnd[6])
+        t0 = time.perf_counter()
+        cpu_pts = GC.prove(ni, na, mats, cpk, inputs, aux, rnd[5], rnd[6])
+        dt = time.perf_counter() - t0
+        out.update({"cpu_prove_ms": dt * 1e3, "cpu_proofs_per_s": 1 / dt, "cpu_cores": os.cpu_count(),
+                    "proof_bytes_equal_cpu": bool((blob == GC.proof_bytes(*cpu_pts)).all()),
+                    "pairing_check_accepts_gpu_proof": bool(GC.verify_py(vk, inputs[1:], pts))})
+    except Exception as e:
+        out["error"] = repr(e)
+    return out
 
 
 def main():
@@ -307,6 +363,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=LOG_N_DEFAULT)
+    ap.add_argument("--no-mpn", action="store_true", help="skip the secondary MPN single-update proof section")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
