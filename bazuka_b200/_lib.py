@@ -72,6 +72,8 @@ SIGNATURES = {
     "bzk_groth16_params_free": (_i32, [_vp, _vp]),
     "bzk_groth16_prove": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "bzk_groth16_proof_bytes": (_i32, [_vp, _vp, _vp, _vp]),
+    "bzk_groth16_verify": (_i32, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp]),
+    "bzk_groth16_verify_bytes": (_i32, [_vp, _sz, _vp, _sz, _vp]),
     "bzk_csr_spmv_dev": (_i32, [_vp, _vp, _vp, _vp, _u64, _vp, _vp]),
     "bzk_g1_fixed_base_mul_dev": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "bzk_g2_fixed_base_mul_dev": (_i32, [_vp, _vp, _vp, _sz, _vp]),

@@ -131,6 +131,9 @@ int32_t bzk_ctx_destroy(bzk_ctx *ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (auto &w : ctx->aux_ws) if (w) cudaFree(w);
+    for (auto &st : ctx->aux_stream) if (st) cudaStreamDestroy(st);
+    for (auto &e : ctx->aux_ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;

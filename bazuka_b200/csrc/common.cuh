@@ -18,6 +18,14 @@ struct PoseidonTable {
     Fr *d_consts = nullptr;  // device: nrc round constants then t*t MDS entries, Montgomery
 };
 
+// MSM window plan (shared by the MSM translation units and the Groth16 driver)
+struct MsmPlan {
+    uint32_t c = 0;   // window bits
+    uint32_t W = 0;   // windows (0: empty sum)
+    uint32_t NB = 0;  // buckets per window = 2^(c-1)
+    uint32_t TB = 0;  // total buckets = W * NB
+};
+
 struct NttTables {
     Fr *d_fwd = nullptr;  // omega^j, j < n/2
     Fr *d_inv = nullptr;  // omega^-j
@@ -44,6 +52,11 @@ struct bzk_ctx {
     bzk::NttTables ntt[29];
     bzk::Fr *d_gpow = nullptr;  // coset generator power tables, see ntt.cu
     int sm_count = bzk::kNumSMs;
+    // side streams + arenas so that independent MSMs of one proof run concurrently (groth16.cu)
+    cudaStream_t aux_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+    void *aux_ws[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t aux_ws_bytes[4] = {0, 0, 0, 0};
+    cudaEvent_t aux_ev[3] = {nullptr, nullptr, nullptr};
     // optional per-stage device timing (CUDA events on the launching stream), see bzk_ctx_set_timing
     bool timing = false;
     static constexpr int kMaxStages = 16;

@@ -16,11 +16,18 @@
 // built once at upload; all vectors stay in HBM between stages.
 #include "common.cuh"
 #include <algorithm>
+#include <chrono>
+#include <future>
+#include <cstdlib>
 
 namespace bzk {
 int32_t msm_g1_run(bzk_ctx *ctx, const G1Affine *d_bases, const Fr *d_scalars, size_t n, bzk_g1_affine *out);
 int32_t msm_g2_run(bzk_ctx *ctx, const G2Affine *d_bases, const Fr *d_scalars, size_t n, bzk_g2_affine *out);
 int32_t groth16_h_launch(bzk_ctx *ctx, Fr *a, Fr *b, Fr *c, uint32_t log_n);
+int32_t msm_g1_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_bytes, const G1Affine *d_bases, const Fr *d_scalars, size_t n, void *h_win, MsmPlan *plan);
+int32_t msm_g2_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_bytes, const G2Affine *d_bases, const Fr *d_scalars, size_t n, void *h_win, MsmPlan *plan);
+void msm_g1_finish(const MsmPlan *plan, const void *h_win, bzk_g1_affine *out);
+void msm_g2_finish(const MsmPlan *plan, const void *h_win, bzk_g2_affine *out);
 
 struct DevCsr {
     uint64_t *rowptr = nullptr;
@@ -256,6 +263,14 @@ int32_t bzk_groth16_prove(bzk_ctx *ctx, const bzk_groth16_params *pk, const bzk_
                           bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c) {
     if (!ctx || !pk || !cs || !inputs || (cs->num_aux && !aux) || !r_mont || !s_mont || !proof_a || !proof_b || !proof_c) return BZK_ERR_BAD_ARG;
     BZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    // BZK_TRACE=1: host-side wall clock of the driver's phases on stderr (development aid)
+    static const bool trace = std::getenv("BZK_TRACE") != nullptr;
+    auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bzk prove] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_start).count());
+    };
     const uint64_t ni = cs->num_inputs, na = cs->num_aux, nv = ni + na, m = (uint64_t)1 << cs->log_m;
     if (pk->h->n < m - 1 || pk->l->n != na || pk->a->n != cs->a_len || pk->b1->n != cs->b_len || pk->b2->n != cs->b_len) return BZK_ERR_BAD_ARG;
     // staging arena: z | a_ev | b_ev | c_ev | gathered scalars
@@ -263,12 +278,12 @@ int32_t bzk_groth16_prove(bzk_ctx *ctx, const bzk_groth16_params *pk, const bzk_
     size_t need = 0;
     {
         Carver cv(nullptr);
-        cv.take<Fr>(nv); cv.take<Fr>(m); cv.take<Fr>(m); cv.take<Fr>(m); cv.take<Fr>(gmax); cv.take<uint32_t>(4);
+        cv.take<Fr>(nv); cv.take<Fr>(m); cv.take<Fr>(m); cv.take<Fr>(m); cv.take<Fr>(gmax); cv.take<Fr>(gmax); cv.take<uint32_t>(4);
         need = cv.used();
     }
     BZK_TRY(ensure_ws(ctx, &ctx->stage, &ctx->stage_bytes, need));
     Carver cv(ctx->stage);
-    Fr *z = cv.take<Fr>(nv), *ea = cv.take<Fr>(m), *eb = cv.take<Fr>(m), *ec = cv.take<Fr>(m), *gs = cv.take<Fr>(gmax);
+    Fr *z = cv.take<Fr>(nv), *ea = cv.take<Fr>(m), *eb = cv.take<Fr>(m), *ec = cv.take<Fr>(m), *gs_a = cv.take<Fr>(gmax), *gs_b = cv.take<Fr>(gmax);
     uint32_t *d_bad = cv.take<uint32_t>(4);
     cudaStream_t st = ctx->stream;
     BZK_CUDA(ctx, cudaMemcpyAsync(z, inputs, ni * sizeof(Fr), cudaMemcpyHostToDevice, st));
@@ -295,42 +310,95 @@ int32_t bzk_groth16_prove(bzk_ctx *ctx, const bzk_groth16_params *pk, const bzk_
             return BZK_ERR_UNSAT;
         }
     }
-    BZK_TRY(groth16_h_launch(ctx, ea, eb, ec, cs->log_m));  // ea <- h coefficients
-    bzk_g1_affine h_ans, l_ans, a_ans, b1_ans;
-    bzk_g2_affine b2_ans;
-    BZK_TRY(msm_g1_run(ctx, pk->h->d, ea, m - 1, &h_ans));
-    BZK_TRY(msm_g1_run(ctx, pk->l->d, z + ni, na, &l_ans));
-    k_gather_fr<<<div_up(cs->a_len, 256), 256, 0, st>>>(z, cs->d_a_idx, cs->a_len, gs);
+    // The five sums are independent once z is on the device (h additionally needs the quotient):
+    // l, a, b_g1, b_g2 run on side streams with their own arenas while the main stream does the
+    // NTT pipeline and the h sum, so the latency-bound phases of one MSM (bucket reduction, side-list
+    // folding) overlap the throughput-bound phases of the others.
+    for (int k = 0; k < 4; k++)
+        if (!ctx->aux_stream[k]) BZK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream[k], cudaStreamNonBlocking));
+    for (int k = 0; k < 3; k++)
+        if (!ctx->aux_ev[k]) BZK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->aux_ev[k], cudaEventDisableTiming));
+    constexpr size_t kWinBytes = 128 * sizeof(G2Xyzz);
+    if (ctx->pinned_bytes < 5 * kWinBytes) {
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr;
+        BZK_CUDA(ctx, cudaHostAlloc(&ctx->pinned, 5 * kWinBytes, cudaHostAllocDefault));
+        ctx->pinned_bytes = 5 * kWinBytes;
+    }
+    char *hw = (char *)ctx->pinned;
+    MsmPlan plan[5];
+    lap("z + evaluations enqueued");
+    cudaStream_t s_l = ctx->aux_stream[0], s_a = ctx->aux_stream[1], s_b1 = ctx->aux_stream[2], s_b2 = ctx->aux_stream[3];
+    BZK_CUDA(ctx, cudaEventRecord(ctx->aux_ev[0], st));  // z and the evaluations are enqueued behind this point
+    BZK_CUDA(ctx, cudaStreamWaitEvent(s_l, ctx->aux_ev[0], 0));
+    BZK_CUDA(ctx, cudaStreamWaitEvent(s_a, ctx->aux_ev[0], 0));
+    BZK_CUDA(ctx, cudaStreamWaitEvent(s_b1, ctx->aux_ev[0], 0));
+    BZK_TRY(msm_g1_enqueue(ctx, s_l, &ctx->aux_ws[0], &ctx->aux_ws_bytes[0], pk->l->d, z + ni, na, hw + 1 * kWinBytes, &plan[1]));
+    k_gather_fr<<<div_up(cs->a_len, 256), 256, 0, s_a>>>(z, cs->d_a_idx, cs->a_len, gs_a);
     BZK_LAUNCHED(ctx);
-    BZK_TRY(msm_g1_run(ctx, pk->a->d, gs, cs->a_len, &a_ans));
+    BZK_TRY(msm_g1_enqueue(ctx, s_a, &ctx->aux_ws[1], &ctx->aux_ws_bytes[1], pk->a->d, gs_a, cs->a_len, hw + 2 * kWinBytes, &plan[2]));
     if (cs->b_len) {
-        k_gather_fr<<<div_up(cs->b_len, 256), 256, 0, st>>>(z, cs->d_b_idx, cs->b_len, gs);
+        k_gather_fr<<<div_up(cs->b_len, 256), 256, 0, s_b1>>>(z, cs->d_b_idx, cs->b_len, gs_b);
         BZK_LAUNCHED(ctx);
     }
-    BZK_TRY(msm_g1_run(ctx, pk->b1->d, gs, cs->b_len, &b1_ans));
-    BZK_TRY(msm_g2_run(ctx, pk->b2->d, gs, cs->b_len, &b2_ans));
-
-    // blinding tail (host group arithmetic; a handful of 255-bit scalar multiplications)
+    BZK_CUDA(ctx, cudaEventRecord(ctx->aux_ev[1], s_b1));
+    BZK_CUDA(ctx, cudaStreamWaitEvent(s_b2, ctx->aux_ev[1], 0));
+    BZK_TRY(msm_g1_enqueue(ctx, s_b1, &ctx->aux_ws[2], &ctx->aux_ws_bytes[2], pk->b1->d, gs_b, cs->b_len, hw + 3 * kWinBytes, &plan[3]));
+    BZK_TRY(msm_g2_enqueue(ctx, s_b2, &ctx->aux_ws[3], &ctx->aux_ws_bytes[3], pk->b2->d, gs_b, cs->b_len, hw + 4 * kWinBytes, &plan[4]));
+    BZK_TRY(groth16_h_launch(ctx, ea, eb, ec, cs->log_m));  // ea <- h coefficients
+    BZK_TRY(msm_g1_enqueue(ctx, st, &ctx->ws, &ctx->ws_bytes, pk->h->d, ea, m - 1, hw, &plan[0]));
+    lap("all kernels enqueued");
+    BZK_CUDA(ctx, cudaStreamSynchronize(st));
+    lap("main stream done");
+    for (int k = 0; k < 4; k++) BZK_CUDA(ctx, cudaStreamSynchronize(ctx->aux_stream[k]));
+    lap("side streams done");
+    // host tail: the five Horner folds and the (r, s) scalar multiplications are independent
+    // sub-millisecond jobs — run them on host threads instead of back to back
+    bzk_g1_affine h_ans, l_ans, a_ans, b1_ans;
+    bzk_g2_affine b2_ans;
     Fr r, s;
     memcpy(r.l, r_mont, 32);
     memcpy(s.l, s_mont, 32);
     const Fr rs = (r * s).from_mont(), rc = r.from_mont(), sc = s.from_mont();
-    const G1Affine a_sum = g1_from_img(&a_ans), b1_sum = g1_from_img(&b1_ans);
+    auto f_b2 = std::async(std::launch::async, [&] {
+        msm_g2_finish(&plan[4], hw + 4 * kWinBytes, &b2_ans);
+        G2Xyzz gb = scalar_mul(pk->delta_g2, sc.l);
+        gb.madd(pk->beta_g2);
+        gb.madd(g2_from_img(&b2_ans));
+        return gb.to_affine();
+    });
+    auto f_a = std::async(std::launch::async, [&] {
+        msm_g1_finish(&plan[2], hw + 2 * kWinBytes, &a_ans);
+        return scalar_mul(g1_from_img(&a_ans), sc.l);  // s * a_sum
+    });
+    auto f_b1 = std::async(std::launch::async, [&] {
+        msm_g1_finish(&plan[3], hw + 3 * kWinBytes, &b1_ans);
+        return scalar_mul(g1_from_img(&b1_ans), rc.l);  // r * b1_sum
+    });
+    auto f_hl = std::async(std::launch::async, [&] {
+        msm_g1_finish(&plan[0], hw, &h_ans);
+        msm_g1_finish(&plan[1], hw + 1 * kWinBytes, &l_ans);
+        G1Xyzz t = G1Xyzz::from_affine(g1_from_img(&h_ans));
+        t.madd(g1_from_img(&l_ans));
+        return t;  // h_sum + l_sum
+    });
+    auto f_c0 = std::async(std::launch::async, [&] {
+        G1Xyzz t = scalar_mul(pk->delta_g1, rs.l);
+        t.add(scalar_mul(pk->alpha_g1, sc.l));
+        t.add(scalar_mul(pk->beta_g1, rc.l));
+        return t;  // r s delta + s alpha + r beta
+    });
     G1Xyzz ga = scalar_mul(pk->delta_g1, rc.l);
     ga.madd(pk->alpha_g1);
-    ga.madd(a_sum);
-    G2Xyzz gb = scalar_mul(pk->delta_g2, sc.l);
-    gb.madd(pk->beta_g2);
-    gb.madd(g2_from_img(&b2_ans));
-    G1Xyzz gc = scalar_mul(pk->delta_g1, rs.l);
-    gc.add(scalar_mul(pk->alpha_g1, sc.l));
-    gc.add(scalar_mul(pk->beta_g1, rc.l));
-    gc.add(scalar_mul(a_sum, sc.l));
-    gc.add(scalar_mul(b1_sum, rc.l));
-    gc.madd(g1_from_img(&h_ans));
-    gc.madd(g1_from_img(&l_ans));
+    G1Xyzz gc = f_c0.get();
+    gc.add(f_a.get());
+    gc.add(f_b1.get());
+    gc.add(f_hl.get());
+    ga.madd(g1_from_img(&a_ans));
+    const G2Affine gb_aff = f_b2.get();
+    lap("host folds + blinding tail");
     g1_to_img(proof_a, ga.to_affine());
-    g2_to_img(proof_b, gb.to_affine());
+    g2_to_img(proof_b, gb_aff);
     g1_to_img(proof_c, gc.to_affine());
     return BZK_OK;
 }

@@ -35,12 +35,6 @@ namespace bzk {
 // ---------------------------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------------------------
-struct MsmPlan {
-    uint32_t c = 0;        // window bits
-    uint32_t W = 0;        // windows
-    uint32_t NB = 0;       // buckets per window = 2^(c-1)
-    uint32_t TB = 0;       // total buckets = W * NB
-};
 
 static MsmPlan make_plan(size_t n, int force_c = 0) {
     // cost model calibrated on B200 at 2^20 (bench.py stage marks, c = 14 vs 16 measured): a bucket
@@ -249,7 +243,7 @@ __global__ void __launch_bounds__(128) k_accumulate(const Affine<F> *__restrict_
 // — a bucket that swallows thousands of chunks, e.g. digit 1 of window 0 when a third of a Groth16
 // witness is boolean — are queued for k_fixup_long, where a whole CTA sums the run with a
 // shared-memory tree instead of one thread walking it serially.
-constexpr uint32_t kLongRun = 24;       // partials; longer runs go to the CTA-wide path
+constexpr uint32_t kLongRun = 6;        // partials; longer runs go to the CTA-wide path
 constexpr uint32_t kLongQueueCap = 4096;
 struct LongRun { uint32_t first, last; int32_t bucket; uint32_t pad; };
 
@@ -508,11 +502,16 @@ template <> struct Wire<Fp2> {
 // host driver
 // ---------------------------------------------------------------------------------------------
 template <class F>
-static int32_t msm_run(bzk_ctx *ctx, const Affine<F> *d_bases, const Fr *d_scalars, size_t n, typename Wire<F>::image *out) {
-    if (!out) return BZK_ERR_BAD_ARG;
-    if (n == 0) { Wire<F>::to_image(out, Affine<F>::inf()); return BZK_OK; }
+// Enqueue one MSM on stream `st` with its own workspace arena; the W window sums are copied into
+// `h_win` (host, ideally pinned; >= 64 entries) by the last operation on the stream.  Nothing here
+// synchronises: several MSMs can be in flight on different streams (the Groth16 driver runs its
+// five sums concurrently), and msm_host_finish folds the window sums once the stream is done.
+static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_bytes, bool timed, const Affine<F> *d_bases,
+                           const Fr *d_scalars, size_t n, Xyzz<F> *h_win, MsmPlan *plan_out) {
+    if (n == 0) { plan_out->W = 0; return BZK_OK; }
     if (n >= ((size_t)1 << 31)) return BZK_ERR_BAD_ARG;
     const MsmPlan pl = make_plan(n);
+    *plan_out = pl;
     if ((double)n * pl.W >= 4294967295.0) return BZK_ERR_BAD_ARG;
     const uint64_t max_entries = (uint64_t)n * pl.W;
 
@@ -551,8 +550,8 @@ static int32_t msm_run(bzk_ctx *ctx, const Affine<F> *d_bases, const Fr *d_scala
         cv.take<Xyzz<F>>(pl.W);
         need = cv.used();
     }
-    BZK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, need));
-    Carver cv(ctx->ws);
+    BZK_TRY(ensure_ws(ctx, ws, ws_bytes, need));
+    Carver cv(*ws);
     uint32_t *counts = cv.take<uint32_t>(pl.TB + 1);
     uint32_t *offsets = cv.take<uint32_t>(pl.TB + 1);
     uint32_t *cursor = cv.take<uint32_t>(pl.TB + 1);
@@ -566,9 +565,10 @@ static int32_t msm_run(bzk_ctx *ctx, const Affine<F> *d_bases, const Fr *d_scala
     Xyzz<F> *slice_out = cv.take<Xyzz<F>>(nslices);
     Xyzz<F> *win_out = cv.take<Xyzz<F>>(pl.W);
 
-    cudaStream_t st = ctx->stream;
     // stage marks: 0 clear+digits/histogram, 1 scan, 2 scatter, 3 accumulate, 4 fixup,
     //              5 bucket slices, 6 window sums (+ D2H of W points)
+    const bool saved_timing = ctx->timing;
+    ctx->timing = saved_timing && timed;
     timing_begin(ctx);
     BZK_CUDA(ctx, cudaMemsetAsync(counts, 0, (pl.TB + 1) * sizeof(uint32_t), st));
     BZK_CUDA(ctx, cudaMemsetAsync(buckets, 0, (size_t)pl.TB * sizeof(Xyzz<F>), st));  // all-zero = identity
@@ -610,18 +610,33 @@ static int32_t msm_run(bzk_ctx *ctx, const Affine<F> *d_bases, const Fr *d_scala
     k_window_sum<F><<<pl.W, ws_threads, smem, st>>>(slice_out, per_win, win_out);
     BZK_LAUNCHED(ctx);
 
-    // 7. host Horner over the W window sums
-    std::vector<Xyzz<F>> h(pl.W);
-    BZK_CUDA(ctx, cudaMemcpyAsync(h.data(), win_out, pl.W * sizeof(Xyzz<F>), cudaMemcpyDeviceToHost, st));
+    // 7. the W window sums go to the host for the Horner chain (msm_host_finish)
+    BZK_CUDA(ctx, cudaMemcpyAsync(h_win, win_out, pl.W * sizeof(Xyzz<F>), cudaMemcpyDeviceToHost, st));
     timing_mark(ctx);
-    BZK_CUDA(ctx, cudaStreamSynchronize(st));
-    timing_collect(ctx);
-    Xyzz<F> acc = h[pl.W - 1];
+    ctx->timing = saved_timing;
+    return BZK_OK;
+}
+
+template <class F>
+static void msm_host_finish(const MsmPlan &pl, const Xyzz<F> *h_win, typename Wire<F>::image *out) {
+    if (pl.W == 0) { Wire<F>::to_image(out, Affine<F>::inf()); return; }
+    Xyzz<F> acc = h_win[pl.W - 1];
     for (int w = (int)pl.W - 2; w >= 0; w--) {
         for (uint32_t k = 0; k < pl.c; k++) acc = acc.dbl();
-        acc.add(h[w]);
+        acc.add(h_win[w]);
     }
     Wire<F>::to_image(out, acc.to_affine());
+}
+
+template <class F>
+static int32_t msm_run(bzk_ctx *ctx, const Affine<F> *d_bases, const Fr *d_scalars, size_t n, typename Wire<F>::image *out) {
+    if (!out) return BZK_ERR_BAD_ARG;
+    Xyzz<F> h_win[128];
+    MsmPlan pl;
+    BZK_TRY(msm_enqueue<F>(ctx, ctx->stream, &ctx->ws, &ctx->ws_bytes, true, d_bases, d_scalars, n, h_win, &pl));
+    BZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    timing_collect(ctx);
+    msm_host_finish<F>(pl, h_win, out);
     return BZK_OK;
 }
 

@@ -145,6 +145,45 @@ class Prover:
         return blob, (pa, pb, pc)
 
 
+def verify(vk, public_inputs, proof_points):
+    """`groth16_verify` (/root/reference/src/zk/groth16/mod.rs:67-121): vk = dict of wire images
+    (alpha_g1, beta_g2, gamma_g2, delta_g2, ic[n+1]), public_inputs [n,4] Montgomery (without ONE),
+    proof_points = (a[104], b[200], c[104]).  Host pairing in libbzk; no GPU needed."""
+    from . import _lib
+    lib = _lib.load()
+    ic = np.ascontiguousarray(vk["ic"], dtype=np.uint8).reshape(-1, G1_BYTES)
+    pub = np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(-1, 4)
+    pts = [np.ascontiguousarray(vk[k], dtype=np.uint8) for k in ("alpha_g1", "beta_g2", "gamma_g2", "delta_g2")]
+    a, b, c = (np.ascontiguousarray(x, dtype=np.uint8) for x in proof_points)
+    st = lib.bzk_groth16_verify(*[_host_ptr(p) for p in pts], _host_ptr(ic), len(ic), _host_ptr(pub), len(pub),
+                                _host_ptr(a), _host_ptr(b), _host_ptr(c))
+    if st < 0:
+        raise _lib.BzkError(st, "groth16_verify")
+    return bool(st)
+
+
+def vk_to_bincode(vk):
+    """1460-byte-style bincode image of `Groth16VerifyingKey` (/root/reference/src/zk/groth16/mod.rs:22-31)."""
+    ic = np.ascontiguousarray(vk["ic"], dtype=np.uint8).reshape(-1, G1_BYTES)
+    parts = [np.asarray(vk["alpha_g1"])[:97], np.asarray(vk["beta_g1"])[:97], np.asarray(vk["beta_g2"])[:193],
+             np.asarray(vk["gamma_g2"])[:193], np.asarray(vk["delta_g1"])[:97], np.asarray(vk["delta_g2"])[:193],
+             np.frombuffer(len(ic).to_bytes(8, "little"), dtype=np.uint8)] + [row[:97] for row in ic]
+    return np.concatenate([np.asarray(p, dtype=np.uint8) for p in parts])
+
+
+def verify_bytes(vk_blob, public_inputs, proof387):
+    """`check_proof` on the reference's byte images."""
+    from . import _lib
+    lib = _lib.load()
+    vk_blob = np.ascontiguousarray(vk_blob, dtype=np.uint8)
+    pub = np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(-1, 4)
+    proof387 = np.ascontiguousarray(proof387, dtype=np.uint8)
+    st = lib.bzk_groth16_verify_bytes(_host_ptr(vk_blob), vk_blob.size, _host_ptr(pub), len(pub), _host_ptr(proof387))
+    if st < 0:
+        raise _lib.BzkError(st, "groth16_verify_bytes")
+    return bool(st)
+
+
 def zkproof_blob(proof_bytes):
     """391-byte bincode of `ZkProof::Groth16(Box<Groth16Proof>)` — u32 tag 0 + 387 B
     (/root/reference/src/zk/mod.rs:646-651)."""

@@ -351,6 +351,9 @@ def mpn_groth16_section(ctx):
         out.update({"cpu_prove_ms": dt * 1e3, "cpu_proofs_per_s": 1 / dt, "cpu_cores": os.cpu_count(),
                     "proof_bytes_equal_cpu": bool((blob == GC.proof_bytes(*cpu_pts)).all()),
                     "pairing_check_accepts_gpu_proof": bool(GC.verify_py(vk, inputs[1:], pts))})
+        t0 = time.perf_counter()
+        ok = BG.verify(vk, inputs[1:], pts)
+        out.update({"libbzk_verify_accepts": bool(ok), "libbzk_verify_ms": (time.perf_counter() - t0) * 1e3})
     except Exception as e:
         out["error"] = repr(e)
     return out

@@ -173,6 +173,17 @@ int32_t bzk_groth16_prove(bzk_ctx *ctx, const bzk_groth16_params *params, const 
 /* 387-byte bincode image of `Groth16Proof {a,b,c}` (/root/reference/src/zk/groth16/mod.rs:33-38);
  * prefix it with the u32 variant tag 0 for `ZkProof::Groth16` (391 B). */
 int32_t bzk_groth16_proof_bytes(const bzk_g1_affine *a, const bzk_g2_affine *b, const bzk_g1_affine *c, uint8_t out[387]);
+/* Verifier.  Replaces `zk::groth16::groth16_verify` / `zk::check_proof`
+ * (/root/reference/src/zk/groth16/mod.rs:67-121, /root/reference/src/zk/mod.rs:157-193): bellman
+ * `prepare_verifying_key` + `verify_proof` with public inputs [commitment, height, prev_state, aux_data,
+ * next_state].  Host arithmetic (one verification is a scalar job; no GPU context needed).
+ * Returns 1 = accepted, 0 = rejected, < 0 = BZK_ERR_BAD_ARG.  `_bytes` takes the reference's bincode
+ * images: `Groth16VerifyingKey` (878 + 97*len B) and `Groth16Proof` (387 B). */
+int32_t bzk_groth16_verify(const bzk_g1_affine *alpha_g1, const bzk_g2_affine *beta_g2, const bzk_g2_affine *gamma_g2,
+                           const bzk_g2_affine *delta_g2, const bzk_g1_affine *ic, size_t n_ic,
+                           const bzk_fr *public_inputs, size_t n_inputs,
+                           const bzk_g1_affine *proof_a, const bzk_g2_affine *proof_b, const bzk_g1_affine *proof_c);
+int32_t bzk_groth16_verify_bytes(const uint8_t *vk, size_t vk_len, const bzk_fr *public_inputs, size_t n_inputs, const uint8_t *proof387);
 /* Building blocks also used by the GPU-side trusted-setup helper (bellman `generate_parameters`):
  * CSR sparse matrix-vector product over Fr (out[row] = sum val*vec[col]) and fixed-base scalar
  * multiplication out[i] = [k_i] base written as wire images. */

@@ -28,10 +28,13 @@ def _prove_and_check(ctx, cref, circ, seed):
     for k in ("h", "l", "a", "b_g1", "b_g2"):
         cpk[k] = pk.device_images[k].cpu().numpy()
     assert (blob == GC.proof_bytes(*GC.prove(ni, na, mats, cpk, inputs, aux, r, s))).all()
+    # the product's own verifier (host pairing in libbzk) and the big-integer oracle both accept
+    assert BG.verify(vk, inputs[1:], pts)
+    assert BG.verify_bytes(BG.vk_to_bincode(vk), inputs[1:], blob)
     assert GC.verify_py(vk, inputs[1:], pts)
     wrong = inputs[1:].copy()
     wrong[4] = wrong[3]  # claim a different next_state
-    assert not GC.verify_py(vk, wrong, pts)
+    assert not BG.verify(vk, wrong, pts)
     return cs, pr
 
 

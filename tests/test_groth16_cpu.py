@@ -100,3 +100,41 @@ def test_synthetic_circuit_is_satisfied_and_proves(cref):
     tampered = aux.copy()
     tampered[0] = cref.fr_add(tampered[0:1], tampered[1:2])[0]
     assert not GC.verify_py(pk["vk"], inputs[1:], GC.prove(ni, na, mats, pk, inputs, tampered, r, s))
+
+
+def test_libbzk_host_verifier_accepts_and_rejects(cref):
+    """the product's own `groth16_verify` (host pairing in libbzk, no GPU) on proofs made by the C
+    oracle: accept; wrong input / tampered proof / swapped key: reject; agrees with the big-integer
+    pairing; bincode entry point takes the reference's VK layout (878 + 97*len bytes)."""
+    from bazuka_b200 import groth16 as BG
+    cs, z = tiny_circuit()
+    mats = to_csr(cs)
+    pk = GC.setup(cs.num_inputs, cs.num_aux, mats, cref.fr_random(5, 5))
+    zz = fr_arr(z)
+    r, s = cref.fr_random(6, 2)
+    proof = GC.prove(cs.num_inputs, cs.num_aux, mats, pk, zz[:2], zz[2:], r, s)
+    assert BG.verify(pk["vk"], zz[1:2], proof)
+    assert GC.verify_py(pk["vk"], zz[1:2], proof)
+    assert not BG.verify(pk["vk"], fr_arr([z[1] + 1]), proof)
+    bad = (proof[0], proof[1], cref.g1_add(proof[2], cref.g1_generator()))
+    assert not BG.verify(pk["vk"], zz[1:2], bad)
+    other = GC.setup(cs.num_inputs, cs.num_aux, mats, cref.fr_random(77, 5))
+    assert not BG.verify(other["vk"], zz[1:2], proof)
+    blob = BG.vk_to_bincode(pk["vk"])
+    assert blob.size == 878 + 97 * 2
+    assert BG.verify_bytes(blob, zz[1:2], GC.proof_bytes(*proof))
+    assert not BG.verify_bytes(blob, fr_arr([5]), GC.proof_bytes(*proof))
+
+
+def test_production_vk_blobs_parse_in_libbzk():
+    """the three production keys (tests/golden/mpn_vks.json) go through the bincode entry point: a
+    random 'proof' made of valid points must be rejected, not crash."""
+    import json, os
+    from bazuka_b200 import groth16 as BG
+    from oracle import cref
+    vks = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mpn_vks.json")))["vks"]
+    g1, g2 = cref.g1_generator(), cref.g2_generator()
+    fake = np.concatenate([g1[:97], g2[:193], g1[:97]])
+    for hx in vks.values():
+        blob = np.frombuffer(bytes.fromhex(hx), dtype=np.uint8)
+        assert BG.verify_bytes(blob, cref.fr_random(1, 5), fake) is False
