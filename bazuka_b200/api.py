@@ -151,6 +151,19 @@ class Context:
         n = d_in.numel() * d_in.element_size() // (32 * arity)
         self._check(self._l.bzk_poseidon_hash_dev(self._h, arity, _dev_ptr(d_in), n, _dev_ptr(d_out)))
 
+    # ---------------------------------------------------------------- 4-ary Poseidon Merkle trees
+    def merkle4_build_dev(self, d_nodes, log4):
+        """d_nodes: CUDA tensor of (4^(log4+1)-1)/3 Fr with the 4^log4 leaves in front; fills the upper levels."""
+        self._check(self._l.bzk_merkle4_build_dev(self._h, _dev_ptr(d_nodes), log4))
+
+    def merkle4_prove_dev(self, d_nodes, log4, d_indices, d_proofs):
+        m = d_indices.numel()
+        self._check(self._l.bzk_merkle4_prove_dev(self._h, _dev_ptr(d_nodes), log4, _dev_ptr(d_indices), m, _dev_ptr(d_proofs)))
+
+    def merkle4_root_dev(self, log4, d_indices, d_leaves, d_proofs, d_roots):
+        m = d_indices.numel()
+        self._check(self._l.bzk_merkle4_root_dev(self._h, log4, _dev_ptr(d_indices), _dev_ptr(d_leaves), _dev_ptr(d_proofs), m, _dev_ptr(d_roots)))
+
     # ---------------------------------------------------------------- NTT
     def ntt(self, a, op):
         """returns the transformed copy of host array a [2^k, 4]."""

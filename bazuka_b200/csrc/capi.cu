@@ -12,6 +12,9 @@ int32_t random_fr(bzk_ctx *ctx, uint64_t seed, size_t n, Fr *d_out);
 int32_t host_g1_add(const bzk_g1_affine *a, const bzk_g1_affine *b, bzk_g1_affine *out);
 int32_t host_g2_add(const bzk_g2_affine *a, const bzk_g2_affine *b, bzk_g2_affine *out);
 int32_t divide_by_z_launch(bzk_ctx *ctx, Fr *d, uint32_t log_n);
+int32_t merkle4_build(bzk_ctx *ctx, Fr *d_nodes, uint32_t log4);
+int32_t merkle4_prove(bzk_ctx *ctx, const Fr *d_nodes, uint32_t log4, const uint64_t *d_idx, size_t m, Fr *d_proofs);
+int32_t merkle4_root(bzk_ctx *ctx, uint32_t log4, const uint64_t *d_idx, const Fr *d_leaves, const Fr *d_proofs, size_t m, Fr *d_roots);
 int32_t groth16_h_launch(bzk_ctx *ctx, Fr *a, Fr *b, Fr *c, uint32_t log_n);
 
 __global__ void __launch_bounds__(256) k_fr_binop(int op, const Fr *__restrict__ a, const Fr *__restrict__ b, Fr *__restrict__ out, size_t n) {
@@ -227,6 +230,19 @@ int32_t bzk_poseidon_hash(bzk_ctx *ctx, uint32_t arity, const bzk_fr *in, size_t
     BZK_CUDA(ctx, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     BZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return BZK_OK;
+}
+
+int32_t bzk_merkle4_build_dev(bzk_ctx *ctx, void *d_nodes, uint32_t log4_size) {
+    BZK_ENTER(ctx);
+    return merkle4_build(ctx, (Fr *)d_nodes, log4_size);
+}
+int32_t bzk_merkle4_prove_dev(bzk_ctx *ctx, const void *d_nodes, uint32_t log4_size, const void *d_indices, size_t m, void *d_proofs) {
+    BZK_ENTER(ctx);
+    return merkle4_prove(ctx, (const Fr *)d_nodes, log4_size, (const uint64_t *)d_indices, m, (Fr *)d_proofs);
+}
+int32_t bzk_merkle4_root_dev(bzk_ctx *ctx, uint32_t log4_size, const void *d_indices, const void *d_leaves, const void *d_proofs, size_t m, void *d_roots) {
+    BZK_ENTER(ctx);
+    return merkle4_root(ctx, log4_size, (const uint64_t *)d_indices, (const Fr *)d_leaves, (const Fr *)d_proofs, m, (Fr *)d_roots);
 }
 
 // ------------------------------------------------------------------ NTT

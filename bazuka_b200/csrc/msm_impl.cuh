@@ -29,6 +29,7 @@
 // integer-ALU bound (≈ W * 10 Fp products per term), see DESIGN.md for both rooflines.
 #pragma once
 #include "common.cuh"
+#include <cstdlib>
 
 namespace bzk {
 
@@ -525,10 +526,12 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
 
     // slice length trades the serial running-sum (2*slice adds) against the [offset]*sum
     // double-and-add (~log2(NB/slice) doublings): short slices keep every SM busy
-    // Pick the shortest slice whose thread count still fits ONE wave of the reduce kernel (3 CTAs
-    // of 128 threads per SM at its register count) — a second, nearly empty wave costs a full
-    // slice time.
-    const uint32_t red_capacity = (uint32_t)ctx->sm_count * 3 * 128;
+    // Slice length: the reduction is bound by the integer-multiply pipe, and its total work is
+    // TB * (2 + smul/slice) additions (smul = the ~19-op [slice offset] double-and-add), so LONGER
+    // slices mean less work; one warp per SM sub-partition already saturates that pipe, so the
+    // kernel runs ONE 128-thread CTA per SM (measured at 2^20: 1 CTA/SM 1.43 ms, 3 CTAs/SM 1.91 ms).
+    static const int red_blocks_per_sm = std::getenv("BZK_RED_BLOCKS") ? atoi(std::getenv("BZK_RED_BLOCKS")) : 1;
+    const uint32_t red_capacity = (uint32_t)ctx->sm_count * (uint32_t)(red_blocks_per_sm > 0 ? red_blocks_per_sm : 1) * 128;
     uint32_t slice = (uint32_t)(((uint64_t)pl.TB + red_capacity - 1) / red_capacity);
     if (slice < 4) slice = pl.NB >= 4 ? 4 : pl.NB;
     if (slice > pl.NB) slice = pl.NB;

@@ -129,6 +129,121 @@ static int32_t launch_reg(bzk_ctx *ctx, const PoseidonTable &pt, const Fr *d_in,
     return BZK_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// 4-ary Poseidon Merkle trees (dense): the hash structure of `KvStoreStateManager`
+// (/root/reference/src/zk/state/mod.rs:218-264 prove, :310-420 set_data) and of the merkle gadget
+// (/root/reference/src/zk/groth16/gadgets/merkle/mod.rs:21-65): node = Poseidon-4(children), proof =
+// per level the 3 siblings in ascending child order with self skipped, leaf level first, child
+// position = 2 index bits per level.
+// Node buffer layout: level 0 (4^k leaves) | level 1 (4^(k-1)) | ... | root; (4^(k+1)-1)/3 elements.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_merkle4_prove(const Fr *__restrict__ nodes, uint32_t log4, const uint64_t *__restrict__ idx,
+                                                       size_t m, Fr *__restrict__ proofs) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * log4) return;
+    const size_t p = t / log4;
+    const uint32_t lvl = (uint32_t)(t % log4);
+    size_t off = 0;
+    for (uint32_t l = 0; l < lvl; l++) off += (size_t)1 << (2 * (log4 - l));
+    const uint64_t node = idx[p] >> (2 * lvl);
+    const uint64_t base = node & ~(uint64_t)3;
+    Fr *out = proofs + (p * log4 + lvl) * 3;
+    int w = 0;
+    for (int k = 0; k < 4; k++)
+        if (base + k != node) store_vec(out + (w++), load_vec(nodes + off + base + k));
+}
+
+// one thread per path: recompute the root from (index, leaf, proof) — log4 sequential Poseidon-4
+__global__ void __launch_bounds__(128) k_merkle4_root(const Fr *__restrict__ consts, uint32_t rf, uint32_t rp, uint32_t log4,
+                                                      const uint64_t *__restrict__ idx, const Fr *__restrict__ leaves,
+                                                      const Fr *__restrict__ proofs, size_t m, Fr *__restrict__ roots) {
+    constexpr int T = 5;
+    extern __shared__ uint4 smem_raw[];
+    Fr *sc = (Fr *)smem_raw;
+    const uint32_t nconst = T * (rf + rp) + T * T;
+    {
+        const uint4 *src = (const uint4 *)consts;
+        uint4 *dst = (uint4 *)sc;
+        for (uint32_t i = threadIdx.x; i < nconst * 2; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const Fr *mds = sc + T * (rf + rp);
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= m) return;
+    Fr cur = load_vec(leaves + p);
+    uint64_t index = idx[p];
+    const uint32_t half = rf / 2;
+    for (uint32_t lvl = 0; lvl < log4; lvl++) {
+        const uint32_t pos = (uint32_t)(index & 3);
+        index >>= 2;
+        Fr s[T];
+        s[0] = Fr::zero();
+        const Fr *sib = proofs + (p * log4 + lvl) * 3;
+        int w = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if ((uint32_t)k == pos) s[1 + k] = cur;
+            else s[1 + k] = load_vec(sib + (w++));
+        }
+        const Fr *rc = sc;
+#pragma unroll 1
+        for (uint32_t rnd = 0; rnd < rf + rp; rnd++) {
+#pragma unroll
+            for (int i = 0; i < T; i++) s[i] = s[i] + lds_fr(rc + i);
+            rc += T;
+            if (rnd < half || rnd >= half + rp) {
+#pragma unroll
+                for (int i = 0; i < T; i++) s[i] = pow5(s[i]);
+            } else {
+                s[0] = pow5(s[0]);
+            }
+            Fr o[T];
+#pragma unroll
+            for (int j = 0; j < T; j++) {
+                Fr acc = lds_fr(mds + j * T) * s[0];
+#pragma unroll
+                for (int k = 1; k < T; k++) acc = acc + lds_fr(mds + j * T + k) * s[k];
+                o[j] = acc;
+            }
+#pragma unroll
+            for (int i = 0; i < T; i++) s[i] = o[i];
+        }
+        cur = s[1];
+    }
+    store_vec(roots + p, cur);
+}
+
+int32_t poseidon_launch(bzk_ctx *ctx, uint32_t arity, const Fr *d_in, size_t n, Fr *d_out);
+
+int32_t merkle4_build(bzk_ctx *ctx, Fr *d_nodes, uint32_t log4) {
+    if (log4 > 15 || !d_nodes) return BZK_ERR_BAD_ARG;
+    size_t off = 0;
+    for (uint32_t lvl = 0; lvl < log4; lvl++) {
+        const size_t n_lvl = (size_t)1 << (2 * (log4 - lvl));
+        BZK_TRY(poseidon_launch(ctx, 4, d_nodes + off, n_lvl / 4, d_nodes + off + n_lvl));
+        off += n_lvl;
+    }
+    return BZK_OK;
+}
+int32_t merkle4_prove(bzk_ctx *ctx, const Fr *d_nodes, uint32_t log4, const uint64_t *d_idx, size_t m, Fr *d_proofs) {
+    if (log4 > 15 || (m && (!d_nodes || !d_idx || !d_proofs))) return BZK_ERR_BAD_ARG;
+    if (m == 0 || log4 == 0) return BZK_OK;
+    k_merkle4_prove<<<div_up(m * log4, 256), 256, 0, ctx->stream>>>(d_nodes, log4, d_idx, m, d_proofs);
+    BZK_LAUNCHED(ctx);
+    return BZK_OK;
+}
+int32_t merkle4_root(bzk_ctx *ctx, uint32_t log4, const uint64_t *d_idx, const Fr *d_leaves, const Fr *d_proofs, size_t m, Fr *d_roots) {
+    if (!ctx->pos_loaded) return BZK_ERR_NO_PARAMS;
+    if (log4 > 32 || (m && (!d_idx || !d_leaves || !d_roots || (log4 && !d_proofs)))) return BZK_ERR_BAD_ARG;
+    if (m == 0) return BZK_OK;
+    const PoseidonTable &pt = ctx->pos[5];
+    const size_t smem = (size_t)(pt.nrc + 25) * sizeof(Fr);
+    BZK_CUDA(ctx, cudaFuncSetAttribute(k_merkle4_root, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_merkle4_root<<<div_up(m, 128), 128, smem, ctx->stream>>>(pt.d_consts, pt.rf, pt.rp, log4, d_idx, d_leaves, d_proofs, m, d_roots);
+    BZK_LAUNCHED(ctx);
+    return BZK_OK;
+}
+
 int32_t poseidon_launch(bzk_ctx *ctx, uint32_t arity, const Fr *d_in, size_t n, Fr *d_out) {
     if (!ctx->pos_loaded) return BZK_ERR_NO_PARAMS;
     if (arity < 1 || arity > 16) return BZK_ERR_BAD_ARG;

@@ -82,6 +82,19 @@ int32_t bzk_poseidon_hash(bzk_ctx *ctx, uint32_t arity, const bzk_fr *in, size_t
 /* device buffers (same layout), asynchronous on the ctx stream */
 int32_t bzk_poseidon_hash_dev(bzk_ctx *ctx, uint32_t arity, const void *d_in, size_t n, void *d_out);
 
+/* 4-ary Poseidon Merkle trees (dense) — the hash structure behind `KvStoreStateManager::{prove,
+ * set_data}` (/root/reference/src/zk/state/mod.rs:218-264,310-420) and the merkle gadget
+ * (/root/reference/src/zk/groth16/gadgets/merkle/mod.rs:21-65): node = Poseidon-4(children); a proof is,
+ * per level from the leaves up, the 3 siblings in ascending child order with self skipped.
+ * d_nodes holds level 0 (4^k leaves) | level 1 | ... | root = (4^(k+1)-1)/3 elements.
+ *   build : leaves pre-filled, fills every upper level (k batched Poseidon-4 launches)
+ *   prove : d_proofs[m][k][3] for m leaf indices (u64)
+ *   root  : recompute the root of m (index, leaf, proof) triples (what the witness builder and the
+ *           circuit's calc_root do), one thread per path */
+int32_t bzk_merkle4_build_dev(bzk_ctx *ctx, void *d_nodes, uint32_t log4_size);
+int32_t bzk_merkle4_prove_dev(bzk_ctx *ctx, const void *d_nodes, uint32_t log4_size, const void *d_indices, size_t m, void *d_proofs);
+int32_t bzk_merkle4_root_dev(bzk_ctx *ctx, uint32_t log4_size, const void *d_indices, const void *d_leaves, const void *d_proofs, size_t m, void *d_roots);
+
 /* ------------------------------------------------------------------ NTT over Fr
  * Replaces bellman 0.14.0 `domain::EvaluationDomain::{fft, ifft, coset_fft, icoset_fft,
  * divide_by_z_on_coset}` reached from `create_proof` (reference call sites

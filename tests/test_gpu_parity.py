@@ -274,3 +274,48 @@ def test_launch_counter_moves(ctx, cref):
     before = ctx.launch_count
     ctx.poseidon(cref.fr_random(1, 8).reshape(2, 4, 4))
     assert ctx.launch_count > before
+
+
+# ------------------------------------------------------------------ 4-ary Poseidon Merkle tree
+def test_merkle4_build_prove_root(ctx, cref):
+    """dense 4^6-leaf tree: every level equals the host SparseTree4 (the state manager's hash
+    structure), proofs equal `prove()`, and recomputed roots equal the tree root; a wrong leaf gives a
+    different root."""
+    t = _t()
+    from bazuka_b200.mpn import native as N
+    log4 = 6
+    n = 1 << (2 * log4)
+    total = (4 ** (log4 + 1) - 1) // 3
+    leaves = cref.fr_random(55, n)
+    nodes = t.zeros((total, 4), dtype=t.int64, device="cuda")
+    nodes[:n] = dev_u64(leaves)
+    ctx.merkle4_build_dev(nodes, log4)
+    ctx.synchronize()
+    host = host_u64(nodes).reshape(-1, 4)
+    # level 1 against the batched hash oracle, root against the big-int tree
+    lvl1 = cref.poseidon(leaves.reshape(n // 4, 4, 4))
+    assert (host[n:n + n // 4] == lvl1).all()
+    tree = N.SparseTree4(log4, 0)
+    ints = fr_ints(leaves)
+    for i, v in enumerate(ints):
+        tree.set_leaf(i, v)
+    assert fr_ints(host[-1:])[0] == tree.root
+    idx = np.array([0, 1, 5, 1000, n - 1, 2731], dtype=np.uint64)
+    d_idx = t.from_numpy(idx.view(np.int64)).cuda()
+    proofs = t.empty((len(idx), log4, 3, 4), dtype=t.int64, device="cuda")
+    ctx.merkle4_prove_dev(nodes, log4, d_idx, proofs)
+    ctx.synchronize()
+    hp = host_u64(proofs).reshape(len(idx), log4, 3, 4)
+    for k, i in enumerate(idx):
+        want = tree.prove(int(i))
+        got = [[fr_ints(hp[k, l, s:s + 1])[0] for s in range(3)] for l in range(log4)]
+        assert got == want
+    d_leaves = dev_u64(leaves[idx.astype(np.int64)])
+    roots = t.empty((len(idx), 4), dtype=t.int64, device="cuda")
+    ctx.merkle4_root_dev(log4, d_idx, d_leaves, proofs, roots)
+    ctx.synchronize()
+    assert all(r == tree.root for r in fr_ints(host_u64(roots).reshape(-1, 4)))
+    bad_leaves = dev_u64(leaves[(idx.astype(np.int64) + 1) % n])
+    ctx.merkle4_root_dev(log4, d_idx, bad_leaves, proofs, roots)
+    ctx.synchronize()
+    assert all(r != tree.root for r in fr_ints(host_u64(roots).reshape(-1, 4)))
