@@ -30,6 +30,9 @@
 #pragma once
 #include "common.cuh"
 #include <cstdlib>
+#ifndef BZK_ACC_MIN_BLOCKS_G1
+#define BZK_ACC_MIN_BLOCKS_G1 4
+#endif
 
 namespace bzk {
 
@@ -181,8 +184,13 @@ __device__ __forceinline__ uint32_t effective_chunk(uint32_t M, uint32_t threads
     return c < min_chunk ? min_chunk : c;
 }
 
+// occupancy target of the accumulate kernel: G1 fits 4 CTAs of 128 threads per SM when capped at 128
+// registers (4 warps per sub-partition keep the integer-multiply pipe fed through the carry chains)
+template <class F> struct AccBlocks { static constexpr int value = 1; };
+template <> struct AccBlocks<Fp> { static constexpr int value = BZK_ACC_MIN_BLOCKS_G1; };
+
 template <class F>
-__global__ void __launch_bounds__(128) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
+__global__ void __launch_bounds__(128, AccBlocks<F>::value) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
                                                     const uint32_t *__restrict__ offsets, uint32_t TB, uint32_t min_chunk,
                                                     Xyzz<F> *__restrict__ buckets, Xyzz<F> *__restrict__ part_pts,
                                                     int32_t *__restrict__ part_bucket) {
@@ -517,7 +525,7 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
     const uint64_t max_entries = (uint64_t)n * pl.W;
 
     // thread geometry of the accumulate kernel
-    const uint32_t acc_threads_target = (uint32_t)ctx->sm_count * 384;
+    const uint32_t acc_threads_target = (uint32_t)ctx->sm_count * 128 * (sizeof(F) == sizeof(Fp) ? BZK_ACC_MIN_BLOCKS_G1 : 2);
     uint32_t chunk = (uint32_t)((max_entries + acc_threads_target - 1) / acc_threads_target);
     if (chunk < 16) chunk = 16;
     const uint32_t acc_threads = (uint32_t)((max_entries + chunk - 1) / chunk);

@@ -131,6 +131,7 @@ class UpdateTransition:
     dst_index: int
     dst_token_index: int
     dst_balance_proof: list
+    pre_root: int = 0   # state root before this transition (bookkeeping for the parallel synthesiser)
 
     @staticmethod
     def null(A, T):
@@ -175,6 +176,7 @@ def update(state: MpnState, txs, log4_batch, fee_token=ZIESHA):
             rejected.append(tx)
             continue
         snap = (dict(state.accounts), _clone_tree(state.tree))
+        pre_root = state.root
         src_proof = state.prove(src_index)
         src_balance_proof = state.prove_token(src_index, sti)
         src_after = src_before.copy()
@@ -204,7 +206,7 @@ def update(state: MpnState, txs, log4_batch, fee_token=ZIESHA):
             True, tx, src_before, src_before.tokens_tree(T).root, Money(src_token.token_id, src_token.amount), src_fee_token,
             src_proof, src_index, sti, src_balance_proof, sfi, src_fee_balance_proof,
             dst_before, dst_before.tokens_tree(T).root, Money(dst_token.token_id, dst_token.amount) if dst_token else Money(),
-            dst_proof, dst_index, dti, dst_balance_proof))
+            dst_proof, dst_index, dti, dst_balance_proof, pre_root))
         fee_sum += tx.fee.amount
     public = {"state": prev_root, "aux_data": N.poseidon([fee_token, fee_sum]), "next_state": state.root}
     return public, transitions, rejected
@@ -235,96 +237,107 @@ class UpdateCircuit:
         """`MpnCircuit::empty` (update_circuit.rs:29-46): the shape used for parameter generation."""
         return UpdateCircuit(log4_tree, log4_token, log4_batch, fee_token=0)
 
-    def synthesize(self, cs: ConstraintSystem):
-        A, T = self.A, self.T
+    def _prologue(self, cs):
         commitment_wit = AllocatedNum.alloc(cs, self.commitment); commitment_wit.inputize(cs)
         height_wit = AllocatedNum.alloc(cs, self.height); height_wit.inputize(cs)
         state_wit = AllocatedNum.alloc(cs, self.state); state_wit.inputize(cs)
         accepted_fee_token = AllocatedNum.alloc(cs, self.fee_token)
         aux_wit = AllocatedNum.alloc(cs, self.aux_data); aux_wit.inputize(cs)
         claimed_next_state_wit = AllocatedNum.alloc(cs, self.next_state); claimed_next_state_wit.inputize(cs)
-        fee_sum = Number.zero()
-        num = Number.of
+        return state_wit, accepted_fee_token, aux_wit, claimed_next_state_wit
 
-        for tr in self.transitions:
-            enabled = Boolean.is_(AllocatedBit.alloc(cs, tr.enabled))
-            tx_src_token_index = UnsignedInteger.alloc(cs, tr.src_token_index, 2 * T)
-            tx_src_fee_token_index = UnsignedInteger.alloc(cs, tr.src_fee_token_index, 2 * T)
-            tx_dst_token_index = UnsignedInteger.alloc(cs, tr.dst_token_index, 2 * T)
-            src_tx_nonce = AllocatedNum.alloc(cs, tr.src_before.tx_nonce)
-            src_withdraw_nonce = AllocatedNum.alloc(cs, tr.src_before.withdraw_nonce)
-            src_addr = G.AllocatedPoint.alloc(cs, tr.src_before.address)
-            src_addr.assert_on_curve(cs, enabled)
-            src_before_balances_hash = AllocatedNum.alloc(cs, tr.src_before_balances_hash)
-            dst_before_balances_hash = AllocatedNum.alloc(cs, tr.dst_before_balances_hash)
-            src_token_id = AllocatedNum.alloc(cs, tr.src_before_balance.token_id)
-            src_balance = UnsignedInteger.alloc_64(cs, tr.src_before_balance.amount)
-            src_token_balance_hash = G.poseidon(cs, [num(src_token_id), num(src_balance)])
-            src_fee_token_id = AllocatedNum.alloc(cs, tr.src_before_fee_balance.token_id)
-            src_fee_balance = UnsignedInteger.alloc_64(cs, tr.src_before_fee_balance.amount)
-            src_fee_token_balance_hash = G.poseidon(cs, [num(src_fee_token_id), num(src_fee_balance)])
-            src_balance_proof = G.alloc_proof(cs, tr.src_balance_proof)
-            G.check_proof_poseidon4(cs, enabled, tx_src_token_index, src_token_balance_hash, src_balance_proof, num(src_before_balances_hash))
-            tx_amount = UnsignedInteger.alloc_64(cs, tr.tx.amount.amount)
-            tx_fee = UnsignedInteger.alloc_64(cs, tr.tx.fee.amount)
-            new_token_balance_hash = G.poseidon(cs, [num(src_token_id), num(src_balance) - num(tx_amount)])
-            balance_middle_root = G.calc_root_poseidon4(cs, tx_src_token_index, new_token_balance_hash, src_balance_proof)
-            src_fee_balance_proof = G.alloc_proof(cs, tr.src_fee_balance_proof)
-            G.check_proof_poseidon4(cs, enabled, tx_src_fee_token_index, src_fee_token_balance_hash, src_fee_balance_proof, balance_middle_root)
-            new_fee_token_balance_hash = G.poseidon(cs, [num(src_fee_token_id), num(src_fee_balance) - num(tx_fee)])
-            src_balance_final_root = G.calc_root_poseidon4(cs, tx_src_fee_token_index, new_fee_token_balance_hash, src_fee_balance_proof)
-            tx_nonce = AllocatedNum.alloc(cs, tr.tx.nonce)
-            tx_src_index = UnsignedInteger.alloc(cs, tr.src_index, 2 * A)
-            tx_amount_token_id = AllocatedNum.alloc(cs, tr.tx.amount.token_id)
-            tx_fee_token_id = AllocatedNum.alloc(cs, tr.tx.fee.token_id)
-            num(accepted_fee_token).assert_equal_if_enabled(cs, enabled, num(tx_fee_token_id))
-            num(src_token_id).assert_equal(cs, num(tx_amount_token_id))
-            num(src_fee_token_id).assert_equal(cs, num(tx_fee_token_id))
-            src_hash = G.poseidon(cs, [num(src_tx_nonce), num(src_withdraw_nonce), num(src_addr.x), num(src_addr.y), num(src_before_balances_hash)])
-            dst_token_id = AllocatedNum.alloc(cs, tr.dst_before_balance.token_id)
-            dst_balance = AllocatedNum.alloc(cs, tr.dst_before_balance.amount)
-            dst_token_balance_hash = G.poseidon(cs, [num(dst_token_id), num(dst_balance)])
-            new_dst_token_balance_hash = G.poseidon(cs, [num(tx_amount_token_id), num(dst_balance) + num(tx_amount)])
-            dst_balance_proof = G.alloc_proof(cs, tr.dst_balance_proof)
-            G.check_proof_poseidon4(cs, enabled, tx_dst_token_index, dst_token_balance_hash, dst_balance_proof, num(dst_before_balances_hash))
-            dst_balance_final_root = G.calc_root_poseidon4(cs, tx_dst_token_index, new_dst_token_balance_hash, dst_balance_proof)
-            src_proof = G.alloc_proof(cs, tr.src_proof)
-            G.check_proof_poseidon4(cs, enabled, tx_src_index, src_hash, src_proof, num(state_wit))
-            new_src_tx_nonce = num(src_tx_nonce) + Number.constant(1)
-            new_src_hash = G.poseidon(cs, [new_src_tx_nonce, num(src_withdraw_nonce), num(src_addr.x), num(src_addr.y), src_balance_final_root])
-            middle_root = G.calc_root_poseidon4(cs, tx_src_index, new_src_hash, src_proof)
-            tx_dst_addr = G.AllocatedPoint.alloc(cs, N.jj_decompress(tr.tx.dst_pub_key))
-            tx_dst_addr.assert_on_curve(cs, enabled)
-            tx_dst_index = UnsignedInteger.alloc(cs, tr.dst_index, 2 * A)
-            dst_tx_nonce = AllocatedNum.alloc(cs, tr.dst_before.tx_nonce)
-            dst_withdraw_nonce = AllocatedNum.alloc(cs, tr.dst_before.withdraw_nonce)
-            dst_addr = G.AllocatedPoint.alloc(cs, tr.dst_before.address)
-            dst_hash = G.poseidon(cs, [num(dst_tx_nonce), num(dst_withdraw_nonce), num(dst_addr.x), num(dst_addr.y), num(dst_before_balances_hash)])
-            dst_proof = G.alloc_proof(cs, tr.dst_proof)
-            is_dst_null = dst_addr.is_null(cs)
-            is_dst_and_tx_dst_equal = dst_addr.is_equal(cs, tx_dst_addr)
-            addr_valid = G.boolean_or(cs, is_dst_null, is_dst_and_tx_dst_equal)
-            G.assert_true(cs, addr_valid)
-            G.check_proof_poseidon4(cs, enabled, tx_dst_index, dst_hash, dst_proof, middle_root)
-            new_dst_hash = G.poseidon(cs, [num(dst_tx_nonce), num(dst_withdraw_nonce), num(tx_dst_addr.x), num(tx_dst_addr.y), dst_balance_final_root])
-            next_state = G.calc_root_poseidon4(cs, tx_dst_index, new_dst_hash, dst_proof)
-            state_wit = G.mux(cs, enabled, num(state_wit), next_state)
-            tx_balance_plus_fee_64 = UnsignedInteger.constrain(cs, num(tx_amount) + num(tx_fee), 64)
-            is_lte = tx_balance_plus_fee_64.lte(cs, src_balance)
-            G.assert_true(cs, is_lte)
-            num(tx_nonce).assert_equal_if_enabled(cs, enabled, num(src_tx_nonce) + Number.constant(1))
-            final_fee = G.mux(cs, enabled, Number.zero(), num(tx_fee))
-            fee_sum = fee_sum.add_num(1, final_fee)
-            tx_hash = G.poseidon(cs, [num(tx_nonce), num(tx_dst_addr.x), num(tx_dst_addr.y), num(tx_amount_token_id), num(tx_amount),
-                                      num(tx_fee_token_id), num(tx_fee)])
-            tx_sig_r = G.AllocatedPoint.alloc(cs, tr.tx.sig["r"])
-            tx_sig_r.assert_on_curve(cs, enabled)
-            tx_sig_s = AllocatedNum.alloc(cs, tr.tx.sig["s"])
-            G.verify_eddsa(cs, enabled, src_addr, tx_hash, tx_sig_r, tx_sig_s)
-
-        fee_sum_and_token_hash = G.poseidon(cs, [num(accepted_fee_token), fee_sum])
+    def _epilogue(self, cs, state_wit, accepted_fee_token, aux_wit, claimed_next_state_wit, fee_sum):
+        fee_sum_and_token_hash = G.poseidon(cs, [Number.of(accepted_fee_token), fee_sum])
         cs.enforce(LC({aux_wit.var: 1}), LC({ONE: 1}), fee_sum_and_token_hash.lc)
         cs.enforce(LC({state_wit.var: 1}), LC({ONE: 1}), LC({claimed_next_state_wit.var: 1}))
+
+    def _tx_block(self, cs, tr, state_wit, accepted_fee_token, fee_sum):
+        """one transition slot (update_circuit.rs:81-469); returns the new (state_wit, fee_sum)."""
+        A, T = self.A, self.T
+        num = Number.of
+        enabled = Boolean.is_(AllocatedBit.alloc(cs, tr.enabled))
+        tx_src_token_index = UnsignedInteger.alloc(cs, tr.src_token_index, 2 * T)
+        tx_src_fee_token_index = UnsignedInteger.alloc(cs, tr.src_fee_token_index, 2 * T)
+        tx_dst_token_index = UnsignedInteger.alloc(cs, tr.dst_token_index, 2 * T)
+        src_tx_nonce = AllocatedNum.alloc(cs, tr.src_before.tx_nonce)
+        src_withdraw_nonce = AllocatedNum.alloc(cs, tr.src_before.withdraw_nonce)
+        src_addr = G.AllocatedPoint.alloc(cs, tr.src_before.address)
+        src_addr.assert_on_curve(cs, enabled)
+        src_before_balances_hash = AllocatedNum.alloc(cs, tr.src_before_balances_hash)
+        dst_before_balances_hash = AllocatedNum.alloc(cs, tr.dst_before_balances_hash)
+        src_token_id = AllocatedNum.alloc(cs, tr.src_before_balance.token_id)
+        src_balance = UnsignedInteger.alloc_64(cs, tr.src_before_balance.amount)
+        src_token_balance_hash = G.poseidon(cs, [num(src_token_id), num(src_balance)])
+        src_fee_token_id = AllocatedNum.alloc(cs, tr.src_before_fee_balance.token_id)
+        src_fee_balance = UnsignedInteger.alloc_64(cs, tr.src_before_fee_balance.amount)
+        src_fee_token_balance_hash = G.poseidon(cs, [num(src_fee_token_id), num(src_fee_balance)])
+        src_balance_proof = G.alloc_proof(cs, tr.src_balance_proof)
+        G.check_proof_poseidon4(cs, enabled, tx_src_token_index, src_token_balance_hash, src_balance_proof, num(src_before_balances_hash))
+        tx_amount = UnsignedInteger.alloc_64(cs, tr.tx.amount.amount)
+        tx_fee = UnsignedInteger.alloc_64(cs, tr.tx.fee.amount)
+        new_token_balance_hash = G.poseidon(cs, [num(src_token_id), num(src_balance) - num(tx_amount)])
+        balance_middle_root = G.calc_root_poseidon4(cs, tx_src_token_index, new_token_balance_hash, src_balance_proof)
+        src_fee_balance_proof = G.alloc_proof(cs, tr.src_fee_balance_proof)
+        G.check_proof_poseidon4(cs, enabled, tx_src_fee_token_index, src_fee_token_balance_hash, src_fee_balance_proof, balance_middle_root)
+        new_fee_token_balance_hash = G.poseidon(cs, [num(src_fee_token_id), num(src_fee_balance) - num(tx_fee)])
+        src_balance_final_root = G.calc_root_poseidon4(cs, tx_src_fee_token_index, new_fee_token_balance_hash, src_fee_balance_proof)
+        tx_nonce = AllocatedNum.alloc(cs, tr.tx.nonce)
+        tx_src_index = UnsignedInteger.alloc(cs, tr.src_index, 2 * A)
+        tx_amount_token_id = AllocatedNum.alloc(cs, tr.tx.amount.token_id)
+        tx_fee_token_id = AllocatedNum.alloc(cs, tr.tx.fee.token_id)
+        num(accepted_fee_token).assert_equal_if_enabled(cs, enabled, num(tx_fee_token_id))
+        num(src_token_id).assert_equal(cs, num(tx_amount_token_id))
+        num(src_fee_token_id).assert_equal(cs, num(tx_fee_token_id))
+        src_hash = G.poseidon(cs, [num(src_tx_nonce), num(src_withdraw_nonce), num(src_addr.x), num(src_addr.y), num(src_before_balances_hash)])
+        dst_token_id = AllocatedNum.alloc(cs, tr.dst_before_balance.token_id)
+        dst_balance = AllocatedNum.alloc(cs, tr.dst_before_balance.amount)
+        dst_token_balance_hash = G.poseidon(cs, [num(dst_token_id), num(dst_balance)])
+        new_dst_token_balance_hash = G.poseidon(cs, [num(tx_amount_token_id), num(dst_balance) + num(tx_amount)])
+        dst_balance_proof = G.alloc_proof(cs, tr.dst_balance_proof)
+        G.check_proof_poseidon4(cs, enabled, tx_dst_token_index, dst_token_balance_hash, dst_balance_proof, num(dst_before_balances_hash))
+        dst_balance_final_root = G.calc_root_poseidon4(cs, tx_dst_token_index, new_dst_token_balance_hash, dst_balance_proof)
+        src_proof = G.alloc_proof(cs, tr.src_proof)
+        G.check_proof_poseidon4(cs, enabled, tx_src_index, src_hash, src_proof, num(state_wit))
+        new_src_tx_nonce = num(src_tx_nonce) + Number.constant(1)
+        new_src_hash = G.poseidon(cs, [new_src_tx_nonce, num(src_withdraw_nonce), num(src_addr.x), num(src_addr.y), src_balance_final_root])
+        middle_root = G.calc_root_poseidon4(cs, tx_src_index, new_src_hash, src_proof)
+        tx_dst_addr = G.AllocatedPoint.alloc(cs, N.jj_decompress(tr.tx.dst_pub_key))
+        tx_dst_addr.assert_on_curve(cs, enabled)
+        tx_dst_index = UnsignedInteger.alloc(cs, tr.dst_index, 2 * A)
+        dst_tx_nonce = AllocatedNum.alloc(cs, tr.dst_before.tx_nonce)
+        dst_withdraw_nonce = AllocatedNum.alloc(cs, tr.dst_before.withdraw_nonce)
+        dst_addr = G.AllocatedPoint.alloc(cs, tr.dst_before.address)
+        dst_hash = G.poseidon(cs, [num(dst_tx_nonce), num(dst_withdraw_nonce), num(dst_addr.x), num(dst_addr.y), num(dst_before_balances_hash)])
+        dst_proof = G.alloc_proof(cs, tr.dst_proof)
+        is_dst_null = dst_addr.is_null(cs)
+        is_dst_and_tx_dst_equal = dst_addr.is_equal(cs, tx_dst_addr)
+        addr_valid = G.boolean_or(cs, is_dst_null, is_dst_and_tx_dst_equal)
+        G.assert_true(cs, addr_valid)
+        G.check_proof_poseidon4(cs, enabled, tx_dst_index, dst_hash, dst_proof, middle_root)
+        new_dst_hash = G.poseidon(cs, [num(dst_tx_nonce), num(dst_withdraw_nonce), num(tx_dst_addr.x), num(tx_dst_addr.y), dst_balance_final_root])
+        next_state = G.calc_root_poseidon4(cs, tx_dst_index, new_dst_hash, dst_proof)
+        state_wit = G.mux(cs, enabled, num(state_wit), next_state)
+        tx_balance_plus_fee_64 = UnsignedInteger.constrain(cs, num(tx_amount) + num(tx_fee), 64)
+        is_lte = tx_balance_plus_fee_64.lte(cs, src_balance)
+        G.assert_true(cs, is_lte)
+        num(tx_nonce).assert_equal_if_enabled(cs, enabled, num(src_tx_nonce) + Number.constant(1))
+        final_fee = G.mux(cs, enabled, Number.zero(), num(tx_fee))
+        fee_sum = fee_sum.add_num(1, final_fee)
+        self._last_final_fee = final_fee
+        tx_hash = G.poseidon(cs, [num(tx_nonce), num(tx_dst_addr.x), num(tx_dst_addr.y), num(tx_amount_token_id), num(tx_amount),
+                                  num(tx_fee_token_id), num(tx_fee)])
+        tx_sig_r = G.AllocatedPoint.alloc(cs, tr.tx.sig["r"])
+        tx_sig_r.assert_on_curve(cs, enabled)
+        tx_sig_s = AllocatedNum.alloc(cs, tr.tx.sig["s"])
+        G.verify_eddsa(cs, enabled, src_addr, tx_hash, tx_sig_r, tx_sig_s)
+        return state_wit, fee_sum
+
+    def synthesize(self, cs: ConstraintSystem):
+        state_wit, accepted_fee_token, aux_wit, claimed = self._prologue(cs)
+        fee_sum = Number.zero()
+        for tr in self.transitions:
+            state_wit, fee_sum = self._tx_block(cs, tr, state_wit, accepted_fee_token, fee_sum)
+        self._epilogue(cs, state_wit, accepted_fee_token, aux_wit, claimed, fee_sum)
         return cs
 
 

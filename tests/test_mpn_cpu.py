@@ -169,3 +169,21 @@ def test_deposit_and_withdraw_circuits():
     assert not D.WithdrawCircuit(3, 3, 1, transitions=t2, **pub).synthesize(C.ConstraintSystem()).is_satisfied()[0]
     null_pub = {"state": 5, "next_state": 5, "aux_data": D.native_list_root(1, [[0] * 7] * 4)}
     assert D.WithdrawCircuit(3, 3, 1, **null_pub).synthesize(C.ConstraintSystem()).is_satisfied()[0]
+
+
+def test_parallel_synthesis_equals_sequential():
+    """the template/replicate synthesiser used for production-size batches yields exactly the R1CS and
+    witness of `UpdateCircuit.synthesize` (4 slots: 3 signed transfers + 1 null)."""
+    import numpy as np
+    from bazuka_b200.mpn import fastsynth as F
+    st, keys = make_state(3, 3, 3)
+    keys.append(N.eddsa_keys(b"newcomer"))
+    txs = [transfer(keys, 0, 1, 1), transfer(keys, 1, 2, 1, amount=5), transfer(keys, 0, 3, 2, amount=77, fee=3)]
+    pub, trans, _ = U.update(st, txs, 1)
+    circ = U.UpdateCircuit(3, 3, 1, commitment=42, height=7, transitions=trans, **pub)
+    ni, na, mats, inputs, aux = circ.synthesize(C.ConstraintSystem()).to_csr()
+    ni2, na2, mats2, inputs2, aux_canon = F.synthesize_update(circ, workers=2)
+    assert (ni, na) == (ni2, na2) and (inputs == inputs2).all()
+    assert (F.canon_to_mont_host(aux_canon) == aux).all()
+    for (rp1, c1, v1), (rp2, c2, v2) in zip(mats, mats2):
+        assert (rp1 == rp2).all() and (c1 == c2).all() and (v1 == v2).all()
