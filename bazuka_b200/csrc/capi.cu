@@ -189,19 +189,24 @@ int32_t bzk_poseidon_load_params(bzk_ctx *ctx, const uint8_t *blob, size_t len) 
         if (t < 2 || t > 17 || nrc != t * (hdr[1] + hdr[2])) return BZK_ERR_BAD_ARG;
         const size_t cnt = (size_t)nrc + (size_t)t * t;
         if (off + 32 * cnt > len) return BZK_ERR_BAD_ARG;
-        std::vector<Fr> host(cnt);
+        // device table: round constants | MDS rows | MDS rows * 2^32 (for the lazily reduced row products)
+        std::vector<Fr> host(cnt + (size_t)t * t);
+        Fr two32 = Fr::zero();
+        two32.l[1] = 1;
+        two32 = two32.to_mont();
         for (size_t k = 0; k < cnt; k++) {
             Fr v;
             memcpy(v.l, blob + off + 32 * k, 32);
             // canonical constants must be < r
             if (Fr::reduce_once(v) != v) return BZK_ERR_BAD_ARG;
             host[k] = v.to_mont();
+            if (k >= nrc) host[cnt + (k - nrc)] = host[k] * two32;
         }
         off += 32 * cnt;
         PoseidonTable &pt = ctx->pos[t];
         if (pt.d_consts) { BZK_CUDA(ctx, cudaFree(pt.d_consts)); pt.d_consts = nullptr; }
-        BZK_CUDA(ctx, cudaMalloc(&pt.d_consts, cnt * sizeof(Fr)));
-        BZK_CUDA(ctx, cudaMemcpy(pt.d_consts, host.data(), cnt * sizeof(Fr), cudaMemcpyHostToDevice));
+        BZK_CUDA(ctx, cudaMalloc(&pt.d_consts, host.size() * sizeof(Fr)));
+        BZK_CUDA(ctx, cudaMemcpy(pt.d_consts, host.data(), host.size() * sizeof(Fr), cudaMemcpyHostToDevice));
         pt.t = t; pt.rf = hdr[1]; pt.rp = hdr[2]; pt.nrc = nrc;
     }
     if (off != len) return BZK_ERR_BAD_ARG;

@@ -287,6 +287,81 @@ struct Fe {
     }
     BZK_HD Fe sqr() const { return (*this) * (*this); }
 
+    // ---- lazy reduction for inner products (Poseidon's MDS rows) --------------------------------
+    // out[0..2N) = a*b as a plain 2N-limb integer: the even/odd IMAD.WIDE chains of mul_evenodd without
+    // the interleaved reduction rows (half the multiply work of a Montgomery product).
+    BZK_HD static void mul_wide(uint32_t out[2 * N], const Fe &a, const Fe &b) {
+        uint32_t E[2 * N + 2], O[2 * N + 2];
+#pragma unroll
+        for (int i = 0; i < 2 * N + 2; i++) E[i] = O[i] = 0;
+        CC cc{0};
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            uint32_t *Pp = (i & 1) ? O : E;
+            uint32_t *Q = (i & 1) ? E : O;
+            const uint32_t bi = b.l[i];
+            if (i == 0) {
+#pragma unroll
+                for (int j = 0; j < N; j += 2) {
+                    Pp[j] = mul_lo(a.l[j], bi);
+                    Pp[j + 1] = mul_hi(a.l[j], bi);
+                    Q[j + 1] = mul_lo(a.l[j + 1], bi);
+                    Q[j + 2] = mul_hi(a.l[j + 1], bi);
+                }
+            } else {
+                mad_pair_first(Q[i + 1], Q[i + 2], a.l[1], bi, cc);
+#pragma unroll
+                for (int j = 3; j < N; j += 2) mad_pair_next(Q[i + j], Q[i + j + 1], a.l[j], bi, cc);
+                Q[i + N + 1] = addc(0, 0, cc);
+                mad_pair_first(Pp[i], Pp[i + 1], a.l[0], bi, cc);
+#pragma unroll
+                for (int j = 2; j < N; j += 2) mad_pair_next(Pp[i + j], Pp[i + j + 1], a.l[j], bi, cc);
+                Pp[i + N] = addc(Pp[i + N], 0, cc);
+            }
+        }
+        out[0] = add_cc(E[0], O[0], cc);
+#pragma unroll
+        for (int k = 1; k < 2 * N; k++) out[k] = addc_cc(E[k], O[k], cc);
+    }
+    // acc[0..2N] += w[0..2N)   (acc has 2N+1 limbs)
+    BZK_HD static void wide_accumulate(uint32_t acc[2 * N + 1], const uint32_t w[2 * N]) {
+        CC cc{0};
+        acc[0] = add_cc(acc[0], w[0], cc);
+#pragma unroll
+        for (int k = 1; k < 2 * N; k++) acc[k] = addc_cc(acc[k], w[k], cc);
+        acc[2 * N] = addc(acc[2 * N], 0, cc);
+    }
+    // Montgomery reduction of a (2N+1)-limb value T < p * 2^(32(N+1)) by N+1 limbs:
+    // returns T / 2^(32(N+1)) mod p, fully reduced.  Runs once per inner product, so it is written as
+    // plain operand scanning with 64-bit carries.
+    BZK_HD static Fe redc_wide(const uint32_t T[2 * N + 1]) {
+        uint32_t t[2 * N + 2];
+#pragma unroll
+        for (int k = 0; k < 2 * N + 1; k++) t[k] = T[k];
+        t[2 * N + 1] = 0;
+#pragma unroll
+        for (int i = 0; i < N + 1; i++) {
+            const uint32_t m = t[i] * P::inv();
+            uint64_t carry = 0;
+#pragma unroll
+            for (int j = 0; j < N; j++) {
+                uint64_t cur = (uint64_t)m * P::p(j) + t[i + j] + carry;
+                t[i + j] = (uint32_t)cur;
+                carry = cur >> 32;
+            }
+#pragma unroll
+            for (int k = i + N; k < 2 * N + 2; k++) {
+                uint64_t cur = (uint64_t)t[k] + carry;
+                t[k] = (uint32_t)cur;
+                carry = cur >> 32;
+            }
+        }
+        Fe r;
+#pragma unroll
+        for (int k = 0; k < N; k++) r.l[k] = t[N + 1 + k];
+        return reduce_once(r);  // < 2p and t[2N+1] == 0 by the bound on T
+    }
+
     BZK_HD Fe to_mont() const { return (*this) * r2(); }
     BZK_HD Fe from_mont() const {
         Fe o = zero();

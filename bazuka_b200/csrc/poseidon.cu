@@ -30,20 +30,38 @@ __device__ __forceinline__ Fr pow5(const Fr &x) {
     return x * x4;
 }
 
+// out = sum_k m[k] * s[k] with ONE Montgomery reduction: the 2N-limb products are accumulated
+// unreduced (Fe::mul_wide / wide_accumulate) and reduced by N+1 limbs at the end (Fe::redc_wide), which is
+// why the MDS rows read here are pre-multiplied by 2^32 at load time.  (64t + 72 limb products per row
+// instead of 128t.)
+template <int T>
+__device__ __forceinline__ Fr mds_row_dot(const Fr *__restrict__ m_scaled, const Fr (&s)[T]) {
+    uint32_t acc[17];
+#pragma unroll
+    for (int i = 0; i < 17; i++) acc[i] = 0;
+#pragma unroll
+    for (int k = 0; k < T; k++) {
+        uint32_t w[16];
+        Fr::mul_wide(w, lds_fr(m_scaled + k), s[k]);
+        Fr::wide_accumulate(acc, w);
+    }
+    return Fr::redc_wide(acc);
+}
+
 // Register-resident state, fully unrolled lanes (T <= 9).
 template <int T>
 __global__ void __launch_bounds__(128) k_poseidon_reg(const Fr *__restrict__ consts, uint32_t rf, uint32_t rp,
                                                       const Fr *__restrict__ in, size_t n, Fr *__restrict__ out) {
     extern __shared__ uint4 smem_raw[];
     Fr *sc = (Fr *)smem_raw;
-    const uint32_t nconst = T * (rf + rp) + T * T;
+    const uint32_t nconst = T * (rf + rp) + 2 * T * T;
     {
         const uint4 *src = (const uint4 *)consts;
         uint4 *dst = (uint4 *)sc;
         for (uint32_t i = threadIdx.x; i < nconst * 2; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const Fr *mds = sc + T * (rf + rp);
+    const Fr *mds = sc + T * (rf + rp) + T * T;  // rows pre-scaled by 2^32 for the lazy row product
     size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= n) return;
     Fr s[T];
@@ -65,12 +83,7 @@ __global__ void __launch_bounds__(128) k_poseidon_reg(const Fr *__restrict__ con
         }
         Fr o[T];
 #pragma unroll
-        for (int j = 0; j < T; j++) {
-            Fr acc = lds_fr(mds + j * T) * s[0];
-#pragma unroll
-            for (int k = 1; k < T; k++) acc = acc + lds_fr(mds + j * T + k) * s[k];
-            o[j] = acc;
-        }
+        for (int j = 0; j < T; j++) o[j] = mds_row_dot<T>(mds + j * T, s);
 #pragma unroll
         for (int i = 0; i < T; i++) s[i] = o[i];
     }
@@ -82,7 +95,7 @@ __global__ void __launch_bounds__(64) k_poseidon_gen(const Fr *__restrict__ cons
                                                      const Fr *__restrict__ in, size_t n, Fr *__restrict__ out) {
     extern __shared__ uint4 smem_raw[];
     Fr *sc = (Fr *)smem_raw;
-    const uint32_t nconst = T * (rf + rp) + T * T;
+    const uint32_t nconst = T * (rf + rp) + T * T;  // the unscaled MDS block only (rolled loops use plain products)
     {
         const uint4 *src = (const uint4 *)consts;
         uint4 *dst = (uint4 *)sc;
@@ -122,7 +135,7 @@ __global__ void __launch_bounds__(64) k_poseidon_gen(const Fr *__restrict__ cons
 template <int T>
 static int32_t launch_reg(bzk_ctx *ctx, const PoseidonTable &pt, const Fr *d_in, size_t n, Fr *d_out) {
     const int threads = 128;
-    size_t smem = (size_t)(pt.nrc + T * T) * sizeof(Fr);
+    size_t smem = (size_t)(pt.nrc + 2 * T * T) * sizeof(Fr);
     BZK_CUDA(ctx, cudaFuncSetAttribute(k_poseidon_reg<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_poseidon_reg<T><<<div_up(n, threads), threads, smem, ctx->stream>>>(pt.d_consts, pt.rf, pt.rp, d_in, n, d_out);
     BZK_LAUNCHED(ctx);
@@ -160,14 +173,14 @@ __global__ void __launch_bounds__(128) k_merkle4_root(const Fr *__restrict__ con
     constexpr int T = 5;
     extern __shared__ uint4 smem_raw[];
     Fr *sc = (Fr *)smem_raw;
-    const uint32_t nconst = T * (rf + rp) + T * T;
+    const uint32_t nconst = T * (rf + rp) + 2 * T * T;
     {
         const uint4 *src = (const uint4 *)consts;
         uint4 *dst = (uint4 *)sc;
         for (uint32_t i = threadIdx.x; i < nconst * 2; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const Fr *mds = sc + T * (rf + rp);
+    const Fr *mds = sc + T * (rf + rp) + T * T;
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= m) return;
     Fr cur = load_vec(leaves + p);
@@ -199,12 +212,7 @@ __global__ void __launch_bounds__(128) k_merkle4_root(const Fr *__restrict__ con
             }
             Fr o[T];
 #pragma unroll
-            for (int j = 0; j < T; j++) {
-                Fr acc = lds_fr(mds + j * T) * s[0];
-#pragma unroll
-                for (int k = 1; k < T; k++) acc = acc + lds_fr(mds + j * T + k) * s[k];
-                o[j] = acc;
-            }
+            for (int j = 0; j < T; j++) o[j] = mds_row_dot<T>(mds + j * T, s);
 #pragma unroll
             for (int i = 0; i < T; i++) s[i] = o[i];
         }
@@ -237,7 +245,7 @@ int32_t merkle4_root(bzk_ctx *ctx, uint32_t log4, const uint64_t *d_idx, const F
     if (log4 > 32 || (m && (!d_idx || !d_leaves || !d_roots || (log4 && !d_proofs)))) return BZK_ERR_BAD_ARG;
     if (m == 0) return BZK_OK;
     const PoseidonTable &pt = ctx->pos[5];
-    const size_t smem = (size_t)(pt.nrc + 25) * sizeof(Fr);
+    const size_t smem = (size_t)(pt.nrc + 50) * sizeof(Fr);
     BZK_CUDA(ctx, cudaFuncSetAttribute(k_merkle4_root, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_merkle4_root<<<div_up(m, 128), 128, smem, ctx->stream>>>(pt.d_consts, pt.rf, pt.rp, log4, d_idx, d_leaves, d_proofs, m, d_roots);
     BZK_LAUNCHED(ctx);

@@ -19,6 +19,19 @@ template <class T, int W> static void bin(const uint32_t *a, const uint32_t *b, 
     }
 }
 extern "C" {
+// lazily reduced inner product (Fe::mul_wide / wide_accumulate / redc_wide): out = sum_k m[k]*s[k],
+// m given UNSCALED in Montgomery form (the shim applies the 2^32 pre-scaling like the loader does)
+void shim_fr_dot(const uint32_t *m, const uint32_t *s, size_t t, uint32_t *out) {
+    uint32_t acc[17] = {0};
+    Fr two32 = Fr::zero(); two32.l[1] = 1; two32 = two32.to_mont();
+    for (size_t k = 0; k < t; k++) {
+        Fr a, b; memcpy(a.l, m + 8 * k, 32); memcpy(b.l, s + 8 * k, 32);
+        uint32_t w[16];
+        Fr::mul_wide(w, a * two32, b);
+        Fr::wide_accumulate(acc, w);
+    }
+    Fr r = Fr::redc_wide(acc); memcpy(out, r.l, 32);
+}
 // carry-free 13x30-bit Fp (ffu.cuh): wire image -> internal -> op -> wire image
 void shim_fpu(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n, int op) {
     for (size_t i = 0; i < n; i++) {

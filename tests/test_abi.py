@@ -82,6 +82,25 @@ def test_host_build_of_device_multiplier(hostshim, cref):
     assert (r[:50] == cref.fp_inv(x[:50])).all()
 
 
+def test_host_build_of_lazy_inner_product(hostshim, cref):
+    """Poseidon's MDS row product with a single Montgomery reduction (mul_wide/redc_wide), worst-case
+    operands included (all r-1)."""
+    R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    from conftest import fr_arr
+    for t in (1, 2, 5, 8, 17):
+        m, s = cref.fr_random(40 + t, t), cref.fr_random(50 + t, t)
+        if t >= 5:
+            m[:] = fr_arr([R - 1] * t)
+            s[:] = fr_arr([R - 1] * t)
+        out = np.zeros(4, dtype=np.uint64)
+        hostshim.shim_fr_dot(m.ctypes.data_as(ct.c_void_p), s.ctypes.data_as(ct.c_void_p), ct.c_size_t(t), out.ctypes.data_as(ct.c_void_p))
+        want = np.zeros((1, 4), dtype=np.uint64)
+        prods = cref.fr_mul(m, s)
+        for k in range(t):
+            want = cref.fr_add(want, prods[k:k + 1])
+        assert (out == want[0]).all(), t
+
+
 def test_host_build_of_group_law(hostshim, cref):
     """XYZZ madd / add / dbl / to_affine (the device group law) against the Jacobian oracle."""
     g1 = cref.g1_generator()
