@@ -18,6 +18,25 @@ import numpy as np
 from .api import Context, G1_BYTES, G2_BYTES, _host_ptr, NTT_IFFT
 
 
+def _mont_fp_bytes(x):
+    P = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
+    return ((x << 384) % P).to_bytes(48, "little")
+
+
+# the standard BLS12-381 generators as wire images (what bellman's `generate_random_parameters` would draw
+# at random; any generator of the prime-order groups works for setup)
+G1_GENERATOR = np.frombuffer(
+    _mont_fp_bytes(0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF97A1AEFFB3AF00ADB22C6BB)
+    + _mont_fp_bytes(0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1) + bytes(8),
+    dtype=np.uint8).copy()
+G2_GENERATOR = np.frombuffer(
+    _mont_fp_bytes(0x024AA2B2F08F0A91260805272DC51051C6E47AD4FA403B02B4510B647AE3D1770BAC0326A805BBEFD48056C8C121BDB8)
+    + _mont_fp_bytes(0x13E02B6052719F607DACD3A088274F65596BD0D09920B61AB5DA61BBDC7F5049334CF11213945D57E5AC7D055D042B7E)
+    + _mont_fp_bytes(0x0CE5D527727D6E118CC9CDC6DA2E351AADFD9BAA8CBDD3A76D429A695160D12C923AC9CC3BACA289E193548608B82801)
+    + _mont_fp_bytes(0x0606C4A02EA734CC32ACD2B02BC28B99CB3E287E85A763AF267492AB572E99AB3F370D275CEC1DA1AAA9075FF05F79BE) + bytes(8),
+    dtype=np.uint8).copy()
+
+
 class R1CS:
     """A, B, C as CSR (rowptr uint64[n+1], col uint32[nnz], val uint64[nnz,4] Montgomery)."""
 

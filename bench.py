@@ -229,6 +229,9 @@ def run_ours(args, rank, local_rank, world):
     e2e_step = e2e_ms / args.steps
     assert (result_e2e == result).all(), "e2e and resident paths disagree"
 
+    mpn_multi = None
+    if world > 1 and not args.no_mpn:
+        mpn_multi = mpn_groth16_section(ctx, with_cpu=False, dist=dist, world=world)
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -297,12 +300,14 @@ def run_ours(args, rank, local_rank, world):
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
         if not args.no_mpn:
             line["mpn_groth16"] = mpn_groth16_section(ctx)
+    if mpn_multi is not None:
+        line["mpn_groth16"] = mpn_multi
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
 
 
-def mpn_groth16_section(ctx):
+def mpn_groth16_section(ctx, with_cpu=True, dist=None, world=1):
     """BASELINE configs[0]: one MPN state update (UpdateCircuit A=15,T=3,B=0: a signed transfer between two
     funded accounts on the production tree shape) — Groth16 prove on the GPU, the same proof on the CPU
     oracle (all host cores) and the pairing check of the GPU proof.  Secondary to the MSM headline; kept
@@ -330,8 +335,7 @@ def mpn_groth16_section(ctx):
         ctx.fr_random_dev(99, 7, d)
         torch.cuda.synchronize()
         rnd = d.cpu().numpy().view(np.uint64)
-        from oracle import cref, groth16_c as GC  # generators + CPU baseline + pairing check only
-        pk, vk = BG.setup_gpu(ctx, pr.r1cs, rnd[:5], cref.g1_generator(), cref.g2_generator())
+        pk, vk = BG.setup_gpu(ctx, pr.r1cs, rnd[:5], BG.G1_GENERATOR, BG.G2_GENERATOR)
         blob, pts = pr.prove(pk, inputs, aux, rnd[5], rnd[6])
         ts = []
         for _ in range(5):
@@ -340,6 +344,23 @@ def mpn_groth16_section(ctx):
             ts.append(time.perf_counter() - t0)
         out.update({"log_m": pr.log_m, "gpu_prove_ms": min(ts) * 1e3, "gpu_proofs_per_s": 1 / min(ts),
                     "timing": "host wall clock around bzk_groth16_prove (host witness in, 387-byte proof out), best of 5"})
+        # replicas: every GPU proves independent works back to back (the reference's own parallel axis:
+        # independent proofs farmed to workers, /root/reference/src/mpn/mod.rs:79-107) — no communication
+        reps = 20
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            pr.prove(pk, inputs, aux, rnd[5], rnd[6], check_satisfied=False)
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if dist:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        out["replicas"] = {"n_gpus": world, "proofs": reps * world, "wall_s_max_over_ranks": float(dt.item()),
+                           "proofs_per_s": reps * world / float(dt.item()), "verified": bool(BG.verify(vk, inputs[1:], pts))}
+        if not with_cpu:
+            return out
+        from oracle import groth16_c as GC  # CPU baseline + big-integer pairing check only
         a_idx, b_idx = GC.density(ni, na, mats)
         cpk = {"log_m": pr.log_m, "vk": vk, "a_idx": a_idx, "b_idx": b_idx}
         for k in ("h", "l", "a", "b_g1", "b_g2"):

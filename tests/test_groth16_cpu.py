@@ -138,3 +138,8 @@ def test_production_vk_blobs_parse_in_libbzk():
     for hx in vks.values():
         blob = np.frombuffer(bytes.fromhex(hx), dtype=np.uint8)
         assert BG.verify_bytes(blob, cref.fr_random(1, 5), fake) is False
+
+
+def test_generator_constants_match_oracle(cref):
+    from bazuka_b200 import groth16 as BG
+    assert (BG.G1_GENERATOR == cref.g1_generator()).all() and (BG.G2_GENERATOR == cref.g2_generator()).all()
