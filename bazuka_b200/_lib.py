@@ -74,6 +74,10 @@ SIGNATURES = {
     "bzk_groth16_params_create": (_i32, [_vp] * 11 + [ct.POINTER(_vp)]),
     "bzk_groth16_params_free": (_i32, [_vp, _vp]),
     "bzk_groth16_prove": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "bzk_groth16_prove_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "bzk_witness_program_upload": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _vp, _u64, _u32, _vp, ct.POINTER(_vp)]),
+    "bzk_witness_program_free": (_i32, [_vp, _vp]),
+    "bzk_witness_run_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _vp]),
     "bzk_groth16_proof_bytes": (_i32, [_vp, _vp, _vp, _vp]),
     "bzk_groth16_verify": (_i32, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp, _vp]),
     "bzk_groth16_verify_bytes": (_i32, [_vp, _sz, _vp, _sz, _vp]),

@@ -258,9 +258,11 @@ int32_t bzk_groth16_params_free(bzk_ctx *ctx, bzk_groth16_params *p) {
     return BZK_OK;
 }
 
-int32_t bzk_groth16_prove(bzk_ctx *ctx, const bzk_groth16_params *pk, const bzk_r1cs *cs, const bzk_fr *inputs, const bzk_fr *aux,
-                          const bzk_fr *r_mont, const bzk_fr *s_mont, int32_t check_satisfied,
-                          bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c) {
+// witness_kind: where `inputs` / `aux` live (cudaMemcpyHostToDevice: host images; cudaMemcpyDeviceToDevice:
+// already resident, e.g. written by bzk_witness_run_dev)
+static int32_t groth16_prove_impl(bzk_ctx *ctx, const bzk_groth16_params *pk, const bzk_r1cs *cs, const bzk_fr *inputs, const bzk_fr *aux,
+                                  cudaMemcpyKind witness_kind, const bzk_fr *r_mont, const bzk_fr *s_mont, int32_t check_satisfied,
+                                  bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c) {
     if (!ctx || !pk || !cs || !inputs || (cs->num_aux && !aux) || !r_mont || !s_mont || !proof_a || !proof_b || !proof_c) return BZK_ERR_BAD_ARG;
     BZK_CUDA(ctx, cudaSetDevice(ctx->device));
     // BZK_TRACE=1: host-side wall clock of the driver's phases on stderr (development aid)
@@ -286,8 +288,8 @@ int32_t bzk_groth16_prove(bzk_ctx *ctx, const bzk_groth16_params *pk, const bzk_
     Fr *z = cv.take<Fr>(nv), *ea = cv.take<Fr>(m), *eb = cv.take<Fr>(m), *ec = cv.take<Fr>(m), *gs_a = cv.take<Fr>(gmax), *gs_b = cv.take<Fr>(gmax);
     uint32_t *d_bad = cv.take<uint32_t>(4);
     cudaStream_t st = ctx->stream;
-    BZK_CUDA(ctx, cudaMemcpyAsync(z, inputs, ni * sizeof(Fr), cudaMemcpyHostToDevice, st));
-    if (na) BZK_CUDA(ctx, cudaMemcpyAsync(z + ni, aux, na * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    BZK_CUDA(ctx, cudaMemcpyAsync(z, inputs, ni * sizeof(Fr), witness_kind, st));
+    if (na) BZK_CUDA(ctx, cudaMemcpyAsync(z + ni, aux, na * sizeof(Fr), witness_kind, st));
     // evaluations (rows >= ncons: the Input(i)*0=0 rows, then zero padding)
     Fr *ev[3] = {ea, eb, ec};
     for (int s = 0; s < 3; s++) {
@@ -401,6 +403,19 @@ int32_t bzk_groth16_prove(bzk_ctx *ctx, const bzk_groth16_params *pk, const bzk_
     g2_to_img(proof_b, gb_aff);
     g1_to_img(proof_c, gc.to_affine());
     return BZK_OK;
+}
+
+int32_t bzk_groth16_prove(bzk_ctx *ctx, const bzk_groth16_params *pk, const bzk_r1cs *cs, const bzk_fr *inputs, const bzk_fr *aux,
+                          const bzk_fr *r_mont, const bzk_fr *s_mont, int32_t check_satisfied,
+                          bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c) {
+    return groth16_prove_impl(ctx, pk, cs, inputs, aux, cudaMemcpyHostToDevice, r_mont, s_mont, check_satisfied, proof_a, proof_b, proof_c);
+}
+
+int32_t bzk_groth16_prove_dev(bzk_ctx *ctx, const bzk_groth16_params *pk, const bzk_r1cs *cs, const void *d_inputs, const void *d_aux,
+                              const bzk_fr *r_mont, const bzk_fr *s_mont, int32_t check_satisfied,
+                              bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c) {
+    return groth16_prove_impl(ctx, pk, cs, (const bzk_fr *)d_inputs, (const bzk_fr *)d_aux, cudaMemcpyDeviceToDevice, r_mont, s_mont,
+                              check_satisfied, proof_a, proof_b, proof_c);
 }
 
 /* 387-byte bincode image of `Groth16Proof {a, b, c}` (/root/reference/src/zk/groth16/mod.rs:33-38) */

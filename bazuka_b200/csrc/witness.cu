@@ -1,0 +1,219 @@
+// bazuka_b200 — witness generation for the MPN update circuit on the GPU.
+//
+// bellman's prover obtains the witness by running the circuit's `synthesize` with value closures
+// (`ProvingAssignment`, driven from /root/reference/src/mpn/circuits/update_circuit.rs:49-494 and the gadgets
+// under /root/reference/src/zk/groth16/gadgets/).  Every slot of the update batch executes the SAME sequence
+// of allocations, so the host compiles that sequence once into a straight-line program
+// (bazuka_b200/mpn/witness_program.py: RAW / MUL / BIT / ISZERO / INVZ / SELECT / JJ over pooled linear
+// combinations) and this kernel interprets it with one thread per slot.
+//
+// Layout: V[slot][tx] (32 B per element, tx fastest) so that a warp's accesses to one variable are one
+// contiguous 1 KB run; the program stream (ops, LC pool, coefficients) is read at warp-uniform addresses
+// (broadcast).  The block's values are also written, slot-major -> tx-major, straight into the z vector the
+// prover consumes (aux_out[tx * n_ops + j]), so the witness never visits the host.
+// Bound: single-thread Fr latency (a slot is one dependent chain of ~10^6 limb-product rounds); batches
+// give the parallelism (256 / 1024 slots), not the slot.
+#include "common.cuh"
+
+namespace bzk {
+
+enum : int32_t { W_RAW = 0, W_MUL, W_BIT, W_ISZERO, W_INVZ, W_SELECT, W_JJ, W_NOP };
+constexpr int kSlotOne = 0, kSlotFeeToken = 1, kSlotStateIn = 2, kSlotBlock0 = 3;
+
+struct WitProgDev {
+    const int32_t *ops;      // [n_ops][6]
+    const int32_t *lc_ptr;   // [n_lc + 1]
+    const int32_t *lc_slot;  // [n_terms]
+    const int32_t *lc_coef;  // [n_terms], 0 = coefficient one
+    const Fr *coefs;         // Montgomery
+    uint32_t n_ops, n_raw;
+};
+
+__device__ __forceinline__ Fr ld_fr(const Fr *p) {
+    Fr r;
+    const uint4 *s = (const uint4 *)p;
+    uint4 a = s[0], b = s[1];
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+
+__device__ __noinline__ Fr wit_eval_lc(const WitProgDev &P, int32_t l, const Fr *V, uint32_t ntx, uint32_t tx) {
+    Fr acc = Fr::zero();
+    const int32_t lo = __ldg(P.lc_ptr + l), hi = __ldg(P.lc_ptr + l + 1);
+    for (int32_t k = lo; k < hi; k++) {
+        const int32_t slot = __ldg(P.lc_slot + k), ci = __ldg(P.lc_coef + k);
+        Fr v = ld_fr(V + (size_t)slot * ntx + tx);
+        if (ci != 0) v = v * load_vec(P.coefs + ci);
+        acc = acc + v;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ bool jj_on_curve(const Fr &x, const Fr &y, const Fr &d) {
+    // a = -1:  y^2 - x^2 == 1 + d x^2 y^2   (/root/reference/src/crypto/jubjub/curve.rs:40-47)
+    Fr x2 = x.sqr(), y2 = y.sqr();
+    return (y2 - x2) == (Fr::one() + d * x2 * y2);
+}
+
+__global__ void __launch_bounds__(32) k_witness_run(WitProgDev P, Fr jj_d, const Fr *__restrict__ raws, Fr fee_token,
+                                                    const Fr *__restrict__ state_in, uint32_t ntx, Fr *V, Fr *__restrict__ aux_out) {
+    const uint32_t tx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tx >= ntx) return;
+    store_vec(V + (size_t)kSlotOne * ntx + tx, Fr::one());
+    store_vec(V + (size_t)kSlotFeeToken * ntx + tx, fee_token.to_mont());
+    store_vec(V + (size_t)kSlotStateIn * ntx + tx, load_vec(state_in + tx).to_mont());
+    for (uint32_t j = 0; j < P.n_ops; j++) {
+        const int32_t *op = P.ops + (size_t)j * 6;
+        const int32_t code = __ldg(op), a0 = __ldg(op + 1), a1 = __ldg(op + 2), a2 = __ldg(op + 3), a3 = __ldg(op + 4), imm = __ldg(op + 5);
+        Fr out = Fr::zero();
+        switch (code) {
+        case W_RAW: out = load_vec(raws + (size_t)tx * P.n_raw + imm).to_mont(); break;
+        case W_MUL: {
+            Fr a = wit_eval_lc(P, a0, V, ntx, tx);
+            out = (a1 == a0) ? a.sqr() : a * wit_eval_lc(P, a1, V, ntx, tx);
+            break;
+        }
+        case W_BIT: {
+            Fr c = wit_eval_lc(P, a0, V, ntx, tx).from_mont();
+            uint32_t w = 0;
+#pragma unroll
+            for (int i = 0; i < Fr::N; i++) w = (i == (imm >> 5)) ? c.l[i] : w;
+            out = ((w >> (imm & 31)) & 1u) ? Fr::one() : Fr::zero();
+            break;
+        }
+        case W_ISZERO: out = wit_eval_lc(P, a0, V, ntx, tx).is_zero() ? Fr::one() : Fr::zero(); break;
+        case W_INVZ: {
+            Fr a = wit_eval_lc(P, a0, V, ntx, tx);
+            out = a.is_zero() ? Fr::zero() : a.inv();
+            break;
+        }
+        case W_SELECT: {
+            Fr s = wit_eval_lc(P, a0, V, ntx, tx), a = wit_eval_lc(P, a1, V, ntx, tx), b = wit_eval_lc(P, a2, V, ntx, tx);
+            out = s.is_zero() ? a : b;
+            break;
+        }
+        case W_JJ: {
+            // twisted Edwards, a = -1 (/root/reference/src/crypto/jubjub/curve.rs:123-160; the gadget's hint
+            // /root/reference/src/zk/groth16/gadgets/eddsa/mod.rs:75-101 yields (0,0) for off-curve inputs)
+            Fr x1 = wit_eval_lc(P, a0, V, ntx, tx), y1 = wit_eval_lc(P, a1, V, ntx, tx);
+            Fr x2 = wit_eval_lc(P, a2, V, ntx, tx), y2 = wit_eval_lc(P, a3, V, ntx, tx);
+            Fr ox = Fr::zero(), oy = Fr::zero();
+            if (jj_on_curve(x1, y1, jj_d) && jj_on_curve(x2, y2, jj_d)) {
+                Fr x1x2 = x1 * x2, y1y2 = y1 * y2;
+                Fr k = jj_d * x1x2 * y1y2;
+                Fr dp = Fr::one() + k, dm = Fr::one() - k;
+                Fr inv = (dp * dm).inv();
+                ox = (x1 * y2 + y1 * x2) * dm * inv;
+                oy = (y1y2 + x1x2) * dp * inv;
+            }
+            out = ox;
+            store_vec(V + (size_t)(kSlotBlock0 + j + 1) * ntx + tx, oy);
+            store_vec(aux_out + (size_t)tx * P.n_ops + j + 1, oy);
+            break;
+        }
+        default: continue;  // W_NOP: written by the preceding JJ
+        }
+        store_vec(V + (size_t)(kSlotBlock0 + j) * ntx + tx, out);
+        store_vec(aux_out + (size_t)tx * P.n_ops + j, out);
+    }
+}
+
+}  // namespace bzk
+
+using namespace bzk;
+
+struct bzk_witness_program {
+    WitProgDev d{};
+    Fr jj_d;
+    void *blob = nullptr;
+    uint64_t n_lc = 0, n_terms = 0, n_coefs = 0;
+};
+
+extern "C" {
+
+int32_t bzk_witness_program_upload(bzk_ctx *ctx, const int32_t *ops, uint64_t n_ops, const int32_t *lc_ptr, uint64_t n_lc,
+                                   const int32_t *lc_slot, const int32_t *lc_coef, uint64_t n_terms, const bzk_fr *coefs,
+                                   uint64_t n_coefs, uint32_t n_raw, const bzk_fr *jj_d, bzk_witness_program **out) {
+    if (!ctx || !ops || !lc_ptr || !coefs || !jj_d || !out || !n_ops || !n_coefs || (n_terms && (!lc_slot || !lc_coef))) return BZK_ERR_BAD_ARG;
+    // validate on the host: the device interpreter trusts the program
+    for (uint64_t j = 0; j < n_ops; j++) {
+        const int32_t *op = ops + j * 6;
+        if (op[0] < W_RAW || op[0] > W_NOP) return BZK_ERR_BAD_ARG;
+        if (op[0] == W_RAW && (op[5] < 0 || (uint32_t)op[5] >= n_raw)) return BZK_ERR_BAD_ARG;
+        if (op[0] == W_BIT && (op[5] < 0 || op[5] > 255)) return BZK_ERR_BAD_ARG;
+        if (op[0] == W_JJ && (j + 1 >= n_ops || ops[(j + 1) * 6] != W_NOP)) return BZK_ERR_BAD_ARG;
+        const int nlc = op[0] == W_JJ ? 4 : op[0] == W_SELECT ? 3 : op[0] == W_MUL ? 2 : (op[0] == W_RAW || op[0] == W_NOP) ? 0 : 1;
+        for (int a = 0; a < nlc; a++) {
+            const int32_t l = op[1 + a];
+            if (l < 0 || (uint64_t)l >= n_lc) return BZK_ERR_BAD_ARG;
+            for (int32_t k = lc_ptr[l]; k < lc_ptr[l + 1]; k++) {
+                if (k < 0 || (uint64_t)k >= n_terms) return BZK_ERR_BAD_ARG;
+                if (lc_slot[k] < 0 || (uint64_t)lc_slot[k] >= kSlotBlock0 + j) return BZK_ERR_BAD_ARG;  // reads only earlier variables
+                if (lc_coef[k] < 0 || (uint64_t)lc_coef[k] >= n_coefs) return BZK_ERR_BAD_ARG;
+            }
+        }
+    }
+    BZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    auto *p = new (std::nothrow) bzk_witness_program;
+    if (!p) return BZK_ERR_OOM;
+    size_t need;
+    {
+        Carver cv(nullptr);
+        cv.take<int32_t>(n_ops * 6); cv.take<int32_t>(n_lc + 1); cv.take<int32_t>(n_terms + 1); cv.take<int32_t>(n_terms + 1); cv.take<Fr>(n_coefs);
+        need = cv.used();
+    }
+    if (cudaMalloc(&p->blob, need) != cudaSuccess) { delete p; cudaGetLastError(); return BZK_ERR_OOM; }
+    Carver cv(p->blob);
+    int32_t *d_ops = cv.take<int32_t>(n_ops * 6), *d_ptr = cv.take<int32_t>(n_lc + 1), *d_slot = cv.take<int32_t>(n_terms + 1),
+            *d_coef = cv.take<int32_t>(n_terms + 1);
+    Fr *d_coefs = cv.take<Fr>(n_coefs);
+    cudaError_t e = cudaMemcpyAsync(d_ops, ops, n_ops * 6 * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ptr, lc_ptr, (n_lc + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && n_terms) e = cudaMemcpyAsync(d_slot, lc_slot, n_terms * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && n_terms) e = cudaMemcpyAsync(d_coef, lc_coef, n_terms * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_coefs, coefs, n_coefs * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(p->blob); delete p; BZK_CUDA(ctx, e); }
+    p->d = WitProgDev{d_ops, d_ptr, d_slot, d_coef, d_coefs, (uint32_t)n_ops, n_raw};
+    memcpy(&p->jj_d, jj_d, sizeof(Fr));
+    p->n_lc = n_lc; p->n_terms = n_terms; p->n_coefs = n_coefs;
+    *out = p;
+    return BZK_OK;
+}
+
+int32_t bzk_witness_program_free(bzk_ctx *ctx, bzk_witness_program *p) {
+    if (!p) return BZK_OK;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (p->blob) cudaFree(p->blob);
+    delete p;
+    return BZK_OK;
+}
+
+int32_t bzk_witness_run_dev(bzk_ctx *ctx, const bzk_witness_program *p, const bzk_fr *raws, const bzk_fr *fee_token,
+                            const bzk_fr *state_in, uint64_t ntx, void *d_aux_out) {
+    if (!ctx || !p || !raws || !fee_token || !state_in || !d_aux_out || !ntx || ntx > (1u << 24)) return BZK_ERR_BAD_ARG;
+    BZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n_slots = (size_t)kSlotBlock0 + p->d.n_ops;
+    size_t need;
+    {
+        Carver cv(nullptr);
+        cv.take<Fr>(n_slots * ntx); cv.take<Fr>((size_t)p->d.n_raw * ntx); cv.take<Fr>(ntx);
+        need = cv.used();
+    }
+    BZK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, need));
+    Carver cv(ctx->ws);
+    Fr *V = cv.take<Fr>(n_slots * ntx), *d_raws = cv.take<Fr>((size_t)p->d.n_raw * ntx), *d_state = cv.take<Fr>(ntx);
+    BZK_CUDA(ctx, cudaMemcpyAsync(d_raws, raws, (size_t)p->d.n_raw * ntx * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    BZK_CUDA(ctx, cudaMemcpyAsync(d_state, state_in, ntx * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    Fr fee;
+    memcpy(&fee, fee_token, sizeof(Fr));
+    k_witness_run<<<(unsigned)div_up(ntx, 32), 32, 0, ctx->stream>>>(p->d, p->jj_d, d_raws, fee, d_state, (uint32_t)ntx, V, (Fr *)d_aux_out);
+    BZK_LAUNCHED(ctx);
+    BZK_CUDA(ctx, cudaGetLastError());
+    // the host buffers may be pageable: the copies above are complete for the caller only after this
+    BZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BZK_OK;
+}
+
+}  // extern "C"

@@ -163,6 +163,21 @@ class Prover:
         c._check(c._l.bzk_groth16_proof_bytes(_host_ptr(pa), _host_ptr(pb), _host_ptr(pc), _host_ptr(blob)))
         return blob, (pa, pb, pc)
 
+    def prove_dev(self, pk: ProvingKey, d_inputs, d_aux, r, s, check_satisfied=True):
+        """`prove` with the witness already resident: d_inputs [num_inputs,4], d_aux [num_aux,4] CUDA int64
+        tensors of Montgomery images (e.g. written by mpn.gpu_witness)."""
+        from .api import _dev_ptr
+        assert d_inputs.numel() == 4 * self.r1cs.num_inputs and d_aux.numel() == 4 * self.r1cs.num_aux
+        r = np.ascontiguousarray(r, dtype=np.uint64).reshape(4)
+        s = np.ascontiguousarray(s, dtype=np.uint64).reshape(4)
+        pa, pb, pc = np.zeros(G1_BYTES, np.uint8), np.zeros(G2_BYTES, np.uint8), np.zeros(G1_BYTES, np.uint8)
+        c = self.ctx
+        c._check(c._l.bzk_groth16_prove_dev(c._h, pk._h, self._h, _dev_ptr(d_inputs), _dev_ptr(d_aux), _host_ptr(r), _host_ptr(s),
+                                             int(check_satisfied), _host_ptr(pa), _host_ptr(pb), _host_ptr(pc)))
+        blob = np.zeros(387, np.uint8)
+        c._check(c._l.bzk_groth16_proof_bytes(_host_ptr(pa), _host_ptr(pb), _host_ptr(pc), _host_ptr(blob)))
+        return blob, (pa, pb, pc)
+
 
 def verify(vk, public_inputs, proof_points):
     """`groth16_verify` (/root/reference/src/zk/groth16/mod.rs:67-121): vk = dict of wire images

@@ -51,14 +51,22 @@ ONE = 0  # Input(0)
 
 
 class ConstraintSystem:
-    def __init__(self):
+    def __init__(self, record=False):
         self.inputs = [1]
         self.aux = []
         self.rows = []  # (LC, LC, LC)
+        # optional "witness program": for every aux variable, HOW its value follows from earlier ones
+        # (see witness_program.py).  None = not recording.
+        self.recipes = [] if record else None
 
     # bellman ConstraintSystem
-    def alloc(self, value):
+    def alloc(self, value, recipe=None):
+        """recipe: None / ('raw',) = external input of the circuit (a field of the transition), or one of
+        ('mul', lcA, lcB), ('bit', lc, i), ('iszero', lc), ('invz', lc), ('select', lcS, lcA, lcB),
+        ('jjx' | 'jjy', lcX1, lcY1, lcX2, lcY2)."""
         self.aux.append(value % R)
+        if self.recipes is not None:
+            self.recipes.append(recipe if recipe is not None else ("raw",))
         return 2 * (len(self.aux) - 1) + 1
 
     def alloc_input(self, value):
@@ -123,17 +131,18 @@ class AllocatedNum:
         self.var, self.value = var, value
 
     @staticmethod
-    def alloc(cs, value):
+    def alloc(cs, value, recipe=None):
         value %= R
-        return AllocatedNum(cs.alloc(value), value)
+        return AllocatedNum(cs.alloc(value, recipe), value)
 
     def inputize(self, cs):
         inp = cs.alloc_input(self.value)
         cs.enforce(LC({inp: 1}), LC({ONE: 1}), LC({self.var: 1}))
 
     def mul(self, cs, other):
-        out = AllocatedNum.alloc(cs, self.value * other.value)
-        cs.enforce(LC({self.var: 1}), LC({other.var: 1}), LC({out.var: 1}))
+        la, lb = LC({self.var: 1}), LC({other.var: 1})
+        out = AllocatedNum.alloc(cs, self.value * other.value, ("mul", la, lb))
+        cs.enforce(la, lb, LC({out.var: 1}))
         return out
 
     def to_bits_le_strict(self, cs):
@@ -142,13 +151,15 @@ class AllocatedNum:
         a_bits = [(self.value >> i) & 1 for i in range(256)][::-1]
         b_bits = [((R - 1) >> i) & 1 for i in range(256)][::-1]
         result, last_run, current_run, found_one = [], None, [], False
-        for a_bit, b in zip(a_bits, b_bits):
+        me = LC({self.var: 1})
+        for pos, (a_bit, b) in enumerate(zip(a_bits, b_bits)):
+            bit_index = 255 - pos  # little-endian index of this bit
             found_one |= bool(b)
             if not found_one:
                 assert a_bit == 0
                 continue
             if b:
-                bit = AllocatedBit.alloc(cs, a_bit)
+                bit = AllocatedBit.alloc(cs, a_bit, ("bit", me, bit_index))
                 current_run.append(bit)
                 result.append(bit)
             else:
@@ -160,7 +171,7 @@ class AllocatedNum:
                         cur = v if cur is None else AllocatedBit.and_(cs, cur, v)
                     last_run = cur
                     current_run = []
-                bit = AllocatedBit.alloc_conditionally(cs, a_bit, last_run)
+                bit = AllocatedBit.alloc_conditionally(cs, a_bit, last_run, ("bit", me, bit_index))
                 result.append(bit)
         assert not current_run
         lc, coeff = LC(), 1
@@ -182,38 +193,41 @@ class AllocatedBit:
         self.var, self.value = var, value
 
     @staticmethod
-    def alloc(cs, value):
+    def alloc(cs, value, recipe=None):
         value = 1 if value else 0
-        var = cs.alloc(value)
+        var = cs.alloc(value, recipe)
         cs.enforce(LC({ONE: 1, var: R - 1}), LC({var: 1}), LC())  # (1 - a) * a = 0
         return AllocatedBit(var, value)
 
     @staticmethod
-    def alloc_conditionally(cs, value, must_be_false):
+    def alloc_conditionally(cs, value, must_be_false, recipe=None):
         value = 1 if value else 0
-        var = cs.alloc(value)
+        var = cs.alloc(value, recipe)
         # (1 - must_be_false - a) * a = 0
         cs.enforce(LC({ONE: 1, must_be_false.var: R - 1}).add_term(R - 1, var), LC({var: 1}), LC())
         return AllocatedBit(var, value)
 
     @staticmethod
     def and_(cs, a, b):
-        out = AllocatedBit(cs.alloc(a.value & b.value), a.value & b.value)
-        cs.enforce(LC({a.var: 1}), LC({b.var: 1}), LC({out.var: 1}))
+        la, lb = LC({a.var: 1}), LC({b.var: 1})
+        out = AllocatedBit(cs.alloc(a.value & b.value, ("mul", la, lb)), a.value & b.value)
+        cs.enforce(la, lb, LC({out.var: 1}))
         return out
 
     @staticmethod
     def and_not(cs, a, b):
         v = a.value & (1 - b.value)
-        out = AllocatedBit(cs.alloc(v), v)
-        cs.enforce(LC({a.var: 1}), LC({ONE: 1, b.var: R - 1}), LC({out.var: 1}))
+        la, lb = LC({a.var: 1}), LC({ONE: 1, b.var: R - 1})
+        out = AllocatedBit(cs.alloc(v, ("mul", la, lb)), v)
+        cs.enforce(la, lb, LC({out.var: 1}))
         return out
 
     @staticmethod
     def nor(cs, a, b):
         v = (1 - a.value) & (1 - b.value)
-        out = AllocatedBit(cs.alloc(v), v)
-        cs.enforce(LC({ONE: 1, a.var: R - 1}), LC({ONE: 1, b.var: R - 1}), LC({out.var: 1}))
+        la, lb = LC({ONE: 1, a.var: R - 1}), LC({ONE: 1, b.var: R - 1})
+        out = AllocatedBit(cs.alloc(v, ("mul", la, lb)), v)
+        cs.enforce(la, lb, LC({out.var: 1}))
         return out
 
 

@@ -35,9 +35,12 @@ def _block(args):
     return vals, info, rows, P_aux, P_rows
 
 
-def synthesize_update(circ: U.UpdateCircuit, workers=None):
+def synthesize_update(circ: U.UpdateCircuit, workers=None, structure_only=False):
     """-> (num_inputs, num_aux, mats, inputs [ni,4] Montgomery, aux_canonical [na,4] uint64 canonical).
-    The caller converts aux to Montgomery (GPU: one elementwise product by R^2)."""
+    The caller converts aux to Montgomery (GPU: one elementwise product by R^2).
+    structure_only: build the R1CS from ONE synthesised slot and skip the other slots' values (the returned
+    aux is then meaningless) — the shape the prover/setup need when the witness comes from the GPU
+    (gpu_witness.py)."""
     n = len(circ.transitions)
     pro_vals = [circ.commitment, circ.height, circ.state, circ.fee_token, circ.aux_data, circ.next_state]
     # state root entering every slot: recorded by update() for real transitions; disabled slots keep the state
@@ -59,7 +62,9 @@ def synthesize_update(circ: U.UpdateCircuit, workers=None):
         roots[k] = circ.next_state if last_enabled >= 0 else circ.state
     jobs = [(circ.A, circ.T, circ.B, pro_vals, tr, roots[k], k == 0) for k, tr in enumerate(circ.transitions)]
     workers = workers or min(os.cpu_count() or 1, n)
-    if workers > 1 and n > 1:
+    if structure_only:
+        res = [_block(jobs[0])] * n
+    elif workers > 1 and n > 1:
         with mp.get_context("fork").Pool(workers) as pool:
             res = pool.map(_block, jobs, chunksize=max(1, n // (workers * 2)))
     else:

@@ -54,7 +54,7 @@ class Number:
         return Number(self.lc + other.lc.scaled(coeff % R), self.value + coeff * other.value)
 
     def mul(self, cs, other):
-        out = AllocatedNum.alloc(cs, self.value * other.value)
+        out = AllocatedNum.alloc(cs, self.value * other.value, ("mul", self.lc, other.lc))
         cs.enforce(self.lc, other.lc, LC({out.var: 1}))
         return out
 
@@ -64,8 +64,8 @@ class Number:
     def is_zero(self, cs):
         """number.rs:75-111 (2 constraints + the bit's booleanity)"""
         z = 1 if self.value == 0 else 0
-        is_zero = AllocatedBit.alloc(cs, z)
-        inv = AllocatedNum.alloc(cs, 0 if z else pow(self.value, -1, R))
+        is_zero = AllocatedBit.alloc(cs, z, ("iszero", self.lc))
+        inv = AllocatedNum.alloc(cs, 0 if z else pow(self.value, -1, R), ("invz", self.lc))
         cs.enforce(LC() - self.lc, LC({inv.var: 1}), LC({is_zero.var: 1, ONE: R - 1}))
         cs.enforce(LC({is_zero.var: 1}), self.lc, LC())
         return Boolean.is_(is_zero)
@@ -80,7 +80,7 @@ class Number:
         """number.rs:132-178"""
         if enabled.kind == "is":
             e = enabled.bit
-            eis = cs.alloc(self.value if e.value else 0)
+            eis = cs.alloc(self.value if e.value else 0, ("mul", LC({e.var: 1}), self.lc))
             cs.enforce(LC({e.var: 1}), self.lc, LC({eis: 1}))
             cs.enforce(LC({e.var: 1}), other.lc, LC({eis: 1}))
         elif enabled.kind == "const":
@@ -113,7 +113,7 @@ class UnsignedInteger:
     def constrain(cs, num, nbits):
         bits, allc, coeff = [], LC(), 1
         for i in range(nbits):
-            bit = AllocatedBit.alloc(cs, (num.value >> i) & 1)
+            bit = AllocatedBit.alloc(cs, (num.value >> i) & 1, ("bit", num.lc, i))
             allc = allc.add_term(coeff, bit.var)
             bits.append(bit)
             coeff = coeff * 2 % R
@@ -161,12 +161,12 @@ def mux(cs, select, a, b):
     """select ? b : a — mux.rs:7-47"""
     if select.kind == "is":
         s = select.bit
-        ret = AllocatedNum.alloc(cs, b.value if s.value else a.value)
+        ret = AllocatedNum.alloc(cs, b.value if s.value else a.value, ("select", LC({s.var: 1}), a.lc, b.lc))
         cs.enforce(a.lc - b.lc, LC({s.var: 1}), a.lc.add_term(R - 1, ret.var))
         return ret
     if select.kind == "not":
         ns = select.bit
-        ret = AllocatedNum.alloc(cs, a.value if ns.value else b.value)
+        ret = AllocatedNum.alloc(cs, a.value if ns.value else b.value, ("select", LC({ns.var: 1}), b.lc, a.lc))
         cs.enforce(b.lc - a.lc, LC({ns.var: 1}), b.lc.add_term(R - 1, ret.var))
         return ret
     raise NotImplementedError
@@ -252,8 +252,13 @@ class AllocatedPoint:
         self.x, self.y = x, y
 
     @staticmethod
-    def alloc(cs, pt):
-        return AllocatedPoint(AllocatedNum.alloc(cs, pt[0]), AllocatedNum.alloc(cs, pt[1]))
+    def alloc(cs, pt, recipe_args=None):
+        """recipe_args = (lcX1, lcY1, lcX2, lcY2) when the point is the sum of two points (witness hint),
+        None when it is an external input."""
+        if recipe_args is None:
+            return AllocatedPoint(AllocatedNum.alloc(cs, pt[0]), AllocatedNum.alloc(cs, pt[1]))
+        return AllocatedPoint(AllocatedNum.alloc(cs, pt[0], ("jjx",) + tuple(recipe_args)),
+                              AllocatedNum.alloc(cs, pt[1], ("jjy",) + tuple(recipe_args)))
 
     @property
     def value(self):
@@ -284,7 +289,8 @@ class AllocatedPoint:
         return N.jj_add(a, b)
 
     def add_const(self, cs, b):
-        s = AllocatedPoint.alloc(cs, AllocatedPoint._sum_value(self.value, b))
+        s = AllocatedPoint.alloc(cs, AllocatedPoint._sum_value(self.value, b),
+                                 (LC({self.x.var: 1}), LC({self.y.var: 1}), LC({ONE: b[0] % R}), LC({ONE: b[1] % R})))
         bx, by = b
         k = N.JJ_D * bx % R * by % R
         common = self.x.mul(cs, self.y)
@@ -294,7 +300,8 @@ class AllocatedPoint:
         return s
 
     def add(self, cs, other):
-        s = AllocatedPoint.alloc(cs, AllocatedPoint._sum_value(self.value, other.value))
+        s = AllocatedPoint.alloc(cs, AllocatedPoint._sum_value(self.value, other.value),
+                                 (LC({self.x.var: 1}), LC({self.y.var: 1}), LC({other.x.var: 1}), LC({other.y.var: 1})))
         common = self.x.mul(cs, other.x).mul(cs, self.y).mul(cs, other.y)
         x1 = self.x.mul(cs, other.y)
         x2 = self.y.mul(cs, other.x)

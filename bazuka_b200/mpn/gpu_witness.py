@@ -1,0 +1,87 @@
+"""UpdateCircuit witness on the GPU: host glue around csrc/witness.cu.
+
+    gw = UpdateWitnessGpu(ctx, A, T)               # compile + upload the slot program once per (A, T)
+    d_inputs, d_aux = gw.witness(circ)             # CUDA tensors [ni,4] / [na,4] (Montgomery), z = inputs ++ aux
+    prover.prove_dev(pk, d_inputs, d_aux, r, s)
+
+What stays on the host is what bellman's synthesize does OUTSIDE the per-slot loop
+(/root/reference/src/mpn/circuits/update_circuit.rs:52-80 and 470-493): the six prologue variables and the
+epilogue's one Poseidon(fee_token, fee_sum) gadget — a few hundred values."""
+import ctypes as ct
+
+import numpy as np
+
+from . import native as N
+from . import witness_program as W
+from .cs import ConstraintSystem, AllocatedNum, R, to_mont
+from .gadgets import Number
+
+_RINV = pow(1 << 256, -1, R)
+
+
+def _canon_rows(values):
+    buf = b"".join((v % R).to_bytes(32, "little") for v in values)
+    return np.frombuffer(buf, dtype=np.uint64).reshape(-1, 4).copy()
+
+
+class UpdateWitnessGpu:
+    def __init__(self, ctx, A, T):
+        from ..api import _host_ptr
+        self.ctx, self.A, self.T = ctx, A, T
+        self.prog = p = W.compile_update_block(A, T)
+        ops = np.ascontiguousarray(p.ops, dtype=np.int32)
+        coefs = np.ascontiguousarray(p.coefs_mont())
+        jj_d = to_mont([N.JJ_D])
+        h = ct.c_void_p()
+        ctx._check(ctx._l.bzk_witness_program_upload(
+            ctx._h, _host_ptr(ops), len(ops), _host_ptr(p.lc_ptr), len(p.lc_ptr) - 1, _host_ptr(p.lc_slot), _host_ptr(p.lc_coef),
+            len(p.lc_slot), _host_ptr(coefs), len(coefs), p.n_raw, _host_ptr(jj_d), ct.byref(h)))
+        self._h = h
+
+    def free(self):
+        if self._h:
+            self.ctx._l.bzk_witness_program_free(self.ctx._h, self._h)
+            self._h = None
+
+    def witness(self, circ):
+        """-> (d_inputs [ni,4], d_aux [na,4]) int64 CUDA tensors holding Montgomery images."""
+        import torch
+        from ..api import _dev_ptr, _host_ptr
+        assert (circ.A, circ.T) == (self.A, self.T)
+        p, ctx = self.prog, self.ctx
+        n, a_tx = len(circ.transitions), self.prog.n_ops
+        # ---- prologue on the host
+        cs = ConstraintSystem()
+        state_wit, fee_tok, aux_wit, claimed = circ._prologue(cs)
+        assert len(cs.aux) == p.p_aux
+        # ---- slots on the device
+        raws = np.concatenate([_canon_rows(W.raw_values(tr, self.A, self.T)) for tr in circ.transitions])
+        roots = _canon_rows(W.slot_roots(circ))
+        fee = _canon_rows([circ.fee_token])
+        # epilogue size is value-independent: synthesise it once with placeholders to learn it
+        probe = ConstraintSystem()
+        circ._epilogue(probe, AllocatedNum(probe.alloc(0), 0), AllocatedNum(probe.alloc(0), 0), AllocatedNum(probe.alloc(0), 0),
+                       AllocatedNum(probe.alloc(0), 0), Number.zero())
+        n_epi = len(probe.aux) - 4
+        na = p.p_aux + n * a_tx + n_epi
+        dev = torch.device("cuda", ctx.device) if hasattr(ctx, "device") else torch.device("cuda")
+        d_aux = torch.empty((na, 4), dtype=torch.int64, device=dev)
+        block = d_aux[p.p_aux:p.p_aux + n * a_tx]
+        ctx._check(ctx._l.bzk_witness_run_dev(ctx._h, self._h, _host_ptr(raws), _host_ptr(fee), _host_ptr(roots), n, _dev_ptr(block)))
+        # ---- epilogue on the host: needs the fee sum and the last state root (read back: n + 1 elements)
+        idx = torch.tensor([k * a_tx + p.final_fee for k in range(n)] + [(n - 1) * a_tx + p.state_out], device=dev)
+        back = block[idx].cpu().numpy().view(np.uint64)
+        vals = [int.from_bytes(row.tobytes(), "little") * _RINV % R for row in back]
+        fee_sum = Number.zero()
+        for k in range(n):
+            fee_sum = Number(fee_sum.lc.add_term(1, 2 * (p.p_aux + k * a_tx + p.final_fee) + 1), fee_sum.value + vals[k])
+        cs.aux.extend([0] * (n * a_tx))
+        last_state = AllocatedNum(2 * (p.p_aux + (n - 1) * a_tx + p.state_out) + 1, vals[n])
+        circ._epilogue(cs, last_state, fee_tok, aux_wit, claimed, fee_sum)
+        epi = cs.aux[p.p_aux + n * a_tx:]
+        assert len(epi) == n_epi
+        d_aux[:p.p_aux] = torch.from_numpy(to_mont(cs.aux[:p.p_aux]).view(np.int64)).to(dev)
+        d_aux[p.p_aux + n * a_tx:] = torch.from_numpy(to_mont(epi).view(np.int64)).to(dev)
+        d_inputs = torch.from_numpy(to_mont(cs.inputs).view(np.int64)).to(dev)
+        torch.cuda.synchronize(dev)
+        return d_inputs, d_aux

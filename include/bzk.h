@@ -183,6 +183,35 @@ int32_t bzk_groth16_params_free(bzk_ctx *ctx, bzk_groth16_params *params);
 int32_t bzk_groth16_prove(bzk_ctx *ctx, const bzk_groth16_params *params, const bzk_r1cs *r1cs,
                           const bzk_fr *inputs, const bzk_fr *aux, const bzk_fr *r, const bzk_fr *s, int32_t check_satisfied,
                           bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c);
+/* Same prover with the witness already in device memory (Montgomery images; written e.g. by
+ * bzk_witness_run_dev): d_inputs[num_inputs], d_aux[num_aux].  Work queued on the context's stream before
+ * the call (the witness kernels) is ordered before the prover's reads. */
+int32_t bzk_groth16_prove_dev(bzk_ctx *ctx, const bzk_groth16_params *params, const bzk_r1cs *r1cs,
+                              const void *d_inputs, const void *d_aux, const bzk_fr *r, const bzk_fr *s, int32_t check_satisfied,
+                              bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c);
+
+/* ------------------------------------------------------------------ witness generation (device)
+ * bellman's `ProvingAssignment` runs `MpnCircuit::synthesize` with value closures
+ * (/root/reference/src/mpn/circuits/update_circuit.rs:49-494).  Every slot of an update batch performs the
+ * same allocations, so the host compiles one slot into a straight-line program (bazuka_b200/mpn/
+ * witness_program.py) and the device interprets it with one thread per slot.
+ *   ops[n_ops][6] = {opcode, lc0, lc1, lc2, lc3, imm}; op j defines block variable j.
+ *     0 RAW  raws[slot][imm]           1 MUL lc0*lc1            2 BIT  bit imm of canonical(lc0)
+ *     3 ISZERO lc0==0                  4 INVZ lc0^-1 (0 -> 0)   5 SELECT lc0 ? lc2 : lc1
+ *     6 JJ   JubJub sum (lc0,lc1)+(lc2,lc3) -> variables j, j+1 ((0,0) if an operand is off-curve)   7 NOP
+ *   linear combination l = sum_{k in [lc_ptr[l], lc_ptr[l+1])} coefs[lc_coef[k]] * V[lc_slot[k]]
+ *   (coefs[0] must be the constant one); slots: 0 = ONE, 1 = fee token, 2 = state root entering the
+ *   slot, 3 + j = block variable j.  coefs and jj_d (the curve's d) are Montgomery images.
+ * bzk_witness_run_dev: raws[ntx][n_raw], fee_token, state_in[ntx] are CANONICAL host images (converted on
+ * the device); writes the Montgomery values of slot t's variables to d_aux_out[t*n_ops + j]. */
+typedef struct bzk_witness_program bzk_witness_program;
+int32_t bzk_witness_program_upload(bzk_ctx *ctx, const int32_t *ops, uint64_t n_ops, const int32_t *lc_ptr, uint64_t n_lc,
+                                   const int32_t *lc_slot, const int32_t *lc_coef, uint64_t n_terms, const bzk_fr *coefs,
+                                   uint64_t n_coefs, uint32_t n_raw, const bzk_fr *jj_d, bzk_witness_program **out);
+int32_t bzk_witness_program_free(bzk_ctx *ctx, bzk_witness_program *prog);
+int32_t bzk_witness_run_dev(bzk_ctx *ctx, const bzk_witness_program *prog, const bzk_fr *raws, const bzk_fr *fee_token,
+                            const bzk_fr *state_in, uint64_t ntx, void *d_aux_out);
+
 /* 387-byte bincode image of `Groth16Proof {a,b,c}` (/root/reference/src/zk/groth16/mod.rs:33-38);
  * prefix it with the u32 variant tag 0 for `ZkProof::Groth16` (391 B). */
 int32_t bzk_groth16_proof_bytes(const bzk_g1_affine *a, const bzk_g2_affine *b, const bzk_g1_affine *c, uint8_t out[387]);

@@ -187,3 +187,32 @@ def test_parallel_synthesis_equals_sequential():
     assert (F.canon_to_mont_host(aux_canon) == aux).all()
     for (rp1, c1, v1), (rp2, c2, v2) in zip(mats, mats2):
         assert (rp1 == rp2).all() and (c1 == c2).all() and (v1 == v2).all()
+
+
+def test_witness_program_reproduces_synthesised_witness():
+    """the compiled straight-line witness program (what csrc/witness.cu interprets, one thread per slot)
+    yields, slot by slot, exactly the aux values `UpdateCircuit.synthesize` assigns — for signed transfers,
+    a transfer to a new account and a null slot."""
+    from bazuka_b200.mpn import witness_program as W
+    st, keys = make_state(3, 3, 3)
+    keys.append(N.eddsa_keys(b"newcomer"))
+    txs = [transfer(keys, 0, 1, 1), transfer(keys, 1, 2, 1, amount=5), transfer(keys, 0, 3, 2, amount=77, fee=3)]
+    pub, trans, _ = U.update(st, txs, 1)
+    circ = U.UpdateCircuit(3, 3, 1, commitment=42, height=7, transitions=trans, **pub)
+    cs = circ.synthesize(C.ConstraintSystem(record=True))
+    prog = W.compile_update_block(3, 3)
+    n = len(circ.transitions)
+    a_tx = prog.n_ops
+    assert len(cs.aux) > prog.p_aux + n * a_tx
+    roots = W.slot_roots(circ)
+    kinds = {r[0] for r in cs.recipes}
+    assert kinds <= {"raw", "mul", "bit", "iszero", "invz", "select", "jjx", "jjy"}
+    for k, tr in enumerate(circ.transitions):
+        raws = W.raw_values(tr, 3, 3)
+        assert len(raws) == prog.n_raw
+        got = W.run_reference(prog, raws, circ.fee_token, roots[k])
+        want = cs.aux[prog.p_aux + k * a_tx: prog.p_aux + (k + 1) * a_tx]
+        assert got == want, (k, next(i for i, (g, w) in enumerate(zip(got, want)) if g != w))
+    # chaining: the state root leaving slot k enters slot k+1
+    for k in range(n - 1):
+        assert cs.aux[prog.p_aux + k * a_tx + prog.state_out] == roots[k + 1]
