@@ -50,6 +50,14 @@ struct bzk_groth16_params {
     bzk::G2Affine beta_g2, delta_g2;
     bzk_g1_bases *h = nullptr, *l = nullptr, *a = nullptr, *b1 = nullptr;
     bzk_g2_bases *b2 = nullptr;
+    // base sharding: this handle holds the contiguous range
+    // [len*rank/world, len*(rank+1)/world) of each of the five base vectors
+    uint32_t rank = 0, world = 1;
+};
+
+struct Groth16Partials {  // the four sums a proof is assembled from (wire images)
+    bzk_g1_affine *a_sum, *b1_sum, *hl_sum;
+    bzk_g2_affine *b2_sum;
 };
 
 namespace bzk {
@@ -262,8 +270,11 @@ int32_t bzk_groth16_params_free(bzk_ctx *ctx, bzk_groth16_params *p) {
 // already resident, e.g. written by bzk_witness_run_dev)
 static int32_t groth16_prove_impl(bzk_ctx *ctx, const bzk_groth16_params *pk, const bzk_r1cs *cs, const bzk_fr *inputs, const bzk_fr *aux,
                                   cudaMemcpyKind witness_kind, const bzk_fr *r_mont, const bzk_fr *s_mont, int32_t check_satisfied,
-                                  bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c) {
-    if (!ctx || !pk || !cs || !inputs || (cs->num_aux && !aux) || !r_mont || !s_mont || !proof_a || !proof_b || !proof_c) return BZK_ERR_BAD_ARG;
+                                  bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c,
+                                  const Groth16Partials *partial = nullptr) {
+    if (!ctx || !pk || !cs || !inputs || (cs->num_aux && !aux)) return BZK_ERR_BAD_ARG;
+    if (!partial && (!r_mont || !s_mont || !proof_a || !proof_b || !proof_c)) return BZK_ERR_BAD_ARG;
+    if (!partial && pk->world != 1) return BZK_ERR_BAD_ARG;  // a shard can only produce partial sums
     BZK_CUDA(ctx, cudaSetDevice(ctx->device));
     // BZK_TRACE=1: host-side wall clock of the driver's phases on stderr (development aid)
     static const bool trace = std::getenv("BZK_TRACE") != nullptr;
@@ -274,7 +285,13 @@ static int32_t groth16_prove_impl(bzk_ctx *ctx, const bzk_groth16_params *pk, co
         fprintf(stderr, "[bzk prove] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_start).count());
     };
     const uint64_t ni = cs->num_inputs, na = cs->num_aux, nv = ni + na, m = (uint64_t)1 << cs->log_m;
-    if (pk->h->n < m - 1 || pk->l->n != na || pk->a->n != cs->a_len || pk->b1->n != cs->b_len || pk->b2->n != cs->b_len) return BZK_ERR_BAD_ARG;
+    // this handle's slice of each sum (the whole range when world == 1)
+    auto lo_of = [&](uint64_t len) { return len * pk->rank / pk->world; };
+    auto cnt_of = [&](uint64_t len) { return len * (pk->rank + 1) / pk->world - len * pk->rank / pk->world; };
+    const uint64_t h_lo = lo_of(m - 1), h_n = cnt_of(m - 1), l_lo = lo_of(na), l_n = cnt_of(na), a_lo = lo_of(cs->a_len), a_n = cnt_of(cs->a_len),
+                   b_lo = lo_of(cs->b_len), b_n = cnt_of(cs->b_len);
+    if ((pk->world == 1 ? pk->h->n < h_n : pk->h->n != h_n) || pk->l->n != l_n || pk->a->n != a_n || pk->b1->n != b_n || pk->b2->n != b_n)
+        return BZK_ERR_BAD_ARG;
     // staging arena: z | a_ev | b_ev | c_ev | gathered scalars
     const size_t gmax = std::max<uint64_t>(std::max(cs->a_len, cs->b_len), 1);
     size_t need = 0;
@@ -335,20 +352,20 @@ static int32_t groth16_prove_impl(bzk_ctx *ctx, const bzk_groth16_params *pk, co
     BZK_CUDA(ctx, cudaStreamWaitEvent(s_l, ctx->aux_ev[0], 0));
     BZK_CUDA(ctx, cudaStreamWaitEvent(s_a, ctx->aux_ev[0], 0));
     BZK_CUDA(ctx, cudaStreamWaitEvent(s_b1, ctx->aux_ev[0], 0));
-    BZK_TRY(msm_g1_enqueue(ctx, s_l, &ctx->aux_ws[0], &ctx->aux_ws_bytes[0], pk->l->d, z + ni, na, hw + 1 * kWinBytes, &plan[1]));
+    BZK_TRY(msm_g1_enqueue(ctx, s_l, &ctx->aux_ws[0], &ctx->aux_ws_bytes[0], pk->l->d, z + ni + l_lo, l_n, hw + 1 * kWinBytes, &plan[1]));
     k_gather_fr<<<div_up(cs->a_len, 256), 256, 0, s_a>>>(z, cs->d_a_idx, cs->a_len, gs_a);
     BZK_LAUNCHED(ctx);
-    BZK_TRY(msm_g1_enqueue(ctx, s_a, &ctx->aux_ws[1], &ctx->aux_ws_bytes[1], pk->a->d, gs_a, cs->a_len, hw + 2 * kWinBytes, &plan[2]));
+    BZK_TRY(msm_g1_enqueue(ctx, s_a, &ctx->aux_ws[1], &ctx->aux_ws_bytes[1], pk->a->d, gs_a + a_lo, a_n, hw + 2 * kWinBytes, &plan[2]));
     if (cs->b_len) {
         k_gather_fr<<<div_up(cs->b_len, 256), 256, 0, s_b1>>>(z, cs->d_b_idx, cs->b_len, gs_b);
         BZK_LAUNCHED(ctx);
     }
     BZK_CUDA(ctx, cudaEventRecord(ctx->aux_ev[1], s_b1));
     BZK_CUDA(ctx, cudaStreamWaitEvent(s_b2, ctx->aux_ev[1], 0));
-    BZK_TRY(msm_g1_enqueue(ctx, s_b1, &ctx->aux_ws[2], &ctx->aux_ws_bytes[2], pk->b1->d, gs_b, cs->b_len, hw + 3 * kWinBytes, &plan[3]));
-    BZK_TRY(msm_g2_enqueue(ctx, s_b2, &ctx->aux_ws[3], &ctx->aux_ws_bytes[3], pk->b2->d, gs_b, cs->b_len, hw + 4 * kWinBytes, &plan[4]));
+    BZK_TRY(msm_g1_enqueue(ctx, s_b1, &ctx->aux_ws[2], &ctx->aux_ws_bytes[2], pk->b1->d, gs_b + b_lo, b_n, hw + 3 * kWinBytes, &plan[3]));
+    BZK_TRY(msm_g2_enqueue(ctx, s_b2, &ctx->aux_ws[3], &ctx->aux_ws_bytes[3], pk->b2->d, gs_b + b_lo, b_n, hw + 4 * kWinBytes, &plan[4]));
     BZK_TRY(groth16_h_launch(ctx, ea, eb, ec, cs->log_m));  // ea <- h coefficients
-    BZK_TRY(msm_g1_enqueue(ctx, st, &ctx->ws, &ctx->ws_bytes, pk->h->d, ea, m - 1, hw, &plan[0]));
+    BZK_TRY(msm_g1_enqueue(ctx, st, &ctx->ws, &ctx->ws_bytes, pk->h->d, ea + h_lo, h_n, hw, &plan[0]));
     lap("all kernels enqueued");
     BZK_CUDA(ctx, cudaStreamSynchronize(st));
     lap("main stream done");
@@ -358,6 +375,20 @@ static int32_t groth16_prove_impl(bzk_ctx *ctx, const bzk_groth16_params *pk, co
     // sub-millisecond jobs — run them on host threads instead of back to back
     bzk_g1_affine h_ans, l_ans, a_ans, b1_ans;
     bzk_g2_affine b2_ans;
+    if (partial) {  // sharded schedule: hand back this rank's four partial sums; the caller folds and finalises
+        auto p_b2 = std::async(std::launch::async, [&] { msm_g2_finish(&plan[4], hw + 4 * kWinBytes, partial->b2_sum); });
+        auto p_a = std::async(std::launch::async, [&] { msm_g1_finish(&plan[2], hw + 2 * kWinBytes, partial->a_sum); });
+        auto p_b1 = std::async(std::launch::async, [&] { msm_g1_finish(&plan[3], hw + 3 * kWinBytes, partial->b1_sum); });
+        auto p_l = std::async(std::launch::async, [&] { msm_g1_finish(&plan[1], hw + 1 * kWinBytes, &l_ans); });
+        msm_g1_finish(&plan[0], hw, &h_ans);
+        p_l.get();
+        G1Xyzz t = G1Xyzz::from_affine(g1_from_img(&h_ans));
+        t.madd(g1_from_img(&l_ans));
+        g1_to_img(partial->hl_sum, t.to_affine());
+        p_b2.get(); p_a.get(); p_b1.get();
+        lap("partial sums folded");
+        return BZK_OK;
+    }
     Fr r, s;
     memcpy(r.l, r_mont, 32);
     memcpy(s.l, s_mont, 32);
@@ -416,6 +447,55 @@ int32_t bzk_groth16_prove_dev(bzk_ctx *ctx, const bzk_groth16_params *pk, const 
                               bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c) {
     return groth16_prove_impl(ctx, pk, cs, (const bzk_fr *)d_inputs, (const bzk_fr *)d_aux, cudaMemcpyDeviceToDevice, r_mont, s_mont,
                               check_satisfied, proof_a, proof_b, proof_c);
+}
+
+int32_t bzk_groth16_params_set_shard(bzk_groth16_params *p, uint32_t rank, uint32_t world) {
+    if (!p || world == 0 || rank >= world) return BZK_ERR_BAD_ARG;
+    p->rank = rank;
+    p->world = world;
+    return BZK_OK;
+}
+
+int32_t bzk_groth16_prove_partial(bzk_ctx *ctx, const bzk_groth16_params *pk, const bzk_r1cs *cs, const void *inputs, const void *aux,
+                                  int32_t witness_on_device, int32_t check_satisfied,
+                                  bzk_g1_affine *a_sum, bzk_g1_affine *b1_sum, bzk_g2_affine *b2_sum, bzk_g1_affine *hl_sum) {
+    if (!a_sum || !b1_sum || !b2_sum || !hl_sum) return BZK_ERR_BAD_ARG;
+    const Groth16Partials part{a_sum, b1_sum, hl_sum, b2_sum};
+    return groth16_prove_impl(ctx, pk, cs, (const bzk_fr *)inputs, (const bzk_fr *)aux,
+                              witness_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, nullptr, nullptr, check_satisfied,
+                              nullptr, nullptr, nullptr, &part);
+}
+
+/* bellman `create_proof`'s last lines from the (summed) answers:
+ *   A = r*delta1 + alpha1 + a;  B = s*delta2 + beta2 + b2;  C = rs*delta1 + s*alpha1 + r*beta1 + s*a + r*b1 + (h + l) */
+int32_t bzk_groth16_finalize(const bzk_g1_affine *alpha_g1, const bzk_g1_affine *beta_g1, const bzk_g2_affine *beta_g2,
+                             const bzk_g1_affine *delta_g1, const bzk_g2_affine *delta_g2,
+                             const bzk_g1_affine *a_sum, const bzk_g1_affine *b1_sum, const bzk_g2_affine *b2_sum, const bzk_g1_affine *hl_sum,
+                             const bzk_fr *r_mont, const bzk_fr *s_mont, bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c) {
+    if (!alpha_g1 || !beta_g1 || !beta_g2 || !delta_g1 || !delta_g2 || !a_sum || !b1_sum || !b2_sum || !hl_sum || !r_mont || !s_mont ||
+        !proof_a || !proof_b || !proof_c)
+        return BZK_ERR_BAD_ARG;
+    Fr r, s;
+    memcpy(r.l, r_mont, 32);
+    memcpy(s.l, s_mont, 32);
+    const Fr rs = (r * s).from_mont(), rc = r.from_mont(), sc = s.from_mont();
+    const G1Affine al = g1_from_img(alpha_g1), be1 = g1_from_img(beta_g1), de1 = g1_from_img(delta_g1), av = g1_from_img(a_sum);
+    G2Xyzz gb = scalar_mul(g2_from_img(delta_g2), sc.l);
+    gb.madd(g2_from_img(beta_g2));
+    gb.madd(g2_from_img(b2_sum));
+    G1Xyzz ga = scalar_mul(de1, rc.l);
+    ga.madd(al);
+    ga.madd(av);
+    G1Xyzz gc = scalar_mul(de1, rs.l);
+    gc.add(scalar_mul(al, sc.l));
+    gc.add(scalar_mul(be1, rc.l));
+    gc.add(scalar_mul(av, sc.l));
+    gc.add(scalar_mul(g1_from_img(b1_sum), rc.l));
+    gc.madd(g1_from_img(hl_sum));
+    g1_to_img(proof_a, ga.to_affine());
+    g2_to_img(proof_b, gb.to_affine());
+    g1_to_img(proof_c, gc.to_affine());
+    return BZK_OK;
 }
 
 /* 387-byte bincode image of `Groth16Proof {a, b, c}` (/root/reference/src/zk/groth16/mod.rs:33-38) */

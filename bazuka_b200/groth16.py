@@ -163,6 +163,24 @@ class Prover:
         c._check(c._l.bzk_groth16_proof_bytes(_host_ptr(pa), _host_ptr(pb), _host_ptr(pc), _host_ptr(blob)))
         return blob, (pa, pb, pc)
 
+    def prove_partial(self, spk: ProvingKey, inputs, aux, check_satisfied=True):
+        """this rank's four partial sums (a, b_g1, b_g2, h+l wire images) under the base-sharded key `spk`
+        (shard_proving_key).  inputs/aux: host arrays, or CUDA tensors for a resident witness."""
+        c = self.ctx
+        on_dev = hasattr(inputs, "is_cuda")
+        if on_dev:
+            from .api import _dev_ptr
+            pi, pa_ = _dev_ptr(inputs), _dev_ptr(aux)
+        else:
+            inputs = np.ascontiguousarray(inputs, dtype=np.uint64).reshape(-1, 4)
+            aux = np.ascontiguousarray(aux, dtype=np.uint64).reshape(-1, 4)
+            assert len(inputs) == self.r1cs.num_inputs and len(aux) == self.r1cs.num_aux
+            pi, pa_ = _host_ptr(inputs), _host_ptr(aux)
+        a_sum, b1_sum, hl_sum, b2_sum = np.zeros(G1_BYTES, np.uint8), np.zeros(G1_BYTES, np.uint8), np.zeros(G1_BYTES, np.uint8), np.zeros(G2_BYTES, np.uint8)
+        c._check(c._l.bzk_groth16_prove_partial(c._h, spk._h, self._h, pi, pa_, int(on_dev), int(check_satisfied),
+                                                 _host_ptr(a_sum), _host_ptr(b1_sum), _host_ptr(b2_sum), _host_ptr(hl_sum)))
+        return a_sum, b1_sum, b2_sum, hl_sum
+
     def prove_dev(self, pk: ProvingKey, d_inputs, d_aux, r, s, check_satisfied=True):
         """`prove` with the witness already resident: d_inputs [num_inputs,4], d_aux [num_aux,4] CUDA int64
         tensors of Montgomery images (e.g. written by mpn.gpu_witness)."""
@@ -177,6 +195,61 @@ class Prover:
         blob = np.zeros(387, np.uint8)
         c._check(c._l.bzk_groth16_proof_bytes(_host_ptr(pa), _host_ptr(pb), _host_ptr(pc), _host_ptr(blob)))
         return blob, (pa, pb, pc)
+
+
+def shard_proving_key(ctx, pk: ProvingKey, log_m, rank, world):
+    """rank's base-sharded key from a full key produced by `setup_gpu` on this GPU: contiguous ranges
+    [len*rank/world, len*(rank+1)/world) of h (first 2^log_m - 1 entries), l, a, b_g1, b_g2."""
+    from .dist import shard_range
+    img = pk.device_images
+
+    def sl(t, n):
+        lo, hi = shard_range(n, rank, world)
+        return t[lo:hi].contiguous(), hi - lo
+
+    m1 = (1 << log_m) - 1
+    parts = {k: sl(img[k], m1 if k == "h" else img[k].shape[0]) for k in ("h", "l", "a", "b_g1", "b_g2")}
+    hb, lb, ab, b1b = (ctx.g1_bases_from_dev(*parts[k]) for k in ("h", "l", "a", "b_g1"))
+    b2b = ctx.g2_bases_from_dev(*parts["b_g2"])
+    ctx.synchronize()
+    spk = _make_pk(ctx, pk.vk, hb, lb, ab, b1b, b2b)
+    ctx._check(ctx._l.bzk_groth16_params_set_shard(spk._h, rank, world))
+    spk.rank, spk.world = rank, world
+    return spk
+
+
+def finalize(vk, partials, r, s):
+    """tail of bellman `create_proof` from the summed answers (a, b_g1, b_g2, h+l) -> (blob[387], points)."""
+    from . import _lib
+    lib = _lib.load()
+    pts = [np.ascontiguousarray(vk[k], dtype=np.uint8) for k in ("alpha_g1", "beta_g1", "beta_g2", "delta_g1", "delta_g2")]
+    a_sum, b1_sum, b2_sum, hl_sum = (np.ascontiguousarray(x, dtype=np.uint8) for x in partials)
+    r = np.ascontiguousarray(r, dtype=np.uint64).reshape(4)
+    s = np.ascontiguousarray(s, dtype=np.uint64).reshape(4)
+    pa, pb, pc = np.zeros(G1_BYTES, np.uint8), np.zeros(G2_BYTES, np.uint8), np.zeros(G1_BYTES, np.uint8)
+    st = lib.bzk_groth16_finalize(*[_host_ptr(p) for p in pts], _host_ptr(a_sum), _host_ptr(b1_sum), _host_ptr(b2_sum), _host_ptr(hl_sum),
+                                  _host_ptr(r), _host_ptr(s), _host_ptr(pa), _host_ptr(pb), _host_ptr(pc))
+    if st != 0:
+        raise _lib.BzkError(st, "groth16_finalize")
+    blob = np.zeros(387, np.uint8)
+    lib.bzk_groth16_proof_bytes(_host_ptr(pa), _host_ptr(pb), _host_ptr(pc), _host_ptr(blob))
+    return blob, (pa, pb, pc)
+
+
+def allgather_partials(partials, group=None, device="cpu"):
+    """one all-gather of world x 512 B, then the local folds: every rank returns the four summed answers."""
+    import torch
+    import torch.distributed as dist
+    from .dist import fold
+    a_sum, b1_sum, b2_sum, hl_sum = (np.ascontiguousarray(x, dtype=np.uint8) for x in partials)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return a_sum, b1_sum, b2_sum, hl_sum
+    world = dist.get_world_size(group)
+    mine = torch.from_numpy(np.concatenate([a_sum, b1_sum, hl_sum, b2_sum])).to(device)  # 104*3 + 200 = 512 B
+    gathered = torch.empty(world * 512, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    g = gathered.cpu().numpy().reshape(world, 512)
+    return (fold(g[:, 0:104], "g1"), fold(g[:, 104:208], "g1"), fold(g[:, 312:512], "g2"), fold(g[:, 208:312], "g1"))
 
 
 def verify(vk, public_inputs, proof_points):

@@ -190,6 +190,22 @@ int32_t bzk_groth16_prove_dev(bzk_ctx *ctx, const bzk_groth16_params *params, co
                               const void *d_inputs, const void *d_aux, const bzk_fr *r, const bzk_fr *s, int32_t check_satisfied,
                               bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c);
 
+/* Base-sharded proving over several GPUs (one process / context per GPU): every MSM of bellman's
+ * `create_proof` is a sum over terms, so rank k of `world` keeps only the contiguous range
+ * [len*k/world, len*(k+1)/world) of each of the five base vectors (pass those slices to
+ * bzk_groth16_params_create, then set_shard), computes the witness-side pipeline on its own GPU, and
+ * returns its four partial sums (a; b_g1; b_g2; h + l).  The caller exchanges world x 512 B (one
+ * all-gather), adds the partials (bzk_g1_add / bzk_g2_add) and calls bzk_groth16_finalize — host arithmetic,
+ * no context — which is the tail of `create_proof` (g_a, g_b, g_c from r, s and the verifying-key points). */
+int32_t bzk_groth16_params_set_shard(bzk_groth16_params *params, uint32_t rank, uint32_t world);
+int32_t bzk_groth16_prove_partial(bzk_ctx *ctx, const bzk_groth16_params *params, const bzk_r1cs *r1cs, const void *inputs, const void *aux,
+                                  int32_t witness_on_device, int32_t check_satisfied,
+                                  bzk_g1_affine *a_sum, bzk_g1_affine *b1_sum, bzk_g2_affine *b2_sum, bzk_g1_affine *hl_sum);
+int32_t bzk_groth16_finalize(const bzk_g1_affine *alpha_g1, const bzk_g1_affine *beta_g1, const bzk_g2_affine *beta_g2,
+                             const bzk_g1_affine *delta_g1, const bzk_g2_affine *delta_g2,
+                             const bzk_g1_affine *a_sum, const bzk_g1_affine *b1_sum, const bzk_g2_affine *b2_sum, const bzk_g1_affine *hl_sum,
+                             const bzk_fr *r, const bzk_fr *s, bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c);
+
 /* ------------------------------------------------------------------ witness generation (device)
  * bellman's `ProvingAssignment` runs `MpnCircuit::synthesize` with value closures
  * (/root/reference/src/mpn/circuits/update_circuit.rs:49-494).  Every slot of an update batch performs the

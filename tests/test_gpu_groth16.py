@@ -102,3 +102,36 @@ def test_prover_2_18_domain_vs_oracle(ctx, cref):
     for k in ("h", "l", "a", "b_g1", "b_g2"):
         cpk[k] = pk.device_images[k].cpu().numpy()
     assert (blob == GC.proof_bytes(*GC.prove(ni, na, mats, cpk, inputs, aux, r, s))).all()
+
+
+def test_base_sharded_partials_fold_to_the_same_proof(ctx, cref):
+    """schedule (S) of SURVEY.md §8e on one GPU: the proving key cut into 3 contiguous base shards, each shard's
+    four partial sums from `bzk_groth16_prove_partial`, folded with the host group law and finalised —
+    byte-equal to the unsharded GPU proof (and so to the oracle's, by the tests above)."""
+    import torch
+    from bazuka_b200 import groth16 as BG, synth, dist as bd
+    ni, na, mats, inputs, aux = synth.build(lanes=16, rounds=6, seed=31, ops=synth.GpuOps(ctx))
+    pr = BG.Prover(ctx, BG.R1CS(ni, na, *mats))
+    pk, vk = BG.setup_gpu(ctx, pr.r1cs, cref.fr_random(41, 5), cref.g1_generator(), cref.g2_generator())
+    r, s = cref.fr_random(42, 2)
+    want, _ = pr.prove(pk, inputs, aux, r, s)
+    world = 3
+    parts = []
+    for rank in range(world):
+        spk = BG.shard_proving_key(ctx, pk, pr.log_m, rank, world)
+        parts.append(pr.prove_partial(spk, inputs, aux))
+        with pytest.raises(Exception):
+            pr.prove(spk, inputs, aux, r, s)  # a shard cannot finish a proof by itself
+        spk.free()
+    sums = (bd.fold([p[0] for p in parts], "g1"), bd.fold([p[1] for p in parts], "g1"),
+            bd.fold([p[2] for p in parts], "g2"), bd.fold([p[3] for p in parts], "g1"))
+    blob, pts = BG.finalize(vk, sums, r, s)
+    assert (blob == want).all()
+    assert BG.verify(vk, inputs[1:], pts)
+    # resident witness through the same entry point
+    d_in = torch.from_numpy(inputs.view(np.int64)).cuda()
+    d_aux = torch.from_numpy(aux.view(np.int64)).cuda()
+    spk = BG.shard_proving_key(ctx, pk, pr.log_m, 0, 1)
+    one = pr.prove_partial(spk, d_in, d_aux)
+    assert (BG.finalize(vk, one, r, s)[0] == want).all()
+    spk.free(); pk.free(); pr.free()
