@@ -232,6 +232,7 @@ def run_ours(args, rank, local_rank, world):
     mpn_multi = None
     if world > 1 and not args.no_mpn:
         mpn_multi = mpn_groth16_section(ctx, with_cpu=False, dist=dist, world=world)
+        mpn_multi["sharded"] = sharded_proof_section(ctx, dist, rank, world)
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -375,6 +376,57 @@ def mpn_groth16_section(ctx, with_cpu=True, dist=None, world=1):
         t0 = time.perf_counter()
         ok = BG.verify(vk, inputs[1:], pts)
         out.update({"libbzk_verify_accepts": bool(ok), "libbzk_verify_ms": (time.perf_counter() - t0) * 1e3})
+    except Exception as e:
+        out["error"] = repr(e)
+    return out
+
+
+def sharded_proof_section(ctx, dist, rank, world):
+    """SURVEY.md §8e schedule (S): ONE proof over all GPUs — every rank keeps a contiguous 1/N of the five base
+    vectors, sums its shard (bzk_groth16_prove_partial), one NCCL all-gather of 512 B per rank, host folds and
+    bzk_groth16_finalize.  Measured on a 2^20-domain synthetic MPN-like circuit; the sharded proof must equal the
+    single-GPU proof byte for byte.  (tools/bench_sharded.py runs larger domains.)"""
+    import numpy as np
+    import torch
+    from bazuka_b200 import groth16 as BG, synth
+    out = {"circuit": "synthetic MPN-like, 1024 lanes x 100 rounds"}
+    try:
+        dev = torch.device("cuda", torch.cuda.current_device())
+        ni, na, mats, inputs, aux = synth.build(1024, 100, seed=17, ops=synth.GpuOps(ctx))
+        pr = BG.Prover(ctx, BG.R1CS(ni, na, *mats))
+        d = torch.empty((7, 4), dtype=torch.int64, device=dev)
+        ctx.fr_random_dev(99, 7, d)
+        torch.cuda.synchronize()
+        rnd = d.cpu().numpy().view(np.uint64)
+        pk, vk = BG.setup_gpu(ctx, pr.r1cs, rnd[:5], BG.G1_GENERATOR, BG.G2_GENERATOR)
+        spk = BG.shard_proving_key(ctx, pk, pr.log_m, rank, world)
+        want, _ = pr.prove(pk, inputs, aux, rnd[5], rnd[6])
+
+        def sharded():
+            sums = BG.allgather_partials(pr.prove_partial(spk, inputs, aux, check_satisfied=False), device=dev)
+            return BG.finalize(vk, sums, rnd[5], rnd[6])
+
+        def timed_max(fn, reps=5):
+            best = None
+            for _ in range(reps):
+                dist.barrier()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize()
+                t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                best = float(t.item()) if best is None else min(best, float(t.item()))
+            return best
+
+        blob, pts = sharded()
+        t_sh = timed_max(sharded)
+        t_one = timed_max(lambda: pr.prove(pk, inputs, aux, rnd[5], rnd[6], check_satisfied=False))
+        out.update({"constraints": pr.r1cs.num_constraints, "log_m": pr.log_m, "n_gpus": world,
+                    "sharded_ms_per_proof": t_sh * 1e3, "single_gpu_ms_per_proof": t_one * 1e3, "exchange_bytes_per_rank": 512,
+                    "proof_bytes_equal_single_gpu": bool((blob == want).all()), "verified": bool(BG.verify(vk, inputs[1:], pts)),
+                    "timing": "wall clock between device synchronisations, max over ranks, best of 5"})
+        spk.free(); pk.free(); pr.free()
     except Exception as e:
         out["error"] = repr(e)
     return out
