@@ -45,6 +45,7 @@ SIGNATURES = {
     "bzk_merkle4_build_dev": (_i32, [_vp, _vp, _u32]),
     "bzk_merkle4_prove_dev": (_i32, [_vp, _vp, _u32, _vp, _sz, _vp]),
     "bzk_merkle4_root_dev": (_i32, [_vp, _u32, _vp, _vp, _vp, _sz, _vp]),
+    "bzk_tree4_versioned_update_dev": (_i32, [_vp, _u32, _vp, _vp, _sz, _vp, _vp, _vp]),
     "bzk_ntt": (_i32, [_vp, _vp, _u32, _i32]),
     "bzk_ntt_dev": (_i32, [_vp, _vp, _u32, _i32]),
     "bzk_divide_by_z_on_coset_dev": (_i32, [_vp, _vp, _u32]),

@@ -164,6 +164,28 @@ class Context:
         m = d_indices.numel()
         self._check(self._l.bzk_merkle4_root_dev(self._h, log4, _dev_ptr(d_indices), _dev_ptr(d_leaves), _dev_ptr(d_proofs), m, _dev_ptr(d_roots)))
 
+    def tree4_versioned_update(self, depth, tree_id, indices, leaf_values, init_proofs):
+        """ordered batch of leaf writes to a forest of sparse 4-ary Poseidon trees (bzk_tree4_versioned_update_dev).
+        Host arrays in: tree_id u32[n], indices u64[n], leaf_values [n,4], init_proofs [n,depth,3,4] (Montgomery).
+        -> (vals [depth+1, n, 4]: node values on each write's path after the write, vals[depth] = roots;
+            proofs [n, depth, 3, 4]: proof of each leaf just before its write)."""
+        import torch
+        n = len(indices)
+        dev = torch.device("cuda", self.device)
+        vals = torch.zeros((depth + 1, n, 4), dtype=torch.int64, device=dev)
+        proofs = torch.empty((n, depth, 3, 4), dtype=torch.int64, device=dev)
+        if n == 0:
+            return vals.cpu().numpy().view(np.uint64), proofs.cpu().numpy().view(np.uint64)
+        vals[0] = torch.from_numpy(np.ascontiguousarray(leaf_values, dtype=np.uint64).reshape(n, 4).view(np.int64)).to(dev)
+        d_tid = torch.from_numpy(np.ascontiguousarray(tree_id, dtype=np.uint32).view(np.int32)).to(dev)
+        d_idx = torch.from_numpy(np.ascontiguousarray(indices, dtype=np.uint64).view(np.int64)).to(dev)
+        d_init = torch.from_numpy(np.ascontiguousarray(init_proofs, dtype=np.uint64).reshape(n, depth, 3, 4).view(np.int64)).to(dev)
+        torch.cuda.synchronize(dev)
+        self._check(self._l.bzk_tree4_versioned_update_dev(self._h, depth, _dev_ptr(d_tid), _dev_ptr(d_idx), n, _dev_ptr(vals), _dev_ptr(d_init),
+                                                            _dev_ptr(proofs)))
+        self.synchronize()
+        return vals.cpu().numpy().view(np.uint64), proofs.cpu().numpy().view(np.uint64)
+
     # ---------------------------------------------------------------- NTT
     def ntt(self, a, op):
         """returns the transformed copy of host array a [2^k, 4]."""

@@ -15,6 +15,8 @@ int32_t divide_by_z_launch(bzk_ctx *ctx, Fr *d, uint32_t log_n);
 int32_t merkle4_build(bzk_ctx *ctx, Fr *d_nodes, uint32_t log4);
 int32_t merkle4_prove(bzk_ctx *ctx, const Fr *d_nodes, uint32_t log4, const uint64_t *d_idx, size_t m, Fr *d_proofs);
 int32_t merkle4_root(bzk_ctx *ctx, uint32_t log4, const uint64_t *d_idx, const Fr *d_leaves, const Fr *d_proofs, size_t m, Fr *d_roots);
+int32_t tree4_versioned_update(bzk_ctx *ctx, uint32_t depth, const uint32_t *d_tree_id, const uint64_t *d_idx, size_t n, Fr *d_vals,
+                               const Fr *d_init_proofs, Fr *d_out_proofs);
 int32_t groth16_h_launch(bzk_ctx *ctx, Fr *a, Fr *b, Fr *c, uint32_t log_n);
 
 __global__ void __launch_bounds__(256) k_fr_binop(int op, const Fr *__restrict__ a, const Fr *__restrict__ b, Fr *__restrict__ out, size_t n) {
@@ -248,6 +250,12 @@ int32_t bzk_merkle4_prove_dev(bzk_ctx *ctx, const void *d_nodes, uint32_t log4_s
 int32_t bzk_merkle4_root_dev(bzk_ctx *ctx, uint32_t log4_size, const void *d_indices, const void *d_leaves, const void *d_proofs, size_t m, void *d_roots) {
     BZK_ENTER(ctx);
     return merkle4_root(ctx, log4_size, (const uint64_t *)d_indices, (const Fr *)d_leaves, (const Fr *)d_proofs, m, (Fr *)d_roots);
+}
+int32_t bzk_tree4_versioned_update_dev(bzk_ctx *ctx, uint32_t depth, const void *d_tree_id, const void *d_indices, size_t n, void *d_vals,
+                                       const void *d_init_proofs, void *d_out_proofs) {
+    BZK_ENTER(ctx);
+    return tree4_versioned_update(ctx, depth, (const uint32_t *)d_tree_id, (const uint64_t *)d_indices, n, (Fr *)d_vals, (const Fr *)d_init_proofs,
+                                  (Fr *)d_out_proofs);
 }
 
 // ------------------------------------------------------------------ NTT

@@ -221,6 +221,113 @@ __global__ void __launch_bounds__(128) k_merkle4_root(const Fr *__restrict__ con
     store_vec(roots + p, cur);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Versioned batch update of sparse 4-ary Poseidon trees (the transition builder's hot loop).
+//
+// The reference applies a batch of leaf writes ONE AT A TIME, re-hashing a root path per write and
+// reading a Merkle proof between writes (`KvStoreStateManager::set_data` / `prove`,
+// /root/reference/src/zk/state/mod.rs:218-264,310-420, driven by /root/reference/src/mpn/update.rs:40-258):
+// n writes = n x depth strictly sequential hashes.  Here the whole batch is ONE pass per tree level: event
+// e (write number e) owns a thread; at level l its node value is H(children), where the child on its own
+// path is its value from level l-1 and each of the three siblings is the value of the LATEST EARLIER event
+// whose path runs through that sibling (found by scanning the event list backwards), or — when no earlier
+// event of the batch touched it — the sibling from the proof against the pre-batch tree that the host reads
+// from its store (`init_proofs`, no hashing).  By induction over levels every event sees exactly the tree
+// the sequential loop would have shown it, so
+//     out_proofs[e]  = the Merkle proof of leaf idx[e] just before write e   (what `prove` returned)
+//     vals[depth][e] = the root just after write e                            (what `set_data` produced)
+// and depth launches replace n x depth dependent hashes.  `tree_id` lets one call update a forest (the
+// per-account token trees).  The backward scan is O(n) per thread; batches are <= a few thousand writes.
+__global__ void __launch_bounds__(128) k_tree4_versioned_level(const Fr *__restrict__ consts, uint32_t rf, uint32_t rp, uint32_t depth,
+                                                               uint32_t lvl, const uint32_t *__restrict__ tree_id,
+                                                               const uint64_t *__restrict__ idx, uint32_t n, Fr *vals,
+                                                               const Fr *__restrict__ init_proofs, Fr *__restrict__ out_proofs) {
+    constexpr int T = 5;
+    extern __shared__ uint4 smem_raw[];
+    Fr *sc = (Fr *)smem_raw;
+    const uint32_t nconst = T * (rf + rp) + 2 * T * T;
+    {
+        const uint4 *src = (const uint4 *)consts;
+        uint4 *dst = (uint4 *)sc;
+        for (uint32_t i = threadIdx.x; i < nconst * 2; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const Fr *mds = sc + T * (rf + rp) + T * T;
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const Fr *cur = vals + (size_t)lvl * n;
+    const uint64_t me = idx[e];
+    const uint32_t tid = tree_id[e], pos = (uint32_t)((me >> (2 * lvl)) & 3);
+    const uint32_t up = 2 * lvl + 2;  // depth 32: the top level's shift is the full word
+    const uint64_t prefix = up >= 64 ? 0 : me >> up;
+    Fr s[T];
+    s[0] = Fr::zero();
+    {
+        const Fr *sib = init_proofs + ((size_t)e * depth + lvl) * 3;
+        int w = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if ((uint32_t)k == pos) s[1 + k] = cur[e];
+            else s[1 + k] = load_vec(sib + (w++));
+        }
+    }
+    uint32_t found = 1u << pos;
+    for (uint32_t b = e; b-- > 0 && found != 15u;) {
+        const uint64_t other = idx[b];
+        if (tree_id[b] != tid || (up >= 64 ? 0 : other >> up) != prefix) continue;
+        const uint32_t k = (uint32_t)((other >> (2 * lvl)) & 3);
+        if (found & (1u << k)) continue;
+        found |= 1u << k;
+        const Fr v = cur[b];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if ((uint32_t)q == k) s[1 + q] = v;
+    }
+    {
+        Fr *po = out_proofs + ((size_t)e * depth + lvl) * 3;
+        int w = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if ((uint32_t)k != pos) store_vec(po + (w++), s[1 + k]);
+    }
+    const uint32_t half = rf / 2;
+    const Fr *rc = sc;
+#pragma unroll 1
+    for (uint32_t rnd = 0; rnd < rf + rp; rnd++) {
+#pragma unroll
+        for (int i = 0; i < T; i++) s[i] = s[i] + lds_fr(rc + i);
+        rc += T;
+        if (rnd < half || rnd >= half + rp) {
+#pragma unroll
+            for (int i = 0; i < T; i++) s[i] = pow5(s[i]);
+        } else {
+            s[0] = pow5(s[0]);
+        }
+        Fr o[T];
+#pragma unroll
+        for (int j = 0; j < T; j++) o[j] = mds_row_dot<T>(mds + j * T, s);
+#pragma unroll
+        for (int i = 0; i < T; i++) s[i] = o[i];
+    }
+    store_vec(vals + (size_t)(lvl + 1) * n + e, s[1]);
+}
+
+int32_t tree4_versioned_update(bzk_ctx *ctx, uint32_t depth, const uint32_t *d_tree_id, const uint64_t *d_idx, size_t n, Fr *d_vals,
+                               const Fr *d_init_proofs, Fr *d_out_proofs) {
+    if (!ctx->pos_loaded) return BZK_ERR_NO_PARAMS;
+    if (depth == 0 || depth > 32 || n > (1u << 24) || (n && (!d_tree_id || !d_idx || !d_vals || !d_init_proofs || !d_out_proofs))) return BZK_ERR_BAD_ARG;
+    if (n == 0) return BZK_OK;
+    const PoseidonTable &pt = ctx->pos[5];
+    const size_t smem = (size_t)(pt.nrc + 50) * sizeof(Fr);
+    BZK_CUDA(ctx, cudaFuncSetAttribute(k_tree4_versioned_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (uint32_t lvl = 0; lvl < depth; lvl++) {
+        k_tree4_versioned_level<<<div_up(n, 128), 128, smem, ctx->stream>>>(pt.d_consts, pt.rf, pt.rp, depth, lvl, d_tree_id, d_idx, (uint32_t)n, d_vals,
+                                                                           d_init_proofs, d_out_proofs);
+        BZK_LAUNCHED(ctx);
+    }
+    return BZK_OK;
+}
+
 int32_t poseidon_launch(bzk_ctx *ctx, uint32_t arity, const Fr *d_in, size_t n, Fr *d_out);
 
 int32_t merkle4_build(bzk_ctx *ctx, Fr *d_nodes, uint32_t log4) {

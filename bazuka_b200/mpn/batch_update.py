@@ -1,0 +1,198 @@
+"""`mpn::update::update` with the hashing done in batches on the GPU.
+
+The reference builds the transitions of an update batch one transaction at a time: per transaction 5
+`prove` calls and 3 `set_mpn_account` calls on the Poseidon state, O(700) sequential hashes
+(/root/reference/src/mpn/update.rs:40-258, /root/reference/src/zk/state/mod.rs:218-264,310-420).  `update()` in
+update.py restates that loop.  Here the same transitions come out of two phases:
+
+  1. ledger logic, sequential, NO hashing: acceptance rules, balances, nonces, slot choice — on an
+     in-memory mirror of the touched accounts (identical decisions to update());
+  2. hashing, batched: token-leaf Poseidon-2 and account-leaf Poseidon-5 as two batch calls, and the
+     token forest and the state tree as two calls of the versioned level-synchronous tree update
+     (csrc/poseidon.cu `k_tree4_versioned_level`: one launch per level for the whole batch), which returns
+     the proof every write saw and the root every write produced.
+
+The result is field-for-field the output of update() (tests compare them), the state object ends in the
+same tree, and a 256-transaction batch costs ~20 kernel launches instead of ~180 000 dependent hashes."""
+import numpy as np
+
+from . import native as N
+from .cs import R, to_mont
+from .update import ZIESHA, Money, MpnAccount, MpnState, UpdateTransition
+
+_RINV = pow(1 << 256, -1, R)
+
+
+def _from_mont_rows(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    return [int.from_bytes(row.tobytes(), "little") * _RINV % R for row in a]
+
+
+class GpuTreeHasher:
+    """the two batched primitives on a `bazuka_b200.Context` (values cross as Python ints)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def poseidon_batch(self, rows):
+        if not rows:
+            return []
+        arity = len(rows[0])
+        flat = to_mont([v for r in rows for v in r]).reshape(len(rows), arity, 4)
+        return _from_mont_rows(self.ctx.poseidon(flat))
+
+    def tree_update(self, depth, tree_ids, indices, leaf_values, init_proofs):
+        n = len(indices)
+        if n == 0:
+            return [[] for _ in range(depth + 1)], []
+        init = to_mont([v for p in init_proofs for lvl in p for v in lvl]).reshape(n, depth, 3, 4)
+        vals, proofs = self.ctx.tree4_versioned_update(depth, np.asarray(tree_ids, dtype=np.uint32), np.asarray(indices, dtype=np.uint64),
+                                                        to_mont(leaf_values), init)
+        v = _from_mont_rows(vals)
+        p = _from_mont_rows(proofs)
+        vals_i = [v[l * n:(l + 1) * n] for l in range(depth + 1)]
+        proofs_i = [[p[(e * depth + l) * 3:(e * depth + l) * 3 + 3] for l in range(depth)] for e in range(n)]
+        return vals_i, proofs_i
+
+
+_TOKEN_DEFAULTS = {}
+
+
+def _token_defaults(T):
+    if T not in _TOKEN_DEFAULTS:
+        _TOKEN_DEFAULTS[T] = N.SparseTree4(T, N.poseidon([0, 0])).defaults
+    return _TOKEN_DEFAULTS[T]
+
+
+def update_batched(hasher, state: MpnState, txs, log4_batch, fee_token=ZIESHA):
+    """same contract as update.update(): -> (public dict, transitions, rejected); `state` is advanced."""
+    A, T = state.A, state.T
+    cap = 1 << (2 * log4_batch)
+    prev_root = state.root
+    # ------------------------------------------------------------------ phase 1: ledger logic on a mirror
+    mirror = {}                                  # account index -> MpnAccount (current value)
+    by_addr = {}
+    for i, a in state.accounts.items():
+        by_addr.setdefault(a.address, i)
+    next_free = (max(state.accounts) + 1) if state.accounts else 0
+
+    def get(i):
+        if i not in mirror:
+            mirror[i] = state.accounts.get(i, MpnAccount()).copy()
+        return mirror[i].copy()
+
+    plan, rejected, fee_sum = [], [], 0
+    for tx in txs:
+        if len(plan) == cap:
+            break
+        if tx.fee.token_id != fee_token:
+            rejected.append(tx)
+            continue
+        src_addr, dst_addr = N.jj_decompress(tx.src_pub_key), N.jj_decompress(tx.dst_pub_key)
+        src_index = by_addr.get(src_addr)
+        if src_index is None:
+            rejected.append(tx)
+            continue
+        dst_index = by_addr.get(dst_addr)
+        if dst_index is None:
+            dst_index = next_free
+        src_before, dst_before0 = get(src_index), get(dst_index)
+        sti = src_before.find_token_index(T, tx.amount.token_id, False)
+        dti = dst_before0.find_token_index(T, tx.amount.token_id, True)
+        sfi = src_before.find_token_index(T, tx.fee.token_id, False)
+        if sti is None or dti is None or sfi is None:
+            rejected.append(tx)
+            continue
+        src_token = src_before.tokens[sti]
+        dst_token0 = dst_before0.tokens.get(dti)
+        if (tx.nonce != src_before.tx_nonce + 1 or src_before.address != src_addr
+                or (N.jj_on_curve(dst_before0.address) and dst_before0.address != dst_addr)
+                or (dst_token0 is not None and src_token.token_id != dst_token0.token_id)
+                or src_token.token_id != tx.amount.token_id or src_token.amount < tx.amount.amount):
+            rejected.append(tx)
+            continue
+        src_mid = src_before.copy()
+        src_mid.tx_nonce += 1
+        src_mid.tokens[sti].amount -= tx.amount.amount
+        fee_tok = src_mid.tokens.get(sfi)
+        if fee_tok is None or fee_tok.token_id != tx.fee.token_id or fee_tok.amount < tx.fee.amount:
+            rejected.append(tx)
+            continue
+        src_fee_token = Money(fee_tok.token_id, fee_tok.amount)
+        src_after = src_mid.copy()
+        src_after.tokens[sfi].amount -= tx.fee.amount
+        mirror[src_index] = src_after.copy()
+        dst_before = get(dst_index)
+        dst_token = dst_before.tokens.get(dti)
+        dst_after = dst_before.copy()
+        dst_after.address = dst_addr
+        dst_after.tokens.setdefault(dti, Money(tx.amount.token_id, 0)).amount += tx.amount.amount
+        mirror[dst_index] = dst_after.copy()
+        by_addr.setdefault(dst_addr, dst_index)
+        if dst_index == next_free:
+            next_free += 1
+        plan.append(dict(tx=tx, src_index=src_index, dst_index=dst_index, sti=sti, sfi=sfi, dti=dti, src_before=src_before,
+                         src_mid=src_mid, src_after=src_after, dst_before=dst_before, dst_after=dst_after,
+                         src_token=Money(src_token.token_id, src_token.amount), src_fee_token=src_fee_token,
+                         dst_token=Money(dst_token.token_id, dst_token.amount) if dst_token else Money()))
+        fee_sum += tx.fee.amount
+    # ------------------------------------------------------------------ phase 2a: the token forest
+    tree_of = {}
+    for p in plan:
+        for i in (p["src_index"], p["dst_index"]):
+            tree_of.setdefault(i, len(tree_of))
+    touched = list(tree_of)
+    tdef = _token_defaults(T)
+    t_rows, t_tree, t_idx = [], [], []
+    for acc in touched:                          # the pre-batch token trees, as writes into empty trees
+        for i, m in state.accounts.get(acc, MpnAccount()).tokens.items():
+            t_rows.append([m.token_id, m.amount]); t_tree.append(tree_of[acc]); t_idx.append(i)
+    n_init = len(t_rows)
+    for p in plan:
+        t_rows.append([p["src_token"].token_id, p["src_mid"].tokens[p["sti"]].amount]); t_tree.append(tree_of[p["src_index"]]); t_idx.append(p["sti"])
+        t_rows.append([p["src_fee_token"].token_id, p["src_after"].tokens[p["sfi"]].amount]); t_tree.append(tree_of[p["src_index"]]); t_idx.append(p["sfi"])
+        t_rows.append([p["dst_after"].tokens[p["dti"]].token_id, p["dst_after"].tokens[p["dti"]].amount]); t_tree.append(tree_of[p["dst_index"]]); t_idx.append(p["dti"])
+    t_leaves = hasher.poseidon_batch(t_rows)
+    default_proof = [[tdef[l]] * 3 for l in range(T)]
+    t_vals, t_proofs = hasher.tree_update(T, t_tree, t_idx, t_leaves, [default_proof] * len(t_rows))
+    tok_root = {k: tdef[T] for k in range(len(touched))}  # current token root per tree while replaying the events
+    for e in range(n_init):
+        tok_root[t_tree[e]] = t_vals[T][e]
+    acct_rows = []
+    for k, p in enumerate(plan):
+        e1, e2, e3 = n_init + 3 * k, n_init + 3 * k + 1, n_init + 3 * k + 2
+        st, dt = tree_of[p["src_index"]], tree_of[p["dst_index"]]
+        p["src_before_balances_hash"] = tok_root[st]
+        p["src_balance_proof"], p["src_fee_balance_proof"] = t_proofs[e1], t_proofs[e2]
+        tok_root[st] = t_vals[T][e2]
+        p["dst_before_balances_hash"] = tok_root[dt]
+        p["dst_balance_proof"] = t_proofs[e3]
+        tok_root[dt] = t_vals[T][e3]
+        sm, sa, da = p["src_mid"], p["src_after"], p["dst_after"]
+        acct_rows.append([sm.tx_nonce, sm.withdraw_nonce, sm.address[0], sm.address[1], t_vals[T][e1]])
+        acct_rows.append([sa.tx_nonce, sa.withdraw_nonce, sa.address[0], sa.address[1], t_vals[T][e2]])
+        acct_rows.append([da.tx_nonce, da.withdraw_nonce, da.address[0], da.address[1], t_vals[T][e3]])
+    # ------------------------------------------------------------------ phase 2b: the state tree
+    s_leaves = hasher.poseidon_batch(acct_rows)
+    s_idx = [i for p in plan for i in (p["src_index"], p["src_index"], p["dst_index"])]
+    init = [state.tree.prove(i) for i in s_idx]
+    s_vals, s_proofs = hasher.tree_update(A, [0] * len(s_idx), s_idx, s_leaves, init)
+    transitions, root = [], prev_root
+    for k, p in enumerate(plan):
+        transitions.append(UpdateTransition(
+            True, p["tx"], p["src_before"], p["src_before_balances_hash"], p["src_token"], p["src_fee_token"],
+            s_proofs[3 * k], p["src_index"], p["sti"], p["src_balance_proof"], p["sfi"], p["src_fee_balance_proof"],
+            p["dst_before"], p["dst_before_balances_hash"], p["dst_token"], s_proofs[3 * k + 2], p["dst_index"], p["dti"],
+            p["dst_balance_proof"], root))
+        root = s_vals[A][3 * k + 2]
+    # ------------------------------------------------------------------ commit: accounts + the nodes every write left behind
+    for e, i in enumerate(s_idx):
+        node = i
+        for lvl in range(A + 1):
+            state.tree._put(lvl, node, s_vals[lvl][e])
+            node >>= 2
+    for i in touched:
+        state.accounts[i] = mirror[i].copy()
+    assert state.root == root
+    public = {"state": prev_root, "aux_data": hasher.poseidon_batch([[fee_token, fee_sum]])[0], "next_state": root}
+    return public, transitions, rejected

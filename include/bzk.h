@@ -94,6 +94,18 @@ int32_t bzk_poseidon_hash_dev(bzk_ctx *ctx, uint32_t arity, const void *d_in, si
 int32_t bzk_merkle4_build_dev(bzk_ctx *ctx, void *d_nodes, uint32_t log4_size);
 int32_t bzk_merkle4_prove_dev(bzk_ctx *ctx, const void *d_nodes, uint32_t log4_size, const void *d_indices, size_t m, void *d_proofs);
 int32_t bzk_merkle4_root_dev(bzk_ctx *ctx, uint32_t log4_size, const void *d_indices, const void *d_leaves, const void *d_proofs, size_t m, void *d_roots);
+/* Batch of `n` ordered leaf writes to a forest of sparse 4-ary Poseidon trees, one pass per level instead of
+ * one root path per write.  Replaces the transition builders' loop of `KvStoreStateManager::set_data` /
+ * `prove` calls (/root/reference/src/zk/state/mod.rs:218-264,310-420; /root/reference/src/mpn/update.rs:40-258).
+ *   d_tree_id u32[n], d_indices u64[n]: write e goes to leaf d_indices[e] of tree d_tree_id[e];
+ *   d_vals Fr[(depth+1)*n]: in: d_vals[e] = the leaf value written; out: d_vals[l*n + e] = the level-l node on
+ *     write e's path after the write (level 0 = leaf, level depth = the tree's root after write e);
+ *   d_init_proofs Fr[n][depth][3]: the Merkle proof of each written leaf in the tree BEFORE the batch
+ *     (leaf level first, siblings in ascending child order — `prove()`'s layout; read from the store, no hashing);
+ *   d_out_proofs Fr[n][depth][3]: the proof of each written leaf just before ITS write, i.e. with every earlier
+ *     write of the batch applied — what the sequential loop's `prove` calls would have returned. */
+int32_t bzk_tree4_versioned_update_dev(bzk_ctx *ctx, uint32_t depth, const void *d_tree_id, const void *d_indices, size_t n, void *d_vals,
+                                       const void *d_init_proofs, void *d_out_proofs);
 
 /* ------------------------------------------------------------------ NTT over Fr
  * Replaces bellman 0.14.0 `domain::EvaluationDomain::{fft, ifft, coset_fft, icoset_fft,

@@ -216,3 +216,62 @@ def test_witness_program_reproduces_synthesised_witness():
     # chaining: the state root leaving slot k enters slot k+1
     for k in range(n - 1):
         assert cs.aux[prog.p_aux + k * a_tx + prog.state_out] == roots[k + 1]
+
+
+def _assert_same_transitions(t1, t2):
+    import dataclasses
+    assert len(t1) == len(t2)
+    for a, b in zip(t1, t2):
+        da, db = dataclasses.asdict(a), dataclasses.asdict(b)
+        for k in da:
+            assert da[k] == db[k], k
+
+
+def _batch_scenario():
+    """transfers incl. a new account, a self-referencing chain, same-token fee, and rejected ones
+    (bad nonce, unknown sender, overdraft, wrong fee token)."""
+    st, keys = make_state(3, 3, 3)
+    keys.append(N.eddsa_keys(b"newcomer"))
+    keys.append(N.eddsa_keys(b"stranger"))
+    txs = [transfer(keys, 0, 1, 1), transfer(keys, 1, 2, 1, amount=5), transfer(keys, 0, 3, 2, amount=77, fee=3),
+           transfer(keys, 0, 1, 9),                     # bad nonce
+           transfer(keys, 4, 1, 1),                     # unknown sender
+           transfer(keys, 2, 0, 1, amount=10 ** 13),    # overdraft
+           transfer(keys, 3, 0, 1, amount=50, fee=2),   # the newcomer spends what it just received
+           transfer(keys, 1, 1, 2, amount=7),           # to itself
+           transfer(keys, 2, 3, 1, amount=1, fee=1)]
+    bad_fee = transfer(keys, 0, 2, 3)
+    bad_fee.fee = U.Money(7, 1)
+    bad_fee.sign(keys[0][1])
+    txs.insert(4, bad_fee)
+    return st, txs
+
+
+def test_batched_transition_builder_equals_sequential_update():
+    """update_batched (ledger logic first, then hashing in batches through the versioned tree update) returns
+    exactly update()'s transitions, public inputs, rejections and final state — here with the host stand-in
+    for the GPU primitives, which applies the writes one by one like the reference's set_data/prove loop."""
+    import copy
+    from bazuka_b200.mpn import batch_update as BU
+    from oracle.py.state import HostTreeHasher
+    st1, txs = _batch_scenario()
+    st2 = copy.deepcopy(st1)
+    pub1, tr1, rej1 = U.update(st1, txs, 2)
+    pub2, tr2, rej2 = BU.update_batched(HostTreeHasher(N.poseidon), st2, txs, 2)
+    assert len(tr1) == 6 and len(rej1) == 4
+    assert pub1 == pub2 and rej1 == rej2
+    _assert_same_transitions(tr1, tr2)
+    assert st1.root == st2.root and st1.tree.levels == st2.tree.levels
+    assert {i: dataclasses_asdict(a) for i, a in st1.accounts.items()} == {i: dataclasses_asdict(a) for i, a in st2.accounts.items()}
+    # the batch cap: only 4^B transactions are taken
+    st3, txs3 = _batch_scenario()
+    st4 = copy.deepcopy(st3)
+    p3, t3, r3 = U.update(st3, txs3, 0)
+    p4, t4, r4 = BU.update_batched(HostTreeHasher(N.poseidon), st4, txs3, 0)
+    assert len(t3) == 1 and p3 == p4 and r3 == r4 and st3.root == st4.root
+    _assert_same_transitions(t3, t4)
+
+
+def dataclasses_asdict(a):
+    import dataclasses
+    return dataclasses.asdict(a)

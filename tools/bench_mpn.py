@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """MPN update proofs on the GPU: real UpdateCircuit instances (signed transfers on a Poseidon state),
 prints one JSON line per shape with constraint count, witness/CSR build time (host, Python) and the
-GPU proving time.  usage: bench_mpn.py [--host-witness] A,T,B[,ntx] ...
+GPU proving time.  usage: bench_mpn.py [--host-witness] [--host-builder] A,T,B[,ntx] ...
 Batches of >= 16 slots take the witness from the GPU (csrc/witness.cu via mpn/gpu_witness.py; R1CS from one
 synthesised slot); --host-witness selects the worker-process synthesiser instead."""
 import json, os, sys, time
@@ -16,6 +16,7 @@ def main():
     ctx = B.Context(0)
     argv = [a for a in sys.argv[1:] if not a.startswith("--")]
     host_witness = "--host-witness" in sys.argv
+    host_builder = "--host-builder" in sys.argv
     shapes = [tuple(int(v) for v in a.split(",")) for a in (argv or ["3,3,1", "15,3,0", "15,3,1"])]
     for shp in shapes:
         A, T, Bb = shp[:3]
@@ -33,7 +34,14 @@ def main():
             nonces[s] += 1
             tx = U.MpnTransaction(nonces[s], N.jj_compress(keys[s][0]), N.jj_compress(keys[d][0]), U.Money(U.ZIESHA, 1000 + k), U.Money(U.ZIESHA, 10))
             tx.sign(keys[s][1]); txs.append(tx)
-        pub, trans, rej = U.update(st, txs, Bb)
+        t_sign = time.time() - t0
+        t0 = time.time()
+        if host_builder or ntx < 16:
+            pub, trans, rej = U.update(st, txs, Bb)
+        else:
+            # batched transition builder: ledger logic on the host, all hashing in ~20 GPU launches
+            from bazuka_b200.mpn import batch_update as BU
+            pub, trans, rej = BU.update_batched(BU.GpuTreeHasher(ctx), st, txs, Bb)
         t_build = time.time() - t0
         t0 = time.time()
         circ = U.UpdateCircuit(A, T, Bb, commitment=1, height=0, transitions=trans, **pub)
@@ -85,7 +93,8 @@ def main():
             t0 = time.perf_counter(); b2, _ = prove(False); ts.append(time.perf_counter() - t0)
         assert (b2 == blob).all()
         print(json.dumps({"circuit": "UpdateCircuit", "A": A, "T": T, "B": Bb, "tx_slots": 1 << (2 * Bb), "accepted": len(trans), "constraints": ncons,
-                          "log_m": pr.log_m, "aux": na, "witness_0_1_fraction": round(ones, 3), "transition_build_s": round(t_build, 2),
+                          "log_m": pr.log_m, "aux": na, "witness_0_1_fraction": round(ones, 3), "ledger_setup_and_signing_s": round(t_sign, 2), "transition_builder": "host sequential" if (host_builder or ntx < 16) else "gpu batched",
+                          "transition_build_s": round(t_build, 3),
                           "synthesize_s": round(t_syn, 2), "witness": "gpu" if d_wit is not None else "host",
                           "gpu_witness_s": None if t_wit is None else round(t_wit, 3), "gpu_setup_s": round(t_setup, 2), "prove_ms_best": round(min(ts) * 1e3, 2),
                           "proofs_per_s": round(1 / min(ts), 2), "tx_per_s": round(len(trans) / min(ts), 1)}), flush=True)
