@@ -18,7 +18,7 @@
 namespace bzk {
 
 enum : int32_t { W_RAW = 0, W_MUL, W_BIT, W_ISZERO, W_INVZ, W_SELECT, W_JJ, W_NOP };
-constexpr int kSlotOne = 0, kSlotFeeToken = 1, kSlotStateIn = 2, kSlotBlock0 = 3;
+constexpr int kSlotOne = 0;  // then n_ext external slots, then the block's own variables
 
 struct WitProgDev {
     const int32_t *ops;      // [n_ops][6]
@@ -26,7 +26,7 @@ struct WitProgDev {
     const int32_t *lc_slot;  // [n_terms]
     const int32_t *lc_coef;  // [n_terms], 0 = coefficient one
     const Fr *coefs;         // Montgomery
-    uint32_t n_ops, n_raw;
+    uint32_t n_ops, n_raw, n_ext;
 };
 
 __device__ __forceinline__ Fr ld_fr(const Fr *p) {
@@ -56,13 +56,13 @@ __device__ __forceinline__ bool jj_on_curve(const Fr &x, const Fr &y, const Fr &
     return (y2 - x2) == (Fr::one() + d * x2 * y2);
 }
 
-__global__ void __launch_bounds__(32) k_witness_run(WitProgDev P, Fr jj_d, const Fr *__restrict__ raws, Fr fee_token,
-                                                    const Fr *__restrict__ state_in, uint32_t ntx, Fr *V, Fr *__restrict__ aux_out) {
+__global__ void __launch_bounds__(32) k_witness_run(WitProgDev P, Fr jj_d, const Fr *__restrict__ raws, const Fr *__restrict__ ext,
+                                                    uint32_t ntx, Fr *V, Fr *__restrict__ aux_out) {
     const uint32_t tx = blockIdx.x * blockDim.x + threadIdx.x;
     if (tx >= ntx) return;
+    const uint32_t kSlotBlock0 = 1 + P.n_ext;
     store_vec(V + (size_t)kSlotOne * ntx + tx, Fr::one());
-    store_vec(V + (size_t)kSlotFeeToken * ntx + tx, fee_token.to_mont());
-    store_vec(V + (size_t)kSlotStateIn * ntx + tx, load_vec(state_in + tx).to_mont());
+    for (uint32_t k = 0; k < P.n_ext; k++) store_vec(V + (size_t)(1 + k) * ntx + tx, load_vec(ext + (size_t)tx * P.n_ext + k).to_mont());
     for (uint32_t j = 0; j < P.n_ops; j++) {
         const int32_t *op = P.ops + (size_t)j * 6;
         const int32_t code = __ldg(op), a0 = __ldg(op + 1), a1 = __ldg(op + 2), a2 = __ldg(op + 3), a3 = __ldg(op + 4), imm = __ldg(op + 5);
@@ -134,9 +134,10 @@ extern "C" {
 
 int32_t bzk_witness_program_upload(bzk_ctx *ctx, const int32_t *ops, uint64_t n_ops, const int32_t *lc_ptr, uint64_t n_lc,
                                    const int32_t *lc_slot, const int32_t *lc_coef, uint64_t n_terms, const bzk_fr *coefs,
-                                   uint64_t n_coefs, uint32_t n_raw, const bzk_fr *jj_d, bzk_witness_program **out) {
+                                   uint64_t n_coefs, uint32_t n_raw, uint32_t n_ext, const bzk_fr *jj_d, bzk_witness_program **out) {
     if (!ctx || !ops || !lc_ptr || !coefs || !jj_d || !out || !n_ops || !n_coefs || (n_terms && (!lc_slot || !lc_coef))) return BZK_ERR_BAD_ARG;
     // validate on the host: the device interpreter trusts the program
+    const uint64_t kSlotBlock0 = 1 + (uint64_t)n_ext;
     for (uint64_t j = 0; j < n_ops; j++) {
         const int32_t *op = ops + j * 6;
         if (op[0] < W_RAW || op[0] > W_NOP) return BZK_ERR_BAD_ARG;
@@ -175,7 +176,7 @@ int32_t bzk_witness_program_upload(bzk_ctx *ctx, const int32_t *ops, uint64_t n_
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_coefs, coefs, n_coefs * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { cudaFree(p->blob); delete p; BZK_CUDA(ctx, e); }
-    p->d = WitProgDev{d_ops, d_ptr, d_slot, d_coef, d_coefs, (uint32_t)n_ops, n_raw};
+    p->d = WitProgDev{d_ops, d_ptr, d_slot, d_coef, d_coefs, (uint32_t)n_ops, n_raw, n_ext};
     memcpy(&p->jj_d, jj_d, sizeof(Fr));
     p->n_lc = n_lc; p->n_terms = n_terms; p->n_coefs = n_coefs;
     *out = p;
@@ -190,25 +191,22 @@ int32_t bzk_witness_program_free(bzk_ctx *ctx, bzk_witness_program *p) {
     return BZK_OK;
 }
 
-int32_t bzk_witness_run_dev(bzk_ctx *ctx, const bzk_witness_program *p, const bzk_fr *raws, const bzk_fr *fee_token,
-                            const bzk_fr *state_in, uint64_t ntx, void *d_aux_out) {
-    if (!ctx || !p || !raws || !fee_token || !state_in || !d_aux_out || !ntx || ntx > (1u << 24)) return BZK_ERR_BAD_ARG;
+int32_t bzk_witness_run_dev(bzk_ctx *ctx, const bzk_witness_program *p, const bzk_fr *raws, const bzk_fr *ext, uint64_t ntx, void *d_aux_out) {
+    if (!ctx || !p || (p->d.n_raw && !raws) || (p->d.n_ext && !ext) || !d_aux_out || !ntx || ntx > (1u << 24)) return BZK_ERR_BAD_ARG;
     BZK_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t n_slots = (size_t)kSlotBlock0 + p->d.n_ops;
+    const size_t n_slots = (size_t)1 + p->d.n_ext + p->d.n_ops;
     size_t need;
     {
         Carver cv(nullptr);
-        cv.take<Fr>(n_slots * ntx); cv.take<Fr>((size_t)p->d.n_raw * ntx); cv.take<Fr>(ntx);
+        cv.take<Fr>(n_slots * ntx); cv.take<Fr>((size_t)p->d.n_raw * ntx + 1); cv.take<Fr>((size_t)p->d.n_ext * ntx + 1);
         need = cv.used();
     }
     BZK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, need));
     Carver cv(ctx->ws);
-    Fr *V = cv.take<Fr>(n_slots * ntx), *d_raws = cv.take<Fr>((size_t)p->d.n_raw * ntx), *d_state = cv.take<Fr>(ntx);
-    BZK_CUDA(ctx, cudaMemcpyAsync(d_raws, raws, (size_t)p->d.n_raw * ntx * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-    BZK_CUDA(ctx, cudaMemcpyAsync(d_state, state_in, ntx * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-    Fr fee;
-    memcpy(&fee, fee_token, sizeof(Fr));
-    k_witness_run<<<(unsigned)div_up(ntx, 32), 32, 0, ctx->stream>>>(p->d, p->jj_d, d_raws, fee, d_state, (uint32_t)ntx, V, (Fr *)d_aux_out);
+    Fr *V = cv.take<Fr>(n_slots * ntx), *d_raws = cv.take<Fr>((size_t)p->d.n_raw * ntx + 1), *d_ext = cv.take<Fr>((size_t)p->d.n_ext * ntx + 1);
+    if (p->d.n_raw) BZK_CUDA(ctx, cudaMemcpyAsync(d_raws, raws, (size_t)p->d.n_raw * ntx * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    if (p->d.n_ext) BZK_CUDA(ctx, cudaMemcpyAsync(d_ext, ext, (size_t)p->d.n_ext * ntx * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    k_witness_run<<<(unsigned)div_up(ntx, 32), 32, 0, ctx->stream>>>(p->d, p->jj_d, d_raws, d_ext, (uint32_t)ntx, V, (Fr *)d_aux_out);
     BZK_LAUNCHED(ctx);
     BZK_CUDA(ctx, cudaGetLastError());
     // the host buffers may be pageable: the copies above are complete for the caller only after this

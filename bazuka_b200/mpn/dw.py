@@ -64,6 +64,7 @@ class DepositTransition:
     account_index: int
     token_index: int
     balance_proof: list
+    pre_root: int = 0   # state root before this transition (bookkeeping for the GPU witness path)
 
     @staticmethod
     def null(A, T):
@@ -88,13 +89,14 @@ def deposit(state: MpnState, deposits, log4_batch):
         if ti is None or (N.jj_on_curve(before.address) and before.address != addr):
             continue
         proof, bproof = state.prove(idx), state.prove_token(idx, ti)
+        pre_root = state.root
         bal = before.tokens.get(ti)
         after = before.copy()
         after.address = addr
         after.tokens.setdefault(ti, Money(d.token_id, 0)).amount += d.amount
         state.set(idx, after)
         trans.append(DepositTransition(True, d, before, before.tokens_tree(state.T).root,
-                                       Money(bal.token_id, bal.amount) if bal else Money(), proof, idx, ti, bproof))
+                                       Money(bal.token_id, bal.amount) if bal else Money(), proof, idx, ti, bproof, pre_root))
     rows = []
     for k in range(n):
         if k < len(trans):
@@ -120,45 +122,58 @@ class DepositCircuit:
         state_wit, aux_wit, claimed = _public_inputs(cs, self)
         wits, rows = [], []
         for tr in self.transitions:
-            enabled = AllocatedBit.alloc(cs, tr.enabled)
-            token_id = AllocatedNum.alloc(cs, tr.tx.token_id)
-            amount = UnsignedInteger.alloc_64(cs, tr.tx.amount)
-            pub_key = G.AllocatedPoint.alloc(cs, N.jj_decompress(tr.tx.mpn_address))
-            wits.append((Boolean.is_(enabled), token_id, amount, pub_key))
-            pk_hash = G.poseidon(cs, [num(pub_key.x), num(pub_key.y)])
-            calldata = G.mux(cs, Boolean.is_(enabled), Number.zero(), pk_hash)
-            rows.append([num(enabled), num(token_id), num(amount), num(calldata)])
+            w, row = self._phase1(cs, tr)
+            wits.append(w)
+            rows.append(row)
         tx_root = reveal_list_of_structs(cs, self.B, rows)
         cs.enforce(LC({aux_wit.var: 1}), LC({ONE: 1}), tx_root.lc)
-        for tr, (enabled, tx_token_id, tx_amount, tx_pub_key) in zip(self.transitions, wits):
-            tx_index = UnsignedInteger.alloc(cs, tr.account_index, 2 * A)
-            tx_token_index = UnsignedInteger.alloc(cs, tr.token_index, 2 * T)
-            tx_pub_key.assert_on_curve(cs, enabled)
-            src_tx_nonce = AllocatedNum.alloc(cs, tr.before.tx_nonce)
-            src_withdraw_nonce = AllocatedNum.alloc(cs, tr.before.withdraw_nonce)
-            src_addr = G.AllocatedPoint.alloc(cs, tr.before.address)
-            src_balances_hash = AllocatedNum.alloc(cs, tr.before_balances_hash)
-            src_token_id = AllocatedNum.alloc(cs, tr.before_balance.token_id)
-            src_balance = AllocatedNum.alloc(cs, tr.before_balance.amount)
-            src_token_balance_hash = G.poseidon(cs, [num(src_token_id), num(src_balance)])
-            bproof = G.alloc_proof(cs, tr.balance_proof)
-            G.check_proof_poseidon4(cs, enabled, tx_token_index, src_token_balance_hash, bproof, num(src_balances_hash))
-            src_hash = G.poseidon(cs, [num(src_tx_nonce), num(src_withdraw_nonce), num(src_addr.x), num(src_addr.y), num(src_balances_hash)])
-            proof = G.alloc_proof(cs, tr.proof)
-            is_null_tok = num(src_token_id).is_zero(cs)
-            is_eq_tok = num(src_token_id).is_equal(cs, num(tx_token_id))
-            G.assert_true(cs, G.boolean_or(cs, is_null_tok, is_eq_tok))
-            is_null_addr = src_addr.is_null(cs)
-            is_eq_addr = src_addr.is_equal(cs, tx_pub_key)
-            G.assert_true(cs, G.boolean_or(cs, is_null_addr, is_eq_addr))
-            G.check_proof_poseidon4(cs, enabled, tx_index, src_hash, proof, num(state_wit))
-            new_bal_hash = G.poseidon(cs, [num(tx_token_id), num(src_balance) + num(tx_amount)])
-            new_balances_hash = G.calc_root_poseidon4(cs, tx_token_index, new_bal_hash, bproof)
-            new_hash = G.poseidon(cs, [num(src_tx_nonce), num(src_withdraw_nonce), num(tx_pub_key.x), num(tx_pub_key.y), new_balances_hash])
-            next_state = G.calc_root_poseidon4(cs, tx_index, new_hash, proof)
-            state_wit = G.mux(cs, enabled, num(state_wit), next_state)
+        for tr, w in zip(self.transitions, wits):
+            state_wit = self._phase2(cs, tr, w, state_wit)
         cs.enforce(LC({state_wit.var: 1}), LC({ONE: 1}), LC({claimed.var: 1}))
         return cs
+
+    def _phase1(self, cs, tr):
+        """the slot's transaction fields and its row of the revealed batch (deposit_circuit.rs, first loop)"""
+        num = Number.of
+        enabled = AllocatedBit.alloc(cs, tr.enabled)
+        token_id = AllocatedNum.alloc(cs, tr.tx.token_id)
+        amount = UnsignedInteger.alloc_64(cs, tr.tx.amount)
+        pub_key = G.AllocatedPoint.alloc(cs, N.jj_decompress(tr.tx.mpn_address))
+        pk_hash = G.poseidon(cs, [num(pub_key.x), num(pub_key.y)])
+        calldata = G.mux(cs, Boolean.is_(enabled), Number.zero(), pk_hash)
+        return (Boolean.is_(enabled), token_id, amount, pub_key), [num(enabled), num(token_id), num(amount), num(calldata)]
+
+    def _phase2(self, cs, tr, wits, state_wit):
+        """the slot's state transition (deposit_circuit.rs, second loop); returns the new state variable"""
+        A, T = self.A, self.T
+        num = Number.of
+        enabled, tx_token_id, tx_amount, tx_pub_key = wits
+        tx_index = UnsignedInteger.alloc(cs, tr.account_index, 2 * A)
+        tx_token_index = UnsignedInteger.alloc(cs, tr.token_index, 2 * T)
+        tx_pub_key.assert_on_curve(cs, enabled)
+        src_tx_nonce = AllocatedNum.alloc(cs, tr.before.tx_nonce)
+        src_withdraw_nonce = AllocatedNum.alloc(cs, tr.before.withdraw_nonce)
+        src_addr = G.AllocatedPoint.alloc(cs, tr.before.address)
+        src_balances_hash = AllocatedNum.alloc(cs, tr.before_balances_hash)
+        src_token_id = AllocatedNum.alloc(cs, tr.before_balance.token_id)
+        src_balance = AllocatedNum.alloc(cs, tr.before_balance.amount)
+        src_token_balance_hash = G.poseidon(cs, [num(src_token_id), num(src_balance)])
+        bproof = G.alloc_proof(cs, tr.balance_proof)
+        G.check_proof_poseidon4(cs, enabled, tx_token_index, src_token_balance_hash, bproof, num(src_balances_hash))
+        src_hash = G.poseidon(cs, [num(src_tx_nonce), num(src_withdraw_nonce), num(src_addr.x), num(src_addr.y), num(src_balances_hash)])
+        proof = G.alloc_proof(cs, tr.proof)
+        is_null_tok = num(src_token_id).is_zero(cs)
+        is_eq_tok = num(src_token_id).is_equal(cs, num(tx_token_id))
+        G.assert_true(cs, G.boolean_or(cs, is_null_tok, is_eq_tok))
+        is_null_addr = src_addr.is_null(cs)
+        is_eq_addr = src_addr.is_equal(cs, tx_pub_key)
+        G.assert_true(cs, G.boolean_or(cs, is_null_addr, is_eq_addr))
+        G.check_proof_poseidon4(cs, enabled, tx_index, src_hash, proof, num(state_wit))
+        new_bal_hash = G.poseidon(cs, [num(tx_token_id), num(src_balance) + num(tx_amount)])
+        new_balances_hash = G.calc_root_poseidon4(cs, tx_token_index, new_bal_hash, bproof)
+        new_hash = G.poseidon(cs, [num(src_tx_nonce), num(src_withdraw_nonce), num(tx_pub_key.x), num(tx_pub_key.y), new_balances_hash])
+        next_state = G.calc_root_poseidon4(cs, tx_index, new_hash, proof)
+        return G.mux(cs, enabled, num(state_wit), next_state)
 
 
 # ---------------------------------------------------------------- withdraw
@@ -192,6 +207,7 @@ class WithdrawTransition:
     before_token_hash: int
     fee_token_index: int
     fee_balance_proof: list
+    pre_root: int = 0   # state root before this transition (bookkeeping for the GPU witness path)
 
     @staticmethod
     def null(A, T):
@@ -217,6 +233,7 @@ def withdraw(state: MpnState, withdraws, log4_batch):
         if before.tokens[ti].amount < w.amount.amount or not N.eddsa_verify(addr, w.message(), w.mpn_sig):
             continue
         proof, tproof = state.prove(idx), state.prove_token(idx, ti)
+        pre_root = state.root
         tok = before.tokens[ti]
         after = before.copy()
         after.tokens[ti].amount -= w.amount.amount
@@ -231,7 +248,7 @@ def withdraw(state: MpnState, withdraws, log4_batch):
         after.withdraw_nonce += 1
         state.set(idx, after)
         trans.append(WithdrawTransition(True, w, before, Money(tok.token_id, tok.amount), fee_before, proof, idx, ti, tproof,
-                                        before.tokens_tree(state.T).root, fi, fproof))
+                                        before.tokens_tree(state.T).root, fi, fproof, pre_root))
     rows = []
     for k in range(n):
         if k < len(trans):
@@ -258,57 +275,69 @@ class WithdrawCircuit:
         state_wit, aux_wit, claimed = _public_inputs(cs, self)
         wits, rows = [], []
         for tr in self.transitions:
-            enabled = AllocatedBit.alloc(cs, tr.enabled)
-            amount_token_id = AllocatedNum.alloc(cs, tr.tx.amount.token_id)
-            amount = UnsignedInteger.alloc_64(cs, tr.tx.amount.amount)
-            fee_token_id = AllocatedNum.alloc(cs, tr.tx.fee.token_id)
-            fee = UnsignedInteger.alloc_64(cs, tr.tx.fee.amount)
-            fingerprint = AllocatedNum.alloc(cs, tr.tx.fingerprint if tr.enabled else 0)
-            pub_key = G.AllocatedPoint.alloc(cs, N.jj_decompress(tr.tx.mpn_address))
-            nonce = AllocatedNum.alloc(cs, tr.tx.mpn_withdraw_nonce)
-            sig_r = G.AllocatedPoint.alloc(cs, tr.tx.mpn_sig["r"])
-            sig_s = AllocatedNum.alloc(cs, tr.tx.mpn_sig["s"])
-            wits.append((Boolean.is_(enabled), amount_token_id, amount, fee_token_id, fee, fingerprint, pub_key, nonce, sig_r, sig_s))
-            cd_hash = G.poseidon(cs, [num(pub_key.x), num(pub_key.y), num(nonce), num(sig_r.x), num(sig_r.y), num(sig_s)])
-            calldata = G.mux(cs, Boolean.is_(enabled), Number.zero(), cd_hash)
-            rows.append([num(enabled), num(amount_token_id), num(amount), num(fee_token_id), num(fee), num(fingerprint), num(calldata)])
+            w, row = self._phase1(cs, tr)
+            wits.append(w)
+            rows.append(row)
         tx_root = reveal_list_of_structs(cs, self.B, rows)
         cs.enforce(LC({aux_wit.var: 1}), LC({ONE: 1}), tx_root.lc)
-        for tr, (enabled, tx_amount_token_id, tx_amount, tx_fee_token_id, tx_fee, fingerprint, tx_pub_key, tx_nonce, tx_sig_r, tx_sig_s) in zip(self.transitions, wits):
-            tx_index = UnsignedInteger.alloc(cs, tr.account_index, 2 * A)
-            tx_token_index = UnsignedInteger.alloc(cs, tr.token_index, 2 * T)
-            tx_fee_token_index = UnsignedInteger.alloc(cs, tr.fee_token_index, 2 * T)
-            tx_pub_key.assert_on_curve(cs, enabled)
-            tx_hash = G.poseidon(cs, [num(fingerprint), num(tx_nonce)])
-            tx_sig_r.assert_on_curve(cs, enabled)
-            G.verify_eddsa(cs, enabled, tx_pub_key, tx_hash, tx_sig_r, tx_sig_s)
-            src_tx_nonce = AllocatedNum.alloc(cs, tr.before.tx_nonce)
-            src_withdraw_nonce = AllocatedNum.alloc(cs, tr.before.withdraw_nonce)
-            src_addr = G.AllocatedPoint.alloc(cs, tr.before.address)
-            src_addr.assert_on_curve(cs, enabled)
-            before_token_hash = AllocatedNum.alloc(cs, tr.before_token_hash)
-            src_token_id = AllocatedNum.alloc(cs, tr.before_token_balance.token_id)
-            num(src_token_id).assert_equal(cs, num(tx_amount_token_id))
-            src_balance = AllocatedNum.alloc(cs, tr.before_token_balance.amount)
-            src_token_balance_hash = G.poseidon(cs, [num(src_token_id), num(src_balance)])
-            tproof = G.alloc_proof(cs, tr.token_balance_proof)
-            G.check_proof_poseidon4(cs, enabled, tx_token_index, src_token_balance_hash, tproof, num(before_token_hash))
-            new_token_balance_hash = G.poseidon(cs, [num(src_token_id), num(src_balance) - num(tx_amount)])
-            balance_middle_root = G.calc_root_poseidon4(cs, tx_token_index, new_token_balance_hash, tproof)
-            src_fee_token_id = AllocatedNum.alloc(cs, tr.before_fee_balance.token_id)
-            num(src_fee_token_id).assert_equal(cs, num(tx_fee_token_id))
-            src_fee_balance = AllocatedNum.alloc(cs, tr.before_fee_balance.amount)
-            src_fee_token_balance_hash = G.poseidon(cs, [num(src_fee_token_id), num(src_fee_balance)])
-            fproof = G.alloc_proof(cs, tr.fee_balance_proof)
-            G.check_proof_poseidon4(cs, enabled, tx_fee_token_index, src_fee_token_balance_hash, fproof, balance_middle_root)
-            new_fee_token_balance_hash = G.poseidon(cs, [num(src_fee_token_id), num(src_fee_balance) - num(tx_fee)])
-            src_hash = G.poseidon(cs, [num(src_tx_nonce), num(src_withdraw_nonce), num(src_addr.x), num(src_addr.y), num(before_token_hash)])
-            proof = G.alloc_proof(cs, tr.proof)
-            G.check_proof_poseidon4(cs, enabled, tx_index, src_hash, proof, num(state_wit))
-            num(tx_nonce).assert_equal_if_enabled(cs, enabled, num(src_withdraw_nonce) + Number.constant(1))
-            balance_final_root = G.calc_root_poseidon4(cs, tx_fee_token_index, new_fee_token_balance_hash, fproof)
-            new_hash = G.poseidon(cs, [num(src_tx_nonce), num(src_withdraw_nonce) + Number.constant(1), num(tx_pub_key.x), num(tx_pub_key.y), balance_final_root])
-            next_state = G.calc_root_poseidon4(cs, tx_index, new_hash, proof)
-            state_wit = G.mux(cs, enabled, num(state_wit), next_state)
+        for tr, w in zip(self.transitions, wits):
+            state_wit = self._phase2(cs, tr, w, state_wit)
         cs.enforce(LC({state_wit.var: 1}), LC({ONE: 1}), LC({claimed.var: 1}))
         return cs
+
+    def _phase1(self, cs, tr):
+        num = Number.of
+        enabled = AllocatedBit.alloc(cs, tr.enabled)
+        amount_token_id = AllocatedNum.alloc(cs, tr.tx.amount.token_id)
+        amount = UnsignedInteger.alloc_64(cs, tr.tx.amount.amount)
+        fee_token_id = AllocatedNum.alloc(cs, tr.tx.fee.token_id)
+        fee = UnsignedInteger.alloc_64(cs, tr.tx.fee.amount)
+        fingerprint = AllocatedNum.alloc(cs, tr.tx.fingerprint if tr.enabled else 0)
+        pub_key = G.AllocatedPoint.alloc(cs, N.jj_decompress(tr.tx.mpn_address))
+        nonce = AllocatedNum.alloc(cs, tr.tx.mpn_withdraw_nonce)
+        sig_r = G.AllocatedPoint.alloc(cs, tr.tx.mpn_sig["r"])
+        sig_s = AllocatedNum.alloc(cs, tr.tx.mpn_sig["s"])
+        cd_hash = G.poseidon(cs, [num(pub_key.x), num(pub_key.y), num(nonce), num(sig_r.x), num(sig_r.y), num(sig_s)])
+        calldata = G.mux(cs, Boolean.is_(enabled), Number.zero(), cd_hash)
+        return ((Boolean.is_(enabled), amount_token_id, amount, fee_token_id, fee, fingerprint, pub_key, nonce, sig_r, sig_s),
+                [num(enabled), num(amount_token_id), num(amount), num(fee_token_id), num(fee), num(fingerprint), num(calldata)])
+
+    def _phase2(self, cs, tr, wits, state_wit):
+        A, T = self.A, self.T
+        num = Number.of
+        enabled, tx_amount_token_id, tx_amount, tx_fee_token_id, tx_fee, fingerprint, tx_pub_key, tx_nonce, tx_sig_r, tx_sig_s = wits
+        tx_index = UnsignedInteger.alloc(cs, tr.account_index, 2 * A)
+        tx_token_index = UnsignedInteger.alloc(cs, tr.token_index, 2 * T)
+        tx_fee_token_index = UnsignedInteger.alloc(cs, tr.fee_token_index, 2 * T)
+        tx_pub_key.assert_on_curve(cs, enabled)
+        tx_hash = G.poseidon(cs, [num(fingerprint), num(tx_nonce)])
+        tx_sig_r.assert_on_curve(cs, enabled)
+        G.verify_eddsa(cs, enabled, tx_pub_key, tx_hash, tx_sig_r, tx_sig_s)
+        src_tx_nonce = AllocatedNum.alloc(cs, tr.before.tx_nonce)
+        src_withdraw_nonce = AllocatedNum.alloc(cs, tr.before.withdraw_nonce)
+        src_addr = G.AllocatedPoint.alloc(cs, tr.before.address)
+        src_addr.assert_on_curve(cs, enabled)
+        before_token_hash = AllocatedNum.alloc(cs, tr.before_token_hash)
+        src_token_id = AllocatedNum.alloc(cs, tr.before_token_balance.token_id)
+        num(src_token_id).assert_equal(cs, num(tx_amount_token_id))
+        src_balance = AllocatedNum.alloc(cs, tr.before_token_balance.amount)
+        src_token_balance_hash = G.poseidon(cs, [num(src_token_id), num(src_balance)])
+        tproof = G.alloc_proof(cs, tr.token_balance_proof)
+        G.check_proof_poseidon4(cs, enabled, tx_token_index, src_token_balance_hash, tproof, num(before_token_hash))
+        new_token_balance_hash = G.poseidon(cs, [num(src_token_id), num(src_balance) - num(tx_amount)])
+        balance_middle_root = G.calc_root_poseidon4(cs, tx_token_index, new_token_balance_hash, tproof)
+        src_fee_token_id = AllocatedNum.alloc(cs, tr.before_fee_balance.token_id)
+        num(src_fee_token_id).assert_equal(cs, num(tx_fee_token_id))
+        src_fee_balance = AllocatedNum.alloc(cs, tr.before_fee_balance.amount)
+        src_fee_token_balance_hash = G.poseidon(cs, [num(src_fee_token_id), num(src_fee_balance)])
+        fproof = G.alloc_proof(cs, tr.fee_balance_proof)
+        G.check_proof_poseidon4(cs, enabled, tx_fee_token_index, src_fee_token_balance_hash, fproof, balance_middle_root)
+        new_fee_token_balance_hash = G.poseidon(cs, [num(src_fee_token_id), num(src_fee_balance) - num(tx_fee)])
+        src_hash = G.poseidon(cs, [num(src_tx_nonce), num(src_withdraw_nonce), num(src_addr.x), num(src_addr.y), num(before_token_hash)])
+        proof = G.alloc_proof(cs, tr.proof)
+        G.check_proof_poseidon4(cs, enabled, tx_index, src_hash, proof, num(state_wit))
+        num(tx_nonce).assert_equal_if_enabled(cs, enabled, num(src_withdraw_nonce) + Number.constant(1))
+        balance_final_root = G.calc_root_poseidon4(cs, tx_fee_token_index, new_fee_token_balance_hash, fproof)
+        new_hash = G.poseidon(cs, [num(src_tx_nonce), num(src_withdraw_nonce) + Number.constant(1), num(tx_pub_key.x), num(tx_pub_key.y), balance_final_root])
+        next_state = G.calc_root_poseidon4(cs, tx_index, new_hash, proof)
+        return G.mux(cs, enabled, num(state_wit), next_state)

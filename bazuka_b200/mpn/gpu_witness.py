@@ -35,7 +35,7 @@ class UpdateWitnessGpu:
         h = ct.c_void_p()
         ctx._check(ctx._l.bzk_witness_program_upload(
             ctx._h, _host_ptr(ops), len(ops), _host_ptr(p.lc_ptr), len(p.lc_ptr) - 1, _host_ptr(p.lc_slot), _host_ptr(p.lc_coef),
-            len(p.lc_slot), _host_ptr(coefs), len(coefs), p.n_raw, _host_ptr(jj_d), ct.byref(h)))
+            len(p.lc_slot), _host_ptr(coefs), len(coefs), p.n_raw, p.n_ext, _host_ptr(jj_d), ct.byref(h)))
         self._h = h
 
     def free(self):
@@ -56,8 +56,7 @@ class UpdateWitnessGpu:
         assert len(cs.aux) == p.p_aux
         # ---- slots on the device
         raws = np.concatenate([_canon_rows(W.raw_values(tr, self.A, self.T)) for tr in circ.transitions])
-        roots = _canon_rows(W.slot_roots(circ))
-        fee = _canon_rows([circ.fee_token])
+        ext = _canon_rows([v for root in W.slot_roots(circ) for v in (circ.fee_token, root)])
         # epilogue size is value-independent: synthesise it once with placeholders to learn it
         probe = ConstraintSystem()
         circ._epilogue(probe, AllocatedNum(probe.alloc(0), 0), AllocatedNum(probe.alloc(0), 0), AllocatedNum(probe.alloc(0), 0),
@@ -67,7 +66,7 @@ class UpdateWitnessGpu:
         dev = torch.device("cuda", ctx.device) if hasattr(ctx, "device") else torch.device("cuda")
         d_aux = torch.empty((na, 4), dtype=torch.int64, device=dev)
         block = d_aux[p.p_aux:p.p_aux + n * a_tx]
-        ctx._check(ctx._l.bzk_witness_run_dev(ctx._h, self._h, _host_ptr(raws), _host_ptr(fee), _host_ptr(roots), n, _dev_ptr(block)))
+        ctx._check(ctx._l.bzk_witness_run_dev(ctx._h, self._h, _host_ptr(raws), _host_ptr(ext), n, _dev_ptr(block)))
         # ---- epilogue on the host: needs the fee sum and the last state root (read back: n + 1 elements)
         idx = torch.tensor([k * a_tx + p.final_fee for k in range(n)] + [(n - 1) * a_tx + p.state_out], device=dev)
         back = block[idx].cpu().numpy().view(np.uint64)

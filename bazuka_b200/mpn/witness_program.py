@@ -17,7 +17,8 @@ compiled program + one thread per slot replaces the per-slot Python/Rust synthes
     NOP    (the y half of a JJ)
 
 Linear combinations live in a pool (deduplicated); variables are addressed by SLOT: 0 = ONE,
-1 = accepted_fee_token, 2 = the state root entering the block, 3 + j = block variable j.
+1..n_ext = "externals" (variables the block reads but does not define: for the update circuit the accepted
+fee token and the state root entering the slot), 1 + n_ext + j = block variable j.
 `run_reference` interprets the program with Python integers (CPU tests); csrc/witness.cu is the device
 interpreter."""
 from dataclasses import dataclass
@@ -31,7 +32,7 @@ from .fastsynth import FAKE_STATE_VAR
 from .gadgets import Number
 
 OP_RAW, OP_MUL, OP_BIT, OP_ISZERO, OP_INVZ, OP_SELECT, OP_JJ, OP_NOP = range(8)
-SLOT_ONE, SLOT_FEE_TOKEN, SLOT_STATE_IN, SLOT_BLOCK0 = 0, 1, 2, 3
+SLOT_ONE = 0
 
 
 def raw_values(tr, A, T):
@@ -67,43 +68,41 @@ class WitnessProgram:
     lc_coef: np.ndarray    # int32 [n_terms]   index into coefs (0 = the constant 1)
     coefs: list            # canonical ints
     n_raw: int
-    p_aux: int             # prologue aux count
-    state_out: int         # block-local index of the state root leaving the slot
-    final_fee: int         # block-local index of the slot's accepted fee
+    n_ext: int             # external slots (values supplied per slot by the caller)
+    p_aux: int = 0         # update circuit: prologue aux count
+    state_out: int = 0     # block-local index of the state root leaving the slot
+    final_fee: int = 0     # update circuit: block-local index of the slot's accepted fee
 
     @property
     def n_ops(self):
         return len(self.ops)
 
     @property
+    def block0(self):
+        return 1 + self.n_ext
+
+    @property
     def n_slots(self):
-        return SLOT_BLOCK0 + len(self.ops)
+        return self.block0 + len(self.ops)
 
     def coefs_mont(self):
         return to_mont(self.coefs)
 
 
-def compile_update_block(A, T) -> WitnessProgram:
-    """record one slot (a null transition: the instruction sequence does not depend on values) and compile it."""
-    tr = U.UpdateTransition.null(A, T)
-    circ = U.UpdateCircuit(A, T, 0, transitions=[tr])
-    cs = ConstraintSystem(record=True)
-    _, fee_tok, _, _ = circ._prologue(cs)
-    p_aux = len(cs.aux)
-    state_in = AllocatedNum(FAKE_STATE_VAR, 0)
-    state_out, _ = circ._tx_block(cs, tr, state_in, fee_tok, Number.zero())
-    recipes = cs.recipes[p_aux:]
-    n_ops = len(recipes)
+def compile_block(recipes, first_aux, externals) -> WitnessProgram:
+    """recipes: the recorded rules of the block's aux variables (aux index first_aux + j for recipes[j]);
+    externals: variable ids the block may read without defining them, in external-slot order."""
+    n_ops, n_ext = len(recipes), len(externals)
+    ext_slot = {v: 1 + k for k, v in enumerate(externals)}
+    block0 = 1 + n_ext
 
     def slot_of(var):
         if var == ONE:
             return SLOT_ONE
-        if var == fee_tok.var:
-            return SLOT_FEE_TOKEN
-        if var == FAKE_STATE_VAR:
-            return SLOT_STATE_IN
-        assert var % 2 == 1 and (var >> 1) >= p_aux, f"block recipe reads prologue/input variable {var}"
-        return SLOT_BLOCK0 + (var >> 1) - p_aux
+        if var in ext_slot:
+            return ext_slot[var]
+        assert var % 2 == 1 and first_aux <= (var >> 1) < first_aux + n_ops, f"block recipe reads foreign variable {var}"
+        return block0 + (var >> 1) - first_aux
 
     coef_index = {1: 0}
     coefs = [1]
@@ -112,7 +111,7 @@ def compile_update_block(A, T) -> WitnessProgram:
     def lc_id(lc, upto):
         terms = tuple(sorted((slot_of(v), c) for v, c in lc.t.items() if c))
         for s, _ in terms:
-            assert s < SLOT_BLOCK0 + upto, "recipe reads a variable allocated later"
+            assert s < block0 + upto, "recipe reads a variable allocated later"
         got = pool.get(terms)
         if got is None:
             got = pool[terms] = len(lc_ptr) - 1
@@ -152,16 +151,36 @@ def compile_update_block(A, T) -> WitnessProgram:
             ops[j] = (OP_NOP, 0, 0, 0, 0, 0)
         else:
             raise ValueError(kind)
-    assert n_raw == len(raw_values(tr, A, T))
-    return WitnessProgram(A, T, ops, np.array(lc_ptr, dtype=np.int32), np.array(lc_slot, dtype=np.int32),
-                          np.array(lc_coef, dtype=np.int32), coefs, n_raw, p_aux,
-                          (state_out.var >> 1) - p_aux, (circ._last_final_fee.var >> 1) - p_aux)
+    return WitnessProgram(0, 0, ops, np.array(lc_ptr, dtype=np.int32), np.array(lc_slot, dtype=np.int32),
+                          np.array(lc_coef, dtype=np.int32), coefs, n_raw, n_ext)
 
 
-def run_reference(prog: WitnessProgram, raws, fee_token, state_in):
-    """interpret the program for one slot with Python integers -> the block's aux values (canonical)."""
+def compile_update_block(A, T) -> WitnessProgram:
+    """record one slot of UpdateCircuit (a null transition: the instruction sequence does not depend on values)
+    and compile it; externals = [accepted_fee_token, state root entering the slot]."""
+    tr = U.UpdateTransition.null(A, T)
+    circ = U.UpdateCircuit(A, T, 0, transitions=[tr])
+    cs = ConstraintSystem(record=True)
+    _, fee_tok, _, _ = circ._prologue(cs)
+    p_aux = len(cs.aux)
+    state_in = AllocatedNum(FAKE_STATE_VAR, 0)
+    state_out, _ = circ._tx_block(cs, tr, state_in, fee_tok, Number.zero())
+    prog = compile_block(cs.recipes[p_aux:], p_aux, [fee_tok.var, FAKE_STATE_VAR])
+    assert prog.n_raw == len(raw_values(tr, A, T))
+    prog.A, prog.T, prog.p_aux = A, T, p_aux
+    prog.state_out, prog.final_fee = (state_out.var >> 1) - p_aux, (circ._last_final_fee.var >> 1) - p_aux
+    return prog
+
+
+def run_reference(prog: WitnessProgram, raws, ext):
+    """interpret the program for one slot with Python integers -> the block's aux values (canonical).
+    ext: the slot's external values (update circuit: [fee_token, state_in])."""
     V = [0] * prog.n_slots
-    V[SLOT_ONE], V[SLOT_FEE_TOKEN], V[SLOT_STATE_IN] = 1, fee_token % R, state_in % R
+    V[SLOT_ONE] = 1
+    assert len(ext) == prog.n_ext
+    for k, v in enumerate(ext):
+        V[1 + k] = v % R
+    SLOT_BLOCK0 = prog.block0
     ptr, slots, cidx, coefs = prog.lc_ptr, prog.lc_slot, prog.lc_coef, prog.coefs
 
     def ev(l):

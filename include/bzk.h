@@ -228,17 +228,18 @@ int32_t bzk_groth16_finalize(const bzk_g1_affine *alpha_g1, const bzk_g1_affine 
  *     3 ISZERO lc0==0                  4 INVZ lc0^-1 (0 -> 0)   5 SELECT lc0 ? lc2 : lc1
  *     6 JJ   JubJub sum (lc0,lc1)+(lc2,lc3) -> variables j, j+1 ((0,0) if an operand is off-curve)   7 NOP
  *   linear combination l = sum_{k in [lc_ptr[l], lc_ptr[l+1])} coefs[lc_coef[k]] * V[lc_slot[k]]
- *   (coefs[0] must be the constant one); slots: 0 = ONE, 1 = fee token, 2 = state root entering the
- *   slot, 3 + j = block variable j.  coefs and jj_d (the curve's d) are Montgomery images.
- * bzk_witness_run_dev: raws[ntx][n_raw], fee_token, state_in[ntx] are CANONICAL host images (converted on
- * the device); writes the Montgomery values of slot t's variables to d_aux_out[t*n_ops + j]. */
+ *   (coefs[0] must be the constant one); slots: 0 = ONE, 1..n_ext = variables the block reads but does not
+ *   define (update circuit: the fee token and the state root entering the slot), 1 + n_ext + j = block
+ *   variable j.  coefs and jj_d (the curve's d) are Montgomery images.
+ * bzk_witness_run_dev: raws[ntx][n_raw] and ext[ntx][n_ext] are CANONICAL host images (converted on the
+ * device); writes the Montgomery values of slot t's variables to d_aux_out[t*n_ops + j]. */
 typedef struct bzk_witness_program bzk_witness_program;
 int32_t bzk_witness_program_upload(bzk_ctx *ctx, const int32_t *ops, uint64_t n_ops, const int32_t *lc_ptr, uint64_t n_lc,
                                    const int32_t *lc_slot, const int32_t *lc_coef, uint64_t n_terms, const bzk_fr *coefs,
-                                   uint64_t n_coefs, uint32_t n_raw, const bzk_fr *jj_d, bzk_witness_program **out);
+                                   uint64_t n_coefs, uint32_t n_raw, uint32_t n_ext, const bzk_fr *jj_d, bzk_witness_program **out);
 int32_t bzk_witness_program_free(bzk_ctx *ctx, bzk_witness_program *prog);
-int32_t bzk_witness_run_dev(bzk_ctx *ctx, const bzk_witness_program *prog, const bzk_fr *raws, const bzk_fr *fee_token,
-                            const bzk_fr *state_in, uint64_t ntx, void *d_aux_out);
+int32_t bzk_witness_run_dev(bzk_ctx *ctx, const bzk_witness_program *prog, const bzk_fr *raws, const bzk_fr *ext, uint64_t ntx,
+                            void *d_aux_out);
 
 /* 387-byte bincode image of `Groth16Proof {a,b,c}` (/root/reference/src/zk/groth16/mod.rs:33-38);
  * prefix it with the u32 variant tag 0 for `ZkProof::Groth16` (391 B). */

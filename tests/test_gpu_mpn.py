@@ -161,3 +161,29 @@ def test_batched_transition_builder_on_gpu_equals_update(ctx):
     assert pub1 == pub2 and rej1 == rej2 and len(tr1) == 6
     _assert_same_transitions(tr1, tr2)
     assert st1.root == st2.root and st1.tree.levels == st2.tree.levels
+
+
+@pytest.mark.parametrize("kind", ["deposit", "withdraw"])
+def test_deposit_withdraw_gpu_witness_and_proof(ctx, cref, kind):
+    """the two-phase slot programs on the GPU (+ host reveal) give `synthesize`'s aux vector for the deposit and
+    withdraw circuits, and the proof from the resident witness verifies with the five public inputs."""
+    from bazuka_b200 import groth16 as BG
+    from bazuka_b200.mpn import cs as C
+    from bazuka_b200.mpn.dw_witness import TwoPhaseWitnessGpu
+    from test_mpn_cpu import _dw_scenario
+    circ = _dw_scenario(kind)
+    ni, na, mats, inputs, aux = circ.synthesize(C.ConstraintSystem()).to_csr()
+    gw = TwoPhaseWitnessGpu(ctx, kind, 3, 3)
+    d_in, d_aux = gw.witness(circ)
+    got = d_aux.cpu().numpy().view(np.uint64)
+    assert got.shape == aux.shape
+    bad = np.nonzero((got != aux).any(axis=1))[0]
+    assert len(bad) == 0, (len(bad), bad[:8])
+    assert (d_in.cpu().numpy().view(np.uint64) == inputs).all()
+    pr = BG.Prover(ctx, BG.R1CS(ni, na, *mats))
+    pk, vk = BG.setup_gpu(ctx, pr.r1cs, cref.fr_random(95, 5), cref.g1_generator(), cref.g2_generator())
+    r, s = cref.fr_random(96, 2)
+    blob, pts = pr.prove_dev(pk, d_in, d_aux, r, s)
+    assert (blob == pr.prove(pk, inputs, aux, r, s)[0]).all()
+    assert BG.verify(vk, inputs[1:], pts)
+    gw.free(); pk.free(); pr.free()

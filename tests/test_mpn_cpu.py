@@ -210,7 +210,7 @@ def test_witness_program_reproduces_synthesised_witness():
     for k, tr in enumerate(circ.transitions):
         raws = W.raw_values(tr, 3, 3)
         assert len(raws) == prog.n_raw
-        got = W.run_reference(prog, raws, circ.fee_token, roots[k])
+        got = W.run_reference(prog, raws, [circ.fee_token, roots[k]])
         want = cs.aux[prog.p_aux + k * a_tx: prog.p_aux + (k + 1) * a_tx]
         assert got == want, (k, next(i for i, (g, w) in enumerate(zip(got, want)) if g != w))
     # chaining: the state root leaving slot k enters slot k+1
@@ -275,3 +275,44 @@ def test_batched_transition_builder_equals_sequential_update():
 def dataclasses_asdict(a):
     import dataclasses
     return dataclasses.asdict(a)
+
+
+def _dw_scenario(kind):
+    from bazuka_b200.mpn import dw as D
+    st, keys = make_state(3, 3, 2)
+    if kind == "deposit":
+        newpk, _ = N.eddsa_keys(b"dep-new")
+        deps = [D.MpnDeposit(N.jj_compress(keys[0][0]), U.ZIESHA, 500), D.MpnDeposit(N.jj_compress(newpk), 77, 9),
+                D.MpnDeposit(N.jj_compress(keys[1][0]), 77, 1)]
+        pub, tr = D.deposit(st, deps, 1)
+        return D.DepositCircuit(3, 3, 1, commitment=3, height=1, transitions=tr, **pub)
+    ws = []
+    for i, amt in enumerate([100, 5]):
+        w = D.MpnWithdraw(N.jj_compress(keys[i][0]), 1, amount=U.Money(U.ZIESHA, amt), fee=U.Money(U.ZIESHA, 2), fingerprint=1000 + i)
+        w.sign(keys[i][1])
+        ws.append(w)
+    pub, tr = D.withdraw(st, ws, 1)
+    return D.WithdrawCircuit(3, 3, 1, commitment=9, height=2, transitions=tr, **pub)
+
+
+@pytest.mark.parametrize("kind", ["deposit", "withdraw"])
+def test_two_phase_witness_programs_reproduce_synthesis(kind):
+    """deposit / withdraw: phase-1 program, host reveal, phase-2 program (reading phase-1 raws and the entering
+    state as externals) assemble to exactly `synthesize`'s aux vector."""
+    from bazuka_b200.mpn import dw_witness as DW, witness_program as W
+    circ = _dw_scenario(kind)
+    cs = circ.synthesize(C.ConstraintSystem())
+    assert cs.is_satisfied()[0]
+    pg = DW.TwoPhasePrograms(kind, 3, 3)
+    inputs, pro, rev = DW.host_parts(pg, circ)
+    roots = DW.slot_roots(circ)
+    b1, b2 = [], []
+    for k, tr in enumerate(circ.transitions):
+        r1, r2 = pg.raws_of(tr, 3, 3)
+        b1 += W.run_reference(pg.prog1, r1, [])
+        out2 = W.run_reference(pg.prog2, r2, pg.ext_values(r1, roots[k]))
+        b2 += out2
+        if k + 1 < len(roots):
+            assert out2[pg.state_out] == roots[k + 1]
+    assert inputs == cs.inputs
+    assert pro + b1 + rev + b2 == cs.aux
