@@ -196,3 +196,180 @@ def update_batched(hasher, state: MpnState, txs, log4_batch, fee_token=ZIESHA):
     assert state.root == root
     public = {"state": prev_root, "aux_data": hasher.poseidon_batch([[fee_token, fee_sum]])[0], "next_state": root}
     return public, transitions, rejected
+
+
+# ---------------------------------------------------------------------------------------------
+# deposit / withdraw builders on the same primitives
+# ---------------------------------------------------------------------------------------------
+class _Ledger:
+    """phase-1 mirror shared by the builders: touched accounts, address index, free-slot counter"""
+
+    def __init__(self, state):
+        self.state, self.mirror, self.by_addr = state, {}, {}
+        for i, a in state.accounts.items():
+            self.by_addr.setdefault(a.address, i)
+        self.next_free = (max(state.accounts) + 1) if state.accounts else 0
+
+    def get(self, i):
+        if i not in self.mirror:
+            self.mirror[i] = self.state.accounts.get(i, MpnAccount()).copy()
+        return self.mirror[i].copy()
+
+    def put(self, i, acc):
+        self.mirror[i] = acc.copy()
+        self.by_addr.setdefault(acc.address, i)
+
+
+class _TokenForest:
+    """collects the ordered token-leaf writes of a batch; pre-batch tokens enter as writes into empty trees"""
+
+    def __init__(self, state, accounts):
+        self.T = state.T
+        self.tree_of = {a: k for k, a in enumerate(accounts)}
+        self.rows, self.tree, self.idx = [], [], []
+        for acc in accounts:
+            for i, m in state.accounts.get(acc, MpnAccount()).tokens.items():
+                self.write(acc, i, m)
+        self.n_init = len(self.rows)
+
+    def write(self, acc, index, money):
+        self.rows.append([money.token_id, money.amount]); self.tree.append(self.tree_of[acc]); self.idx.append(index)
+        return len(self.rows) - 1
+
+    def run(self, hasher):
+        tdef = _token_defaults(self.T)
+        leaves = hasher.poseidon_batch(self.rows)
+        self.vals, self.proofs = hasher.tree_update(self.T, self.tree, self.idx, leaves, [[[tdef[l]] * 3 for l in range(self.T)]] * len(self.rows))
+        self.cur = {k: tdef[self.T] for k in self.tree_of.values()}
+        for e in range(self.n_init):
+            self.cur[self.tree[e]] = self.vals[self.T][e]
+
+    def root(self, acc):
+        return self.cur[self.tree_of[acc]]
+
+    def applied(self, acc, e):
+        """advance the replay past write e; returns the root after it"""
+        self.cur[self.tree_of[acc]] = self.vals[self.T][e]
+        return self.vals[self.T][e]
+
+
+def _commit(state, ledger, touched, s_idx, s_vals):
+    A = state.A
+    for e, i in enumerate(s_idx):
+        node = i
+        for lvl in range(A + 1):
+            state.tree._put(lvl, node, s_vals[lvl][e])
+            node >>= 2
+    for i in touched:
+        state.accounts[i] = ledger.mirror[i].copy()
+
+
+def _list_root(hasher, rows):
+    leaves = hasher.poseidon_batch(rows)
+    while len(leaves) != 1:
+        leaves = hasher.poseidon_batch([leaves[i:i + 4] for i in range(0, len(leaves), 4)])
+    return leaves[0]
+
+
+def deposit_batched(hasher, state: MpnState, deposits, log4_batch):
+    """dw.deposit() with batched hashing (/root/reference/src/mpn/deposit.rs:11-233): same transitions, public inputs, state."""
+    from .dw import DepositTransition
+    n, prev = 1 << (2 * log4_batch), state.root
+    led, plan = _Ledger(state), []
+    for d in deposits:
+        if len(plan) == n:
+            break
+        addr = N.jj_decompress(d.mpn_address)
+        idx = led.by_addr.get(addr)
+        if idx is None:
+            idx, led.next_free = led.next_free, led.next_free + 1
+        before = led.get(idx)
+        ti = before.find_token_index(state.T, d.token_id, True)
+        if ti is None or (N.jj_on_curve(before.address) and before.address != addr):
+            continue
+        bal = before.tokens.get(ti)
+        after = before.copy()
+        after.address = addr
+        after.tokens.setdefault(ti, Money(d.token_id, 0)).amount += d.amount
+        led.put(idx, after)
+        plan.append(dict(d=d, idx=idx, ti=ti, before=before, after=after, bal=Money(bal.token_id, bal.amount) if bal else Money(), addr=addr))
+    touched = list(dict.fromkeys(p["idx"] for p in plan))
+    forest = _TokenForest(state, touched)
+    for p in plan:
+        p["e"] = forest.write(p["idx"], p["ti"], p["after"].tokens[p["ti"]])
+    forest.run(hasher)
+    acct_rows = []
+    for p in plan:
+        p["before_balances_hash"] = forest.root(p["idx"])
+        p["bproof"] = forest.proofs[p["e"]]
+        a = p["after"]
+        acct_rows.append([a.tx_nonce, a.withdraw_nonce, a.address[0], a.address[1], forest.applied(p["idx"], p["e"])])
+    s_idx = [p["idx"] for p in plan]
+    s_vals, s_proofs = hasher.tree_update(state.A, [0] * len(plan), s_idx, hasher.poseidon_batch(acct_rows), [state.tree.prove(i) for i in s_idx])
+    trans, root = [], prev
+    for k, p in enumerate(plan):
+        trans.append(DepositTransition(True, p["d"], p["before"], p["before_balances_hash"], p["bal"], s_proofs[k], p["idx"], p["ti"], p["bproof"], root))
+        root = s_vals[state.A][k]
+    _commit(state, led, touched, s_idx, s_vals)
+    pk_hashes = hasher.poseidon_batch([[p["addr"][0], p["addr"][1]] for p in plan])
+    rows = [[1, p["d"].token_id, p["d"].amount, pk_hashes[k]] for k, p in enumerate(plan)] + [[0, 0, 0, 0]] * (n - len(plan))
+    return {"state": prev, "aux_data": _list_root(hasher, rows), "next_state": root}, trans
+
+
+def withdraw_batched(hasher, state: MpnState, withdraws, log4_batch):
+    """dw.withdraw() with batched hashing (/root/reference/src/mpn/withdraw.rs:10-259)."""
+    from .dw import WithdrawTransition
+    n, prev = 1 << (2 * log4_batch), state.root
+    led, plan = _Ledger(state), []
+    for w in withdraws:
+        if len(plan) == n:
+            break
+        addr = N.jj_decompress(w.mpn_address)
+        idx = led.by_addr.get(addr)
+        if idx is None:
+            continue
+        before = led.get(idx)
+        ti = before.find_token_index(state.T, w.amount.token_id, False)
+        fi = before.find_token_index(state.T, w.fee.token_id, False)
+        if ti is None or fi is None or w.mpn_withdraw_nonce != before.withdraw_nonce + 1:
+            continue
+        if before.tokens[ti].amount < w.amount.amount or not N.eddsa_verify(addr, w.message(), w.mpn_sig):
+            continue
+        tok = before.tokens[ti]
+        mid = before.copy()
+        mid.tokens[ti].amount -= w.amount.amount
+        feeb = mid.tokens[fi]
+        if feeb.amount < w.fee.amount:
+            continue
+        fee_before = Money(feeb.token_id, feeb.amount)
+        after = mid.copy()
+        after.tokens[fi].amount -= w.fee.amount
+        after.withdraw_nonce += 1
+        led.put(idx, after)
+        plan.append(dict(w=w, idx=idx, ti=ti, fi=fi, before=before, mid=mid, after=after, tok=Money(tok.token_id, tok.amount), fee_before=fee_before, addr=addr))
+    touched = list(dict.fromkeys(p["idx"] for p in plan))
+    forest = _TokenForest(state, touched)
+    for p in plan:
+        p["e1"] = forest.write(p["idx"], p["ti"], p["mid"].tokens[p["ti"]])
+        p["e2"] = forest.write(p["idx"], p["fi"], p["after"].tokens[p["fi"]])
+    forest.run(hasher)
+    acct_rows = []
+    for p in plan:
+        p["before_token_hash"] = forest.root(p["idx"])
+        p["tproof"], p["fproof"] = forest.proofs[p["e1"]], forest.proofs[p["e2"]]
+        m, a = p["mid"], p["after"]
+        acct_rows.append([m.tx_nonce, m.withdraw_nonce, m.address[0], m.address[1], forest.applied(p["idx"], p["e1"])])
+        acct_rows.append([a.tx_nonce, a.withdraw_nonce, a.address[0], a.address[1], forest.applied(p["idx"], p["e2"])])
+    s_idx = [p["idx"] for p in plan for _ in (0, 1)]
+    s_vals, s_proofs = hasher.tree_update(state.A, [0] * len(s_idx), s_idx, hasher.poseidon_batch(acct_rows), [state.tree.prove(i) for i in s_idx])
+    trans, root = [], prev
+    for k, p in enumerate(plan):
+        trans.append(WithdrawTransition(True, p["w"], p["before"], p["tok"], p["fee_before"], s_proofs[2 * k], p["idx"], p["ti"], p["tproof"],
+                                        p["before_token_hash"], p["fi"], p["fproof"], root))
+        root = s_vals[state.A][2 * k + 1]
+    _commit(state, led, touched, s_idx, s_vals)
+    cds = hasher.poseidon_batch([[p["addr"][0], p["addr"][1], p["w"].mpn_withdraw_nonce, p["w"].mpn_sig["r"][0], p["w"].mpn_sig["r"][1], p["w"].mpn_sig["s"]]
+                                 for p in plan])
+    rows = [[1, p["w"].amount.token_id, p["w"].amount.amount, p["w"].fee.token_id, p["w"].fee.amount, p["w"].fingerprint, cds[k]]
+            for k, p in enumerate(plan)] + [[0] * 7] * (n - len(plan))
+    return {"state": prev, "aux_data": _list_root(hasher, rows), "next_state": root}, trans

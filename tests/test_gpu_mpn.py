@@ -187,3 +187,29 @@ def test_deposit_withdraw_gpu_witness_and_proof(ctx, cref, kind):
     assert (blob == pr.prove(pk, inputs, aux, r, s)[0]).all()
     assert BG.verify(vk, inputs[1:], pts)
     gw.free(); pk.free(); pr.free()
+
+
+def test_batched_deposit_withdraw_builders_on_gpu(ctx):
+    """deposit_batched / withdraw_batched with the GPU primitives == the sequential builders."""
+    import copy
+    from bazuka_b200.mpn import batch_update as BU, dw as D, native as N, update as U
+    from test_mpn_cpu import _assert_same_transitions
+    h = BU.GpuTreeHasher(ctx)
+    st1, keys = make_state(3, 3, 2)
+    newpk, _ = N.eddsa_keys(b"dep-new")
+    deps = [D.MpnDeposit(N.jj_compress(keys[0][0]), U.ZIESHA, 500), D.MpnDeposit(N.jj_compress(newpk), 77, 9),
+            D.MpnDeposit(N.jj_compress(keys[1][0]), 77, 1), D.MpnDeposit(N.jj_compress(keys[0][0]), 77, 4)]
+    st2 = copy.deepcopy(st1)
+    pub1, tr1 = D.deposit(st1, deps, 1)
+    pub2, tr2 = BU.deposit_batched(h, st2, deps, 1)
+    assert pub1 == pub2 and st1.tree.levels == st2.tree.levels
+    _assert_same_transitions(tr1, tr2)
+    ws = []
+    for i, amt, nonce in ((0, 100, 1), (1, 5, 1), (0, 30, 2)):
+        w = D.MpnWithdraw(N.jj_compress(keys[i][0]), nonce, amount=U.Money(U.ZIESHA, amt), fee=U.Money(U.ZIESHA, 2), fingerprint=1000 + amt)
+        w.sign(keys[i][1])
+        ws.append(w)
+    pub1, tr1 = D.withdraw(st1, ws, 1)
+    pub2, tr2 = BU.withdraw_batched(h, st2, ws, 1)
+    assert pub1 == pub2 and st1.tree.levels == st2.tree.levels and len(tr1) == 3
+    _assert_same_transitions(tr1, tr2)

@@ -316,3 +316,36 @@ def test_two_phase_witness_programs_reproduce_synthesis(kind):
             assert out2[pg.state_out] == roots[k + 1]
     assert inputs == cs.inputs
     assert pro + b1 + rev + b2 == cs.aux
+
+
+def test_batched_deposit_and_withdraw_builders_equal_sequential():
+    """deposit_batched / withdraw_batched (batched hashing through the versioned tree update; here the host
+    stand-in) == dw.deposit / dw.withdraw: transitions, public inputs, final state — including a deposit to a new
+    address, a second token, two deposits to one account, a rejected withdraw (bad nonce) and a chain of two
+    withdraws from one account."""
+    import copy
+    from bazuka_b200.mpn import batch_update as BU, dw as D
+    from oracle.py.state import HostTreeHasher
+    h = HostTreeHasher(N.poseidon)
+    st1, keys = make_state(3, 3, 2)
+    newpk, _ = N.eddsa_keys(b"dep-new")
+    deps = [D.MpnDeposit(N.jj_compress(keys[0][0]), U.ZIESHA, 500), D.MpnDeposit(N.jj_compress(newpk), 77, 9),
+            D.MpnDeposit(N.jj_compress(keys[1][0]), 77, 1), D.MpnDeposit(N.jj_compress(keys[0][0]), 77, 4),
+            D.MpnDeposit(N.jj_compress(newpk), 77, 1)]
+    st2 = copy.deepcopy(st1)
+    pub1, tr1 = D.deposit(st1, deps, 2)
+    pub2, tr2 = BU.deposit_batched(h, st2, deps, 2)
+    assert len(tr1) == 5 and pub1 == pub2
+    _assert_same_transitions(tr1, tr2)
+    assert st1.root == st2.root and st1.tree.levels == st2.tree.levels
+    ws = []
+    for i, amt, nonce in ((0, 100, 1), (1, 5, 1), (0, 7, 5), (0, 30, 2)):
+        w = D.MpnWithdraw(N.jj_compress(keys[i][0]), nonce, amount=U.Money(U.ZIESHA, amt), fee=U.Money(U.ZIESHA, 2), fingerprint=1000 + amt)
+        w.sign(keys[i][1])
+        ws.append(w)
+    pub1, tr1 = D.withdraw(st1, ws, 1)
+    pub2, tr2 = BU.withdraw_batched(h, st2, ws, 1)
+    assert len(tr1) == 3 and pub1 == pub2
+    _assert_same_transitions(tr1, tr2)
+    assert st1.root == st2.root and st1.tree.levels == st2.tree.levels
+    assert {i: dataclasses_asdict(a) for i, a in st1.accounts.items()} == {i: dataclasses_asdict(a) for i, a in st2.accounts.items()}
