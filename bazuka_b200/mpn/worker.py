@@ -1,0 +1,66 @@
+"""The prover worker's job as one object: transactions in, `ZkProof::Groth16` blob out, all heavy steps on the GPU.
+
+In the reference a validator turns a batch into an `MpnWork` (`prepare_works`, /root/reference/src/mpn/mod.rs:298-424:
+`update()` builds the transitions and public inputs), an external worker proves it (bellman `create_proof` on the
+`UpdateCircuit`) and posts a `ZkProof` that `MpnWork::verify` checks (`mod.rs:281-295` -> `check_proof`,
+/root/reference/src/zk/mod.rs:157-193).  `MpnUpdateWorker` is that path for one circuit shape (A, T, B):
+
+    worker = MpnUpdateWorker(ctx, A, T, B, toxic)        # once: R1CS template, proving key, witness program
+    work   = worker.build(state, txs, commitment, height)  # batched transition builder  (batch_update.py)
+    blob   = worker.prove(work, r, s)                      # GPU witness -> resident z -> proof (391 bytes)
+    worker.verify(work, blob)                              # the validator's check_proof
+
+The trusted setup is bellman's `generate_parameters` with explicit toxic waste (the reference's production keys
+come from an external ceremony; /root/reference/src/config/blockchain.rs:372-400 is its test-key path)."""
+from dataclasses import dataclass
+
+import numpy as np
+
+from .. import groth16 as BG
+from . import batch_update as BU
+from . import fastsynth as FS
+from . import update as U
+from .cs import to_mont
+from .gpu_witness import UpdateWitnessGpu
+
+
+@dataclass
+class UpdateWork:
+    circuit: U.UpdateCircuit
+    public_inputs: np.ndarray      # [5,4] Montgomery: commitment, height, state, aux_data, next_state
+    accepted: int
+    rejected: list
+
+
+class MpnUpdateWorker:
+    def __init__(self, ctx, A, T, B, toxic, g1=None, g2=None):
+        self.ctx, self.A, self.T, self.B = ctx, A, T, B
+        shape = U.UpdateCircuit(A, T, B, fee_token=U.ZIESHA)   # all-null batch: the R1CS does not depend on values
+        ni, na, mats, _, _ = FS.synthesize_update(shape, structure_only=True)
+        self.prover = BG.Prover(ctx, BG.R1CS(ni, na, *mats))
+        self.pk, self.vk = BG.setup_gpu(ctx, self.prover.r1cs, toxic, BG.G1_GENERATOR if g1 is None else g1, BG.G2_GENERATOR if g2 is None else g2)
+        self.vk_blob = BG.vk_to_bincode(self.vk)
+        self.witness = UpdateWitnessGpu(ctx, A, T)
+        self.hasher = BU.GpuTreeHasher(ctx)
+
+    def build(self, state, txs, commitment=0, height=0, fee_token=U.ZIESHA) -> UpdateWork:
+        pub, trans, rejected = BU.update_batched(self.hasher, state, txs, self.B, fee_token)
+        circ = U.UpdateCircuit(self.A, self.T, self.B, commitment=commitment, height=height, fee_token=fee_token, transitions=trans, **pub)
+        inputs = to_mont([commitment, height, pub["state"], pub["aux_data"], pub["next_state"]])
+        return UpdateWork(circ, inputs, len(trans), rejected)
+
+    def prove(self, work: UpdateWork, r, s, check_satisfied=True):
+        """-> 391-byte bincode image of `ZkProof::Groth16` for the work."""
+        d_in, d_aux = self.witness.witness(work.circuit)
+        blob, _ = self.prover.prove_dev(self.pk, d_in, d_aux, r, s, check_satisfied=check_satisfied)
+        return BG.zkproof_blob(blob)
+
+    def verify(self, work: UpdateWork, zkproof) -> bool:
+        """`check_proof(vk, commitment, height, state, aux_data, next_state, proof)` on the reference's byte images"""
+        z = np.asarray(zkproof, dtype=np.uint8)
+        if z.size != 391 or z[:4].any():
+            return False
+        return BG.verify_bytes(self.vk_blob, work.public_inputs, z[4:])
+
+    def free(self):
+        self.witness.free(); self.pk.free(); self.prover.free()

@@ -213,3 +213,33 @@ def test_batched_deposit_withdraw_builders_on_gpu(ctx):
     pub2, tr2 = BU.withdraw_batched(h, st2, ws, 1)
     assert pub1 == pub2 and st1.tree.levels == st2.tree.levels and len(tr1) == 3
     _assert_same_transitions(tr1, tr2)
+
+
+def test_worker_object_end_to_end(ctx, cref):
+    """MpnUpdateWorker: transactions -> batched builder -> GPU witness -> resident proof -> 391-byte ZkProof that the
+    validator-side byte-image check accepts; byte-equal to the proof of the host-synthesised witness of the
+    sequentially built work under the same key; a different claimed state is rejected."""
+    import copy
+    from bazuka_b200.mpn import cs as C, native as N, update as U
+    from bazuka_b200.mpn.worker import MpnUpdateWorker
+    st, keys = make_state(3, 3, 3)
+    keys.append(N.eddsa_keys(b"newcomer"))
+    txs = [transfer(keys, 0, 1, 1), transfer(keys, 1, 2, 1, amount=5), transfer(keys, 0, 3, 2, amount=77, fee=3)]
+    st_seq = copy.deepcopy(st)
+    worker = MpnUpdateWorker(ctx, 3, 3, 1, cref.fr_random(77, 5))
+    work = worker.build(st, txs, commitment=42, height=7)
+    assert work.accepted == 3 and not work.rejected
+    r, s = cref.fr_random(78, 2)
+    zk = worker.prove(work, r, s)
+    assert zk.shape == (391,) and worker.verify(work, zk)
+    pub, trans, _ = U.update(st_seq, txs, 1)
+    assert st_seq.root == st.root
+    ni, na, mats, inputs, aux = U.UpdateCircuit(3, 3, 1, commitment=42, height=7, transitions=trans, **pub).synthesize(C.ConstraintSystem()).to_csr()
+    assert (inputs[1:] == work.public_inputs).all()
+    blob, _ = worker.prover.prove(worker.pk, inputs, aux, r, s)
+    assert (zk[4:] == blob).all()
+    bad = copy.copy(work)
+    bad.public_inputs = work.public_inputs.copy()
+    bad.public_inputs[4] = bad.public_inputs[2]
+    assert not worker.verify(bad, zk)
+    worker.free()
