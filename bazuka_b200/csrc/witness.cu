@@ -50,6 +50,17 @@ __device__ __noinline__ Fr wit_eval_lc(const WitProgDev &P, int32_t l, const Fr 
     return acc;
 }
 
+// Pull every operand of the op's linear combinations towards L1 before the dependent evaluation starts: the
+// interpreter's loads are otherwise serialised behind one another (V of a 256-slot batch is ~460 MB, so they
+// are DRAM latencies).  Addresses are warp-uniform in the slot and consecutive in tx.
+__device__ __forceinline__ void wit_prefetch_lc(const WitProgDev &P, int32_t l, const Fr *V, uint32_t ntx, uint32_t tx) {
+    const int32_t lo = __ldg(P.lc_ptr + l), hi = __ldg(P.lc_ptr + l + 1);
+    for (int32_t k = lo; k < hi; k++) {
+        const Fr *p = V + (size_t)__ldg(P.lc_slot + k) * ntx + tx;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(__cvta_generic_to_global(p)));
+    }
+}
+
 __device__ __forceinline__ bool jj_on_curve(const Fr &x, const Fr &y, const Fr &d) {
     // a = -1:  y^2 - x^2 == 1 + d x^2 y^2   (/root/reference/src/crypto/jubjub/curve.rs:40-47)
     Fr x2 = x.sqr(), y2 = y.sqr();
@@ -67,6 +78,13 @@ __global__ void __launch_bounds__(32) k_witness_run(WitProgDev P, Fr jj_d, const
         const int32_t *op = P.ops + (size_t)j * 6;
         const int32_t code = __ldg(op), a0 = __ldg(op + 1), a1 = __ldg(op + 2), a2 = __ldg(op + 3), a3 = __ldg(op + 4), imm = __ldg(op + 5);
         Fr out = Fr::zero();
+        {
+            const int nlc = code == W_JJ ? 4 : code == W_SELECT ? 3 : code == W_MUL ? 2 : (code == W_RAW || code == W_NOP) ? 0 : 1;
+            if (nlc > 0) wit_prefetch_lc(P, a0, V, ntx, tx);
+            if (nlc > 1 && a1 != a0) wit_prefetch_lc(P, a1, V, ntx, tx);
+            if (nlc > 2) wit_prefetch_lc(P, a2, V, ntx, tx);
+            if (nlc > 3) wit_prefetch_lc(P, a3, V, ntx, tx);
+        }
         switch (code) {
         case W_RAW: out = load_vec(raws + (size_t)tx * P.n_raw + imm).to_mont(); break;
         case W_MUL: {

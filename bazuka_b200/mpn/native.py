@@ -4,6 +4,7 @@ Follows /root/reference/src/zk/poseidon/mod.rs:24-84 (Poseidon), /root/reference
 curve.rs:19-164 + mod.rs:108-168 (twisted Edwards curve, EdDSA-Poseidon), /root/reference/src/zk/mod.rs:
 262-271 (`ZkScalar::new`), /root/reference/src/zk/state/mod.rs:218-264,310-420 (4-ary Merkle state:
 node = Poseidon-4 of its children, missing = level default, proofs leaf-first with self skipped)."""
+import functools
 import hashlib
 import os
 import struct
@@ -125,8 +126,10 @@ def jj_compress(p):
     return (p[0], p[1] & 1 == 1)
 
 
+@functools.lru_cache(maxsize=65536)
 def jj_decompress(c):
-    """PointCompressed::decompress (curve.rs:78-88)."""
+    """PointCompressed::decompress (curve.rs:78-88).  Memoised: the Fr square root is ~20 modular powers and the
+    same few thousand keys recur in every batch."""
     x, odd = c
     y = fr_sqrt((1 - JJ_A * x * x) % R * pow((1 - JJ_D * x * x) % R, -1, R) % R)
     assert y is not None
