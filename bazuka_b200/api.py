@@ -180,7 +180,7 @@ class Context:
         d_tid = torch.from_numpy(np.ascontiguousarray(tree_id, dtype=np.uint32).view(np.int32)).to(dev)
         d_idx = torch.from_numpy(np.ascontiguousarray(indices, dtype=np.uint64).view(np.int64)).to(dev)
         d_init = torch.from_numpy(np.ascontiguousarray(init_proofs, dtype=np.uint64).reshape(n, depth, 3, 4).view(np.int64)).to(dev)
-        torch.cuda.synchronize(dev)
+        torch.cuda.current_stream(dev).synchronize()  # the uploads; not a device-wide sync (other contexts keep running)
         self._check(self._l.bzk_tree4_versioned_update_dev(self._h, depth, _dev_ptr(d_tid), _dev_ptr(d_idx), n, _dev_ptr(vals), _dev_ptr(d_init),
                                                             _dev_ptr(proofs)))
         self.synchronize()

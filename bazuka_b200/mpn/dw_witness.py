@@ -187,5 +187,5 @@ class TwoPhaseWitnessGpu:
         d_aux[:p0] = torch.from_numpy(to_mont(pro).view(np.int64)).to(dev)
         d_aux[p0 + n * pg.n1:o2] = torch.from_numpy(to_mont(rev).view(np.int64)).to(dev)
         d_inputs = torch.from_numpy(to_mont(inputs).view(np.int64)).to(dev)
-        torch.cuda.synchronize(dev)
+        torch.cuda.current_stream(dev).synchronize()
         return d_inputs, d_aux

@@ -82,5 +82,5 @@ class UpdateWitnessGpu:
         d_aux[:p.p_aux] = torch.from_numpy(to_mont(cs.aux[:p.p_aux]).view(np.int64)).to(dev)
         d_aux[p.p_aux + n * a_tx:] = torch.from_numpy(to_mont(epi).view(np.int64)).to(dev)
         d_inputs = torch.from_numpy(to_mont(cs.inputs).view(np.int64)).to(dev)
-        torch.cuda.synchronize(dev)
+        torch.cuda.current_stream(dev).synchronize()  # stream-level: other contexts (the prover) keep running
         return d_inputs, d_aux

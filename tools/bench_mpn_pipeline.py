@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Steady-state MPN update proving: batches of 4^B signed transfers flow through
-    batched transition builder                     (context 3, thread 1)
-    GPU witness                                    (context 2, thread 2)
+    batched transition builder                     (own context, 1 thread)
+    GPU witness                                    (own contexts, 2 threads taking alternate batches: a slot is one
+                                                    latency-bound chain, slower still next to the prover's kernels)
     Groth16 prove from the resident witness        (context 1, main thread)
 so the transitions of batch k+2 are built and the witness of batch k+1 is computed while batch k is being proved
 (the witness kernel occupies a handful of warps).  Prints one JSON line: wall time per batch in steady state, proofs/s, transactions/s, and the stage times.
@@ -20,11 +21,13 @@ def main():
     A, T, Bb = (int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "15,3,2").split(","))
     n_batches = int(sys.argv[2]) if len(sys.argv) > 2 else 4
     ntx = 1 << (2 * Bb)
-    ctx1, ctx2, ctx3 = B.Context(0), B.Context(0), B.Context(0)
+    N_WIT = 2
+    ctx1, ctx3 = B.Context(0), B.Context(0)
+    wctx = [B.Context(0) for _ in range(N_WIT)]
     # the builder's and the witness kernels are small and latency-bound; the prover's saturate the SMs.  Give the
     # small ones high-priority streams so their CTAs are placed first whenever an MSM CTA retires.
-    hp = [torch.cuda.Stream(priority=-1), torch.cuda.Stream(priority=-1)]
-    for c, s_ in zip((ctx2, ctx3), hp):
+    hp = [torch.cuda.Stream(priority=-1) for _ in range(N_WIT + 1)]
+    for c, s_ in zip(wctx + [ctx3], hp):
         with torch.cuda.stream(s_):
             c.use_torch_stream()
     d = torch.empty((7, 4), dtype=torch.int64, device="cuda"); ctx1.fr_random_dev(99, 7, d); ctx1.synchronize()
@@ -32,7 +35,7 @@ def main():
     t0 = time.time()
     worker = MpnUpdateWorker(ctx1, A, T, Bb, rnd[:5])
     t_setup = time.time() - t0
-    wit2, hasher3 = UpdateWitnessGpu(ctx2, A, T), BU.GpuTreeHasher(ctx3)
+    wits, hasher3 = [UpdateWitnessGpu(c, A, T) for c in wctx], BU.GpuTreeHasher(ctx3)
     # ledger + signed transfers for all batches (host signing is outside the measured pipeline: it is the wallets' work)
     nacc = max(2, min(ntx + 1, 64))
     st, keys = U.MpnState(A, T), []
@@ -66,32 +69,42 @@ def main():
             qb.put((b, circ, pub))
         qb.put(None)
 
-    def witnesser():
+    def witnesser(w):
         while True:
             item = qb.get()
             if item is None:
+                qb.put(None)      # let the other witness thread see the end marker too
                 break
             b, circ, pub = item
             t = time.perf_counter()
-            wit = wit2.witness(circ)
+            wit = wits[w].witness(circ)
             stage["witness"].append(time.perf_counter() - t)
             q.put((b, circ, pub, wit))
         q.put(None)
 
     marks = []
-    th, th2 = threading.Thread(target=builder), threading.Thread(target=witnesser)
-    th.start(); th2.start()
+    th = threading.Thread(target=builder)
+    th2 = [threading.Thread(target=witnesser, args=(w,)) for w in range(N_WIT)]
+    th.start()
+    for t_ in th2:
+        t_.start()
+    ended = 0
     while True:
         item = q.get()
         if item is None:
-            break
+            ended += 1
+            if ended == N_WIT:
+                break
+            continue
         b, circ, pub, (d_in, d_aux) = item
         t = time.perf_counter()
         blob, pts = worker.prover.prove_dev(worker.pk, d_in, d_aux, rnd[5], rnd[6], check_satisfied=(b == 0))
         stage["prove"].append(time.perf_counter() - t)
         marks.append(time.perf_counter())
         blobs.append(blob); works.append((b, pub))
-    th.join(); th2.join()
+    th.join()
+    for t_ in th2:
+        t_.join()
     from bazuka_b200.mpn.cs import to_mont
     ok = all(BG.verify_bytes(worker.vk_blob, to_mont([b + 1, b, pub["state"], pub["aux_data"], pub["next_state"]]), blob) for (b, pub), blob in zip(works, blobs))
     per_batch = (marks[-1] - marks[0]) / (len(marks) - 1)   # batch 0 is the warm-up
@@ -100,7 +113,7 @@ def main():
                       "steady_state_s_per_batch": round(per_batch, 4), "proofs_per_s": round(1 / per_batch, 3), "tx_per_s": round(ntx / per_batch, 1),
                       "stage_s_median": {k: round(med(v), 4) for k, v in stage.items()}, "all_proofs_verify": bool(ok),
                       "one_off_s": {"r1cs_template_key_setup": round(t_setup, 1), "host_signing_all_batches": round(t_sign, 1)},
-                      "pipeline": "builder (ctx 3), witness (ctx 2) and prover (ctx 1) run on three threads, one batch apart; wall clock between consecutive proofs"}), flush=True)
+                      "pipeline": "builder, 2 witness workers (alternate batches) and the prover run on their own threads and contexts; wall clock between consecutive proofs"}), flush=True)
 
 
 if __name__ == "__main__":
