@@ -243,3 +243,33 @@ def test_worker_object_end_to_end(ctx, cref):
     bad.public_inputs[4] = bad.public_inputs[2]
     assert not worker.verify(bad, zk)
     worker.free()
+
+
+def test_witness_program_upload_rejects_malformed_programs(ctx):
+    """the device interpreter trusts its program, so the upload validates it: unknown opcode, an operand that
+    reads a variable defined later, a RAW index past n_raw, a JJ without its NOP half -> BZK_ERR_BAD_ARG."""
+    import ctypes as ct
+    from bazuka_b200 import _lib
+    from bazuka_b200.api import _host_ptr
+    from bazuka_b200.mpn.cs import to_mont
+    from bazuka_b200.mpn import native as N
+    coefs, jj_d = to_mont([1]), to_mont([N.JJ_D])
+    lc_ptr = np.array([0, 1, 2], dtype=np.int32)      # lc 0 = V[0] (ONE), lc 1 = V[2] (block variable 1)
+    lc_slot = np.array([0, 2], dtype=np.int32)
+    lc_coef = np.array([0, 0], dtype=np.int32)
+
+    def upload(ops, n_raw=1):
+        ops = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1, 6)
+        h = ct.c_void_p()
+        st = ctx._l.bzk_witness_program_upload(ctx._h, _host_ptr(ops), len(ops), _host_ptr(lc_ptr), 2, _host_ptr(lc_slot), _host_ptr(lc_coef), 2,
+                                               _host_ptr(coefs), 1, n_raw, 0, _host_ptr(jj_d), ct.byref(h))
+        if st == 0:
+            ctx._l.bzk_witness_program_free(ctx._h, h)
+        return st
+
+    assert upload([[0, 0, 0, 0, 0, 0], [1, 0, 0, 0, 0, 0]]) == 0                     # RAW; MUL(ONE, ONE)
+    assert upload([[0, 0, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0], [1, 1, 0, 0, 0, 0]]) == 0  # lc 1 reads block variable 1, defined earlier
+    assert upload([[9, 0, 0, 0, 0, 0]]) == -1
+    assert upload([[0, 0, 0, 0, 0, 0], [1, 1, 0, 0, 0, 0]]) == -1   # reads block variable 1 while defining it
+    assert upload([[0, 0, 0, 0, 0, 5]]) == -1
+    assert upload([[6, 0, 0, 0, 0, 0], [1, 0, 0, 0, 0, 0]]) == -1
