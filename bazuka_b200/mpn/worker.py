@@ -64,3 +64,43 @@ class MpnUpdateWorker:
 
     def free(self):
         self.witness.free(); self.pk.free(); self.prover.free()
+
+
+class MpnDepositWithdrawWorker:
+    """the same worker for the deposit / withdraw circuits (`kind` = "deposit" | "withdraw"): batched builder
+    (batch_update.deposit_batched / withdraw_batched), two-phase GPU witness (dw_witness.py), resident prover.
+    The R1CS comes from one host synthesis of the all-null batch (value-independent; one-off per shape)."""
+
+    def __init__(self, ctx, kind, A, T, B, toxic, g1=None, g2=None):
+        from . import dw as D
+        from .cs import ConstraintSystem
+        from .dw_witness import TwoPhaseWitnessGpu
+        self.ctx, self.kind, self.A, self.T, self.B = ctx, kind, A, T, B
+        self.circ_cls = D.DepositCircuit if kind == "deposit" else D.WithdrawCircuit
+        ni, na, mats, _, _ = self.circ_cls(A, T, B).synthesize(ConstraintSystem()).to_csr()
+        self.prover = BG.Prover(ctx, BG.R1CS(ni, na, *mats))
+        self.pk, self.vk = BG.setup_gpu(ctx, self.prover.r1cs, toxic, BG.G1_GENERATOR if g1 is None else g1, BG.G2_GENERATOR if g2 is None else g2)
+        self.vk_blob = BG.vk_to_bincode(self.vk)
+        self.witness = TwoPhaseWitnessGpu(ctx, kind, A, T)
+        self.hasher = BU.GpuTreeHasher(ctx)
+
+    def build(self, state, items, commitment=0, height=0) -> UpdateWork:
+        fn = BU.deposit_batched if self.kind == "deposit" else BU.withdraw_batched
+        pub, trans = fn(self.hasher, state, items, self.B)
+        circ = self.circ_cls(self.A, self.T, self.B, commitment=commitment, height=height, transitions=trans, **pub)
+        inputs = to_mont([commitment, height, pub["state"], pub["aux_data"], pub["next_state"]])
+        return UpdateWork(circ, inputs, len(trans), [])
+
+    def prove(self, work: UpdateWork, r, s, check_satisfied=True):
+        d_in, d_aux = self.witness.witness(work.circuit)
+        blob, _ = self.prover.prove_dev(self.pk, d_in, d_aux, r, s, check_satisfied=check_satisfied)
+        return BG.zkproof_blob(blob)
+
+    def verify(self, work: UpdateWork, zkproof) -> bool:
+        z = np.asarray(zkproof, dtype=np.uint8)
+        if z.size != 391 or z[:4].any():
+            return False
+        return BG.verify_bytes(self.vk_blob, work.public_inputs, z[4:])
+
+    def free(self):
+        self.witness.free(); self.pk.free(); self.prover.free()

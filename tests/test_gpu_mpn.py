@@ -273,3 +273,39 @@ def test_witness_program_upload_rejects_malformed_programs(ctx):
     assert upload([[0, 0, 0, 0, 0, 0], [1, 1, 0, 0, 0, 0]]) == -1   # reads block variable 1 while defining it
     assert upload([[0, 0, 0, 0, 0, 5]]) == -1
     assert upload([[6, 0, 0, 0, 0, 0], [1, 0, 0, 0, 0, 0]]) == -1
+
+
+@pytest.mark.parametrize("kind", ["deposit", "withdraw"])
+def test_deposit_withdraw_worker_end_to_end(ctx, cref, kind):
+    """deposits / withdrawals -> batched builder -> two-phase GPU witness -> proof blob accepted by the byte-image
+    verifier, rejected for another claimed next state; the builder's work equals the sequential builder's."""
+    import copy
+    from bazuka_b200.mpn import dw as D, native as N, update as U
+    from bazuka_b200.mpn.worker import MpnDepositWithdrawWorker
+    st, keys = make_state(3, 3, 2)
+    if kind == "deposit":
+        newpk, _ = N.eddsa_keys(b"dep-new")
+        items = [D.MpnDeposit(N.jj_compress(keys[0][0]), U.ZIESHA, 500), D.MpnDeposit(N.jj_compress(newpk), 77, 9),
+                 D.MpnDeposit(N.jj_compress(keys[1][0]), 77, 1)]
+        seq = lambda s: D.deposit(s, items, 1)
+    else:
+        items = []
+        for i, amt in enumerate([100, 5]):
+            w = D.MpnWithdraw(N.jj_compress(keys[i][0]), 1, amount=U.Money(U.ZIESHA, amt), fee=U.Money(U.ZIESHA, 2), fingerprint=1000 + i)
+            w.sign(keys[i][1])
+            items.append(w)
+        seq = lambda s: D.withdraw(s, items, 1)
+    st_seq = copy.deepcopy(st)
+    worker = MpnDepositWithdrawWorker(ctx, kind, 3, 3, 1, cref.fr_random(81, 5))
+    work = worker.build(st, items, commitment=11, height=3)
+    pub, trans = seq(st_seq)
+    assert work.accepted == len(trans) and st.root == st_seq.root
+    assert {k: getattr(work.circuit, k) for k in ("state", "aux_data", "next_state")} == pub
+    r, s = cref.fr_random(82, 2)
+    zk = worker.prove(work, r, s)
+    assert worker.verify(work, zk)
+    bad = copy.copy(work)
+    bad.public_inputs = work.public_inputs.copy()
+    bad.public_inputs[4] = bad.public_inputs[2]
+    assert not worker.verify(bad, zk)
+    worker.free()
