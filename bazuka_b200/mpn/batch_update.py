@@ -137,41 +137,26 @@ def update_batched(hasher, state: MpnState, txs, log4_batch, fee_token=ZIESHA):
                          dst_token=Money(dst_token.token_id, dst_token.amount) if dst_token else Money()))
         fee_sum += tx.fee.amount
     # ------------------------------------------------------------------ phase 2a: the token forest
-    tree_of = {}
+    touched = list(dict.fromkeys(i for p in plan for i in (p["src_index"], p["dst_index"])))
+    forest = _TokenForest(state, touched)        # pre-batch token trees enter as writes into empty trees
     for p in plan:
-        for i in (p["src_index"], p["dst_index"]):
-            tree_of.setdefault(i, len(tree_of))
-    touched = list(tree_of)
-    tdef = _token_defaults(T)
-    t_rows, t_tree, t_idx = [], [], []
-    for acc in touched:                          # the pre-batch token trees, as writes into empty trees
-        for i, m in state.accounts.get(acc, MpnAccount()).tokens.items():
-            t_rows.append([m.token_id, m.amount]); t_tree.append(tree_of[acc]); t_idx.append(i)
-    n_init = len(t_rows)
-    for p in plan:
-        t_rows.append([p["src_token"].token_id, p["src_mid"].tokens[p["sti"]].amount]); t_tree.append(tree_of[p["src_index"]]); t_idx.append(p["sti"])
-        t_rows.append([p["src_fee_token"].token_id, p["src_after"].tokens[p["sfi"]].amount]); t_tree.append(tree_of[p["src_index"]]); t_idx.append(p["sfi"])
-        t_rows.append([p["dst_after"].tokens[p["dti"]].token_id, p["dst_after"].tokens[p["dti"]].amount]); t_tree.append(tree_of[p["dst_index"]]); t_idx.append(p["dti"])
-    t_leaves = hasher.poseidon_batch(t_rows)
-    default_proof = [[tdef[l]] * 3 for l in range(T)]
-    t_vals, t_proofs = hasher.tree_update(T, t_tree, t_idx, t_leaves, [default_proof] * len(t_rows))
-    tok_root = {k: tdef[T] for k in range(len(touched))}  # current token root per tree while replaying the events
-    for e in range(n_init):
-        tok_root[t_tree[e]] = t_vals[T][e]
+        p["e1"] = forest.write(p["src_index"], p["sti"], p["src_mid"].tokens[p["sti"]])
+        p["e2"] = forest.write(p["src_index"], p["sfi"], p["src_after"].tokens[p["sfi"]])
+        p["e3"] = forest.write(p["dst_index"], p["dti"], p["dst_after"].tokens[p["dti"]])
+    forest.run(hasher)
     acct_rows = []
-    for k, p in enumerate(plan):
-        e1, e2, e3 = n_init + 3 * k, n_init + 3 * k + 1, n_init + 3 * k + 2
-        st, dt = tree_of[p["src_index"]], tree_of[p["dst_index"]]
-        p["src_before_balances_hash"] = tok_root[st]
-        p["src_balance_proof"], p["src_fee_balance_proof"] = t_proofs[e1], t_proofs[e2]
-        tok_root[st] = t_vals[T][e2]
-        p["dst_before_balances_hash"] = tok_root[dt]
-        p["dst_balance_proof"] = t_proofs[e3]
-        tok_root[dt] = t_vals[T][e3]
+    for p in plan:
+        p["src_before_balances_hash"] = forest.root(p["src_index"])
+        p["src_balance_proof"], p["src_fee_balance_proof"] = forest.proofs[p["e1"]], forest.proofs[p["e2"]]
+        r1 = forest.applied(p["src_index"], p["e1"])
+        r2 = forest.applied(p["src_index"], p["e2"])
+        p["dst_before_balances_hash"] = forest.root(p["dst_index"])
+        p["dst_balance_proof"] = forest.proofs[p["e3"]]
+        r3 = forest.applied(p["dst_index"], p["e3"])
         sm, sa, da = p["src_mid"], p["src_after"], p["dst_after"]
-        acct_rows.append([sm.tx_nonce, sm.withdraw_nonce, sm.address[0], sm.address[1], t_vals[T][e1]])
-        acct_rows.append([sa.tx_nonce, sa.withdraw_nonce, sa.address[0], sa.address[1], t_vals[T][e2]])
-        acct_rows.append([da.tx_nonce, da.withdraw_nonce, da.address[0], da.address[1], t_vals[T][e3]])
+        acct_rows.append([sm.tx_nonce, sm.withdraw_nonce, sm.address[0], sm.address[1], r1])
+        acct_rows.append([sa.tx_nonce, sa.withdraw_nonce, sa.address[0], sa.address[1], r2])
+        acct_rows.append([da.tx_nonce, da.withdraw_nonce, da.address[0], da.address[1], r3])
     # ------------------------------------------------------------------ phase 2b: the state tree
     s_leaves = hasher.poseidon_batch(acct_rows)
     s_idx = [i for p in plan for i in (p["src_index"], p["src_index"], p["dst_index"])]
@@ -186,13 +171,7 @@ def update_batched(hasher, state: MpnState, txs, log4_batch, fee_token=ZIESHA):
             p["dst_balance_proof"], root))
         root = s_vals[A][3 * k + 2]
     # ------------------------------------------------------------------ commit: accounts + the nodes every write left behind
-    for e, i in enumerate(s_idx):
-        node = i
-        for lvl in range(A + 1):
-            state.tree._put(lvl, node, s_vals[lvl][e])
-            node >>= 2
-    for i in touched:
-        state.accounts[i] = mirror[i].copy()
+    _commit(state, mirror, touched, s_idx, s_vals)
     assert state.root == root
     public = {"state": prev_root, "aux_data": hasher.poseidon_batch([[fee_token, fee_sum]])[0], "next_state": root}
     return public, transitions, rejected
@@ -253,7 +232,7 @@ class _TokenForest:
         return self.vals[self.T][e]
 
 
-def _commit(state, ledger, touched, s_idx, s_vals):
+def _commit(state, mirror, touched, s_idx, s_vals):
     A = state.A
     for e, i in enumerate(s_idx):
         node = i
@@ -261,7 +240,7 @@ def _commit(state, ledger, touched, s_idx, s_vals):
             state.tree._put(lvl, node, s_vals[lvl][e])
             node >>= 2
     for i in touched:
-        state.accounts[i] = ledger.mirror[i].copy()
+        state.accounts[i] = mirror[i].copy()
 
 
 def _list_root(hasher, rows):
@@ -310,7 +289,7 @@ def deposit_batched(hasher, state: MpnState, deposits, log4_batch):
     for k, p in enumerate(plan):
         trans.append(DepositTransition(True, p["d"], p["before"], p["before_balances_hash"], p["bal"], s_proofs[k], p["idx"], p["ti"], p["bproof"], root))
         root = s_vals[state.A][k]
-    _commit(state, led, touched, s_idx, s_vals)
+    _commit(state, led.mirror, touched, s_idx, s_vals)
     pk_hashes = hasher.poseidon_batch([[p["addr"][0], p["addr"][1]] for p in plan])
     rows = [[1, p["d"].token_id, p["d"].amount, pk_hashes[k]] for k, p in enumerate(plan)] + [[0, 0, 0, 0]] * (n - len(plan))
     return {"state": prev, "aux_data": _list_root(hasher, rows), "next_state": root}, trans
@@ -367,7 +346,7 @@ def withdraw_batched(hasher, state: MpnState, withdraws, log4_batch):
         trans.append(WithdrawTransition(True, p["w"], p["before"], p["tok"], p["fee_before"], s_proofs[2 * k], p["idx"], p["ti"], p["tproof"],
                                         p["before_token_hash"], p["fi"], p["fproof"], root))
         root = s_vals[state.A][2 * k + 1]
-    _commit(state, led, touched, s_idx, s_vals)
+    _commit(state, led.mirror, touched, s_idx, s_vals)
     cds = hasher.poseidon_batch([[p["addr"][0], p["addr"][1], p["w"].mpn_withdraw_nonce, p["w"].mpn_sig["r"][0], p["w"].mpn_sig["r"][1], p["w"].mpn_sig["s"]]
                                  for p in plan])
     rows = [[1, p["w"].amount.token_id, p["w"].amount.amount, p["w"].fee.token_id, p["w"].fee.amount, p["w"].fingerprint, cds[k]]
