@@ -79,6 +79,12 @@ SIGNATURES = {
     "bzk_groth16_params_set_shard": (_i32, [_vp, _u32, _u32]),
     "bzk_groth16_prove_partial": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "bzk_groth16_finalize": (_i32, [_vp] * 14),
+    "bzk_mpn_state_create": (_i32, [_vp, _u32, _u32, _vp, ct.POINTER(_vp)]),
+    "bzk_mpn_state_free": (_i32, [_vp]),
+    "bzk_mpn_state_root": (_i32, [_vp, _vp]),
+    "bzk_mpn_state_set_account": (_i32, [_vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _u32]),
+    "bzk_mpn_update_raw_width": (_i32, [_u32, _u32, _vp]),
+    "bzk_mpn_update_build": (_i32, [_vp, _vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bzk_witness_program_upload": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _vp, _u64, _u32, _u32, _vp, ct.POINTER(_vp)]),
     "bzk_witness_program_free": (_i32, [_vp, _vp]),
     "bzk_witness_run_dev": (_i32, [_vp, _vp, _vp, _vp, _u64, _vp]),

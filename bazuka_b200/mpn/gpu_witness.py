@@ -45,18 +45,26 @@ class UpdateWitnessGpu:
 
     def witness(self, circ):
         """-> (d_inputs [ni,4], d_aux [na,4]) int64 CUDA tensors holding Montgomery images."""
+        assert (circ.A, circ.T) == (self.A, self.T)
+        raws = np.concatenate([_canon_rows(W.raw_values(tr, self.A, self.T)) for tr in circ.transitions])
+        ext = _canon_rows([v for root in W.slot_roots(circ) for v in (circ.fee_token, root)])
+        return self.witness_rows(raws, ext, circ)
+
+    def witness_rows(self, raws, ext, circ):
+        """same from ready-made rows (e.g. the native builder's, mpn/ledger.py): raws [n, n_raw, 4], ext [n, 2, 4]
+        canonical; `circ` only supplies the six public / prologue values (its transitions are not read)."""
         import torch
         from ..api import _dev_ptr, _host_ptr
-        assert (circ.A, circ.T) == (self.A, self.T)
         p, ctx = self.prog, self.ctx
-        n, a_tx = len(circ.transitions), self.prog.n_ops
+        raws = np.ascontiguousarray(raws, dtype=np.uint64).reshape(-1, 4)
+        ext = np.ascontiguousarray(ext, dtype=np.uint64).reshape(-1, 4)
+        n, a_tx = len(ext) // 2, self.prog.n_ops
+        assert len(raws) == n * p.n_raw
         # ---- prologue on the host
         cs = ConstraintSystem()
         state_wit, fee_tok, aux_wit, claimed = circ._prologue(cs)
         assert len(cs.aux) == p.p_aux
         # ---- slots on the device
-        raws = np.concatenate([_canon_rows(W.raw_values(tr, self.A, self.T)) for tr in circ.transitions])
-        ext = _canon_rows([v for root in W.slot_roots(circ) for v in (circ.fee_token, root)])
         # epilogue size is value-independent: synthesise it once with placeholders to learn it
         probe = ConstraintSystem()
         circ._epilogue(probe, AllocatedNum(probe.alloc(0), 0), AllocatedNum(probe.alloc(0), 0), AllocatedNum(probe.alloc(0), 0),

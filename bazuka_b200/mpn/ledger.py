@@ -1,0 +1,90 @@
+"""ctypes front-end of the native MPN ledger and update builder (csrc/mpn_host.cu).
+
+    led = NativeLedger(ctx, A, T)
+    led.set_account(index, MpnAccount(...))
+    raws, ext, accepted, public = led.update_build(txs, log4_batch)       # rows for the witness program
+
+`raws` [4^B, n_raw, 4] / `ext` [4^B, 2, 4] are canonical uint64 images, exactly what bzk_witness_run_dev consumes
+(`UpdateWitnessGpu.witness_rows`); `public` = {"state", "aux_data", "next_state"} as Python ints."""
+import ctypes as ct
+
+import numpy as np
+
+from . import native as N
+from .cs import R
+from .update import ZIESHA, MpnAccount
+
+_TX = np.dtype([("nonce", "<u8"), ("amount", "<u8"), ("fee", "<u8"), ("src_pk_odd", "u1"), ("dst_pk_odd", "u1"), ("pad", "u1", 6),
+                ("src_pk_x", "<u8", 4), ("dst_pk_x", "<u8", 4), ("amount_token_id", "<u8", 4), ("fee_token_id", "<u8", 4),
+                ("sig_rx", "<u8", 4), ("sig_ry", "<u8", 4), ("sig_s", "<u8", 4)])
+assert _TX.itemsize == 32 + 7 * 32
+
+
+def _canon(v):
+    return np.frombuffer((v % R).to_bytes(32, "little"), dtype=np.uint64)
+
+
+def _int(a):
+    return int.from_bytes(np.ascontiguousarray(a, dtype=np.uint64).tobytes(), "little")
+
+
+def pack_txs(txs):
+    """list of update.MpnTransaction -> array of bzk_mpn_tx"""
+    out = np.zeros(len(txs), dtype=_TX)
+    for k, tx in enumerate(txs):
+        o = out[k]
+        o["nonce"], o["amount"], o["fee"] = tx.nonce, tx.amount.amount, tx.fee.amount
+        o["src_pk_odd"], o["dst_pk_odd"] = int(tx.src_pub_key[1]), int(tx.dst_pub_key[1])
+        o["src_pk_x"], o["dst_pk_x"] = _canon(tx.src_pub_key[0]), _canon(tx.dst_pub_key[0])
+        o["amount_token_id"], o["fee_token_id"] = _canon(tx.amount.token_id), _canon(tx.fee.token_id)
+        o["sig_rx"], o["sig_ry"], o["sig_s"] = _canon(tx.sig["r"][0]), _canon(tx.sig["r"][1]), _canon(tx.sig["s"])
+    return out
+
+
+class NativeLedger:
+    def __init__(self, ctx, A, T):
+        from ..api import _host_ptr
+        self.ctx, self.A, self.T = ctx, A, T
+        h = ct.c_void_p()
+        jj_d = np.ascontiguousarray(_canon(N.JJ_D))
+        ctx._check(ctx._l.bzk_mpn_state_create(ctx._h, A, T, _host_ptr(jj_d), ct.byref(h)))
+        self._h = h
+        w = ct.c_uint32()
+        ctx._check(ctx._l.bzk_mpn_update_raw_width(A, T, ct.byref(w)))
+        self.n_raw = w.value
+
+    def free(self):
+        if self._h:
+            self.ctx._l.bzk_mpn_state_free(self._h)
+            self._h = None
+
+    @property
+    def root(self):
+        from ..api import _host_ptr
+        out = np.zeros(4, dtype=np.uint64)
+        self.ctx._check(self.ctx._l.bzk_mpn_state_root(self._h, _host_ptr(out)))
+        return _int(out)
+
+    def set_account(self, index, acc: MpnAccount):
+        from ..api import _host_ptr
+        idx = np.array(sorted(acc.tokens), dtype=np.uint32)
+        ids = np.ascontiguousarray(np.stack([_canon(acc.tokens[i].token_id) for i in idx]) if len(idx) else np.zeros((0, 4), np.uint64))
+        amts = np.array([acc.tokens[i].amount for i in idx], dtype=np.uint64)
+        ax, ay = np.ascontiguousarray(_canon(acc.address[0])), np.ascontiguousarray(_canon(acc.address[1]))
+        self.ctx._check(self.ctx._l.bzk_mpn_state_set_account(self.ctx._h, self._h, index, acc.tx_nonce, acc.withdraw_nonce, _host_ptr(ax), _host_ptr(ay),
+                                                              _host_ptr(idx), _host_ptr(ids), _host_ptr(amts), len(idx)))
+
+    def update_build(self, txs, log4_batch, fee_token=ZIESHA):
+        from ..api import _host_ptr
+        packed = txs if isinstance(txs, np.ndarray) else pack_txs(txs)
+        slots = 1 << (2 * log4_batch)
+        raws = np.zeros((slots, self.n_raw, 4), dtype=np.uint64)
+        ext = np.zeros((slots, 2, 4), dtype=np.uint64)
+        acc = np.zeros(max(len(packed), 1), dtype=np.uint8)
+        pub = np.zeros((3, 4), dtype=np.uint64)
+        n_acc = ct.c_uint64()
+        fee = np.ascontiguousarray(_canon(fee_token))
+        self.ctx._check(self.ctx._l.bzk_mpn_update_build(self.ctx._h, self._h, _host_ptr(packed), len(packed), log4_batch, _host_ptr(fee),
+                                                         _host_ptr(raws), _host_ptr(ext), _host_ptr(acc), _host_ptr(pub), ct.byref(n_acc)))
+        public = {"state": _int(pub[0]), "aux_data": _int(pub[1]), "next_state": _int(pub[2])}
+        return raws, ext, acc[:len(packed)].astype(bool), public, n_acc.value

@@ -218,6 +218,37 @@ int32_t bzk_groth16_finalize(const bzk_g1_affine *alpha_g1, const bzk_g1_affine 
                              const bzk_g1_affine *a_sum, const bzk_g1_affine *b1_sum, const bzk_g2_affine *b2_sum, const bzk_g1_affine *hl_sum,
                              const bzk_fr *r, const bzk_fr *s, bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c);
 
+/* ------------------------------------------------------------------ MPN ledger + update transition builder
+ * Native host logic of `mpn::update::update` (/root/reference/src/mpn/update.rs:8-299) over the state model of
+ * /root/reference/src/mpn/mod.rs:219-240 (accounts with a token sub-tree in a 4-ary sparse Poseidon tree): ledger
+ * decisions first (no hashing), then all hashing in batches on the GPU (bzk_poseidon_hash + the versioned tree
+ * update).  Scalars are CANONICAL 32-byte little-endian integers here (amounts and nonces are u64, as in the
+ * reference).  bzk_mpn_update_build consumes up to 4^log4_batch acceptable transactions in order and writes
+ *   raws[4^B][n_raw]  each slot's circuit inputs in UpdateCircuit's allocation order (n_raw = 32 + 9T + 6A,
+ *                     bzk_mpn_update_raw_width) — the RAW operands of the witness program; null slots padded,
+ *   ext[4^B][2]       {fee token, state root entering the slot} — the program's external slots,
+ *   accepted[n_txs]   1 where the transaction was taken (rejected or beyond the batch: 0), optional,
+ *   public3           {state before, aux_data = Poseidon(fee_token, fee sum), state after},
+ * and advances the ledger.  BZK_ERR_NOT_ON_CURVE: a compressed key does not decompress. */
+typedef struct bzk_mpn_state bzk_mpn_state;
+typedef struct {
+    uint64_t nonce, amount, fee;
+    uint8_t src_pk_odd, dst_pk_odd, pad[6];
+    bzk_fr src_pk_x, dst_pk_x;              /* PointCompressed(x, is_odd) of the two JubJub keys */
+    bzk_fr amount_token_id, fee_token_id;
+    bzk_fr sig_rx, sig_ry, sig_s;           /* EdDSA signature (checked in the circuit, not by the builder) */
+} bzk_mpn_tx;
+int32_t bzk_mpn_state_create(bzk_ctx *ctx, uint32_t log4_tree, uint32_t log4_token, const bzk_fr *jubjub_d, bzk_mpn_state **out);
+int32_t bzk_mpn_state_free(bzk_mpn_state *state);
+int32_t bzk_mpn_state_root(const bzk_mpn_state *state, bzk_fr *root);
+int32_t bzk_mpn_state_set_account(bzk_ctx *ctx, bzk_mpn_state *state, uint64_t index, uint64_t tx_nonce, uint64_t withdraw_nonce,
+                                  const bzk_fr *addr_x, const bzk_fr *addr_y, const uint32_t *token_index, const bzk_fr *token_id,
+                                  const uint64_t *token_amount, uint32_t n_tokens);
+int32_t bzk_mpn_update_raw_width(uint32_t log4_tree, uint32_t log4_token, uint32_t *n_raw);
+int32_t bzk_mpn_update_build(bzk_ctx *ctx, bzk_mpn_state *state, const bzk_mpn_tx *txs, uint64_t n_txs, uint32_t log4_batch,
+                             const bzk_fr *fee_token, bzk_fr *raws, bzk_fr *ext, uint8_t *accepted, bzk_fr public3[3],
+                             uint64_t *n_accepted);
+
 /* ------------------------------------------------------------------ witness generation (device)
  * bellman's `ProvingAssignment` runs `MpnCircuit::synthesize` with value closures
  * (/root/reference/src/mpn/circuits/update_circuit.rs:49-494).  Every slot of an update batch performs the

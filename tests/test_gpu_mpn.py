@@ -309,3 +309,41 @@ def test_deposit_withdraw_worker_end_to_end(ctx, cref, kind):
     bad.public_inputs[4] = bad.public_inputs[2]
     assert not worker.verify(bad, zk)
     worker.free()
+
+
+def test_native_ledger_update_build_equals_python_builder(ctx, cref):
+    """csrc/mpn_host.cu (C++ ledger logic + batched GPU hashing) against the Python restatement of `update()`:
+    same accepted set, same rows of circuit inputs (raw_values order), same entering roots, public inputs and final
+    state, over two consecutive batches (new account, self-transfer, same-token fee, four kinds of rejection); and
+    the proof made from the native rows equals the proof made from the Python transitions."""
+    import copy
+    from bazuka_b200 import groth16 as BG
+    from bazuka_b200.mpn import cs as C, native as N, update as U, witness_program as W
+    from bazuka_b200.mpn.gpu_witness import UpdateWitnessGpu, _canon_rows
+    from bazuka_b200.mpn.ledger import NativeLedger
+    from test_mpn_cpu import _batch_scenario
+    st, txs = _batch_scenario()
+    led = NativeLedger(ctx, 3, 3)
+    assert led.n_raw == len(W.raw_values(U.UpdateTransition.null(3, 3), 3, 3))
+    for i, a in st.accounts.items():
+        led.set_account(i, a)
+    assert led.root == st.root
+    assert NativeLedger(ctx, 30, 1).root == int("501a18871f186db1437e77e2c33acfa81405608cc60806399347215dbe98f714", 16)  # reference KAT
+    circs = []
+    for batch, B in ((txs, 2), (txs[:0] + [t for t in txs[6:]], 1)):
+        pub, trans, rej = U.update(st, batch, B)
+        circ = U.UpdateCircuit(3, 3, B, commitment=5, height=1, transitions=trans, **pub)
+        raws, ext, acc, public, n_acc = led.update_build(batch, B)
+        assert n_acc == len(trans) and public == pub and led.root == st.root
+        assert [t for t, a in zip(batch, acc) if not a][:len(rej)] == rej or len(trans) == (1 << (2 * B))
+        want_raws = np.stack([_canon_rows(W.raw_values(tr, 3, 3)) for tr in circ.transitions])
+        want_ext = np.stack([_canon_rows([circ.fee_token, r]) for r in W.slot_roots(circ)])
+        assert (raws == want_raws).all(), np.nonzero((raws != want_raws).any(axis=2))
+        assert (ext == want_ext).all()
+        circs.append((circ, raws, ext))
+    circ, raws, ext = circs[0]
+    gw = UpdateWitnessGpu(ctx, 3, 3)
+    d_in1, d_aux1 = gw.witness(circ)
+    d_in2, d_aux2 = gw.witness_rows(raws, ext, circ)
+    assert (d_aux1 == d_aux2).all() and (d_in1 == d_in2).all()
+    gw.free(); led.free()
