@@ -496,3 +496,41 @@ int32_t bzk_mpn_update_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_tx *t
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// witness of a whole update batch from the builder's rows: what `UpdateCircuit::synthesize` assigns
+// (/root/reference/src/mpn/circuits/update_circuit.rs:49-494), laid out as z = inputs ++ aux:
+//   inputs  = [1, commitment, height, state, aux_data, next_state]
+//   aux     = [commitment, height, state, fee_token, aux_data, next_state]      (the six prologue allocations)
+//             ++ slot program x n_slots                                          (bzk_witness_run_dev)
+//             ++ epilogue program (the Poseidon(fee_token, sum of accepted fees) gadget; externals =
+//                fee_token, then every slot's accepted fee)
+// ---------------------------------------------------------------------------------------------
+extern "C" int32_t bzk_mpn_update_witness(bzk_ctx *ctx, const bzk_witness_program *slot_prog, const bzk_witness_program *epilogue_prog,
+                                          uint64_t n_slots, uint32_t log4_token, uint64_t slot_vars, uint64_t epilogue_vars, const bzk_fr *raws,
+                                          const bzk_fr *ext, uint32_t n_raw, const bzk_fr prologue[6], void *d_inputs, void *d_aux) {
+    if (!ctx || !slot_prog || !epilogue_prog || !n_slots || !raws || !ext || !prologue || !d_inputs || !d_aux || n_raw < 16 + 3 * log4_token)
+        return BZK_ERR_BAD_ARG;
+    BZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    Fr head[12];  // 6 inputs, 6 prologue aux (Montgomery)
+    const Fr commitment = fr_from_canon(prologue + 0), height = fr_from_canon(prologue + 1), state = fr_from_canon(prologue + 2),
+             fee_token = fr_from_canon(prologue + 3), aux_data = fr_from_canon(prologue + 4), next_state = fr_from_canon(prologue + 5);
+    head[0] = Fr::one(); head[1] = commitment; head[2] = height; head[3] = state; head[4] = aux_data; head[5] = next_state;
+    head[6] = commitment; head[7] = height; head[8] = state; head[9] = fee_token; head[10] = aux_data; head[11] = next_state;
+    Fr *z_in = (Fr *)d_inputs, *z_aux = (Fr *)d_aux;
+    BZK_CUDA(ctx, cudaMemcpyAsync(z_in, head, 6 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    BZK_CUDA(ctx, cudaMemcpyAsync(z_aux, head + 6, 6 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    BZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `head` is a stack buffer
+    BZK_TRY(bzk_witness_run_dev(ctx, slot_prog, raws, ext, n_slots, z_aux + 6));
+    // accepted fee of a slot = enabled ? tx.fee : 0; both are raw inputs (positions 0 and 15 + 3T of a row)
+    std::vector<bzk_fr> epi_ext(1 + n_slots);
+    epi_ext[0] = prologue[3];
+    const bzk_fr zero{};
+    for (uint64_t k = 0; k < n_slots; k++) {
+        const bzk_fr *row = raws + k * n_raw;
+        epi_ext[1 + k] = row[0].l[0] ? row[15 + 3 * log4_token] : zero;
+    }
+    BZK_TRY(bzk_witness_run_dev(ctx, epilogue_prog, nullptr, epi_ext.data(), 1, z_aux + 6 + n_slots * slot_vars));
+    (void)epilogue_vars;
+    return BZK_OK;
+}

@@ -149,16 +149,9 @@ def host_parts(progs: TwoPhasePrograms, circ):
 
 class TwoPhaseWitnessGpu:
     def __init__(self, ctx, kind, A, T):
-        from ..api import _host_ptr
+        from .gpu_witness import upload_program
         self.ctx, self.progs = ctx, TwoPhasePrograms(kind, A, T)
-        jj_d = to_mont([N.JJ_D])
-        self._h = []
-        for p in (self.progs.prog1, self.progs.prog2):
-            ops, coefs, h = np.ascontiguousarray(p.ops, dtype=np.int32), np.ascontiguousarray(p.coefs_mont()), ct.c_void_p()
-            ctx._check(ctx._l.bzk_witness_program_upload(
-                ctx._h, _host_ptr(ops), len(ops), _host_ptr(p.lc_ptr), len(p.lc_ptr) - 1, _host_ptr(p.lc_slot), _host_ptr(p.lc_coef),
-                len(p.lc_slot), _host_ptr(coefs), len(coefs), p.n_raw, p.n_ext, _host_ptr(jj_d), ct.byref(h)))
-            self._h.append(h)
+        self._h = [upload_program(ctx, p) for p in (self.progs.prog1, self.progs.prog2)]
 
     def free(self):
         for h in self._h:

@@ -24,24 +24,54 @@ def _canon_rows(values):
     return np.frombuffer(buf, dtype=np.uint64).reshape(-1, 4).copy()
 
 
+def upload_program(ctx, p):
+    from ..api import _host_ptr
+    ops = np.ascontiguousarray(p.ops, dtype=np.int32)
+    coefs = np.ascontiguousarray(p.coefs_mont())
+    jj_d = to_mont([N.JJ_D])
+    h = ct.c_void_p()
+    ctx._check(ctx._l.bzk_witness_program_upload(
+        ctx._h, _host_ptr(ops), len(ops), _host_ptr(p.lc_ptr), len(p.lc_ptr) - 1, _host_ptr(p.lc_slot), _host_ptr(p.lc_coef),
+        len(p.lc_slot), _host_ptr(coefs), len(coefs), p.n_raw, p.n_ext, _host_ptr(jj_d), ct.byref(h)))
+    return h
+
+
 class UpdateWitnessGpu:
     def __init__(self, ctx, A, T):
-        from ..api import _host_ptr
         self.ctx, self.A, self.T = ctx, A, T
-        self.prog = p = W.compile_update_block(A, T)
-        ops = np.ascontiguousarray(p.ops, dtype=np.int32)
-        coefs = np.ascontiguousarray(p.coefs_mont())
-        jj_d = to_mont([N.JJ_D])
-        h = ct.c_void_p()
-        ctx._check(ctx._l.bzk_witness_program_upload(
-            ctx._h, _host_ptr(ops), len(ops), _host_ptr(p.lc_ptr), len(p.lc_ptr) - 1, _host_ptr(p.lc_slot), _host_ptr(p.lc_coef),
-            len(p.lc_slot), _host_ptr(coefs), len(coefs), p.n_raw, p.n_ext, _host_ptr(jj_d), ct.byref(h)))
-        self._h = h
+        self.prog = W.compile_update_block(A, T)
+        self._h = upload_program(ctx, self.prog)
+        self._epi = {}   # log4_batch -> (program, handle)
 
     def free(self):
         if self._h:
             self.ctx._l.bzk_witness_program_free(self.ctx._h, self._h)
             self._h = None
+        for _, h in self._epi.values():
+            self.ctx._l.bzk_witness_program_free(self.ctx._h, h)
+        self._epi = {}
+
+    def witness_native(self, raws, ext, prologue, log4_batch):
+        """the whole batch witness through bzk_mpn_update_witness (no Python between the builder's rows and z):
+        raws [4^B, n_raw, 4], ext [4^B, 2, 4] canonical (mpn/ledger.py), prologue = [commitment, height, state,
+        fee_token, aux_data, next_state] as ints.  -> (d_inputs, d_aux) CUDA tensors."""
+        import torch
+        from ..api import _dev_ptr, _host_ptr
+        ctx, p = self.ctx, self.prog
+        if log4_batch not in self._epi:
+            ep = W.compile_update_epilogue(p, log4_batch)
+            self._epi[log4_batch] = (ep, upload_program(ctx, ep))
+        ep, eh = self._epi[log4_batch]
+        n = 1 << (2 * log4_batch)
+        raws = np.ascontiguousarray(raws, dtype=np.uint64).reshape(n, p.n_raw, 4)
+        ext = np.ascontiguousarray(ext, dtype=np.uint64).reshape(n, 2, 4)
+        pro = _canon_rows(prologue)
+        dev = torch.device("cuda", ctx.device)
+        d_in = torch.empty((6, 4), dtype=torch.int64, device=dev)
+        d_aux = torch.empty((p.p_aux + n * p.n_ops + ep.n_ops, 4), dtype=torch.int64, device=dev)
+        ctx._check(ctx._l.bzk_mpn_update_witness(ctx._h, self._h, eh, n, self.T, p.n_ops, ep.n_ops, _host_ptr(raws), _host_ptr(ext), p.n_raw,
+                                                 _host_ptr(pro), _dev_ptr(d_in), _dev_ptr(d_aux)))
+        return d_in, d_aux
 
     def witness(self, circ):
         """-> (d_inputs [ni,4], d_aux [na,4]) int64 CUDA tensors holding Montgomery images."""

@@ -172,6 +172,24 @@ def compile_update_block(A, T) -> WitnessProgram:
     return prog
 
 
+def compile_update_epilogue(slot_prog: WitnessProgram, B) -> WitnessProgram:
+    """the part of `synthesize` after the slot loop (update_circuit.rs:470-493): the Poseidon(fee_token, fee_sum)
+    gadget.  Externals = [accepted_fee_token, slot 0's accepted fee, ..., slot n-1's accepted fee]."""
+    A, T, n, a_tx, p_aux = slot_prog.A, slot_prog.T, 1 << (2 * B), slot_prog.n_ops, slot_prog.p_aux
+    circ = U.UpdateCircuit(A, T, B)
+    cs = ConstraintSystem(record=True)
+    _, fee_tok, aux_wit, claimed = circ._prologue(cs)
+    cs.aux.extend([0] * (n * a_tx))
+    cs.recipes.extend([("raw",)] * (n * a_tx))
+    fee_vars = [2 * (p_aux + k * a_tx + slot_prog.final_fee) + 1 for k in range(n)]
+    start = len(cs.aux)
+    last_state = AllocatedNum(2 * (p_aux + (n - 1) * a_tx + slot_prog.state_out) + 1, 0)
+    circ._epilogue(cs, last_state, fee_tok, aux_wit, claimed, Number(LC({v: 1 for v in fee_vars}), 0))
+    prog = compile_block(cs.recipes[start:], start, [fee_tok.var] + fee_vars)
+    prog.A, prog.T = A, T
+    return prog
+
+
 def run_reference(prog: WitnessProgram, raws, ext):
     """interpret the program for one slot with Python integers -> the block's aux values (canonical).
     ext: the slot's external values (update circuit: [fee_token, state_in])."""

@@ -55,6 +55,16 @@ class MpnUpdateWorker:
         blob, _ = self.prover.prove_dev(self.pk, d_in, d_aux, r, s, check_satisfied=check_satisfied)
         return BG.zkproof_blob(blob)
 
+    def prove_native(self, ledger, txs, r, s, commitment=0, height=0, fee_token=U.ZIESHA, check_satisfied=True):
+        """the per-batch path with nothing but native calls between the transactions and the proof:
+        bzk_mpn_update_build (C++ ledger + batched GPU hashing) -> bzk_mpn_update_witness (slot + epilogue
+        programs, z resident) -> bzk_groth16_prove_dev.  `ledger` = mpn.ledger.NativeLedger.
+        -> (391-byte ZkProof image, public inputs [5,4] Montgomery, accepted mask)."""
+        raws, ext, accepted, pub, _ = ledger.update_build(txs, self.B, fee_token)
+        d_in, d_aux = self.witness.witness_native(raws, ext, [commitment, height, pub["state"], fee_token, pub["aux_data"], pub["next_state"]], self.B)
+        blob, _ = self.prover.prove_dev(self.pk, d_in, d_aux, r, s, check_satisfied=check_satisfied)
+        return BG.zkproof_blob(blob), to_mont([commitment, height, pub["state"], pub["aux_data"], pub["next_state"]]), accepted
+
     def verify(self, work: UpdateWork, zkproof) -> bool:
         """`check_proof(vk, commitment, height, state, aux_data, next_state, proof)` on the reference's byte images"""
         z = np.asarray(zkproof, dtype=np.uint8)

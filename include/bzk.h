@@ -249,6 +249,16 @@ int32_t bzk_mpn_update_build(bzk_ctx *ctx, bzk_mpn_state *state, const bzk_mpn_t
                              const bzk_fr *fee_token, bzk_fr *raws, bzk_fr *ext, uint8_t *accepted, bzk_fr public3[3],
                              uint64_t *n_accepted);
 
+/* Whole-batch witness from the builder's rows, resident in device memory as z = d_inputs[6] ++ d_aux
+ * (6 + n_slots*slot_vars + epilogue_vars elements): the six public / prologue values
+ * prologue[6] = {commitment, height, state, fee_token, aux_data, next_state} (canonical), the slot program on
+ * every slot, and the epilogue program (the fee-commitment Poseidon gadget; its externals are the fee token and
+ * every slot's accepted fee, taken from the rows).  Feeds bzk_groth16_prove_dev directly. */
+typedef struct bzk_witness_program bzk_witness_program;
+int32_t bzk_mpn_update_witness(bzk_ctx *ctx, const bzk_witness_program *slot_prog, const bzk_witness_program *epilogue_prog,
+                               uint64_t n_slots, uint32_t log4_token, uint64_t slot_vars, uint64_t epilogue_vars, const bzk_fr *raws,
+                               const bzk_fr *ext, uint32_t n_raw, const bzk_fr prologue[6], void *d_inputs, void *d_aux);
+
 /* ------------------------------------------------------------------ witness generation (device)
  * bellman's `ProvingAssignment` runs `MpnCircuit::synthesize` with value closures
  * (/root/reference/src/mpn/circuits/update_circuit.rs:49-494).  Every slot of an update batch performs the
@@ -264,7 +274,6 @@ int32_t bzk_mpn_update_build(bzk_ctx *ctx, bzk_mpn_state *state, const bzk_mpn_t
  *   variable j.  coefs and jj_d (the curve's d) are Montgomery images.
  * bzk_witness_run_dev: raws[ntx][n_raw] and ext[ntx][n_ext] are CANONICAL host images (converted on the
  * device); writes the Montgomery values of slot t's variables to d_aux_out[t*n_ops + j]. */
-typedef struct bzk_witness_program bzk_witness_program;
 int32_t bzk_witness_program_upload(bzk_ctx *ctx, const int32_t *ops, uint64_t n_ops, const int32_t *lc_ptr, uint64_t n_lc,
                                    const int32_t *lc_slot, const int32_t *lc_coef, uint64_t n_terms, const bzk_fr *coefs,
                                    uint64_t n_coefs, uint32_t n_raw, uint32_t n_ext, const bzk_fr *jj_d, bzk_witness_program **out);

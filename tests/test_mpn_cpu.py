@@ -349,3 +349,18 @@ def test_batched_deposit_and_withdraw_builders_equal_sequential():
     _assert_same_transitions(tr1, tr2)
     assert st1.root == st2.root and st1.tree.levels == st2.tree.levels
     assert {i: dataclasses_asdict(a) for i, a in st1.accounts.items()} == {i: dataclasses_asdict(a) for i, a in st2.accounts.items()}
+
+
+def test_update_epilogue_program_reproduces_synthesis():
+    """the part of the witness after the slot loop (fee-commitment Poseidon gadget) as a program whose externals are
+    the fee token and every slot's accepted fee — what bzk_mpn_update_witness runs after the slots."""
+    from bazuka_b200.mpn import witness_program as W
+    st, keys = make_state(3, 3, 3)
+    pub, trans, _ = U.update(st, [transfer(keys, 0, 1, 1), transfer(keys, 1, 2, 1, amount=5, fee=7)], 1)
+    circ = U.UpdateCircuit(3, 3, 1, commitment=4, height=2, transitions=trans, **pub)
+    cs = circ.synthesize(C.ConstraintSystem())
+    prog = W.compile_update_block(3, 3)
+    ep = W.compile_update_epilogue(prog, 1)
+    fees = [tr.tx.fee.amount if tr.enabled else 0 for tr in circ.transitions]
+    assert ep.n_raw == 0 and ep.n_ext == 5
+    assert W.run_reference(ep, [], [circ.fee_token] + fees) == cs.aux[prog.p_aux + 4 * prog.n_ops:]
