@@ -149,22 +149,17 @@ int find_token_index(const Account &a, uint32_t T, const Fr &token_id, bool empt
     return -1;
 }
 
-struct Dev {  // scoped device scratch
-    void *p = nullptr;
-    ~Dev() { if (p) cudaFree(p); }
-};
-
 // host front-end of the versioned tree update: vals[(depth+1)*n] (vals[0..n) in), proofs [n][depth][3]
 int32_t tree_update_host(bzk_ctx *ctx, uint32_t depth, const std::vector<uint32_t> &tid, const std::vector<uint64_t> &idx,
                          std::vector<Fr> &vals, const std::vector<Fr> &init, std::vector<Fr> &proofs) {
     const size_t n = idx.size();
     proofs.assign(n * depth * 3, Fr::zero());
     if (n == 0) return BZK_OK;
-    Dev d;
     size_t o_tid = 0, o_idx = (n * 4 + 255) & ~(size_t)255, o_vals = o_idx + ((n * 8 + 255) & ~(size_t)255),
            o_init = o_vals + (depth + 1) * n * sizeof(Fr), o_pr = o_init + n * depth * 3 * sizeof(Fr), total = o_pr + n * depth * 3 * sizeof(Fr);
-    if (cudaMalloc(&d.p, total) != cudaSuccess) { cudaGetLastError(); return BZK_ERR_OOM; }
-    char *b = (char *)d.p;
+    // the context's grow-only arena: no cudaMalloc / cudaFree (device-wide synchronisations) per batch
+    BZK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, total));
+    char *b = (char *)ctx->ws;
     cudaStream_t st = ctx->stream;
     BZK_CUDA(ctx, cudaMemcpyAsync(b + o_tid, tid.data(), n * 4, cudaMemcpyHostToDevice, st));
     BZK_CUDA(ctx, cudaMemcpyAsync(b + o_idx, idx.data(), n * 8, cudaMemcpyHostToDevice, st));

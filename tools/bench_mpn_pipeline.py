@@ -6,7 +6,9 @@
     Groth16 prove from the resident witness        (context 1, main thread)
 so the transitions of batch k+2 are built and the witness of batch k+1 is computed while batch k is being proved
 (the witness kernel occupies a handful of warps).  Prints one JSON line: wall time per batch in steady state, proofs/s, transactions/s, and the stage times.
-usage: bench_mpn_pipeline.py A,T,B [n_batches]"""
+usage: bench_mpn_pipeline.py A,T,B [n_batches] [--python-host]
+Default: the native per-batch path (bzk_mpn_update_build -> bzk_mpn_update_witness -> bzk_groth16_prove_dev; Python only
+moves buffers between the three calls); --python-host uses the Python builder and witness glue instead."""
 import json, os, queue, sys, threading, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np, torch
@@ -18,8 +20,10 @@ from bazuka_b200.mpn.worker import MpnUpdateWorker
 
 
 def main():
-    A, T, Bb = (int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "15,3,2").split(","))
-    n_batches = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+    native = "--python-host" not in sys.argv
+    A, T, Bb = (int(v) for v in (argv[0] if argv else "15,3,2").split(","))
+    n_batches = int(argv[1]) if len(argv) > 1 else 4
     ntx = 1 << (2 * Bb)
     N_WIT = 2
     ctx1, ctx3 = B.Context(0), B.Context(0)
@@ -42,6 +46,13 @@ def main():
     for i in range(nacc):
         pk, sk = N.eddsa_keys(b"acct%d" % i); keys.append((pk, sk))
         st.set(i, U.MpnAccount(0, 0, pk, {0: U.Money(U.ZIESHA, 10 ** 12)}))
+    led = None
+    if native:
+        from bazuka_b200.mpn.ledger import NativeLedger, pack_txs
+        led = NativeLedger(ctx3, A, T)
+        for i, a in st.accounts.items():
+            led.set_account(i, a)
+        assert led.root == st.root
     nonces, batches = [0] * nacc, []
     t0 = time.time()
     for b in range(n_batches + 1):
@@ -51,7 +62,7 @@ def main():
             nonces[s] += 1
             tx = U.MpnTransaction(nonces[s], N.jj_compress(keys[s][0]), N.jj_compress(keys[dd][0]), U.Money(U.ZIESHA, 1000 + k), U.Money(U.ZIESHA, 10))
             tx.sign(keys[s][1]); txs.append(tx)
-        batches.append(txs)
+        batches.append(pack_txs(txs) if native else txs)
     t_sign = time.time() - t0
     q = queue.Queue(maxsize=1)
     stage = {"build": [], "witness": [], "prove": []}
@@ -62,9 +73,14 @@ def main():
     def builder():
         for b, txs in enumerate(batches):
             t = time.perf_counter()
-            pub, trans, rej = BU.update_batched(hasher3, st, txs, Bb)
-            assert len(trans) == ntx and not rej
-            circ = U.UpdateCircuit(A, T, Bb, commitment=b + 1, height=b, transitions=trans, **pub)
+            if native:
+                raws, ext, acc, pub, n_acc = led.update_build(txs, Bb)
+                assert n_acc == ntx
+                circ = (raws, ext)
+            else:
+                pub, trans, rej = BU.update_batched(hasher3, st, txs, Bb)
+                assert len(trans) == ntx and not rej
+                circ = U.UpdateCircuit(A, T, Bb, commitment=b + 1, height=b, transitions=trans, **pub)
             stage["build"].append(time.perf_counter() - t)
             qb.put((b, circ, pub))
         qb.put(None)
@@ -77,7 +93,10 @@ def main():
                 break
             b, circ, pub = item
             t = time.perf_counter()
-            wit = wits[w].witness(circ)
+            if native:
+                wit = wits[w].witness_native(circ[0], circ[1], [b + 1, b, pub["state"], U.ZIESHA, pub["aux_data"], pub["next_state"]], Bb)
+            else:
+                wit = wits[w].witness(circ)
             stage["witness"].append(time.perf_counter() - t)
             q.put((b, circ, pub, wit))
         q.put(None)
@@ -112,6 +131,7 @@ def main():
     print(json.dumps({"circuit": "UpdateCircuit", "A": A, "T": T, "B": Bb, "tx_per_batch": ntx, "batches_timed": len(marks) - 1,
                       "steady_state_s_per_batch": round(per_batch, 4), "proofs_per_s": round(1 / per_batch, 3), "tx_per_s": round(ntx / per_batch, 1),
                       "stage_s_median": {k: round(med(v), 4) for k, v in stage.items()}, "all_proofs_verify": bool(ok),
+                      "host_path": "native (libbzk builder + witness driver)" if native else "python builder + witness glue",
                       "one_off_s": {"r1cs_template_key_setup": round(t_setup, 1), "host_signing_all_batches": round(t_sign, 1)},
                       "pipeline": "builder, 2 witness workers (alternate batches) and the prover run on their own threads and contexts; wall clock between consecutive proofs"}), flush=True)
 
