@@ -83,6 +83,7 @@ SIGNATURES = {
     "bzk_mpn_state_free": (_i32, [_vp]),
     "bzk_mpn_state_root": (_i32, [_vp, _vp]),
     "bzk_mpn_state_set_account": (_i32, [_vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _u32]),
+    "bzk_jubjub_decompress": (_i32, [_vp, _vp, _i32, _vp]),
     "bzk_mpn_update_raw_width": (_i32, [_u32, _u32, _vp]),
     "bzk_mpn_update_build": (_i32, [_vp, _vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bzk_mpn_update_witness": (_i32, [_vp, _vp, _vp, _u64, _u32, _u64, _u64, _vp, _vp, _u32, _vp, _vp, _vp]),

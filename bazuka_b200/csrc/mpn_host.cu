@@ -529,3 +529,16 @@ extern "C" int32_t bzk_mpn_update_witness(bzk_ctx *ctx, const bzk_witness_progra
     (void)epilogue_vars;
     return BZK_OK;
 }
+
+// `PublicKey::decompress` as a stand-alone host call (no context): x canonical, y parity flag -> affine point
+// (canonical); BZK_ERR_NOT_ON_CURVE when x is not the abscissa of a curve point.
+extern "C" int32_t bzk_jubjub_decompress(const bzk_fr *jubjub_d, const bzk_fr *x, int32_t y_is_odd, bzk_fr out_xy[2]) {
+    if (!jubjub_d || !x || !out_xy) return BZK_ERR_BAD_ARG;
+    bzk_mpn_state tmp;
+    tmp.jj_d = fr_from_canon(jubjub_d);
+    Point p;
+    if (!jj_decompress(&tmp, x, y_is_odd != 0, &p) || !tmp.on_curve(p.x, p.y)) return BZK_ERR_NOT_ON_CURVE;
+    fr_to_canon(out_xy + 0, p.x);
+    fr_to_canon(out_xy + 1, p.y);
+    return BZK_OK;
+}

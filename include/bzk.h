@@ -245,6 +245,9 @@ int32_t bzk_mpn_state_set_account(bzk_ctx *ctx, bzk_mpn_state *state, uint64_t i
                                   const bzk_fr *addr_x, const bzk_fr *addr_y, const uint32_t *token_index, const bzk_fr *token_id,
                                   const uint64_t *token_amount, uint32_t n_tokens);
 int32_t bzk_mpn_update_raw_width(uint32_t log4_tree, uint32_t log4_token, uint32_t *n_raw);
+/* `PublicKey::decompress` (/root/reference/src/crypto/jubjub/curve.rs:78-88) on the host field arithmetic, no
+ * context: y = sqrt((1 + x^2) / (1 - d x^2)) with the parity rule; canonical scalars. */
+int32_t bzk_jubjub_decompress(const bzk_fr *jubjub_d, const bzk_fr *x, int32_t y_is_odd, bzk_fr out_xy[2]);
 int32_t bzk_mpn_update_build(bzk_ctx *ctx, bzk_mpn_state *state, const bzk_mpn_tx *txs, uint64_t n_txs, uint32_t log4_batch,
                              const bzk_fr *fee_token, bzk_fr *raws, bzk_fr *ext, uint8_t *accepted, bzk_fr public3[3],
                              uint64_t *n_accepted);

@@ -364,3 +364,32 @@ def test_update_epilogue_program_reproduces_synthesis():
     fees = [tr.tx.fee.amount if tr.enabled else 0 for tr in circ.transitions]
     assert ep.n_raw == 0 and ep.n_ext == 5
     assert W.run_reference(ep, [], [circ.fee_token] + fees) == cs.aux[prog.p_aux + 4 * prog.n_ops:]
+
+
+def test_genesis_mpn_addresses_decompress_on_curve():
+    """reference fixture: the 211 `jub…` keys of the genesis allocation
+    (/root/reference/src/config/initials.rs:13027+) all parse (x < r) and decompress — Fr square root plus the parity
+    rule of curve.rs:78-88 — to points on the curve; the Python restatement and libbzk's host C++ agree on each."""
+    import ctypes as ct
+    import json
+    import numpy as np
+    from bazuka_b200 import _lib
+    addrs = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "genesis_mpn_addresses.json")))["addresses"]
+    assert len(addrs) == 211
+    lib = _lib.load()
+    canon = lambda v: np.frombuffer((v % N.R).to_bytes(32, "little"), dtype=np.uint64).copy()
+    d = canon(N.JJ_D)
+    for s in addrs:
+        odd, x = s[3] == "3", int(s[4:], 16)
+        assert x < N.R
+        p = N.jj_decompress((x, odd))
+        assert p[0] == x and (p[1] & 1 == 1) == odd and N.jj_on_curve(p)
+        xc, out = canon(x), np.zeros((2, 4), dtype=np.uint64)
+        assert lib.bzk_jubjub_decompress(ct.c_void_p(d.ctypes.data), ct.c_void_p(xc.ctypes.data), int(odd), ct.c_void_p(out.ctypes.data)) == 0
+        assert int.from_bytes(out[0].tobytes(), "little") == p[0] and int.from_bytes(out[1].tobytes(), "little") == p[1]
+    # x = 2 is not the abscissa of a point? whichever it is, both sides must agree
+    for x in (2, 3, 5, 7, 11):
+        rhs = (1 + x * x) * pow((1 - N.JJ_D * x * x) % N.R, -1, N.R) % N.R
+        xc, out = canon(x), np.zeros((2, 4), dtype=np.uint64)
+        st = lib.bzk_jubjub_decompress(ct.c_void_p(d.ctypes.data), ct.c_void_p(xc.ctypes.data), 0, ct.c_void_p(out.ctypes.data))
+        assert (st == 0) == (N.fr_sqrt(rhs) is not None)

@@ -9,6 +9,9 @@ container, where /root/reference is mounted; the GPU box only sees the committed
   empty_root.json      the empty MPN state root printed in the explorer test vector
                        (/root/reference/src/node/api/get_explorer_blocks.rs:29), with the state
                        model sizes it was produced with
+  genesis_mpn_addresses.json  the `jub…` MPN public keys of the genesis allocation
+                       (/root/reference/src/config/initials.rs:13027+): PointCompressed(x, is_odd) strings, every one
+                       must decompress (Fr square root + parity rule, src/crypto/jubjub/curve.rs:78-88) to a curve point
 """
 import json, os, re
 
@@ -39,6 +42,11 @@ def main():
     roots = re.findall(r'0x[0-9a-f]{64}', ex)
     json.dump({"source": "src/node/api/get_explorer_blocks.rs:29", "hex_scalars_in_vector": sorted(set(roots))},
               open(f"{OUT}/empty_root.json", "w"), indent=1)
+    ini = open(f"{REF}/config/initials.rs").read()
+    addrs = sorted(set(re.findall(r'"(jub[23][0-9a-f]{64})"', ini)))
+    assert len(addrs) > 100
+    json.dump({"source": "src/config/initials.rs:13027+", "format": "jub{2|3 = y parity}{x as 64 hex digits, big-endian} (src/crypto/jubjub/mod.rs:60-106)",
+               "addresses": addrs}, open(f"{OUT}/genesis_mpn_addresses.json", "w"), indent=0)
     print("wrote", os.listdir(OUT))
 
 
