@@ -14,127 +14,37 @@
 // Bound: single-thread Fr latency (a slot is one dependent chain of ~10^6 limb-product rounds); batches
 // give the parallelism (256 / 1024 slots), not the slot.
 #include "common.cuh"
+#include "witness_core.cuh"
 
 namespace bzk {
 
-enum : int32_t { W_RAW = 0, W_MUL, W_BIT, W_ISZERO, W_INVZ, W_SELECT, W_JJ, W_NOP };
-constexpr int kSlotOne = 0;  // then n_ext external slots, then the block's own variables
-
-struct WitProgDev {
-    const int32_t *ops;      // [n_ops][6]
-    const int32_t *lc_ptr;   // [n_lc + 1]
-    const int32_t *lc_slot;  // [n_terms]
-    const int32_t *lc_coef;  // [n_terms], 0 = coefficient one
-    const Fr *coefs;         // Montgomery
-    uint32_t n_ops, n_raw, n_ext;
+// V[variable][slot] in global memory, tx fastest; block values also go slot-major into z
+struct WitMemDev {
+    Fr *V, *aux_out;
+    uint32_t ntx, tx, n_ops;
+    __device__ __forceinline__ Fr load(int32_t slot) const {
+        Fr r;
+        const uint4 *s = (const uint4 *)(V + (size_t)slot * ntx + tx);
+        uint4 a = s[0], b = s[1];
+        r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+        r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+        return r;
+    }
+    __device__ __forceinline__ void store(uint32_t slot, const Fr &v) const { store_vec(V + (size_t)slot * ntx + tx, v); }
+    __device__ __forceinline__ void out(uint32_t j, const Fr &v) const { store_vec(aux_out + (size_t)tx * n_ops + j, v); }
+    // the interpreter's loads are otherwise serialised behind one another (V of a 256-slot batch is ~460 MB, so
+    // they are DRAM latencies); addresses are warp-uniform in the slot and consecutive in tx
+    __device__ __forceinline__ void prefetch(int32_t slot) const {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(__cvta_generic_to_global(V + (size_t)slot * ntx + tx)));
+    }
 };
-
-__device__ __forceinline__ Fr ld_fr(const Fr *p) {
-    Fr r;
-    const uint4 *s = (const uint4 *)p;
-    uint4 a = s[0], b = s[1];
-    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
-    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
-    return r;
-}
-
-__device__ __noinline__ Fr wit_eval_lc(const WitProgDev &P, int32_t l, const Fr *V, uint32_t ntx, uint32_t tx) {
-    Fr acc = Fr::zero();
-    const int32_t lo = __ldg(P.lc_ptr + l), hi = __ldg(P.lc_ptr + l + 1);
-    for (int32_t k = lo; k < hi; k++) {
-        const int32_t slot = __ldg(P.lc_slot + k), ci = __ldg(P.lc_coef + k);
-        Fr v = ld_fr(V + (size_t)slot * ntx + tx);
-        if (ci != 0) v = v * load_vec(P.coefs + ci);
-        acc = acc + v;
-    }
-    return acc;
-}
-
-// Pull every operand of the op's linear combinations towards L1 before the dependent evaluation starts: the
-// interpreter's loads are otherwise serialised behind one another (V of a 256-slot batch is ~460 MB, so they
-// are DRAM latencies).  Addresses are warp-uniform in the slot and consecutive in tx.
-__device__ __forceinline__ void wit_prefetch_lc(const WitProgDev &P, int32_t l, const Fr *V, uint32_t ntx, uint32_t tx) {
-    const int32_t lo = __ldg(P.lc_ptr + l), hi = __ldg(P.lc_ptr + l + 1);
-    for (int32_t k = lo; k < hi; k++) {
-        const Fr *p = V + (size_t)__ldg(P.lc_slot + k) * ntx + tx;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(__cvta_generic_to_global(p)));
-    }
-}
-
-__device__ __forceinline__ bool jj_on_curve(const Fr &x, const Fr &y, const Fr &d) {
-    // a = -1:  y^2 - x^2 == 1 + d x^2 y^2   (/root/reference/src/crypto/jubjub/curve.rs:40-47)
-    Fr x2 = x.sqr(), y2 = y.sqr();
-    return (y2 - x2) == (Fr::one() + d * x2 * y2);
-}
 
 __global__ void __launch_bounds__(32) k_witness_run(WitProgDev P, Fr jj_d, const Fr *__restrict__ raws, const Fr *__restrict__ ext,
                                                     uint32_t ntx, Fr *V, Fr *__restrict__ aux_out) {
     const uint32_t tx = blockIdx.x * blockDim.x + threadIdx.x;
     if (tx >= ntx) return;
-    const uint32_t kSlotBlock0 = 1 + P.n_ext;
-    store_vec(V + (size_t)kSlotOne * ntx + tx, Fr::one());
-    for (uint32_t k = 0; k < P.n_ext; k++) store_vec(V + (size_t)(1 + k) * ntx + tx, load_vec(ext + (size_t)tx * P.n_ext + k).to_mont());
-    for (uint32_t j = 0; j < P.n_ops; j++) {
-        const int32_t *op = P.ops + (size_t)j * 6;
-        const int32_t code = __ldg(op), a0 = __ldg(op + 1), a1 = __ldg(op + 2), a2 = __ldg(op + 3), a3 = __ldg(op + 4), imm = __ldg(op + 5);
-        Fr out = Fr::zero();
-        {
-            const int nlc = code == W_JJ ? 4 : code == W_SELECT ? 3 : code == W_MUL ? 2 : (code == W_RAW || code == W_NOP) ? 0 : 1;
-            if (nlc > 0) wit_prefetch_lc(P, a0, V, ntx, tx);
-            if (nlc > 1 && a1 != a0) wit_prefetch_lc(P, a1, V, ntx, tx);
-            if (nlc > 2) wit_prefetch_lc(P, a2, V, ntx, tx);
-            if (nlc > 3) wit_prefetch_lc(P, a3, V, ntx, tx);
-        }
-        switch (code) {
-        case W_RAW: out = load_vec(raws + (size_t)tx * P.n_raw + imm).to_mont(); break;
-        case W_MUL: {
-            Fr a = wit_eval_lc(P, a0, V, ntx, tx);
-            out = (a1 == a0) ? a.sqr() : a * wit_eval_lc(P, a1, V, ntx, tx);
-            break;
-        }
-        case W_BIT: {
-            Fr c = wit_eval_lc(P, a0, V, ntx, tx).from_mont();
-            uint32_t w = 0;
-#pragma unroll
-            for (int i = 0; i < Fr::N; i++) w = (i == (imm >> 5)) ? c.l[i] : w;
-            out = ((w >> (imm & 31)) & 1u) ? Fr::one() : Fr::zero();
-            break;
-        }
-        case W_ISZERO: out = wit_eval_lc(P, a0, V, ntx, tx).is_zero() ? Fr::one() : Fr::zero(); break;
-        case W_INVZ: {
-            Fr a = wit_eval_lc(P, a0, V, ntx, tx);
-            out = a.is_zero() ? Fr::zero() : a.inv();
-            break;
-        }
-        case W_SELECT: {
-            Fr s = wit_eval_lc(P, a0, V, ntx, tx), a = wit_eval_lc(P, a1, V, ntx, tx), b = wit_eval_lc(P, a2, V, ntx, tx);
-            out = s.is_zero() ? a : b;
-            break;
-        }
-        case W_JJ: {
-            // twisted Edwards, a = -1 (/root/reference/src/crypto/jubjub/curve.rs:123-160; the gadget's hint
-            // /root/reference/src/zk/groth16/gadgets/eddsa/mod.rs:75-101 yields (0,0) for off-curve inputs)
-            Fr x1 = wit_eval_lc(P, a0, V, ntx, tx), y1 = wit_eval_lc(P, a1, V, ntx, tx);
-            Fr x2 = wit_eval_lc(P, a2, V, ntx, tx), y2 = wit_eval_lc(P, a3, V, ntx, tx);
-            Fr ox = Fr::zero(), oy = Fr::zero();
-            if (jj_on_curve(x1, y1, jj_d) && jj_on_curve(x2, y2, jj_d)) {
-                Fr x1x2 = x1 * x2, y1y2 = y1 * y2;
-                Fr k = jj_d * x1x2 * y1y2;
-                Fr dp = Fr::one() + k, dm = Fr::one() - k;
-                Fr inv = (dp * dm).inv();
-                ox = (x1 * y2 + y1 * x2) * dm * inv;
-                oy = (y1y2 + x1x2) * dp * inv;
-            }
-            out = ox;
-            store_vec(V + (size_t)(kSlotBlock0 + j + 1) * ntx + tx, oy);
-            store_vec(aux_out + (size_t)tx * P.n_ops + j + 1, oy);
-            break;
-        }
-        default: continue;  // W_NOP: written by the preceding JJ
-        }
-        store_vec(V + (size_t)(kSlotBlock0 + j) * ntx + tx, out);
-        store_vec(aux_out + (size_t)tx * P.n_ops + j, out);
-    }
+    WitMemDev mem{V, aux_out, ntx, tx, P.n_ops};
+    wit_run_slot(P, jj_d, raws + (size_t)tx * P.n_raw, ext + (size_t)tx * P.n_ext, mem);
 }
 
 }  // namespace bzk

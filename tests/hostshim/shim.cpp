@@ -4,6 +4,8 @@
 #include <cstring>
 #include "ec.cuh"
 #include "ffu.cuh"
+#include "witness_core.cuh"
+#include <vector>
 using namespace bzk;
 template <class T, int W> static void bin(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n, int op) {
     for (size_t i = 0; i < n; i++) {
@@ -69,5 +71,25 @@ void shim_g1_add(const uint32_t *pa, const uint32_t *pb, uint32_t *out_madd, uin
     G1Xyzz z = G1Xyzz::from_affine(b); z = z.dbl(); z.madd(b.neg());
     G1Xyzz w = x; w.add(z);
     G1Affine r2 = w.to_affine(); memcpy(out_add, &r2, 96);
+}
+
+// the witness interpreter's per-slot loop (witness_core.cuh, the code the device kernel runs) on the host:
+// one slot, values in a plain array; aux_out[n_ops] receives the block's variables (Montgomery)
+void shim_witness_run(const int32_t *ops, uint32_t n_ops, const int32_t *lc_ptr, const int32_t *lc_slot, const int32_t *lc_coef,
+                      const uint32_t *coefs, uint32_t n_raw, uint32_t n_ext, const uint32_t *jj_d, const uint32_t *raws,
+                      const uint32_t *ext, uint32_t *aux_out) {
+    struct Mem {
+        std::vector<Fr> V;
+        Fr *out_;
+        Fr load(int32_t slot) const { return V[slot]; }
+        void store(uint32_t slot, const Fr &v) { V[slot] = v; }
+        void out(uint32_t j, const Fr &v) { out_[j] = v; }
+        void prefetch(int32_t) const {}
+    } mem;
+    mem.V.assign(1 + n_ext + n_ops, Fr::zero());
+    mem.out_ = (Fr *)aux_out;
+    WitProgDev P{ops, lc_ptr, lc_slot, lc_coef, (const Fr *)coefs, n_ops, n_raw, n_ext};
+    Fr d; memcpy(d.l, jj_d, 32);
+    wit_run_slot(P, d, (const Fr *)raws, (const Fr *)ext, mem);
 }
 }

@@ -127,3 +127,31 @@ def test_host_build_of_group_law(hostshim, cref):
     hostshim.shim_g1_add(bs[0][:96].ctypes.data_as(ct.c_void_p), negp[:96].ctypes.data_as(ct.c_void_p),
                          o1.ctypes.data_as(ct.c_void_p), o2.ctypes.data_as(ct.c_void_p))
     assert not o1.any() and not o2.any()
+
+
+def test_host_build_of_witness_interpreter(hostshim):
+    """the device interpreter's per-slot loop (csrc/witness_core.cuh) compiled for the host runs the real update-slot
+    program on signed transfers and a null slot and reproduces `UpdateCircuit.synthesize`'s aux values — the same
+    C++ the kernel executes, checked without a GPU."""
+    import ctypes as ct
+    from bazuka_b200.mpn import cs as C, native as N, update as U, witness_program as W
+    from test_mpn_cpu import make_state, transfer
+    st, keys = make_state(3, 3, 3)
+    keys.append(N.eddsa_keys(b"newcomer"))
+    txs = [transfer(keys, 0, 1, 1), transfer(keys, 0, 3, 2, amount=77, fee=3)]
+    pub, trans, _ = U.update(st, txs, 1)
+    circ = U.UpdateCircuit(3, 3, 1, commitment=42, height=7, transitions=trans, **pub)
+    cs = circ.synthesize(C.ConstraintSystem())
+    prog = W.compile_update_block(3, 3)
+    roots = W.slot_roots(circ)
+    ops = np.ascontiguousarray(prog.ops, dtype=np.int32)
+    coefs, jj_d = np.ascontiguousarray(prog.coefs_mont()), C.to_mont([N.JJ_D])
+    canon = lambda vals: np.frombuffer(b"".join((v % N.R).to_bytes(32, "little") for v in vals), dtype=np.uint64).copy()
+    p = lambda a: a.ctypes.data_as(ct.c_void_p)
+    for k in (0, 1, 3):  # two real slots and a null one
+        raws, ext = canon(W.raw_values(circ.transitions[k], 3, 3)), canon([circ.fee_token, roots[k]])
+        out = np.zeros((prog.n_ops, 4), dtype=np.uint64)
+        hostshim.shim_witness_run(p(ops), ct.c_uint32(prog.n_ops), p(prog.lc_ptr), p(prog.lc_slot), p(prog.lc_coef), p(coefs),
+                                  ct.c_uint32(prog.n_raw), ct.c_uint32(prog.n_ext), p(jj_d), p(raws), p(ext), p(out))
+        want = C.to_mont(cs.aux[prog.p_aux + k * prog.n_ops: prog.p_aux + (k + 1) * prog.n_ops])
+        assert (out == want).all(), (k, np.nonzero((out != want).any(axis=1))[0][:5])
