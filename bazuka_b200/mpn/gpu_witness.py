@@ -37,11 +37,13 @@ def upload_program(ctx, p):
 
 
 class UpdateWitnessGpu:
-    def __init__(self, ctx, A, T):
+    def __init__(self, ctx, A, T, prog=None, epilogues=None):
+        """prog / epilogues ({log4_batch: program}): ready-made programs, e.g. from the native compiler
+        (mpn/native_circuit.py); by default the Python definition is compiled here."""
         self.ctx, self.A, self.T = ctx, A, T
-        self.prog = W.compile_update_block(A, T)
+        self.prog = prog if prog is not None else W.compile_update_block(A, T)
         self._h = upload_program(ctx, self.prog)
-        self._epi = {}   # log4_batch -> (program, handle)
+        self._epi = {b: (ep, upload_program(ctx, ep)) for b, ep in (epilogues or {}).items()}   # log4_batch -> (program, handle)
 
     def free(self):
         if self._h:

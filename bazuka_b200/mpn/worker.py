@@ -33,14 +33,25 @@ class UpdateWork:
 
 
 class MpnUpdateWorker:
-    def __init__(self, ctx, A, T, B, toxic, g1=None, g2=None):
+    def __init__(self, ctx, A, T, B, toxic, g1=None, g2=None, compiler="python"):
+        """compiler: "python" = R1CS template and witness programs from the Python circuit definition;
+        "native" = from libbzk's C++ definition (csrc/mpn_circuit.cu) — the emitted arrays are identical
+        (tests/test_mpn_cpu.py::test_native_circuit_compiler_equals_python)."""
         self.ctx, self.A, self.T, self.B = ctx, A, T, B
-        shape = U.UpdateCircuit(A, T, B, fee_token=U.ZIESHA)   # all-null batch: the R1CS does not depend on values
-        ni, na, mats, _, _ = FS.synthesize_update(shape, structure_only=True)
+        prog = epilogues = None
+        if compiler == "native":
+            from .native_circuit import NativeUpdateCircuit
+            nc = NativeUpdateCircuit(A, T, B)
+            ni, na, mats = nc.r1cs()
+            prog, epilogues = nc.program(0), {B: nc.program(1)}
+            nc.free()
+        else:
+            shape = U.UpdateCircuit(A, T, B, fee_token=U.ZIESHA)   # all-null batch: the R1CS does not depend on values
+            ni, na, mats, _, _ = FS.synthesize_update(shape, structure_only=True)
         self.prover = BG.Prover(ctx, BG.R1CS(ni, na, *mats))
         self.pk, self.vk = BG.setup_gpu(ctx, self.prover.r1cs, toxic, BG.G1_GENERATOR if g1 is None else g1, BG.G2_GENERATOR if g2 is None else g2)
         self.vk_blob = BG.vk_to_bincode(self.vk)
-        self.witness = UpdateWitnessGpu(ctx, A, T)
+        self.witness = UpdateWitnessGpu(ctx, A, T, prog, epilogues)
         self.hasher = BU.GpuTreeHasher(ctx)
 
     def build(self, state, txs, commitment=0, height=0, fee_token=U.ZIESHA) -> UpdateWork:

@@ -262,6 +262,24 @@ int32_t bzk_mpn_update_witness(bzk_ctx *ctx, const bzk_witness_program *slot_pro
                                uint64_t n_slots, uint32_t log4_token, uint64_t slot_vars, uint64_t epilogue_vars, const bzk_fr *raws,
                                const bzk_fr *ext, uint32_t n_raw, const bzk_fr prologue[6], void *d_inputs, void *d_aux);
 
+/* ------------------------------------------------------------------ MPN update circuit, compiled natively
+ * Structure-only synthesis (bellman's `KeypairAssembly` role) of `UpdateCircuit`
+ * (/root/reference/src/mpn/circuits/update_circuit.rs:49-494) over the reference's gadgets and bellman's
+ * AllocatedNum / AllocatedBit / Boolean / to_bits_le_strict, in C++: emits the R1CS of a 4^log4_batch-slot batch
+ * (arrays for bzk_r1cs_upload) and the slot / epilogue witness programs (arrays for bzk_witness_program_upload).
+ * poseidon_blob = the table bzk_poseidon_load_params takes; jubjub = {d, 8*BASE.x, 8*BASE.y}, canonical.  No GPU. */
+typedef struct bzk_mpn_circuit bzk_mpn_circuit;
+int32_t bzk_mpn_update_circuit_compile(uint32_t log4_tree, uint32_t log4_token, uint32_t log4_batch, const uint8_t *poseidon_blob,
+                                       size_t blob_len, const bzk_fr jubjub[3], bzk_mpn_circuit **out);
+int32_t bzk_mpn_circuit_free(bzk_mpn_circuit *circuit);
+/* shape = {num_inputs, num_aux, num_constraints, nnz_a, nnz_b, nnz_c, prologue_aux, slot_vars, state_out (slot-local),
+ *          final_fee (slot-local), epilogue_vars, 0} */
+int32_t bzk_mpn_circuit_shape(const bzk_mpn_circuit *circuit, uint64_t shape[12]);
+int32_t bzk_mpn_circuit_matrix(const bzk_mpn_circuit *circuit, uint32_t side, uint64_t *rowptr, uint32_t *col, bzk_fr *val);
+/* which: 0 = slot program, 1 = epilogue program; sizes = {n_ops, n_lc, n_terms, n_coefs, n_raw, n_ext}; array outputs optional */
+int32_t bzk_mpn_circuit_program(const bzk_mpn_circuit *circuit, uint32_t which, uint64_t sizes[6], int32_t *ops, int32_t *lc_ptr,
+                                int32_t *lc_slot, int32_t *lc_coef, bzk_fr *coefs);
+
 /* ------------------------------------------------------------------ witness generation (device)
  * bellman's `ProvingAssignment` runs `MpnCircuit::synthesize` with value closures
  * (/root/reference/src/mpn/circuits/update_circuit.rs:49-494).  Every slot of an update batch performs the

@@ -372,3 +372,28 @@ def test_native_per_batch_path_equals_python_path(ctx, cref):
     assert accepted.all() and (pub_native == work.public_inputs).all() and led.root == st.root
     assert (zk_native == zk_py).all() and worker.verify(work, zk_native)
     worker.free(); led.free()
+
+
+def test_worker_on_natively_compiled_circuit(ctx, cref):
+    """everything native: circuit (R1CS + witness programs) compiled by C++, ledger + builder in C++, witness driver,
+    prover — the 391-byte proof equals the one from the Python-defined circuit under the same toxic waste."""
+    from bazuka_b200.mpn import native as N
+    from bazuka_b200.mpn.ledger import NativeLedger
+    from bazuka_b200.mpn.worker import MpnUpdateWorker
+    st, keys = make_state(3, 3, 3)
+    keys.append(N.eddsa_keys(b"newcomer"))
+    txs = [transfer(keys, 0, 1, 1), transfer(keys, 1, 2, 1, amount=5), transfer(keys, 0, 3, 2, amount=77, fee=3)]
+    tox, (r, s) = cref.fr_random(77, 5), cref.fr_random(78, 2)
+    proofs = []
+    for compiler in ("native", "python"):
+        led = NativeLedger(ctx, 3, 3)
+        for i, a in st.accounts.items():
+            led.set_account(i, a)
+        worker = MpnUpdateWorker(ctx, 3, 3, 1, tox, compiler=compiler)
+        zk, pub, accepted = worker.prove_native(led, txs, r, s, commitment=42, height=7)
+        assert accepted.all()
+        from bazuka_b200 import groth16 as BG
+        assert BG.verify_bytes(worker.vk_blob, pub, zk[4:])
+        proofs.append(zk)
+        worker.free(); led.free()
+    assert (proofs[0] == proofs[1]).all()

@@ -393,3 +393,27 @@ def test_genesis_mpn_addresses_decompress_on_curve():
         xc, out = canon(x), np.zeros((2, 4), dtype=np.uint64)
         st = lib.bzk_jubjub_decompress(ct.c_void_p(d.ctypes.data), ct.c_void_p(xc.ctypes.data), 0, ct.c_void_p(out.ctypes.data))
         assert (st == 0) == (N.fr_sqrt(rhs) is not None)
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 1), (5, 2, 0)])
+def test_native_circuit_compiler_equals_python(shape):
+    """csrc/mpn_circuit.cu — UpdateCircuit, the gadgets and bellman's vocabulary in C++, structure-only — emits
+    exactly the R1CS (three CSR matrices: row pointers, columns, Montgomery coefficients) and exactly the slot and
+    epilogue witness programs (ops, LC pool, coefficient table) of the Python definition."""
+    from bazuka_b200.mpn import witness_program as W
+    from bazuka_b200.mpn.native_circuit import NativeUpdateCircuit
+    A, T, B = shape
+    nc = NativeUpdateCircuit(A, T, B)
+    ni, na, mats = nc.r1cs()
+    cs = U.UpdateCircuit(A, T, B).synthesize(C.ConstraintSystem())
+    pni, pna, pmats, _, _ = cs.to_csr()
+    assert (ni, na, nc.num_constraints) == (pni, pna, cs.num_constraints)
+    for (rp, col, val), (prp, pcol, pval) in zip(mats, pmats):
+        assert (rp == prp).all() and (col == pcol).all() and (val == pval).all()
+    want = W.compile_update_block(A, T)
+    for got, ref in ((nc.program(0), want), (nc.program(1), W.compile_update_epilogue(want, B))):
+        assert (got.n_raw, got.n_ext) == (ref.n_raw, ref.n_ext)
+        assert (got.ops == ref.ops).all() and (got.lc_ptr == ref.lc_ptr).all()
+        assert (got.lc_slot == ref.lc_slot).all() and (got.lc_coef == ref.lc_coef).all() and got.coefs == ref.coefs
+    assert (nc.p_aux, nc.slot_vars, nc.state_out, nc.final_fee) == (want.p_aux, want.n_ops, want.state_out, want.final_fee)
+    nc.free()
