@@ -537,6 +537,122 @@ inline void epilogue(CS &cs, const Ctx &cx, Var state_wit, const Prologue &p, co
     cs.enforce(LC(state_wit, Fr::one()), LC(ONE, Fr::one()), LC(p.claimed, Fr::one()));
 }
 
+// ------------------------------------------------------------------ Deposit / Withdraw circuits
+// (/root/reference/src/mpn/circuits/deposit_circuit.rs:47-293, withdraw_circuit.rs:49-413; `reveal` of the batch:
+//  /root/reference/src/zk/groth16/gadgets/reveal/mod.rs:13-64)
+struct PublicInputs { Var state, aux, claimed; };
+inline PublicInputs public_inputs(CS &cs) {
+    PublicInputs p;
+    alloc_inputized(cs);  // commitment
+    alloc_inputized(cs);  // height
+    p.state = alloc_inputized(cs);
+    p.aux = alloc_inputized(cs);
+    p.claimed = alloc_inputized(cs);
+    return p;
+}
+inline Number reveal_list_of_structs(CS &cs, const Ctx &cx, const std::vector<std::vector<Number>> &rows) {
+    std::vector<Number> leaves;
+    for (auto &r : rows) leaves.push_back(poseidon(cs, cx, r));
+    while (leaves.size() != 1) {
+        std::vector<Number> up;
+        for (size_t i = 0; i < leaves.size(); i += 4) up.push_back(poseidon(cs, cx, {leaves[i], leaves[i + 1], leaves[i + 2], leaves[i + 3]}));
+        leaves = up;
+    }
+    return leaves[0];
+}
+struct DepositWits { Boolean enabled; Var token_id; UInt amount; Point pub_key; };
+inline DepositWits deposit_phase1(CS &cs, const Ctx &cx, std::vector<Number> *row) {
+    DepositWits w;
+    Var en = alloc_bit(cs);
+    w.enabled = Boolean::is(en);
+    w.token_id = cs.alloc();
+    w.amount = UInt::alloc(cs, 64);
+    w.pub_key = Point::alloc(cs);
+    Number pk_hash = poseidon(cs, cx, {Number::of(w.pub_key.x), Number::of(w.pub_key.y)});
+    Var calldata = mux(cs, w.enabled, Number::zero(), pk_hash);
+    *row = {Number::of(en), Number::of(w.token_id), w.amount.num, Number::of(calldata)};
+    return w;
+}
+inline Var deposit_phase2(CS &cs, const Ctx &cx, uint32_t A, uint32_t T, const DepositWits &w, Var state_wit) {
+    auto num = [](Var v) { return Number::of(v); };
+    UInt tx_index = UInt::alloc(cs, 2 * A), tx_token_index = UInt::alloc(cs, 2 * T);
+    w.pub_key.assert_on_curve(cs, cx, w.enabled);
+    Var src_tx_nonce = cs.alloc(), src_withdraw_nonce = cs.alloc();
+    Point src_addr = Point::alloc(cs);
+    Var src_balances_hash = cs.alloc(), src_token_id = cs.alloc(), src_balance = cs.alloc();
+    Number src_token_balance_hash = poseidon(cs, cx, {num(src_token_id), num(src_balance)});
+    Proof bproof = alloc_proof(cs, T);
+    check_proof4(cs, cx, w.enabled, tx_token_index, src_token_balance_hash, bproof, num(src_balances_hash));
+    Number src_hash = poseidon(cs, cx, {num(src_tx_nonce), num(src_withdraw_nonce), num(src_addr.x), num(src_addr.y), num(src_balances_hash)});
+    Proof proof = alloc_proof(cs, A);
+    Boolean is_null_tok = num(src_token_id).is_zero(cs);
+    Boolean is_eq_tok = num(src_token_id).is_equal(cs, num(w.token_id));
+    assert_true(cs, boolean_or(cs, is_null_tok, is_eq_tok));
+    Boolean is_null_addr = src_addr.is_null(cs);
+    Boolean is_eq_addr = src_addr.is_equal(cs, w.pub_key);
+    assert_true(cs, boolean_or(cs, is_null_addr, is_eq_addr));
+    check_proof4(cs, cx, w.enabled, tx_index, src_hash, proof, num(state_wit));
+    Number new_bal_hash = poseidon(cs, cx, {num(w.token_id), num(src_balance) + w.amount.num});
+    Number new_balances_hash = calc_root4(cs, cx, tx_token_index, new_bal_hash, bproof);
+    Number new_hash = poseidon(cs, cx, {num(src_tx_nonce), num(src_withdraw_nonce), num(w.pub_key.x), num(w.pub_key.y), new_balances_hash});
+    Number next_state = calc_root4(cs, cx, tx_index, new_hash, proof);
+    return mux(cs, w.enabled, num(state_wit), next_state);
+}
+struct WithdrawWits { Boolean enabled; Var amount_token_id; UInt amount; Var fee_token_id; UInt fee; Var fingerprint; Point pub_key; Var nonce; Point sig_r; Var sig_s; };
+inline WithdrawWits withdraw_phase1(CS &cs, const Ctx &cx, std::vector<Number> *row) {
+    WithdrawWits w;
+    Var en = alloc_bit(cs);
+    w.enabled = Boolean::is(en);
+    w.amount_token_id = cs.alloc();
+    w.amount = UInt::alloc(cs, 64);
+    w.fee_token_id = cs.alloc();
+    w.fee = UInt::alloc(cs, 64);
+    w.fingerprint = cs.alloc();
+    w.pub_key = Point::alloc(cs);
+    w.nonce = cs.alloc();
+    w.sig_r = Point::alloc(cs);
+    w.sig_s = cs.alloc();
+    auto num = [](Var v) { return Number::of(v); };
+    Number cd_hash = poseidon(cs, cx, {num(w.pub_key.x), num(w.pub_key.y), num(w.nonce), num(w.sig_r.x), num(w.sig_r.y), num(w.sig_s)});
+    Var calldata = mux(cs, w.enabled, Number::zero(), cd_hash);
+    *row = {num(en), num(w.amount_token_id), w.amount.num, num(w.fee_token_id), w.fee.num, num(w.fingerprint), num(calldata)};
+    return w;
+}
+inline Var withdraw_phase2(CS &cs, const Ctx &cx, uint32_t A, uint32_t T, const WithdrawWits &w, Var state_wit) {
+    auto num = [](Var v) { return Number::of(v); };
+    UInt tx_index = UInt::alloc(cs, 2 * A), tx_token_index = UInt::alloc(cs, 2 * T), tx_fee_token_index = UInt::alloc(cs, 2 * T);
+    w.pub_key.assert_on_curve(cs, cx, w.enabled);
+    Number tx_hash = poseidon(cs, cx, {num(w.fingerprint), num(w.nonce)});
+    w.sig_r.assert_on_curve(cs, cx, w.enabled);
+    verify_eddsa(cs, cx, w.enabled, w.pub_key, tx_hash, w.sig_r, w.sig_s);
+    Var src_tx_nonce = cs.alloc(), src_withdraw_nonce = cs.alloc();
+    Point src_addr = Point::alloc(cs);
+    src_addr.assert_on_curve(cs, cx, w.enabled);
+    Var before_token_hash = cs.alloc(), src_token_id = cs.alloc();
+    num(src_token_id).assert_equal(cs, num(w.amount_token_id));
+    Var src_balance = cs.alloc();
+    Number src_token_balance_hash = poseidon(cs, cx, {num(src_token_id), num(src_balance)});
+    Proof tproof = alloc_proof(cs, T);
+    check_proof4(cs, cx, w.enabled, tx_token_index, src_token_balance_hash, tproof, num(before_token_hash));
+    Number new_token_balance_hash = poseidon(cs, cx, {num(src_token_id), num(src_balance) - w.amount.num});
+    Number balance_middle_root = calc_root4(cs, cx, tx_token_index, new_token_balance_hash, tproof);
+    Var src_fee_token_id = cs.alloc();
+    num(src_fee_token_id).assert_equal(cs, num(w.fee_token_id));
+    Var src_fee_balance = cs.alloc();
+    Number src_fee_token_balance_hash = poseidon(cs, cx, {num(src_fee_token_id), num(src_fee_balance)});
+    Proof fproof = alloc_proof(cs, T);
+    check_proof4(cs, cx, w.enabled, tx_fee_token_index, src_fee_token_balance_hash, fproof, balance_middle_root);
+    Number new_fee_token_balance_hash = poseidon(cs, cx, {num(src_fee_token_id), num(src_fee_balance) - w.fee.num});
+    Number src_hash = poseidon(cs, cx, {num(src_tx_nonce), num(src_withdraw_nonce), num(src_addr.x), num(src_addr.y), num(before_token_hash)});
+    Proof proof = alloc_proof(cs, A);
+    check_proof4(cs, cx, w.enabled, tx_index, src_hash, proof, num(state_wit));
+    num(w.nonce).assert_equal_if_enabled(cs, w.enabled, num(src_withdraw_nonce) + Number::constant(Fr::one()));
+    Number balance_final_root = calc_root4(cs, cx, tx_fee_token_index, new_fee_token_balance_hash, fproof);
+    Number new_hash = poseidon(cs, cx, {num(src_tx_nonce), num(src_withdraw_nonce) + Number::constant(Fr::one()), num(w.pub_key.x), num(w.pub_key.y), balance_final_root});
+    Number next_state = calc_root4(cs, cx, tx_index, new_hash, proof);
+    return mux(cs, w.enabled, num(state_wit), next_state);
+}
+
 // ------------------------------------------------------------------ witness program compilation (witness_program.py compile_block)
 struct Program {
     std::vector<int32_t> ops, lc_ptr{0}, lc_slot, lc_coef;
@@ -606,6 +722,30 @@ inline bool compile_block(const std::vector<Recipe> &rec, size_t rec_first, uint
     return ok;
 }
 
+// constants of the gadgets: the Poseidon table (the blob bzk_poseidon_load_params takes) and JubJub's d, 8*BASE
+inline bool load_constants(const uint8_t *blob, size_t len, const bzk_fr jubjub[3], Ctx *cx) {
+    cx->jj_d = fr_canon(jubjub + 0); cx->base8_x = fr_canon(jubjub + 1); cx->base8_y = fr_canon(jubjub + 2);
+    uint32_t n;
+    memcpy(&n, blob + 8, 4);
+    size_t off = 12;
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t hdr[4];
+        if (off + 16 > len) return false;
+        memcpy(hdr, blob + off, 16);
+        off += 16;
+        const uint32_t t = hdr[0], nrc = hdr[3];
+        if (off + 32ull * (nrc + t * t) > len) return false;
+        Ctx::Pos P;
+        P.rf = hdr[1]; P.rp = hdr[2];
+        for (uint32_t k = 0; k < nrc; k++) P.rc.push_back(fr_canon((const bzk_fr *)(blob + off + 32ull * k)));
+        off += 32ull * nrc;
+        for (uint32_t k = 0; k < t * t; k++) P.mds.push_back(fr_canon((const bzk_fr *)(blob + off + 32ull * k)));
+        off += 32ull * t * t;
+        cx->pos[t] = std::move(P);
+    }
+    return true;
+}
+
 }  // namespace cc
 
 struct bzk_mpn_circuit {
@@ -614,6 +754,11 @@ struct bzk_mpn_circuit {
     cc::Program slot, epi;
     uint64_t p_aux = 0, slot_vars = 0, state_out = 0, final_fee = 0;
     std::vector<uint32_t> col[3];  // z indices
+    // deposit / withdraw (two-phase circuits): slot = phase-1 program, epi = phase-2 program
+    uint32_t kind = 0;
+    uint64_t reveal_vars = 0;
+    std::vector<int32_t> row_local;  // where each entry of the revealed row sits in the phase-1 block
+    std::vector<int32_t> ext_src;    // per phase-2 external: -1 = the entering state, else the phase-1 RAW index it copies
 };
 
 extern "C" {
@@ -629,27 +774,7 @@ int32_t bzk_mpn_update_circuit_compile(uint32_t log4_tree, uint32_t log4_token, 
     if (!c) return BZK_ERR_OOM;
     c->A = log4_tree; c->T = log4_token; c->B = log4_batch;
     cc::Ctx cx;
-    cx.jj_d = cc::fr_canon(jubjub + 0); cx.base8_x = cc::fr_canon(jubjub + 1); cx.base8_y = cc::fr_canon(jubjub + 2);
-    {
-        uint32_t n;
-        memcpy(&n, poseidon_blob + 8, 4);
-        size_t off = 12;
-        for (uint32_t i = 0; i < n; i++) {
-            uint32_t hdr[4];
-            if (off + 16 > blob_len) return BZK_ERR_BAD_ARG;
-            memcpy(hdr, poseidon_blob + off, 16);
-            off += 16;
-            const uint32_t t = hdr[0], nrc = hdr[3];
-            if (off + 32ull * (nrc + t * t) > blob_len) return BZK_ERR_BAD_ARG;
-            cc::Ctx::Pos P;
-            P.rf = hdr[1]; P.rp = hdr[2];
-            for (uint32_t k = 0; k < nrc; k++) P.rc.push_back(cc::fr_canon((const bzk_fr *)(poseidon_blob + off + 32ull * k)));
-            off += 32ull * nrc;
-            for (uint32_t k = 0; k < t * t; k++) P.mds.push_back(cc::fr_canon((const bzk_fr *)(poseidon_blob + off + 32ull * k)));
-            off += 32ull * t * t;
-            cx.pos[t] = std::move(P);
-        }
-    }
+    if (!cc::load_constants(poseidon_blob, blob_len, jubjub, &cx)) return BZK_ERR_BAD_ARG;
     const uint64_t n = 1ull << (2 * log4_batch);
     // ---- the slot program: prologue + ONE slot on a recording system, the entering state as a stand-in variable
     {
@@ -709,7 +834,7 @@ int32_t bzk_mpn_circuit_free(bzk_mpn_circuit *c) {
 int32_t bzk_mpn_circuit_shape(const bzk_mpn_circuit *c, uint64_t shape[12]) {
     if (!c || !shape) return BZK_ERR_BAD_ARG;
     const uint64_t s[12] = {c->cs.n_inputs, c->cs.n_aux, c->cs.n_rows, c->col[0].size(), c->col[1].size(), c->col[2].size(),
-                            c->p_aux, c->slot_vars, c->state_out, c->final_fee, c->epi.ops.size() / 6, 0};
+                            c->p_aux, c->slot_vars, c->state_out, c->final_fee, c->epi.ops.size() / 6, c->reveal_vars};
     memcpy(shape, s, sizeof s);
     return BZK_OK;
 }
@@ -737,6 +862,115 @@ int32_t bzk_mpn_circuit_program(const bzk_mpn_circuit *c, uint32_t which, uint64
     if (lc_slot) memcpy(lc_slot, P.lc_slot.data(), P.lc_slot.size() * 4);
     if (lc_coef) memcpy(lc_coef, P.lc_coef.data(), P.lc_coef.size() * 4);
     if (coefs) memcpy(coefs, P.coefs.data(), P.coefs.size() * sizeof(Fr));
+    return BZK_OK;
+}
+
+
+/* kind: 1 = DepositCircuit, 2 = WithdrawCircuit.  Program 0 = phase 1 (the slot's transaction fields and calldata),
+ * program 1 = phase 2 (the slot's state transition; externals per bzk_mpn_circuit_two_phase_info).  aux layout of the
+ * batch = [5 public-input copies][phase 1 x n][reveal][phase 2 x n].
+ * shape: slot_vars = phase-1 variables per slot, epilogue_vars = phase-2 variables per slot, last = reveal variables. */
+int32_t bzk_mpn_dw_circuit_compile(uint32_t kind, uint32_t log4_tree, uint32_t log4_token, uint32_t log4_batch, const uint8_t *poseidon_blob,
+                                   size_t blob_len, const bzk_fr jubjub[3], bzk_mpn_circuit **out) {
+    if ((kind != 1 && kind != 2) || !out) return BZK_ERR_BAD_ARG;
+    if (!poseidon_blob || !jubjub || blob_len < 12 || memcmp(poseidon_blob, "BZKPOSv1", 8) || log4_tree == 0 || log4_tree > 31 ||
+        log4_token == 0 || log4_token > 8 || log4_batch > 6)
+        return BZK_ERR_BAD_ARG;
+    std::unique_ptr<bzk_mpn_circuit> c(new (std::nothrow) bzk_mpn_circuit);
+    if (!c) return BZK_ERR_OOM;
+    c->A = log4_tree; c->T = log4_token; c->B = log4_batch; c->kind = kind;
+    cc::Ctx cx;
+    if (!cc::load_constants(poseidon_blob, blob_len, jubjub, &cx)) return BZK_ERR_BAD_ARG;
+    const uint64_t n = 1ull << (2 * log4_batch);
+    // ---- the two slot programs: public inputs + phase 1 + phase 2 of ONE slot on a recording system
+    {
+        cc::CS rs;
+        rs.record = true;
+        cc::public_inputs(rs);
+        c->p_aux = rs.n_aux;
+        std::vector<cc::Number> row;
+        cc::DepositWits dw;
+        cc::WithdrawWits ww;
+        if (kind == 1) dw = cc::deposit_phase1(rs, cx, &row); else ww = cc::withdraw_phase1(rs, cx, &row);
+        c->slot_vars = rs.n_aux - c->p_aux;
+        for (auto &nm : row) {
+            if (nm.lc.t.size() != 1 || !(nm.lc.t[0].first & 1)) return BZK_ERR_BAD_ARG;
+            c->row_local.push_back((int32_t)((nm.lc.t[0].first >> 1) - c->p_aux));
+        }
+        const uint64_t start2 = rs.n_aux;
+        const cc::Var so = kind == 1 ? cc::deposit_phase2(rs, cx, log4_tree, log4_token, dw, cc::FAKE_STATE)
+                                     : cc::withdraw_phase2(rs, cx, log4_tree, log4_token, ww, cc::FAKE_STATE);
+        const uint64_t n2 = rs.n_aux - start2;
+        c->state_out = (so >> 1) - start2;
+        if (!cc::compile_block(rs.recipes, c->p_aux, c->p_aux, c->slot_vars, {}, &c->slot)) return BZK_ERR_BAD_ARG;
+        // externals of phase 2 in order of first appearance: phase-1 variables of the slot (raw fields) and the entering state
+        std::vector<cc::Var> ext;
+        auto scan = [&](const cc::LC &lc) {
+            for (auto &kv : lc.t) {
+                const cc::Var v = kv.first;
+                if (v == cc::ONE) continue;
+                if ((v & 1) && (v >> 1) >= start2 && (v >> 1) < start2 + n2) continue;
+                if (std::find(ext.begin(), ext.end(), v) == ext.end()) ext.push_back(v);
+            }
+        };
+        for (uint64_t j = 0; j < n2; j++) {
+            const cc::Recipe &r = rs.recipes[start2 + j];
+            if (r.kind == cc::K_RAW || r.kind == cc::K_NOP) continue;
+            scan(r.a);
+            if (r.kind == cc::K_MUL || r.kind == cc::K_SELECT || r.kind == cc::K_JJ) scan(r.b);
+            if (r.kind == cc::K_SELECT || r.kind == cc::K_JJ) scan(r.c);
+            if (r.kind == cc::K_JJ) scan(r.d);
+        }
+        std::map<cc::Var, int32_t> raw_index;
+        int32_t k = 0;
+        for (uint64_t j = 0; j < c->slot_vars; j++)
+            if (rs.recipes[c->p_aux + j].kind == cc::K_RAW) raw_index[2 * (c->p_aux + j) + 1] = k++;
+        for (cc::Var v : ext) {
+            if (v == cc::FAKE_STATE) c->ext_src.push_back(-1);
+            else if (raw_index.count(v)) c->ext_src.push_back(raw_index[v]);
+            else return BZK_ERR_BAD_ARG;  // phase 2 reads a derived phase-1 variable
+        }
+        if (!cc::compile_block(rs.recipes, start2, start2, n2, ext, &c->epi)) return BZK_ERR_BAD_ARG;
+    }
+    // ---- the whole batch: R1CS
+    cc::CS &cs = c->cs;
+    cc::PublicInputs p = cc::public_inputs(cs);
+    std::vector<std::vector<cc::Number>> rows(n);
+    std::vector<cc::DepositWits> dws;
+    std::vector<cc::WithdrawWits> wws;
+    for (uint64_t k = 0; k < n; k++) {
+        if (kind == 1) dws.push_back(cc::deposit_phase1(cs, cx, &rows[k])); else wws.push_back(cc::withdraw_phase1(cs, cx, &rows[k]));
+    }
+    const uint64_t before_reveal = cs.n_aux;
+    cc::Number tx_root = cc::reveal_list_of_structs(cs, cx, rows);
+    c->reveal_vars = cs.n_aux - before_reveal;
+    cs.enforce(cc::LC(p.aux, Fr::one()), cc::LC(cc::ONE, Fr::one()), tx_root.lc);
+    cc::Var state = p.state;
+    for (uint64_t k = 0; k < n; k++)
+        state = kind == 1 ? cc::deposit_phase2(cs, cx, log4_tree, log4_token, dws[k], state) : cc::withdraw_phase2(cs, cx, log4_tree, log4_token, wws[k], state);
+    cs.enforce(cc::LC(state, Fr::one()), cc::LC(cc::ONE, Fr::one()), cc::LC(p.claimed, Fr::one()));
+    for (int s = 0; s < 3; s++) {
+        c->col[s].resize(cs.m[s].col.size());
+        for (size_t i = 0; i < cs.m[s].col.size(); i++) {
+            const cc::Var v = cs.m[s].col[i];
+            c->col[s][i] = (uint32_t)((v & 1) ? cs.n_inputs + (v >> 1) : (v >> 1));
+        }
+        cs.m[s].col.clear();
+        cs.m[s].col.shrink_to_fit();
+    }
+    *out = c.release();
+    return BZK_OK;
+}
+
+/* two-phase circuits: row_local[n_row] (position of each revealed-row entry in the phase-1 block) and ext_src[n_ext]
+ * (per phase-2 external: -1 = the state root entering the slot, k >= 0 = the slot's phase-1 RAW input number k).
+ * counts[2] = {n_row, n_ext}; array outputs optional. */
+int32_t bzk_mpn_circuit_two_phase_info(const bzk_mpn_circuit *c, uint64_t counts[2], int32_t *row_local, int32_t *ext_src) {
+    if (!c || !counts) return BZK_ERR_BAD_ARG;
+    counts[0] = c->row_local.size();
+    counts[1] = c->ext_src.size();
+    if (row_local) memcpy(row_local, c->row_local.data(), c->row_local.size() * 4);
+    if (ext_src) memcpy(ext_src, c->ext_src.data(), c->ext_src.size() * 4);
     return BZK_OK;
 }
 

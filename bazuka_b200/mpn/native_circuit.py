@@ -68,3 +68,36 @@ class NativeUpdateCircuit:
         if which == 0:
             prog.p_aux, prog.state_out, prog.final_fee = self.p_aux, self.state_out, self.final_fee
         return prog
+
+
+class NativeTwoPhaseCircuit(NativeUpdateCircuit):
+    """DepositCircuit / WithdrawCircuit compiled by libbzk (bzk_mpn_dw_circuit_compile): r1cs() as above,
+    program(0) = phase 1, program(1) = phase 2, plus the placement data the witness glue needs
+    (n1 / n2 = variables per slot of each phase, reveal_vars, row_local, ext_src, state_out)."""
+
+    def __init__(self, kind, A, T, B):
+        from .. import _lib
+        self._l = _lib.load()
+        self.kind, self.A, self.T, self.B = kind, A, T, B
+        blob = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "data", "poseidon_params.bin"), "rb").read()
+        jj = np.ascontiguousarray(np.stack([_canon(N.JJ_D), _canon(N.JJ_BASE_COFACTOR[0]), _canon(N.JJ_BASE_COFACTOR[1])]))
+        h = ct.c_void_p()
+        st = self._l.bzk_mpn_dw_circuit_compile({"deposit": 1, "withdraw": 2}[kind], A, T, B, blob, len(blob), ct.c_void_p(jj.ctypes.data), ct.byref(h))
+        if st != 0:
+            raise _lib.BzkError(st, "bzk_mpn_dw_circuit_compile")
+        self._h = h
+        shape = np.zeros(12, dtype=np.uint64)
+        self._l.bzk_mpn_circuit_shape(h, ct.c_void_p(shape.ctypes.data))
+        (self.num_inputs, self.num_aux, self.num_constraints, self.nnz_a, self.nnz_b, self.nnz_c, self.p_aux, self.n1,
+         self.state_out, _, self.n2, self.reveal_vars) = (int(v) for v in shape)
+        self.slot_vars, self.final_fee, self.epilogue_vars = self.n1, 0, self.n2
+        counts = np.zeros(2, dtype=np.uint64)
+        self._l.bzk_mpn_circuit_two_phase_info(h, ct.c_void_p(counts.ctypes.data), None, None)
+        self.row_local, ext = np.zeros(int(counts[0]), dtype=np.int32), np.zeros(int(counts[1]), dtype=np.int32)
+        self._l.bzk_mpn_circuit_two_phase_info(h, ct.c_void_p(counts.ctypes.data), ct.c_void_p(self.row_local.ctypes.data), ct.c_void_p(ext.ctypes.data))
+        self.ext_src = [("state",) if e < 0 else ("raw1", int(e)) for e in ext]
+
+    def program(self, which) -> WitnessProgram:
+        prog = super().program(which)
+        prog.p_aux = prog.state_out = prog.final_fee = 0
+        return prog

@@ -271,9 +271,17 @@ int32_t bzk_mpn_update_witness(bzk_ctx *ctx, const bzk_witness_program *slot_pro
 typedef struct bzk_mpn_circuit bzk_mpn_circuit;
 int32_t bzk_mpn_update_circuit_compile(uint32_t log4_tree, uint32_t log4_token, uint32_t log4_batch, const uint8_t *poseidon_blob,
                                        size_t blob_len, const bzk_fr jubjub[3], bzk_mpn_circuit **out);
+/* DepositCircuit (kind 1) / WithdrawCircuit (kind 2) (/root/reference/src/mpn/circuits/{deposit,withdraw}_circuit.rs):
+ * these walk the batch twice around the `reveal` of the batch root, so there are two slot programs — program 0 =
+ * phase 1, program 1 = phase 2 (externals described by bzk_mpn_circuit_two_phase_info) — and the batch's aux layout is
+ * [5 public-input copies][phase 1 x n][reveal][phase 2 x n].  In `shape`: slot_vars = phase-1 variables per slot,
+ * epilogue_vars = phase-2 variables per slot, last entry = reveal variables. */
+int32_t bzk_mpn_dw_circuit_compile(uint32_t kind, uint32_t log4_tree, uint32_t log4_token, uint32_t log4_batch, const uint8_t *poseidon_blob,
+                                   size_t blob_len, const bzk_fr jubjub[3], bzk_mpn_circuit **out);
+int32_t bzk_mpn_circuit_two_phase_info(const bzk_mpn_circuit *circuit, uint64_t counts[2], int32_t *row_local, int32_t *ext_src);
 int32_t bzk_mpn_circuit_free(bzk_mpn_circuit *circuit);
 /* shape = {num_inputs, num_aux, num_constraints, nnz_a, nnz_b, nnz_c, prologue_aux, slot_vars, state_out (slot-local),
- *          final_fee (slot-local), epilogue_vars, 0} */
+ *          final_fee (slot-local), epilogue_vars, reveal_vars (two-phase circuits; 0 for the update circuit)} */
 int32_t bzk_mpn_circuit_shape(const bzk_mpn_circuit *circuit, uint64_t shape[12]);
 int32_t bzk_mpn_circuit_matrix(const bzk_mpn_circuit *circuit, uint32_t side, uint64_t *rowptr, uint32_t *col, bzk_fr *val);
 /* which: 0 = slot program, 1 = epilogue program; sizes = {n_ops, n_lc, n_terms, n_coefs, n_raw, n_ext}; array outputs optional */

@@ -417,3 +417,28 @@ def test_native_circuit_compiler_equals_python(shape):
         assert (got.lc_slot == ref.lc_slot).all() and (got.lc_coef == ref.lc_coef).all() and got.coefs == ref.coefs
     assert (nc.p_aux, nc.slot_vars, nc.state_out, nc.final_fee) == (want.p_aux, want.n_ops, want.state_out, want.final_fee)
     nc.free()
+
+
+@pytest.mark.parametrize("kind", ["deposit", "withdraw"])
+def test_native_two_phase_circuit_compiler_equals_python(kind):
+    """DepositCircuit / WithdrawCircuit in C++ (csrc/mpn_circuit.cu): R1CS of a 4-slot batch, both slot programs and
+    the placement data (row positions, phase-2 externals) equal the Python definition's."""
+    from bazuka_b200.mpn import dw as D, dw_witness as DW
+    from bazuka_b200.mpn.native_circuit import NativeTwoPhaseCircuit
+    nc = NativeTwoPhaseCircuit(kind, 3, 3, 1)
+    ni, na, mats = nc.r1cs()
+    circ_cls = D.DepositCircuit if kind == "deposit" else D.WithdrawCircuit
+    cs = circ_cls(3, 3, 1).synthesize(C.ConstraintSystem())
+    pni, pna, pmats, _, _ = cs.to_csr()
+    assert (ni, na, nc.num_constraints) == (pni, pna, cs.num_constraints)
+    for (rp, col, val), (prp, pcol, pval) in zip(mats, pmats):
+        assert (rp == prp).all() and (col == pcol).all() and (val == pval).all()
+    pg = DW.TwoPhasePrograms(kind, 3, 3)
+    assert (nc.p_aux, nc.n1, nc.n2, nc.state_out) == (pg.p_aux, pg.n1, pg.n2, pg.state_out)
+    assert list(nc.row_local) == pg.row_local and nc.ext_src == pg.ext_src
+    assert nc.reveal_vars == na - nc.p_aux - 4 * (nc.n1 + nc.n2)
+    for got, ref in ((nc.program(0), pg.prog1), (nc.program(1), pg.prog2)):
+        assert (got.n_raw, got.n_ext) == (ref.n_raw, ref.n_ext)
+        assert (got.ops == ref.ops).all() and (got.lc_ptr == ref.lc_ptr).all()
+        assert (got.lc_slot == ref.lc_slot).all() and (got.lc_coef == ref.lc_coef).all() and got.coefs == ref.coefs
+    nc.free()
