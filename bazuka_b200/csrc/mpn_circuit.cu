@@ -751,7 +751,7 @@ inline bool load_constants(const uint8_t *blob, size_t len, const bzk_fr jubjub[
 struct bzk_mpn_circuit {
     uint32_t A = 0, T = 0, B = 0;
     cc::CS cs;                    // the whole batch (structure only)
-    cc::Program slot, epi;
+    cc::Program slot, epi, reveal;  // reveal: two-phase circuits only (externals = every slot's revealed row, slot-major)
     uint64_t p_aux = 0, slot_vars = 0, state_out = 0, final_fee = 0;
     std::vector<uint32_t> col[3];  // z indices
     // deposit / withdraw (two-phase circuits): slot = phase-1 program, epi = phase-2 program
@@ -853,8 +853,8 @@ int32_t bzk_mpn_circuit_matrix(const bzk_mpn_circuit *c, uint32_t side, uint64_t
  * coefs Fr[n_coefs] Montgomery) — the arguments of bzk_witness_program_upload */
 int32_t bzk_mpn_circuit_program(const bzk_mpn_circuit *c, uint32_t which, uint64_t sizes[6], int32_t *ops, int32_t *lc_ptr, int32_t *lc_slot,
                                 int32_t *lc_coef, bzk_fr *coefs) {
-    if (!c || which > 1 || !sizes) return BZK_ERR_BAD_ARG;
-    const cc::Program &P = which ? c->epi : c->slot;
+    if (!c || which > 2 || !sizes) return BZK_ERR_BAD_ARG;
+    const cc::Program &P = which == 2 ? c->reveal : which ? c->epi : c->slot;
     const uint64_t s[6] = {P.ops.size() / 6, P.lc_ptr.size() - 1, P.lc_slot.size(), P.coefs.size(), P.n_raw, P.n_ext};
     memcpy(sizes, s, sizeof s);
     if (ops) memcpy(ops, P.ops.data(), P.ops.size() * 4);
@@ -942,8 +942,18 @@ int32_t bzk_mpn_dw_circuit_compile(uint32_t kind, uint32_t log4_tree, uint32_t l
         if (kind == 1) dws.push_back(cc::deposit_phase1(cs, cx, &rows[k])); else wws.push_back(cc::withdraw_phase1(cs, cx, &rows[k]));
     }
     const uint64_t before_reveal = cs.n_aux;
+    cs.record = true;  // only the reveal's allocations are recorded: its program's externals are the rows' variables
     cc::Number tx_root = cc::reveal_list_of_structs(cs, cx, rows);
+    cs.record = false;
     c->reveal_vars = cs.n_aux - before_reveal;
+    {
+        std::vector<cc::Var> ext;
+        for (auto &r : rows)
+            for (auto &nm : r) ext.push_back(nm.lc.t[0].first);
+        if (!cc::compile_block(cs.recipes, 0, before_reveal, c->reveal_vars, ext, &c->reveal)) return BZK_ERR_BAD_ARG;
+        cs.recipes.clear();
+        cs.recipes.shrink_to_fit();
+    }
     cs.enforce(cc::LC(p.aux, Fr::one()), cc::LC(cc::ONE, Fr::one()), tx_root.lc);
     cc::Var state = p.state;
     for (uint64_t k = 0; k < n; k++)

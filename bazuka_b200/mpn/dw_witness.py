@@ -182,3 +182,25 @@ class TwoPhaseWitnessGpu:
         d_inputs = torch.from_numpy(to_mont(inputs).view(np.int64)).to(dev)
         torch.cuda.current_stream(dev).synchronize()
         return d_inputs, d_aux
+
+
+def compile_reveal_program(progs: TwoPhasePrograms, B):
+    """the `reveal` of the batch (reveal/mod.rs:13-64: one Poseidon per row, then a 4-ary Poseidon tree) as a
+    witness program of ONE instance whose externals are every slot's revealed row, slot-major — the piece that lets
+    the whole two-phase witness run through the interpreter (host_parts() evaluates it with the Python gadget)."""
+    circ_cls = KINDS[progs.kind][0]
+    n = 1 << (2 * B)
+    circ = circ_cls(progs.A, progs.T, B)
+    cs = ConstraintSystem(record=True)
+    D._public_inputs(cs, circ)
+    p0 = len(cs.aux)
+    cs.aux.extend([0] * (n * progs.n1))
+    cs.recipes.extend([("raw",)] * (n * progs.n1))
+    rows, ext = [], []
+    for k in range(n):
+        row_vars = [2 * (p0 + k * progs.n1 + j) + 1 for j in progs.row_local]
+        ext += row_vars
+        rows.append([Number.of(AllocatedNum(v, 0)) for v in row_vars])
+    start = len(cs.aux)
+    D.reveal_list_of_structs(cs, B, rows)
+    return W.compile_block(cs.recipes[start:], start, ext)

@@ -284,7 +284,9 @@ int32_t bzk_mpn_circuit_free(bzk_mpn_circuit *circuit);
  *          final_fee (slot-local), epilogue_vars, reveal_vars (two-phase circuits; 0 for the update circuit)} */
 int32_t bzk_mpn_circuit_shape(const bzk_mpn_circuit *circuit, uint64_t shape[12]);
 int32_t bzk_mpn_circuit_matrix(const bzk_mpn_circuit *circuit, uint32_t side, uint64_t *rowptr, uint32_t *col, bzk_fr *val);
-/* which: 0 = slot program, 1 = epilogue program; sizes = {n_ops, n_lc, n_terms, n_coefs, n_raw, n_ext}; array outputs optional */
+/* which: 0 = slot program (two-phase circuits: phase 1), 1 = epilogue program (phase 2), 2 = the `reveal` of a two-phase
+ * batch (one instance; externals = every slot's revealed row, slot-major); sizes = {n_ops, n_lc, n_terms, n_coefs, n_raw,
+ * n_ext}; array outputs optional */
 int32_t bzk_mpn_circuit_program(const bzk_mpn_circuit *circuit, uint32_t which, uint64_t sizes[6], int32_t *ops, int32_t *lc_ptr,
                                 int32_t *lc_slot, int32_t *lc_coef, bzk_fr *coefs);
 

@@ -442,3 +442,32 @@ def test_native_two_phase_circuit_compiler_equals_python(kind):
         assert (got.ops == ref.ops).all() and (got.lc_ptr == ref.lc_ptr).all()
         assert (got.lc_slot == ref.lc_slot).all() and (got.lc_coef == ref.lc_coef).all() and got.coefs == ref.coefs
     nc.free()
+
+
+@pytest.mark.parametrize("kind", ["deposit", "withdraw"])
+def test_two_phase_witness_entirely_through_programs(kind):
+    """phase 1, the reveal and phase 2 as three witness programs (the reveal's externals are the rows produced by phase 1)
+    reproduce `synthesize`'s aux vector with no gadget evaluation at all; the natively compiled reveal program is
+    identical to the Python one."""
+    from bazuka_b200.mpn import dw_witness as DW, witness_program as W
+    from bazuka_b200.mpn.native_circuit import NativeTwoPhaseCircuit
+    circ = _dw_scenario(kind)
+    cs = circ.synthesize(C.ConstraintSystem())
+    pg = DW.TwoPhasePrograms(kind, 3, 3)
+    rv = DW.compile_reveal_program(pg, 1)
+    roots = DW.slot_roots(circ)
+    b1, b2, rows = [], [], []
+    for k, tr in enumerate(circ.transitions):
+        r1, r2 = pg.raws_of(tr, 3, 3)
+        out1 = W.run_reference(pg.prog1, r1, [])
+        b1 += out1
+        rows += [out1[j] for j in pg.row_local]
+        b2 += W.run_reference(pg.prog2, r2, pg.ext_values(r1, roots[k]))
+    rev = W.run_reference(rv, [], rows)
+    assert cs.aux[:pg.p_aux] + b1 + rev + b2 == cs.aux
+    nc = NativeTwoPhaseCircuit(kind, 3, 3, 1)
+    got = nc.program(2)
+    assert (got.n_raw, got.n_ext) == (rv.n_raw, rv.n_ext) == (0, 4 * len(pg.row_local))
+    assert (got.ops == rv.ops).all() and (got.lc_ptr == rv.lc_ptr).all() and (got.lc_slot == rv.lc_slot).all()
+    assert (got.lc_coef == rv.lc_coef).all() and got.coefs == rv.coefs
+    nc.free()
