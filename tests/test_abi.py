@@ -155,3 +155,41 @@ def test_host_build_of_witness_interpreter(hostshim):
                                   ct.c_uint32(prog.n_raw), ct.c_uint32(prog.n_ext), p(jj_d), p(raws), p(ext), p(out))
         want = C.to_mont(cs.aux[prog.p_aux + k * prog.n_ops: prog.p_aux + (k + 1) * prog.n_ops])
         assert (out == want).all(), (k, np.nonzero((out != want).any(axis=1))[0][:5])
+
+
+@pytest.mark.parametrize("kind", ["deposit", "withdraw"])
+def test_native_programs_through_native_interpreter_on_host(hostshim, kind):
+    """all-native on the CPU tier: the deposit / withdraw programs emitted by the C++ circuit compiler (phase 1, reveal,
+    phase 2), run by the C++ interpreter core (host build of witness_core.cuh), assemble to `synthesize`'s aux vector."""
+    import ctypes as ct
+    from bazuka_b200.mpn import cs as C, dw_witness as DW, native as N
+    from bazuka_b200.mpn.native_circuit import NativeTwoPhaseCircuit
+    from test_mpn_cpu import _dw_scenario
+    circ = _dw_scenario(kind)
+    cs = circ.synthesize(C.ConstraintSystem())
+    nc = NativeTwoPhaseCircuit(kind, 3, 3, 1)
+    p1, p2, rv = nc.program(0), nc.program(1), nc.program(2)
+    raws_of = DW.KINDS[kind][2]
+    roots = DW.slot_roots(circ)
+    jj_d = C.to_mont([N.JJ_D])
+    canon = lambda vals: np.frombuffer(b"".join((v % N.R).to_bytes(32, "little") for v in vals), dtype=np.uint64).copy() if vals else np.zeros(4, np.uint64)
+    ptr = lambda a: a.ctypes.data_as(ct.c_void_p)
+    rinv = pow(1 << 256, -1, N.R)
+
+    def run(prog, raws, ext):
+        ops, coefs = np.ascontiguousarray(prog.ops, dtype=np.int32), np.ascontiguousarray(prog.coefs_mont())
+        r, e, out = canon(raws), canon(ext), np.zeros((prog.n_ops, 4), dtype=np.uint64)
+        hostshim.shim_witness_run(ptr(ops), ct.c_uint32(prog.n_ops), ptr(prog.lc_ptr), ptr(prog.lc_slot), ptr(prog.lc_coef), ptr(coefs),
+                                  ct.c_uint32(prog.n_raw), ct.c_uint32(prog.n_ext), ptr(jj_d), ptr(r), ptr(e), ptr(out))
+        return [int.from_bytes(row.tobytes(), "little") * rinv % N.R for row in out]
+
+    b1, b2, rows = [], [], []
+    for k, tr in enumerate(circ.transitions):
+        r1, r2 = raws_of(tr, 3, 3)
+        out1 = run(p1, r1, [])
+        b1 += out1
+        rows += [out1[j] for j in nc.row_local]
+        ext2 = [roots[k] if s[0] == "state" else r1[s[1]] for s in nc.ext_src]
+        b2 += run(p2, r2, ext2)
+    assert cs.aux[:nc.p_aux] + b1 + run(rv, [], rows) + b2 == cs.aux
+    nc.free()

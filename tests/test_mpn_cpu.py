@@ -471,3 +471,30 @@ def test_two_phase_witness_entirely_through_programs(kind):
     assert (got.ops == rv.ops).all() and (got.lc_ptr == rv.lc_ptr).all() and (got.lc_slot == rv.lc_slot).all()
     assert (got.lc_coef == rv.lc_coef).all() and got.coefs == rv.coefs
     nc.free()
+
+
+def test_reference_sum_hasher_membership_kat(monkeypatch):
+    """the reference's own state-tree test (`test_zk_list_membership_proof`, /root/reference/src/zk/test/mod.rs:44-71):
+    with the additive SumHasher, a list of 4^4 scalars i -> i, every proof's siblings plus the leaf sum to 32640.
+    Checked on the sparse tree restatement (`set_leaf` / `prove`) and on the write-by-write reference semantics of
+    the batched tree update (oracle.py.state.sequential_tree_updates), whose proofs are taken just before each write."""
+    from oracle.py.state import sequential_tree_updates
+    summing = lambda vals: sum(vals) % N.R
+    monkeypatch.setattr(N, "poseidon", summing)
+    t = N.SparseTree4(4, 0)
+    for i in range(256):
+        t.set_leaf(i, i)
+    assert t.root == 32640
+    for i in range(256):
+        assert (i + sum(v for lvl in t.prove(i) for v in lvl)) % N.R == 32640
+    # batched semantics: first pass writes i -> i into the empty tree, second pass rewrites the same values, so the
+    # second pass's "proof before the write" is the proof in the final tree
+    empty = N.SparseTree4(4, 0)
+    idx = list(range(256)) * 2
+    init = [empty.prove(i) for i in idx]
+    vals, proofs = sequential_tree_updates(4, [0] * 512, idx, idx, init, summing)
+    assert vals[4][255] == 32640 and vals[4][511] == 32640
+    for e in range(256, 512):
+        assert (idx[e] + sum(v for lvl in proofs[e] for v in lvl)) % N.R == 32640
+    for e in range(256):  # during the first pass the proof sees exactly the leaves written so far
+        assert sum(v for lvl in proofs[e] for v in lvl) % N.R == sum(range(e))
