@@ -795,7 +795,16 @@ int32_t bzk_mpn_update_circuit_compile(uint32_t log4_tree, uint32_t log4_token, 
     cc::Number fee_sum = cc::Number::zero();
     std::vector<cc::Var> fee_vars;
     for (uint64_t k = 0; k < n; k++) {
+        size_t before[3], rows_before = cs.m[0].rowptr.size();
+        for (int s = 0; s < 3; s++) before[s] = cs.m[s].col.size();
         cc::BlockOut o = cc::tx_block(cs, cx, log4_tree, log4_token, state, p.fee_token);
+        if (k == 0 && n > 1)  // every slot emits the same amount: size the arrays once instead of doubling through GBs
+            for (int s = 0; s < 3; s++) {
+                const size_t per = cs.m[s].col.size() - before[s], rows_per = cs.m[s].rowptr.size() - rows_before;
+                cs.m[s].col.reserve(cs.m[s].col.size() + per * (n - 1) + 4096);
+                cs.m[s].val.reserve(cs.m[s].val.size() + per * (n - 1) + 4096);
+                cs.m[s].rowptr.reserve(cs.m[s].rowptr.size() + rows_per * (n - 1) + 4096);
+            }
         state = o.state;
         fee_sum = fee_sum.add_num(Fr::one(), o.final_fee);
         fee_vars.push_back(o.final_fee);
