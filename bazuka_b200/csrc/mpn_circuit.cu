@@ -794,17 +794,51 @@ int32_t bzk_mpn_update_circuit_compile(uint32_t log4_tree, uint32_t log4_token, 
     cc::Var state = p.state;
     cc::Number fee_sum = cc::Number::zero();
     std::vector<cc::Var> fee_vars;
+    // Slots 0 and 1 are synthesised; every later slot is slot 1's chunk of the matrices with the block-local variable
+    // ids (its own block AND the entering state, which is the previous slot's output) advanced by one block — the slots
+    // of `synthesize`'s loop differ in nothing else (update_circuit.rs:81-469).
+    const uint64_t first_block = cs.n_aux;
+    size_t chunk_lo[3] = {0, 0, 0}, chunk_hi[3] = {0, 0, 0}, rows_lo = 0, rows_hi = 0;
+    uint64_t a_tx = 0;
+    cc::BlockOut o1{};
     for (uint64_t k = 0; k < n; k++) {
-        size_t before[3], rows_before = cs.m[0].rowptr.size();
-        for (int s = 0; s < 3; s++) before[s] = cs.m[s].col.size();
-        cc::BlockOut o = cc::tx_block(cs, cx, log4_tree, log4_token, state, p.fee_token);
-        if (k == 0 && n > 1)  // every slot emits the same amount: size the arrays once instead of doubling through GBs
-            for (int s = 0; s < 3; s++) {
-                const size_t per = cs.m[s].col.size() - before[s], rows_per = cs.m[s].rowptr.size() - rows_before;
-                cs.m[s].col.reserve(cs.m[s].col.size() + per * (n - 1) + 4096);
-                cs.m[s].val.reserve(cs.m[s].val.size() + per * (n - 1) + 4096);
-                cs.m[s].rowptr.reserve(cs.m[s].rowptr.size() + rows_per * (n - 1) + 4096);
+        cc::BlockOut o;
+        if (k < 2) {
+            const size_t rows_before = cs.m[0].rowptr.size();
+            size_t before[3];
+            for (int s = 0; s < 3; s++) before[s] = cs.m[s].col.size();
+            const uint64_t aux_before = cs.n_aux;
+            o = cc::tx_block(cs, cx, log4_tree, log4_token, state, p.fee_token);
+            if (k == 0 && n > 1)  // every slot emits the same amount: size the arrays once instead of doubling through GBs
+                for (int s = 0; s < 3; s++) {
+                    const size_t per = cs.m[s].col.size() - before[s], rows_per = cs.m[s].rowptr.size() - rows_before;
+                    cs.m[s].col.reserve(cs.m[s].col.size() + per * (n - 1) + 4096);
+                    cs.m[s].val.reserve(cs.m[s].val.size() + per * (n - 1) + 4096);
+                    cs.m[s].rowptr.reserve(cs.m[s].rowptr.size() + rows_per * (n - 1) + 4096);
+                }
+            if (k == 1) {
+                a_tx = cs.n_aux - aux_before;
+                o1 = o;
+                rows_lo = rows_before; rows_hi = cs.m[0].rowptr.size();
+                for (int s = 0; s < 3; s++) { chunk_lo[s] = before[s]; chunk_hi[s] = cs.m[s].col.size(); }
             }
+        } else {
+            const uint64_t shift = 2 * (k - 1) * a_tx;  // Var encoding: aux j = 2j + 1
+            for (int s = 0; s < 3; s++) {
+                cc::Csr &m = cs.m[s];
+                const size_t base = m.col.size() - chunk_lo[s];
+                for (size_t i = chunk_lo[s]; i < chunk_hi[s]; i++) {
+                    const cc::Var v = m.col[i];
+                    m.col.push_back(((v & 1) && (v >> 1) >= first_block) ? v + shift : v);
+                }
+                m.val.insert(m.val.end(), m.val.begin() + chunk_lo[s], m.val.begin() + chunk_hi[s]);
+                for (size_t r = rows_lo; r < rows_hi; r++) m.rowptr.push_back(m.rowptr[r] + base);
+            }
+            cs.n_aux += a_tx;
+            cs.n_rows += rows_hi - rows_lo;
+            o.state = o1.state + shift;
+            o.final_fee = o1.final_fee + shift;
+        }
         state = o.state;
         fee_sum = fee_sum.add_num(Fr::one(), o.final_fee);
         fee_vars.push_back(o.final_fee);
