@@ -193,3 +193,60 @@ def test_native_programs_through_native_interpreter_on_host(hostshim, kind):
         b2 += run(p2, r2, ext2)
     assert cs.aux[:nc.p_aux] + b1 + run(rv, [], rows) + b2 == cs.aux
     nc.free()
+
+
+def test_native_circuit_and_native_interpreter_satisfy_each_other(hostshim):
+    """end to end on the CPU tier without the Python circuit definition: the R1CS emitted by the C++ compiler is
+    satisfied (a*b == c on every constraint, incl. the Input*0 = 0 convention being absent here) by the witness that
+    the C++ interpreter computes from the C++-emitted slot and epilogue programs for a real signed batch."""
+    import ctypes as ct
+    from bazuka_b200.mpn import native as N, update as U, witness_program as W
+    from bazuka_b200.mpn.cs import to_mont
+    from bazuka_b200.mpn.native_circuit import NativeUpdateCircuit
+    from test_mpn_cpu import make_state, transfer
+    st, keys = make_state(3, 3, 3)
+    txs = [transfer(keys, 0, 1, 1), transfer(keys, 1, 2, 1, amount=5, fee=7), transfer(keys, 2, 0, 1, amount=1)]
+    pub, trans, _ = U.update(st, txs, 1)
+    circ = U.UpdateCircuit(3, 3, 1, commitment=9, height=4, transitions=trans, **pub)   # only a container of values here
+    nc = NativeUpdateCircuit(3, 3, 1)
+    ni, na, mats = nc.r1cs()
+    slot, epi = nc.program(0), nc.program(1)
+    jj_d = to_mont([N.JJ_D])
+    canon = lambda vals: np.frombuffer(b"".join((v % N.R).to_bytes(32, "little") for v in vals), dtype=np.uint64).copy() if vals else np.zeros(4, np.uint64)
+    ptr = lambda a: a.ctypes.data_as(ct.c_void_p)
+    rinv = pow(1 << 256, -1, N.R)
+
+    def run(prog, raws, ext):
+        ops, coefs = np.ascontiguousarray(prog.ops, dtype=np.int32), np.ascontiguousarray(prog.coefs_mont())
+        r, e, out = canon(raws), canon(ext), np.zeros((prog.n_ops, 4), dtype=np.uint64)
+        hostshim.shim_witness_run(ptr(ops), ct.c_uint32(prog.n_ops), ptr(prog.lc_ptr), ptr(prog.lc_slot), ptr(prog.lc_coef), ptr(coefs),
+                                  ct.c_uint32(prog.n_raw), ct.c_uint32(prog.n_ext), ptr(jj_d), ptr(r), ptr(e), ptr(out))
+        return [int.from_bytes(row.tobytes(), "little") * rinv % N.R for row in out]
+
+    roots = W.slot_roots(circ)
+    aux = [circ.commitment, circ.height, circ.state, circ.fee_token, circ.aux_data, circ.next_state]
+    fees = []
+    for k, tr in enumerate(circ.transitions):
+        block = run(slot, W.raw_values(tr, 3, 3), [circ.fee_token, roots[k]])
+        fees.append(block[nc.final_fee])
+        aux += block
+    aux += run(epi, [], [circ.fee_token] + fees)
+    z = [1, circ.commitment, circ.height, circ.state, circ.aux_data, circ.next_state] + aux
+    assert len(z) == ni + na
+    ev = []
+    for rp, col, val in mats:
+        coef = [int.from_bytes(row.tobytes(), "little") * rinv % N.R for row in val]
+        rp = rp.tolist(); col = col.tolist()
+        ev.append([sum(coef[i] * z[col[i]] for i in range(rp[j], rp[j + 1])) % N.R for j in range(nc.num_constraints)])
+    bad = [j for j in range(nc.num_constraints) if ev[0][j] * ev[1][j] % N.R != ev[2][j]]
+    assert not bad, bad[:5]
+    # and a wrong claimed next_state breaks exactly the final equality constraint
+    z[5] = (z[5] + 1) % N.R
+    z[ni + 5] = z[5]
+    j = nc.num_constraints - 1
+    rp, col, val = mats[0]
+    lhs = sum(int.from_bytes(val[i].tobytes(), "little") * rinv % N.R * z[int(col[i])] for i in range(int(rp[j]), int(rp[j + 1]))) % N.R
+    rp, col, val = mats[2]
+    rhs = sum(int.from_bytes(val[i].tobytes(), "little") * rinv % N.R * z[int(col[i])] for i in range(int(rp[j]), int(rp[j + 1]))) % N.R
+    assert lhs != rhs
+    nc.free()
