@@ -76,6 +76,7 @@ SIGNATURES = {
     "bzk_groth16_params_free": (_i32, [_vp, _vp]),
     "bzk_groth16_prove": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "bzk_groth16_prove_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "bzk_groth16_stage_ms": (_i32, [_vp, _vp]),
     "bzk_groth16_params_set_shard": (_i32, [_vp, _u32, _u32]),
     "bzk_groth16_prove_partial": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "bzk_groth16_finalize": (_i32, [_vp] * 14),

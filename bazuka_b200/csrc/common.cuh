@@ -65,6 +65,11 @@ struct bzk_ctx {
     float stage_ms[kMaxStages] = {0};
     double stage_ms_sum[kMaxStages] = {0};
     uint64_t stage_runs = 0;
+    // Groth16 driver marks (timing on): 0 start, 1 z+evaluations done, 2 quotient (7 NTTs) done, 3 h sum done
+    // (all on the main stream); 4..7 = end of the l / a / b_g1 / b_g2 side streams
+    cudaEvent_t g16_ev[8] = {nullptr};
+    float g16_ms[8] = {0};
+    bool g16_valid = false;
 };
 
 struct bzk_g1_bases {

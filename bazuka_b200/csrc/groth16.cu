@@ -305,6 +305,14 @@ static int32_t groth16_prove_impl(bzk_ctx *ctx, const bzk_groth16_params *pk, co
     Fr *z = cv.take<Fr>(nv), *ea = cv.take<Fr>(m), *eb = cv.take<Fr>(m), *ec = cv.take<Fr>(m), *gs_a = cv.take<Fr>(gmax), *gs_b = cv.take<Fr>(gmax);
     uint32_t *d_bad = cv.take<uint32_t>(4);
     cudaStream_t st = ctx->stream;
+    const bool timed = ctx->timing;
+    auto g16_mark = [&](int k, cudaStream_t s) {
+        if (!timed) return;
+        if (!ctx->g16_ev[k]) cudaEventCreate(&ctx->g16_ev[k]);
+        cudaEventRecord(ctx->g16_ev[k], s);
+    };
+    ctx->g16_valid = false;
+    g16_mark(0, st);
     BZK_CUDA(ctx, cudaMemcpyAsync(z, inputs, ni * sizeof(Fr), witness_kind, st));
     if (na) BZK_CUDA(ctx, cudaMemcpyAsync(z + ni, aux, na * sizeof(Fr), witness_kind, st));
     // evaluations (rows >= ncons: the Input(i)*0=0 rows, then zero padding)
@@ -348,6 +356,7 @@ static int32_t groth16_prove_impl(bzk_ctx *ctx, const bzk_groth16_params *pk, co
     MsmPlan plan[5];
     lap("z + evaluations enqueued");
     cudaStream_t s_l = ctx->aux_stream[0], s_a = ctx->aux_stream[1], s_b1 = ctx->aux_stream[2], s_b2 = ctx->aux_stream[3];
+    g16_mark(1, st);
     BZK_CUDA(ctx, cudaEventRecord(ctx->aux_ev[0], st));  // z and the evaluations are enqueued behind this point
     BZK_CUDA(ctx, cudaStreamWaitEvent(s_l, ctx->aux_ev[0], 0));
     BZK_CUDA(ctx, cudaStreamWaitEvent(s_a, ctx->aux_ev[0], 0));
@@ -365,12 +374,20 @@ static int32_t groth16_prove_impl(bzk_ctx *ctx, const bzk_groth16_params *pk, co
     BZK_TRY(msm_g1_enqueue(ctx, s_b1, &ctx->aux_ws[2], &ctx->aux_ws_bytes[2], pk->b1->d, gs_b + b_lo, b_n, hw + 3 * kWinBytes, &plan[3]));
     BZK_TRY(msm_g2_enqueue(ctx, s_b2, &ctx->aux_ws[3], &ctx->aux_ws_bytes[3], pk->b2->d, gs_b + b_lo, b_n, hw + 4 * kWinBytes, &plan[4]));
     BZK_TRY(groth16_h_launch(ctx, ea, eb, ec, cs->log_m));  // ea <- h coefficients
+    g16_mark(2, st);
     BZK_TRY(msm_g1_enqueue(ctx, st, &ctx->ws, &ctx->ws_bytes, pk->h->d, ea + h_lo, h_n, hw, &plan[0]));
+    g16_mark(3, st);
+    for (int k = 0; k < 4; k++) g16_mark(4 + k, ctx->aux_stream[k]);
     lap("all kernels enqueued");
     BZK_CUDA(ctx, cudaStreamSynchronize(st));
     lap("main stream done");
     for (int k = 0; k < 4; k++) BZK_CUDA(ctx, cudaStreamSynchronize(ctx->aux_stream[k]));
     lap("side streams done");
+    if (timed) {
+        for (int k = 1; k < 8; k++) cudaEventElapsedTime(&ctx->g16_ms[k], ctx->g16_ev[0], ctx->g16_ev[k]);
+        ctx->g16_ms[0] = 0;
+        ctx->g16_valid = true;
+    }
     // host tail: the five Horner folds and the (r, s) scalar multiplications are independent
     // sub-millisecond jobs — run them on host threads instead of back to back
     bzk_g1_affine h_ans, l_ans, a_ans, b1_ans;
@@ -447,6 +464,15 @@ int32_t bzk_groth16_prove_dev(bzk_ctx *ctx, const bzk_groth16_params *pk, const 
                               bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c) {
     return groth16_prove_impl(ctx, pk, cs, (const bzk_fr *)d_inputs, (const bzk_fr *)d_aux, cudaMemcpyDeviceToDevice, r_mont, s_mont,
                               check_satisfied, proof_a, proof_b, proof_c);
+}
+
+/* milliseconds since the start of the last timed prove call (bzk_ctx_set_timing on) at which: [1] z upload + the three
+ * SpMVs (+ satisfiability check) finished, [2] the quotient pipeline (7 NTTs) finished, [3] the h sum finished (main
+ * stream), [4..7] the l / a / b_g1 / b_g2 sums finished (side streams, concurrent with the main one).  Returns 1 if valid. */
+int32_t bzk_groth16_stage_ms(const bzk_ctx *ctx, float out[8]) {
+    if (!ctx || !out) return BZK_ERR_BAD_ARG;
+    for (int k = 0; k < 8; k++) out[k] = ctx->g16_ms[k];
+    return ctx->g16_valid ? 1 : 0;
 }
 
 int32_t bzk_groth16_params_set_shard(bzk_groth16_params *p, uint32_t rank, uint32_t world) {

@@ -163,6 +163,15 @@ class Prover:
         c._check(c._l.bzk_groth16_proof_bytes(_host_ptr(pa), _host_ptr(pb), _host_ptr(pc), _host_ptr(blob)))
         return blob, (pa, pb, pc)
 
+    STAGES = ("z_spmv_done", "quotient_ntts_done", "h_msm_done", "l_msm_done", "a_msm_done", "b_g1_msm_done", "b_g2_msm_done")
+
+    def stage_ms(self):
+        """CUDA-event marks of the last prove call made with ctx.set_timing(True): ms since the call's first kernel at
+        which each stage finished (main stream: z+SpMV, quotient NTTs, h sum; side streams: l, a, b_g1, b_g2 sums)."""
+        out = np.zeros(8, dtype=np.float32)
+        ok = self.ctx._l.bzk_groth16_stage_ms(self.ctx._h, _host_ptr(out))
+        return {k: float(out[i + 1]) for i, k in enumerate(self.STAGES)} if ok == 1 else None
+
     def prove_partial(self, spk: ProvingKey, inputs, aux, check_satisfied=True):
         """this rank's four partial sums (a, b_g1, b_g2, h+l wire images) under the base-sharded key `spk`
         (shard_proving_key).  inputs/aux: host arrays, or CUDA tensors for a resident witness."""

@@ -35,6 +35,7 @@ METRIC = "g1_msm_scalars_per_sec"
 UNIT = "scalars/s"
 LOG_N_DEFAULT = 20
 ALGO_BYTES_PER_TERM = 128  # 32 B scalar + 96 B affine base
+DTYPE = "u32x12 Montgomery (Fp) / u32x8 (Fr) on the GPU; u64 limbs on the CPU"
 
 
 def env_int(name, default):
@@ -108,32 +109,53 @@ def ncu_traffic():
 
 
 # ------------------------------------------------------------------------------------------------
+def workload_string(log_n, world):
+    """identical in both arms (the driver compares the strings)"""
+    return (f"BLS12-381 G1 Pippenger MSM, {world} x 2^{log_n} random scalars/bases (BASELINE configs[1]); "
+            f"one sum of {world << log_n} terms, base-sharded over {world} GPU(s)")
+
+
+def rank_inputs_seeds(rank):
+    """rank r owns terms [r*n, (r+1)*n) of the N*n-term job: bases stream seed, scalars stream seed"""
+    return 2 + 7919 * rank, 1 + 104729 * rank
+
+
 def run_reference(args, rank, world):
     """CPU arm: the reference's algorithm (bellman multiexp restated in C — the reference itself is
-    Rust on un-vendored crates and cannot be built here) on all host cores, same metric/config."""
+    Rust on un-vendored crates and cannot be built here) on the host cores this process may use, on
+    the SAME workload as our arm at every N: one sum of N * 2^log_n terms (rank r's 2^log_n terms are
+    generated from the same seeds as on the GPU side)."""
     if rank != 0:
         return
+    import numpy as np
     from oracle import cref  # the only other place bench.py may execute oracle/
     n = 1 << args.log_n
-    cores = os.cpu_count() or 1
-    bases = cref.g1_random_bases(2, n, cores)
-    scalars = cref.fr_random(1, n)
+    info = cref.cpu_info()
+    cores = info["usable"]
+    bases = np.concatenate([cref.g1_random_bases(rank_inputs_seeds(r)[0], n, cores) for r in range(world)])
+    scalars = np.concatenate([cref.fr_random(rank_inputs_seeds(r)[1], n) for r in range(world)])
+    total = world * n
     for _ in range(args.warmup):
         cref.msm_g1(bases, scalars, cores)
-    t0 = time.perf_counter()
+    per_step = []
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         cref.msm_g1(bases, scalars, cores)
-    dt = (time.perf_counter() - t0) / max(args.steps, 1)
-    val = n / dt
+        per_step.append(time.perf_counter() - t0)
+    dt = sum(per_step) / max(len(per_step), 1)
+    val = total / dt
+    srt = sorted(per_step)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32x12 Montgomery (Fp), u64 limbs on CPU", "data": "synthetic",
-        "config": {"workload": f"BLS12-381 G1 Pippenger MSM, 2^{args.log_n} random scalars/bases (BASELINE configs[1])",
-                   "note": "CPU restatement of bellman 0.14 multiexp (window ceil(ln n), threads = windows x base chunks); "
-                           "one 2^%d-term sample per step whatever N" % args.log_n},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} x full 2^{args.log_n}-term MSM, wall clock"},
+        "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": {"workload": workload_string(args.log_n, world), "terms_total": total,
+                   "note": "CPU restatement of bellman 0.14 multiexp (window ceil(ln n), threads = windows x base chunks), "
+                           "not bellman; full job per step"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "cpu": info,
+                         "sample": f"{args.steps} x full {world} x 2^{args.log_n}-term MSM, wall clock per step",
+                         "step_s_min": srt[0], "step_s_median": srt[len(srt) // 2], "step_s_max": srt[-1],
+                         "value_at_min_step": total / srt[0]},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -159,10 +181,10 @@ def run_ours(args, rank, local_rank, world):
     # ---- synthetic inputs, generated by libbzk kernels straight into HBM -------------------------
     # rank r owns terms [r*n, (r+1)*n) of the N*n-term job: bases from stream seed 2, scalars seed 1
     d_img = torch.empty((n, 104), dtype=torch.uint8, device="cuda")
-    ctx.g1_random_bases_dev(2 + 7919 * rank, n, d_img)
+    ctx.g1_random_bases_dev(rank_inputs_seeds(rank)[0], n, d_img)
     bases = ctx.g1_bases_from_dev(d_img, n)
     d_scalars = torch.empty((n, 4), dtype=torch.int64, device="cuda")
-    ctx.fr_random_dev(1 + 104729 * rank, n, d_scalars)
+    ctx.fr_random_dev(rank_inputs_seeds(rank)[1], n, d_scalars)
     h_scalars = d_scalars.cpu().pin_memory()
     h_img = d_img.cpu().pin_memory() if rank == 0 else None
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -231,8 +253,16 @@ def run_ours(args, rank, local_rank, world):
 
     mpn_multi = None
     if world > 1 and not args.no_mpn:
-        mpn_multi = mpn_groth16_section(ctx, with_cpu=False, dist=dist, world=world)
-        mpn_multi["sharded"] = sharded_proof_section(ctx, dist, rank, world)
+        mpn_multi = {"single_update": mpn_groth16_section(ctx, with_cpu=False, dist=dist, world=world)}
+    batch = None
+    if not args.no_mpn:
+        # the proofs/s half of the metric on a whole update batch (all ranks: the N>1 schedules have collectives)
+        from tools.mpn_batch_bench import batch_section
+        shape = (16, 3, 5) if args.workload == "mpn1024" else (15, 3, 4)
+        try:
+            batch = batch_section(ctx, *shape, steps=args.mpn_steps, dist=dist, rank=rank, world=world, peak_gbs=measured_peak()[0])
+        except Exception as e:
+            batch = {"error": repr(e)}
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -247,9 +277,9 @@ def run_ours(args, rank, local_rank, world):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32x12 Montgomery (Fp) / u32x8 (Fr)", "data": "synthetic",
+        "dtype": DTYPE, "data": "synthetic",
         "config": {
-            "workload": f"BLS12-381 G1 Pippenger MSM, 2^{args.log_n} random scalars/bases per GPU (BASELINE configs[1])",
+            "workload": workload_string(args.log_n, world),
             "terms_total": world * n, "parallelism": f"base-sharded x{world}, 1 NCCL all-gather of {104 * world} B" if world > 1 else "single GPU",
             "l2": "512 MiB write before every timed step (L2 flushed); inputs 132 MB > 126 MB L2",
             "timing": "CUDA events on the launching stream per step, barrier+sync around region, max over ranks",
@@ -287,22 +317,30 @@ def run_ours(args, rank, local_rank, world):
         # CPU baseline on this box's host cores, same inputs (bounded: one full-size MSM + one warm-up)
         try:
             from oracle import cref  # cpu_baseline leg only
-            cores = os.cpu_count() or 1
+            cpu = cref.cpu_info()
+            cores = cpu["usable"]
             hb = h_img.numpy()
             hs = h_scalars.numpy().view(np.uint64)
             cref.msm_g1(hb[: n // 8], hs[: n // 8], cores)
             t0 = time.perf_counter()
             cpu_out = cref.msm_g1(hb, hs, cores)
             dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu,
                                     "sample": f"1 x full 2^{args.log_n}-term MSM ({dt:.2f} s wall), bellman-equivalent C restatement, not bellman",
                                     "matches_gpu": bool((cpu_out == result).all())}
         except Exception as e:  # the oracle is test infrastructure; its absence must not break the bench
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
         if not args.no_mpn:
-            line["mpn_groth16"] = mpn_groth16_section(ctx)
+            line["mpn_groth16"] = {"single_update": mpn_groth16_section(ctx)}
     if mpn_multi is not None:
         line["mpn_groth16"] = mpn_multi
+    if batch is not None:
+        line["mpn_groth16"]["update_batch"] = batch
+        po = batch.get("prove_only") or {}
+        line["mpn_groth16"]["headline"] = {"metric": "mpn_groth16_proofs_per_sec", "circuit": batch.get("circuit"), "n_gpus": world,
+                                           "proofs_per_s_1gpu_prove_only": po.get("proofs_per_s"),
+                                           "proofs_per_s_replicas": (batch.get("replicas") or {}).get("proofs_per_s"),
+                                           "ms_per_proof_sharded": (batch.get("sharded") or {}).get("ms_per_proof")}
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
@@ -370,7 +408,7 @@ def mpn_groth16_section(ctx, with_cpu=True, dist=None, world=1):
         t0 = time.perf_counter()
         cpu_pts = GC.prove(ni, na, mats, cpk, inputs, aux, rnd[5], rnd[6])
         dt = time.perf_counter() - t0
-        out.update({"cpu_prove_ms": dt * 1e3, "cpu_proofs_per_s": 1 / dt, "cpu_cores": os.cpu_count(),
+        out.update({"cpu_prove_ms": dt * 1e3, "cpu_proofs_per_s": 1 / dt, "cpu_cores": GC.cref.usable_cpus(),
                     "proof_bytes_equal_cpu": bool((blob == GC.proof_bytes(*cpu_pts)).all()),
                     "pairing_check_accepts_gpu_proof": bool(GC.verify_py(vk, inputs[1:], pts))})
         t0 = time.perf_counter()
@@ -439,7 +477,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=LOG_N_DEFAULT)
-    ap.add_argument("--no-mpn", action="store_true", help="skip the secondary MPN single-update proof section")
+    ap.add_argument("--no-mpn", action="store_true", help="skip the MPN proof sections (single update + whole update batch)")
+    ap.add_argument("--workload", default="mpn256", choices=["mpn256", "mpn1024"],
+                    help="update batch proved in the mpn_groth16 section: production 256-tx batch (2^24) or BASELINE configs[3] 1024-tx (2^26)")
+    ap.add_argument("--mpn-steps", type=int, default=3, help="timed update-batch proofs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -202,6 +202,11 @@ int32_t bzk_groth16_prove_dev(bzk_ctx *ctx, const bzk_groth16_params *params, co
                               const void *d_inputs, const void *d_aux, const bzk_fr *r, const bzk_fr *s, int32_t check_satisfied,
                               bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c);
 
+/* Stage times of the last prove call made while bzk_ctx_set_timing was on (CUDA events): milliseconds after the start
+ * of the call at which [1] z upload + the three SpMVs finished, [2] the quotient pipeline (7 NTTs), [3] the h sum (main
+ * stream), [4..7] the l / a / b_g1 / b_g2 sums (side streams, concurrent with the main one).  Returns 1 when valid. */
+int32_t bzk_groth16_stage_ms(const bzk_ctx *ctx, float out[8]);
+
 /* Base-sharded proving over several GPUs (one process / context per GPU): every MSM of bellman's
  * `create_proof` is a sum over terms, so rank k of `world` keeps only the contiguous range
  * [len*k/world, len*(k+1)/world) of each of the five base vectors (pass those slices to

@@ -42,7 +42,51 @@ def _u64(a, w):
     return a
 
 
-NCPU = os.cpu_count() or 1
+def usable_cpus():
+    """host threads this process may really use: the scheduler affinity mask, capped by the cgroup
+    CPU quota (cpu.max of cgroup v2 / cfs_quota of v1).  os.cpu_count() alone reports the machine's
+    cores even inside a container limited to a fraction of them — the round-1 CPU arm oversubscribed
+    such a box 16x and ran 5x slower than on an unrestricted one."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(period)
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / period
+        except Exception:
+            pass
+    if quota is not None:
+        n = max(1, min(n, int(quota + 0.5)))
+    return max(1, n)
+
+
+def cpu_info():
+    """what the CPU arm ran on (printed in every bench line that times the oracle)."""
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except AttributeError:
+        aff = os.cpu_count() or 1
+    return {"model": model, "os_cpu_count": os.cpu_count(), "affinity": aff, "usable": usable_cpus()}
+
+
+NCPU = usable_cpus()
 
 
 def _binop(name, w):
