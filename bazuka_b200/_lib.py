@@ -77,6 +77,11 @@ SIGNATURES = {
     "bzk_groth16_prove": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "bzk_groth16_prove_dev": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "bzk_groth16_stage_ms": (_i32, [_vp, _vp]),
+    "bzk_groth16_params_precompute": (_i32, [_vp, _vp, ct.c_uint32, ct.c_uint32]),
+    "bzk_g1_bases_precompute": (_i32, [_vp, _vp, ct.c_uint32]),
+    "bzk_g2_bases_precompute": (_i32, [_vp, _vp, ct.c_uint32]),
+    "bzk_g1_bases_levels": (ct.c_uint32, [_vp]),
+    "bzk_g2_bases_levels": (ct.c_uint32, [_vp]),
     "bzk_groth16_params_set_shard": (_i32, [_vp, _u32, _u32]),
     "bzk_groth16_prove_partial": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "bzk_groth16_finalize": (_i32, [_vp] * 14),

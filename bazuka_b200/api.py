@@ -57,6 +57,16 @@ class _Bases:
             self._ctx._check(getattr(self._ctx._l, f"bzk_{self._kind}_bases_free")(self._ctx._h, self._h))
             self._h = None
 
+    def precompute(self, max_levels=16):
+        """fixed-base table [2^(c*G*t)] P for t < levels (bzk_g*_bases_precompute): the vector's MSMs then use
+        ceil(W/levels) bucket groups.  Same results, levels x the memory.  Returns the level count in use."""
+        self._ctx._check(getattr(self._ctx._l, f"bzk_{self._kind}_bases_precompute")(self._ctx._h, self._h, int(max_levels)))
+        return self.levels
+
+    @property
+    def levels(self):
+        return int(getattr(self._ctx._l, f"bzk_{self._kind}_bases_levels")(self._h))
+
     def __del__(self):
         try:
             self.free()

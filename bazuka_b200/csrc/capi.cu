@@ -2,8 +2,10 @@
 #include "common.cuh"
 
 namespace bzk {
-int32_t msm_g1_run(bzk_ctx *ctx, const G1Affine *d_bases, const Fr *d_scalars, size_t n, bzk_g1_affine *out);
-int32_t msm_g2_run(bzk_ctx *ctx, const G2Affine *d_bases, const Fr *d_scalars, size_t n, bzk_g2_affine *out);
+int32_t msm_g1_run(bzk_ctx *ctx, const BasesRef<Fp> &d_bases, const Fr *d_scalars, size_t n, bzk_g1_affine *out);
+int32_t msm_g2_run(bzk_ctx *ctx, const BasesRef<Fp2> &d_bases, const Fr *d_scalars, size_t n, bzk_g2_affine *out);
+int32_t precompute_g1(bzk_ctx *ctx, bzk_g1_bases *b, uint32_t max_levels);
+int32_t precompute_g2(bzk_ctx *ctx, bzk_g2_bases *b, uint32_t max_levels);
 int32_t pack_g1(bzk_ctx *ctx, const uint8_t *d_images, size_t n, G1Affine *d_out, uint32_t *d_bad);
 int32_t pack_g2(bzk_ctx *ctx, const uint8_t *d_images, size_t n, G2Affine *d_out, uint32_t *d_bad);
 int32_t random_g1(bzk_ctx *ctx, uint64_t seed, size_t n, uint8_t *d_out);
@@ -316,6 +318,18 @@ int32_t bzk_g2_bases_free(bzk_ctx *ctx, bzk_g2_bases *b) {
     delete b;
     return BZK_OK;
 }
+int32_t bzk_g1_bases_precompute(bzk_ctx *ctx, bzk_g1_bases *b, uint32_t max_levels) {
+    BZK_ENTER(ctx);
+    if (!b) return BZK_ERR_BAD_ARG;
+    return precompute_g1(ctx, b, max_levels);
+}
+int32_t bzk_g2_bases_precompute(bzk_ctx *ctx, bzk_g2_bases *b, uint32_t max_levels) {
+    BZK_ENTER(ctx);
+    if (!b) return BZK_ERR_BAD_ARG;
+    return precompute_g2(ctx, b, max_levels);
+}
+uint32_t bzk_g1_bases_levels(const bzk_g1_bases *b) { return b ? b->tab_T : 0; }
+uint32_t bzk_g2_bases_levels(const bzk_g2_bases *b) { return b ? b->tab_T : 0; }
 size_t bzk_g1_bases_len(const bzk_g1_bases *b) { return b ? b->n : 0; }
 size_t bzk_g2_bases_len(const bzk_g2_bases *b) { return b ? b->n : 0; }
 
@@ -331,26 +345,26 @@ static int32_t stage_scalars(bzk_ctx *ctx, const bzk_fr *scalars, size_t n, Fr *
 int32_t bzk_msm_g1_resident_dev(bzk_ctx *ctx, const bzk_g1_bases *b, size_t offset, const void *d_scalars, size_t n, bzk_g1_affine *out) {
     BZK_ENTER(ctx);
     if (!b || !out || offset > b->n || n > b->n - offset || (n && !d_scalars)) return BZK_ERR_BAD_ARG;
-    return msm_g1_run(ctx, b->d + offset, (const Fr *)d_scalars, n, out);
+    return msm_g1_run(ctx, bases_ref(b, offset), (const Fr *)d_scalars, n, out);
 }
 int32_t bzk_msm_g2_resident_dev(bzk_ctx *ctx, const bzk_g2_bases *b, size_t offset, const void *d_scalars, size_t n, bzk_g2_affine *out) {
     BZK_ENTER(ctx);
     if (!b || !out || offset > b->n || n > b->n - offset || (n && !d_scalars)) return BZK_ERR_BAD_ARG;
-    return msm_g2_run(ctx, b->d + offset, (const Fr *)d_scalars, n, out);
+    return msm_g2_run(ctx, bases_ref(b, offset), (const Fr *)d_scalars, n, out);
 }
 int32_t bzk_msm_g1_resident(bzk_ctx *ctx, const bzk_g1_bases *b, size_t offset, const bzk_fr *scalars, size_t n, bzk_g1_affine *out) {
     BZK_ENTER(ctx);
     if (!b || !out || offset > b->n || n > b->n - offset || (n && !scalars)) return BZK_ERR_BAD_ARG;
     Fr *d_s = nullptr;
     BZK_TRY(stage_scalars(ctx, scalars, n, &d_s));
-    return msm_g1_run(ctx, b->d + offset, d_s, n, out);
+    return msm_g1_run(ctx, bases_ref(b, offset), d_s, n, out);
 }
 int32_t bzk_msm_g2_resident(bzk_ctx *ctx, const bzk_g2_bases *b, size_t offset, const bzk_fr *scalars, size_t n, bzk_g2_affine *out) {
     BZK_ENTER(ctx);
     if (!b || !out || offset > b->n || n > b->n - offset || (n && !scalars)) return BZK_ERR_BAD_ARG;
     Fr *d_s = nullptr;
     BZK_TRY(stage_scalars(ctx, scalars, n, &d_s));
-    return msm_g2_run(ctx, b->d + offset, d_s, n, out);
+    return msm_g2_run(ctx, bases_ref(b, offset), d_s, n, out);
 }
 int32_t bzk_msm_g1(bzk_ctx *ctx, const bzk_g1_affine *bases, const bzk_fr *scalars, size_t n, bzk_g1_affine *out) {
     BZK_ENTER(ctx);

@@ -22,8 +22,10 @@ struct PoseidonTable {
 struct MsmPlan {
     uint32_t c = 0;   // window bits
     uint32_t W = 0;   // windows (0: empty sum)
-    uint32_t NB = 0;  // buckets per window = 2^(c-1)
-    uint32_t TB = 0;  // total buckets = W * NB
+    uint32_t NB = 0;  // buckets per bucket group = 2^(c-1)
+    uint32_t TB = 0;  // total buckets = G * NB
+    uint32_t T = 1;   // table levels in use: level t holds [2^(c*G*t)] P (1 = plain bases)
+    uint32_t G = 0;   // bucket groups = ceil(W / T): window j = t*G + g feeds group g from level t
 };
 
 struct NttTables {
@@ -72,14 +74,34 @@ struct bzk_ctx {
     bool g16_valid = false;
 };
 
+// A resident base vector.  After bzk_g*_bases_precompute `d` holds tab_T levels of n points each: level t =
+// [2^(tab_c * tab_G * t)] P_i (level 0 = the bases), so that the windows t*G+g of every scalar share bucket group g.
 struct bzk_g1_bases {
     bzk::G1Affine *d = nullptr;
     size_t n = 0;
+    uint32_t tab_c = 0, tab_T = 1, tab_G = 0;
 };
 struct bzk_g2_bases {
     bzk::G2Affine *d = nullptr;
     size_t n = 0;
+    uint32_t tab_c = 0, tab_T = 1, tab_G = 0;
 };
+
+namespace bzk {
+// what one MSM call sees of a base vector: the sub-range [off, off + n) of a (possibly multi-level) table
+template <class F>
+struct BasesRef {
+    const Affine<F> *tab = nullptr;
+    size_t n_tab = 0, off = 0;
+    uint32_t c = 0, T = 1, G = 0;  // c == 0: no table, the plan is free to choose its window
+};
+template <class B>
+inline auto bases_ref(const B *b, size_t off = 0) {
+    BasesRef<decltype(b->d->x)> r;
+    r.tab = b->d; r.n_tab = b->n; r.off = off; r.c = b->tab_c; r.T = b->tab_T; r.G = b->tab_G;
+    return r;
+}
+}  // namespace bzk
 
 namespace bzk {
 

@@ -21,11 +21,11 @@
 #include <cstdlib>
 
 namespace bzk {
-int32_t msm_g1_run(bzk_ctx *ctx, const G1Affine *d_bases, const Fr *d_scalars, size_t n, bzk_g1_affine *out);
-int32_t msm_g2_run(bzk_ctx *ctx, const G2Affine *d_bases, const Fr *d_scalars, size_t n, bzk_g2_affine *out);
+int32_t precompute_g1(bzk_ctx *ctx, bzk_g1_bases *b, uint32_t max_levels);
+int32_t precompute_g2(bzk_ctx *ctx, bzk_g2_bases *b, uint32_t max_levels);
 int32_t groth16_h_launch(bzk_ctx *ctx, Fr *a, Fr *b, Fr *c, uint32_t log_n);
-int32_t msm_g1_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_bytes, const G1Affine *d_bases, const Fr *d_scalars, size_t n, void *h_win, MsmPlan *plan);
-int32_t msm_g2_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_bytes, const G2Affine *d_bases, const Fr *d_scalars, size_t n, void *h_win, MsmPlan *plan);
+int32_t msm_g1_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_bytes, const BasesRef<Fp> &d_bases, const Fr *d_scalars, size_t n, void *h_win, MsmPlan *plan);
+int32_t msm_g2_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_bytes, const BasesRef<Fp2> &d_bases, const Fr *d_scalars, size_t n, void *h_win, MsmPlan *plan);
 void msm_g1_finish(const MsmPlan *plan, const void *h_win, bzk_g1_affine *out);
 void msm_g2_finish(const MsmPlan *plan, const void *h_win, bzk_g2_affine *out);
 
@@ -361,21 +361,21 @@ static int32_t groth16_prove_impl(bzk_ctx *ctx, const bzk_groth16_params *pk, co
     BZK_CUDA(ctx, cudaStreamWaitEvent(s_l, ctx->aux_ev[0], 0));
     BZK_CUDA(ctx, cudaStreamWaitEvent(s_a, ctx->aux_ev[0], 0));
     BZK_CUDA(ctx, cudaStreamWaitEvent(s_b1, ctx->aux_ev[0], 0));
-    BZK_TRY(msm_g1_enqueue(ctx, s_l, &ctx->aux_ws[0], &ctx->aux_ws_bytes[0], pk->l->d, z + ni + l_lo, l_n, hw + 1 * kWinBytes, &plan[1]));
+    BZK_TRY(msm_g1_enqueue(ctx, s_l, &ctx->aux_ws[0], &ctx->aux_ws_bytes[0], bases_ref(pk->l), z + ni + l_lo, l_n, hw + 1 * kWinBytes, &plan[1]));
     k_gather_fr<<<div_up(cs->a_len, 256), 256, 0, s_a>>>(z, cs->d_a_idx, cs->a_len, gs_a);
     BZK_LAUNCHED(ctx);
-    BZK_TRY(msm_g1_enqueue(ctx, s_a, &ctx->aux_ws[1], &ctx->aux_ws_bytes[1], pk->a->d, gs_a + a_lo, a_n, hw + 2 * kWinBytes, &plan[2]));
+    BZK_TRY(msm_g1_enqueue(ctx, s_a, &ctx->aux_ws[1], &ctx->aux_ws_bytes[1], bases_ref(pk->a), gs_a + a_lo, a_n, hw + 2 * kWinBytes, &plan[2]));
     if (cs->b_len) {
         k_gather_fr<<<div_up(cs->b_len, 256), 256, 0, s_b1>>>(z, cs->d_b_idx, cs->b_len, gs_b);
         BZK_LAUNCHED(ctx);
     }
     BZK_CUDA(ctx, cudaEventRecord(ctx->aux_ev[1], s_b1));
     BZK_CUDA(ctx, cudaStreamWaitEvent(s_b2, ctx->aux_ev[1], 0));
-    BZK_TRY(msm_g1_enqueue(ctx, s_b1, &ctx->aux_ws[2], &ctx->aux_ws_bytes[2], pk->b1->d, gs_b + b_lo, b_n, hw + 3 * kWinBytes, &plan[3]));
-    BZK_TRY(msm_g2_enqueue(ctx, s_b2, &ctx->aux_ws[3], &ctx->aux_ws_bytes[3], pk->b2->d, gs_b + b_lo, b_n, hw + 4 * kWinBytes, &plan[4]));
+    BZK_TRY(msm_g1_enqueue(ctx, s_b1, &ctx->aux_ws[2], &ctx->aux_ws_bytes[2], bases_ref(pk->b1), gs_b + b_lo, b_n, hw + 3 * kWinBytes, &plan[3]));
+    BZK_TRY(msm_g2_enqueue(ctx, s_b2, &ctx->aux_ws[3], &ctx->aux_ws_bytes[3], bases_ref(pk->b2), gs_b + b_lo, b_n, hw + 4 * kWinBytes, &plan[4]));
     BZK_TRY(groth16_h_launch(ctx, ea, eb, ec, cs->log_m));  // ea <- h coefficients
     g16_mark(2, st);
-    BZK_TRY(msm_g1_enqueue(ctx, st, &ctx->ws, &ctx->ws_bytes, pk->h->d, ea + h_lo, h_n, hw, &plan[0]));
+    BZK_TRY(msm_g1_enqueue(ctx, st, &ctx->ws, &ctx->ws_bytes, bases_ref(pk->h), ea + h_lo, h_n, hw, &plan[0]));
     g16_mark(3, st);
     for (int k = 0; k < 4; k++) g16_mark(4 + k, ctx->aux_stream[k]);
     lap("all kernels enqueued");
@@ -473,6 +473,30 @@ int32_t bzk_groth16_stage_ms(const bzk_ctx *ctx, float out[8]) {
     if (!ctx || !out) return BZK_ERR_BAD_ARG;
     for (int k = 0; k < 8; k++) out[k] = ctx->g16_ms[k];
     return ctx->g16_valid ? 1 : 0;
+}
+
+/* Fixed-base tables for the five base vectors of a key (they never change between proofs): up to `max_levels` levels
+ * [2^(c*G*t)] P per base, so that the windows of a scalar share ceil(W/levels) bucket groups — fewer, larger windows and
+ * one bucket reduction per group instead of per window.  max_levels = 0 picks the largest count (<= 16) whose tables fit
+ * in `mem_fraction_percent` % of the currently free device memory.  Memory: levels x the key's size. */
+int32_t bzk_groth16_params_precompute(bzk_ctx *ctx, bzk_groth16_params *p, uint32_t max_levels, uint32_t mem_fraction_percent) {
+    if (!ctx || !p) return BZK_ERR_BAD_ARG;
+    BZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (max_levels == 0) {
+        size_t free_b = 0, total_b = 0;
+        BZK_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+        const double key_bytes = (double)(p->h->n + p->l->n + p->a->n + p->b1->n) * sizeof(G1Affine) + (double)p->b2->n * sizeof(G2Affine);
+        const double budget = (double)free_b * (mem_fraction_percent ? mem_fraction_percent : 50) / 100.0;
+        uint32_t lv = key_bytes > 0 ? (uint32_t)(budget / key_bytes) + 1 : 16;  // level 0 is already resident
+        max_levels = lv > 16 ? 16 : lv;
+    }
+    if (max_levels <= 1) return BZK_OK;
+    BZK_TRY(precompute_g1(ctx, p->h, max_levels));
+    BZK_TRY(precompute_g1(ctx, p->l, max_levels));
+    BZK_TRY(precompute_g1(ctx, p->a, max_levels));
+    BZK_TRY(precompute_g1(ctx, p->b1, max_levels));
+    BZK_TRY(precompute_g2(ctx, p->b2, max_levels));
+    return BZK_OK;
 }
 
 int32_t bzk_groth16_params_set_shard(bzk_groth16_params *p, uint32_t rank, uint32_t world) {

@@ -40,24 +40,51 @@ namespace bzk {
 // plan
 // ---------------------------------------------------------------------------------------------
 
-static MsmPlan make_plan(size_t n, int force_c = 0) {
-    // cost model calibrated on B200 at 2^20 (bench.py stage marks, c = 14 vs 16 measured): a bucket
-    // costs about 6 mixed additions in the reduction (2 full additions, the [slice offset]
-    // double-and-add, the latency-bound tree and the extra digit/scatter work of more windows).
-    uint32_t best_c = 1;
-    double best = 1e300;
-    for (uint32_t c = 2; c <= 18; c++) {
-        uint32_t W = (256 + c - 1) / c;
-        double cost = (double)n * W + 6.0 * W * (double)(1u << (c - 1));
-        if (cost < best) { best = cost; best_c = c; }
+// cost of a plan in "mixed additions": n*W bucket insertions + kReduceCost per bucket for the reduction
+// (calibrated on B200 at 2^20: two full additions per bucket in the running sums, the latency-bound
+// tree and the extra digit / scatter work of more windows)
+constexpr double kReduceCost = 6.0;
+static double plan_cost(size_t n, uint32_t c, uint32_t T) {
+    const uint32_t W = (256 + c - 1) / c;
+    const uint32_t Te = T < W ? T : W, G = (W + Te - 1) / Te;
+    return (double)n * W + kReduceCost * G * (double)(1u << (c - 1));
+}
+// window plan for n terms over a base table of T levels built for window c_tab (0 = free choice)
+static MsmPlan make_plan(size_t n, uint32_t c_tab = 0, uint32_t T = 1, uint32_t G_tab = 0) {
+    uint32_t best_c = c_tab;
+    if (!c_tab) {
+        double best = 1e300;
+        for (uint32_t c = 2; c <= 18; c++) {
+            double cost = plan_cost(n, c, 1);
+            if (cost < best) { best = cost; best_c = c; }
+        }
+        T = 1;
     }
     MsmPlan p;
-    p.c = force_c ? (uint32_t)force_c : best_c;
+    p.c = best_c;
     // W*c >= 256 guarantees the recoding carry never leaves the top window (scalars < 2^255)
     p.W = (256 + p.c - 1) / p.c;
+    p.T = T < p.W ? T : p.W;
+    p.G = c_tab ? G_tab : p.W;
     p.NB = 1u << (p.c - 1);
-    p.TB = p.W * p.NB;
+    p.TB = p.G * p.NB;
     return p;
+}
+// window size and level count of the table to build for an n-point resident vector
+static void choose_table(size_t n, uint32_t max_levels, uint32_t *c_out, uint32_t *T_out, uint32_t *G_out) {
+    double best = 1e300;
+    uint32_t bc = 16, bT = 1;
+    for (uint32_t c = 8; c <= 23; c++) {
+        const uint32_t W = (256 + c - 1) / c;
+        const uint32_t T = max_levels < W ? max_levels : W;
+        if ((double)n * T >= 1073741824.0) continue;  // table index must fit 30 bits
+        double cost = plan_cost(n, c, T);
+        if (cost < best) { best = cost; bc = c; bT = T; }
+    }
+    const uint32_t W = (256 + bc - 1) / bc;
+    *c_out = bc;
+    *G_out = (W + bT - 1) / bT;
+    *T_out = (W + *G_out - 1) / *G_out;  // levels really needed for that many groups
 }
 
 // signed digit w of canonical scalar k (8 LE 32-bit limbs): value in [-2^(c-1), 2^(c-1)]
@@ -83,8 +110,8 @@ __host__ __device__ __forceinline__ int32_t signed_digit(const uint32_t k[8], ui
 // 1. digits + histogram          3. scatter
 // ---------------------------------------------------------------------------------------------
 template <bool SCATTER>
-__global__ void __launch_bounds__(256) k_digits(const Fr *__restrict__ scalars, size_t n, uint32_t c, uint32_t W, uint32_t NB,
-                                                uint32_t *__restrict__ counts_or_cursor, uint32_t *__restrict__ sorted) {
+__global__ void __launch_bounds__(256) k_digits(const Fr *__restrict__ scalars, size_t n, uint32_t c, uint32_t W, uint32_t NB, uint32_t G,
+                                                uint32_t n_tab, uint32_t off, uint32_t *__restrict__ counts_or_cursor, uint32_t *__restrict__ sorted) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Fr k = load_vec(scalars + i).from_mont();
@@ -94,10 +121,12 @@ __global__ void __launch_bounds__(256) k_digits(const Fr *__restrict__ scalars, 
         if (d == 0) continue;
         uint32_t neg = d < 0;
         uint32_t b = (uint32_t)(neg ? -d : d) - 1;
-        uint32_t slot = w * NB + b;
+        // window w = t*G + g: bucket group g, point [2^(c*G*t)] P_i from level t of the table
+        const uint32_t t = w / G, g = w - t * G;
+        uint32_t slot = g * NB + b;
         if (SCATTER) {
             uint32_t pos = atomicAdd(&counts_or_cursor[slot], 1u);
-            sorted[pos] = (uint32_t)i | (neg << 31);
+            sorted[pos] = (t * n_tab + off + (uint32_t)i) | (neg << 31);
         } else {
             atomicAdd(&counts_or_cursor[slot], 1u);
         }
@@ -508,6 +537,62 @@ template <> struct Wire<Fp2> {
 };
 
 // ---------------------------------------------------------------------------------------------
+// fixed-base table: level t of point i = [2^(bits*t)] P_i, affine.  One thread per base walks the doubling
+// chain in XYZZ, keeps the T-1 level points in local memory and converts them with ONE inversion
+// (Montgomery's trick over q_t = ZZ_t * ZZZ_t).  Run once per resident vector (a proving-key column).
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kMaxLevels = 16;
+template <class F>
+__global__ void __launch_bounds__(128) k_precompute(Affine<F> *__restrict__ tab, size_t n, uint32_t T, uint32_t bits) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Affine<F> P = load_vec(tab + i);
+    Xyzz<F> L[kMaxLevels - 1];
+    F pre[kMaxLevels - 1];
+    Xyzz<F> acc = Xyzz<F>::from_affine(P);
+    F run = F::one();
+    for (uint32_t t = 1; t < T; t++) {
+        for (uint32_t k = 0; k < bits; k++) acc = acc.dbl();
+        L[t - 1] = acc;
+        pre[t - 1] = run;
+        if (!acc.is_inf()) run = run * (acc.ZZ * acc.ZZZ);
+    }
+    F inv = run.inv();
+    for (uint32_t t = T - 1; t >= 1; t--) {
+        const Xyzz<F> &Q = L[t - 1];
+        Affine<F> out = Affine<F>::inf();
+        if (!Q.is_inf()) {
+            const F qi = inv * pre[t - 1];  // 1 / (ZZ * ZZZ)
+            inv = inv * (Q.ZZ * Q.ZZZ);
+            out.x = Q.X * Q.ZZZ * qi;
+            out.y = Q.Y * Q.ZZ * qi;
+        }
+        store_vec(tab + (size_t)t * n + i, out);
+    }
+}
+
+// grow a resident vector into a table of up to max_levels levels (the bases stay level 0)
+template <class F>
+static int32_t bases_precompute(bzk_ctx *ctx, Affine<F> **d, size_t n, uint32_t max_levels, uint32_t *c_out, uint32_t *T_out, uint32_t *G_out) {
+    if (max_levels > kMaxLevels) max_levels = kMaxLevels;
+    uint32_t c = 0, T = 1, G = 0;
+    if (n == 0 || max_levels <= 1) { *c_out = 0; *T_out = 1; *G_out = 0; return BZK_OK; }
+    choose_table(n, max_levels, &c, &T, &G);
+    if (T <= 1) { *c_out = 0; *T_out = 1; *G_out = 0; return BZK_OK; }
+    Affine<F> *tab = nullptr;
+    cudaError_t e = cudaMalloc(&tab, (size_t)T * n * sizeof(Affine<F>));
+    if (e != cudaSuccess) return set_cuda_err(ctx, e, "cudaMalloc(base table)", __FILE__, __LINE__);
+    BZK_CUDA(ctx, cudaMemcpyAsync(tab, *d, n * sizeof(Affine<F>), cudaMemcpyDeviceToDevice, ctx->stream));
+    k_precompute<F><<<div_up(n, 128), 128, 0, ctx->stream>>>(tab, n, T, c * G);
+    BZK_LAUNCHED(ctx);
+    BZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(*d);
+    *d = tab;
+    *c_out = c; *T_out = T; *G_out = G;
+    return BZK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------
 template <class F>
@@ -515,11 +600,13 @@ template <class F>
 // `h_win` (host, ideally pinned; >= 64 entries) by the last operation on the stream.  Nothing here
 // synchronises: several MSMs can be in flight on different streams (the Groth16 driver runs its
 // five sums concurrently), and msm_host_finish folds the window sums once the stream is done.
-static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_bytes, bool timed, const Affine<F> *d_bases,
+static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_bytes, bool timed, const BasesRef<F> &bases,
                            const Fr *d_scalars, size_t n, Xyzz<F> *h_win, MsmPlan *plan_out) {
     if (n == 0) { plan_out->W = 0; return BZK_OK; }
-    if (n >= ((size_t)1 << 31)) return BZK_ERR_BAD_ARG;
-    const MsmPlan pl = make_plan(n);
+    if (n >= ((size_t)1 << 31) || bases.off + n > bases.n_tab) return BZK_ERR_BAD_ARG;
+    const MsmPlan pl = make_plan(n, bases.c, bases.T, bases.G);
+    if ((double)bases.n_tab * pl.T >= 2147483648.0) return BZK_ERR_BAD_ARG;
+    const Affine<F> *d_bases = bases.tab;
     *plan_out = pl;
     if ((double)n * pl.W >= 4294967295.0) return BZK_ERR_BAD_ARG;
     const uint64_t max_entries = (uint64_t)n * pl.W;
@@ -544,7 +631,7 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
     if (slice < 4) slice = pl.NB >= 4 ? 4 : pl.NB;
     if (slice > pl.NB) slice = pl.NB;
     const uint32_t per_win = (pl.NB + slice - 1) / slice;
-    const uint32_t nslices = per_win * pl.W;
+    const uint32_t nslices = per_win * pl.G;
     const uint32_t ntiles = div_up(pl.TB, kScanTile);
 
     // workspace
@@ -558,7 +645,7 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
         cv.take<Xyzz<F>>(nslots); cv.take<int32_t>(nslots);
         cv.take<LongRun>(kLongQueueCap); cv.take<uint32_t>(4);
         cv.take<Xyzz<F>>(nslices);
-        cv.take<Xyzz<F>>(pl.W);
+        cv.take<Xyzz<F>>(pl.G);
         need = cv.used();
     }
     BZK_TRY(ensure_ws(ctx, ws, ws_bytes, need));
@@ -574,7 +661,7 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
     LongRun *long_queue = cv.take<LongRun>(kLongQueueCap);
     uint32_t *long_len = cv.take<uint32_t>(4);
     Xyzz<F> *slice_out = cv.take<Xyzz<F>>(nslices);
-    Xyzz<F> *win_out = cv.take<Xyzz<F>>(pl.W);
+    Xyzz<F> *win_out = cv.take<Xyzz<F>>(pl.G);
 
     // stage marks: 0 clear+digits/histogram, 1 scan, 2 scatter, 3 accumulate, 4 fixup,
     //              5 bucket slices, 6 window sums (+ D2H of W points)
@@ -584,7 +671,7 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
     BZK_CUDA(ctx, cudaMemsetAsync(counts, 0, (pl.TB + 1) * sizeof(uint32_t), st));
     BZK_CUDA(ctx, cudaMemsetAsync(buckets, 0, (size_t)pl.TB * sizeof(Xyzz<F>), st));  // all-zero = identity
 
-    k_digits<false><<<div_up(n, 256), 256, 0, st>>>(d_scalars, n, pl.c, pl.W, pl.NB, counts, nullptr);
+    k_digits<false><<<div_up(n, 256), 256, 0, st>>>(d_scalars, n, pl.c, pl.W, pl.NB, pl.G, (uint32_t)bases.n_tab, (uint32_t)bases.off, counts, nullptr);
     BZK_LAUNCHED(ctx);
     timing_mark(ctx);
     k_scan_tile_sums<<<ntiles, kScanBlock, 0, st>>>(counts, pl.TB, tile_sums);
@@ -594,7 +681,7 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
     k_scan_apply<<<ntiles, kScanBlock, 0, st>>>(counts, pl.TB, tile_sums, ntiles, offsets, cursor);
     BZK_LAUNCHED(ctx);
     timing_mark(ctx);
-    k_digits<true><<<div_up(n, 256), 256, 0, st>>>(d_scalars, n, pl.c, pl.W, pl.NB, cursor, sorted);
+    k_digits<true><<<div_up(n, 256), 256, 0, st>>>(d_scalars, n, pl.c, pl.W, pl.NB, pl.G, (uint32_t)bases.n_tab, (uint32_t)bases.off, cursor, sorted);
     BZK_LAUNCHED(ctx);
     timing_mark(ctx);
     k_accumulate<F><<<acc_blocks, 128, 0, st>>>(d_bases, sorted, offsets, pl.TB, 16u, buckets, part_pts, part_bucket);
@@ -618,11 +705,11 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
     while (ws_threads > 32 && ws_threads / 2 >= per_win) ws_threads /= 2;
     const size_t smem = (size_t)ws_threads * sizeof(Xyzz<F>);
     BZK_CUDA(ctx, cudaFuncSetAttribute(k_window_sum<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_window_sum<F><<<pl.W, ws_threads, smem, st>>>(slice_out, per_win, win_out);
+    k_window_sum<F><<<pl.G, ws_threads, smem, st>>>(slice_out, per_win, win_out);
     BZK_LAUNCHED(ctx);
 
     // 7. the W window sums go to the host for the Horner chain (msm_host_finish)
-    BZK_CUDA(ctx, cudaMemcpyAsync(h_win, win_out, pl.W * sizeof(Xyzz<F>), cudaMemcpyDeviceToHost, st));
+    BZK_CUDA(ctx, cudaMemcpyAsync(h_win, win_out, pl.G * sizeof(Xyzz<F>), cudaMemcpyDeviceToHost, st));
     timing_mark(ctx);
     ctx->timing = saved_timing;
     return BZK_OK;
@@ -631,8 +718,9 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
 template <class F>
 static void msm_host_finish(const MsmPlan &pl, const Xyzz<F> *h_win, typename Wire<F>::image *out) {
     if (pl.W == 0) { Wire<F>::to_image(out, Affine<F>::inf()); return; }
-    Xyzz<F> acc = h_win[pl.W - 1];
-    for (int w = (int)pl.W - 2; w >= 0; w--) {
+    // group g carries weight 2^(c*g) (the level factor 2^(c*G*t) is already in the table points)
+    Xyzz<F> acc = h_win[pl.G - 1];
+    for (int w = (int)pl.G - 2; w >= 0; w--) {
         for (uint32_t k = 0; k < pl.c; k++) acc = acc.dbl();
         acc.add(h_win[w]);
     }
@@ -640,7 +728,7 @@ static void msm_host_finish(const MsmPlan &pl, const Xyzz<F> *h_win, typename Wi
 }
 
 template <class F>
-static int32_t msm_run(bzk_ctx *ctx, const Affine<F> *d_bases, const Fr *d_scalars, size_t n, typename Wire<F>::image *out) {
+static int32_t msm_run(bzk_ctx *ctx, const BasesRef<F> &d_bases, const Fr *d_scalars, size_t n, typename Wire<F>::image *out) {
     if (!out) return BZK_ERR_BAD_ARG;
     Xyzz<F> h_win[128];
     MsmPlan pl;

@@ -97,6 +97,12 @@ class ProvingKey:
             self._ctx._check(self._ctx._l.bzk_groth16_params_free(self._ctx._h, self._h))
             self._h = None
 
+    def precompute(self, max_levels=0, mem_fraction_percent=60):
+        """fixed-base tables for the key's five base vectors (bzk_groth16_params_precompute); max_levels=0: as many
+        levels (<= 16) as fit in mem_fraction_percent % of the free device memory.  Proofs are unchanged."""
+        self._ctx._check(self._ctx._l.bzk_groth16_params_precompute(self._ctx._h, self._h, int(max_levels), int(mem_fraction_percent)))
+        return self
+
     def __del__(self):
         try:
             self.free()
@@ -118,7 +124,12 @@ def _make_pk(ctx, vk, hb, lb, ab, b1b, b2b):
     ctx._check(ctx._l.bzk_groth16_params_create(ctx._h, *[_host_ptr(p) for p in pts], hb._h, lb._h, ab._h, b1b._h, b2b._h, ct.byref(out)))
     for b in (hb, lb, ab, b1b, b2b):
         b._h = None  # adopted by the params handle
-    return ProvingKey(ctx, out, vk)
+    pk = ProvingKey(ctx, out, vk)
+    import os
+    lv = os.environ.get("BZK_TABLE_LEVELS")   # development override: 1 = no tables
+    if lv is None or int(lv) != 1:
+        pk.precompute(int(lv) if lv else 0)
+    return pk
 
 
 class Prover:

@@ -142,6 +142,13 @@ int32_t bzk_g1_bases_from_dev(bzk_ctx *ctx, const void *d_images, size_t n, bzk_
 int32_t bzk_g2_bases_from_dev(bzk_ctx *ctx, const void *d_images, size_t n, bzk_g2_bases **out);
 int32_t bzk_g1_bases_free(bzk_ctx *ctx, bzk_g1_bases *b);
 int32_t bzk_g2_bases_free(bzk_ctx *ctx, bzk_g2_bases *b);
+/* Fixed-base table for a resident vector (bases of a proving key never change): grows the vector to up to `max_levels`
+ * levels, level t = [2^(c*G*t)] P_i, so that every MSM over it needs only G = ceil(W/levels) bucket groups.  Results are
+ * the same group elements; memory grows to levels x n points.  No-op for max_levels <= 1 or an already tabled vector. */
+int32_t bzk_g1_bases_precompute(bzk_ctx *ctx, bzk_g1_bases *bases, uint32_t max_levels);
+int32_t bzk_g2_bases_precompute(bzk_ctx *ctx, bzk_g2_bases *bases, uint32_t max_levels);
+uint32_t bzk_g1_bases_levels(const bzk_g1_bases *bases);
+uint32_t bzk_g2_bases_levels(const bzk_g2_bases *bases);
 size_t bzk_g1_bases_len(const bzk_g1_bases *b);
 size_t bzk_g2_bases_len(const bzk_g2_bases *b);
 /* sum over bases[offset .. offset+n) with host scalars (copied in) or device scalars */
@@ -201,6 +208,10 @@ int32_t bzk_groth16_prove(bzk_ctx *ctx, const bzk_groth16_params *params, const 
 int32_t bzk_groth16_prove_dev(bzk_ctx *ctx, const bzk_groth16_params *params, const bzk_r1cs *r1cs,
                               const void *d_inputs, const void *d_aux, const bzk_fr *r, const bzk_fr *s, int32_t check_satisfied,
                               bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c);
+
+/* Fixed-base tables for the five base vectors of a key; max_levels = 0: as many levels (<= 16) as fit in
+ * mem_fraction_percent % (0 = 50) of the free device memory.  See bzk_g1_bases_precompute. */
+int32_t bzk_groth16_params_precompute(bzk_ctx *ctx, bzk_groth16_params *params, uint32_t max_levels, uint32_t mem_fraction_percent);
 
 /* Stage times of the last prove call made while bzk_ctx_set_timing was on (CUDA events): milliseconds after the start
  * of the call at which [1] z upload + the three SpMVs finished, [2] the quotient pipeline (7 NTTs), [3] the h sum (main

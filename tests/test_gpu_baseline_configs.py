@@ -44,6 +44,7 @@ def test_ntt_2_24_all_ops_bit_exact_vs_oracle(ctx, cref):
     d = t.from_numpy(a.view(np.int64)).cuda()
     for op in range(4):
         x = d.clone()
+        t.cuda.synchronize()                       # the clone runs on torch's stream, the transform on the context's
         ctx.ntt_dev(x, log_n, op)
         ctx.synchronize()
         got = host_u64(x).reshape(-1, 4)

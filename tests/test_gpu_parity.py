@@ -319,3 +319,61 @@ def test_merkle4_build_prove_root(ctx, cref):
     ctx.merkle4_root_dev(log4, d_idx, bad_leaves, proofs, roots)
     ctx.synchronize()
     assert all(r != tree.root for r in fr_ints(host_u64(roots).reshape(-1, 4)))
+
+
+# ------------------------------------------------------------------ fixed-base tables (resident proving-key columns)
+@pytest.mark.parametrize("levels", [2, 3, 7, 16])
+def test_msm_g1_fixed_base_table_equals_oracle(ctx, cref, levels):
+    """bzk_g1_bases_precompute: level t = [2^(c*G*t)] P.  Same group element as the plain sum for uniform, witness-like and
+    adversarial inputs (identity bases, repeated bases -> equal points inside a bucket, r-1, zero), and for sub-ranges."""
+    n = 6000
+    bases = cref.g1_random_bases(9, n)
+    inf = np.zeros(104, dtype=np.uint8)
+    inf[96] = 1
+    bases[::7] = inf
+    bases[1::7] = bases[1]
+    vals = fr_ints(cref.fr_random(10, n))
+    R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    for i in range(0, n, 3):
+        vals[i] = i % 2
+    vals[5], vals[6], vals[8] = R - 1, 0, (1 << 255) % R
+    scalars = fr_arr(vals)
+    rb = ctx.g1_bases(bases)
+    got_levels = rb.precompute(levels)
+    assert 2 <= got_levels <= levels and rb.levels == got_levels
+    assert (ctx.msm_g1_resident(rb, scalars) == cref.msm_g1(bases, scalars)).all()
+    assert (ctx.msm_g1_resident(rb, scalars[1000:3001], offset=1000) == cref.msm_g1(bases[1000:3001], scalars[1000:3001])).all()
+    ones = fr_arr([1] * n)
+    assert (ctx.msm_g1_resident(rb, ones) == cref.msm_g1(bases, ones)).all()
+    rb.free()
+
+
+@pytest.mark.parametrize("levels", [2, 16])
+def test_msm_g2_fixed_base_table_equals_oracle(ctx, cref, levels):
+    n = 1500
+    bases = cref.g2_random_bases(7, n)
+    bases[3] = bases[4]
+    v = fr_ints(cref.fr_random(8, n))
+    v[0], v[1], v[2] = 0, 1, 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000000
+    scalars = fr_arr(v)
+    rb = ctx.g2_bases(bases)
+    rb.precompute(levels)
+    assert (ctx.msm_g2_resident(rb, scalars) == cref.msm_g2(bases, scalars)).all()
+    assert (ctx.msm_g2_resident(rb, scalars[100:900], offset=100) == cref.msm_g2(bases[100:900], scalars[100:900])).all()
+    rb.free()
+
+
+def test_msm_g1_2_20_fixed_base_table_vs_oracle(ctx, cref):
+    """BASELINE configs[1] size through the table path (what bench.py times): value against the threaded C oracle."""
+    t = _t()
+    n = 1 << 20
+    d_img = t.empty((n, 104), dtype=t.uint8, device="cuda")
+    ctx.g1_random_bases_dev(2, n, d_img)
+    rb = ctx.g1_bases_from_dev(d_img, n)
+    rb.precompute(16)
+    s = t.empty((n, 4), dtype=t.int64, device="cuda")
+    ctx.fr_random_dev(1, n, s)
+    ctx.synchronize()
+    got = ctx.msm_g1_resident(rb, s)
+    assert (got == cref.msm_g1(d_img.cpu().numpy(), host_u64(s).reshape(-1, 4))).all()
+    rb.free()
