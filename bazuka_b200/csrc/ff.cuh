@@ -18,6 +18,7 @@
 // verified without a GPU.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define BZK_HD __host__ __device__ __forceinline__
@@ -160,6 +161,83 @@ struct Fe {
         return r;
     }
     BZK_HD friend Fe operator+(const Fe &a, const Fe &b) {
+#if defined(__CUDA_ARCH__)
+        return add_limbs32(a, b);
+#else
+        return add_host64(a, b);
+#endif
+    }
+    BZK_HD friend Fe operator-(const Fe &a, const Fe &b) {
+#if defined(__CUDA_ARCH__)
+        return sub_limbs32(a, b);
+#else
+        return sub_host64(a, b);
+#endif
+    }
+    // host constants as 64-bit limbs, built once (the constexpr limb tables would otherwise be re-materialised on
+    // the stack at every call with a runtime index)
+    struct HostConsts {
+        uint64_t p[N / 2];
+        uint64_t inv64;  // -p^-1 mod 2^64
+    };
+    static inline const HostConsts &host_consts() {
+        static const HostConsts hc = [] {
+            HostConsts c;
+            for (int i = 0; i < N / 2; i++) c.p[i] = (uint64_t)P::p(2 * i) | ((uint64_t)P::p(2 * i + 1) << 32);
+            uint64_t x = (uint64_t)(0u - P::inv());  // p^-1 mod 2^32
+            x *= 2 - c.p[0] * x;                      // one Newton step: p^-1 mod 2^64
+            c.inv64 = (uint64_t)0 - x;
+            return c;
+        }();
+        return hc;
+    }
+    // host fast paths on 64-bit limbs (the 32-bit-limb image is the same bytes on a little-endian host)
+    static inline Fe add_host64(const Fe &a, const Fe &b) {
+        constexpr int M = N / 2;
+        uint64_t A[M], B[M], t[M], s[M];
+        memcpy(A, a.l, sizeof A);
+        memcpy(B, b.l, sizeof B);
+        unsigned __int128 c = 0;
+        for (int i = 0; i < M; i++) { c += (unsigned __int128)A[i] + B[i]; t[i] = (uint64_t)c; c >>= 64; }
+        uint64_t borrow = 0;
+        const uint64_t *Pm = host_consts().p;
+        for (int i = 0; i < M; i++) {
+            const uint64_t pm = Pm[i];
+            const unsigned __int128 d = (unsigned __int128)t[i] - pm - borrow;
+            s[i] = (uint64_t)d;
+            borrow = (uint64_t)(d >> 64) & 1;
+        }
+        Fe r;
+        memcpy(r.l, borrow ? t : s, sizeof t);
+        return r;
+    }
+    static inline Fe sub_host64(const Fe &a, const Fe &b) {
+        constexpr int M = N / 2;
+        uint64_t A[M], B[M], t[M];
+        memcpy(A, a.l, sizeof A);
+        memcpy(B, b.l, sizeof B);
+        uint64_t borrow = 0;
+        for (int i = 0; i < M; i++) {
+            const unsigned __int128 d = (unsigned __int128)A[i] - B[i] - borrow;
+            t[i] = (uint64_t)d;
+            borrow = (uint64_t)(d >> 64) & 1;
+        }
+        if (borrow) {
+            unsigned __int128 c = 0;
+            const uint64_t *Pm = host_consts().p;
+            for (int i = 0; i < M; i++) {
+                const uint64_t pm = Pm[i];
+                c += (unsigned __int128)t[i] + pm;
+                t[i] = (uint64_t)c;
+                c >>= 64;
+            }
+        }
+        Fe r;
+        memcpy(r.l, t, sizeof t);
+        return r;
+    }
+    // the device algorithm (32-bit limbs, carry chain); also compiled for the host so tests can check it
+    BZK_HD static Fe add_limbs32(const Fe &a, const Fe &b) {
         Fe t;
         CC cc{0};
         t.l[0] = add_cc(a.l[0], b.l[0], cc);
@@ -167,7 +245,7 @@ struct Fe {
         for (int i = 1; i < N; i++) t.l[i] = addc_cc(a.l[i], b.l[i], cc);
         return reduce_once(t);  // both moduli leave a spare top bit: no carry out of limb N-1
     }
-    BZK_HD friend Fe operator-(const Fe &a, const Fe &b) {
+    BZK_HD static Fe sub_limbs32(const Fe &a, const Fe &b) {
         Fe t;
         CC cc{0};
         t.l[0] = sub_cc(a.l[0], b.l[0], cc);
@@ -196,16 +274,12 @@ struct Fe {
     // host fast path: plain CIOS on 64-bit limbs (unsigned __int128 products); same result
     static inline Fe mul_host64(const Fe &a, const Fe &b) {
         constexpr int M = N / 2;
-        uint64_t A[M], B[M], Pm[M], t[M + 2];
-        for (int i = 0; i < M; i++) {
-            A[i] = (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32);
-            B[i] = (uint64_t)b.l[2 * i] | ((uint64_t)b.l[2 * i + 1] << 32);
-            Pm[i] = (uint64_t)P::p(2 * i) | ((uint64_t)P::p(2 * i + 1) << 32);
-        }
-        // -p^-1 mod 2^64 from the 32-bit constant by one Newton step
-        uint64_t x = (uint64_t)(0u - P::inv());           // p^-1 mod 2^32
-        x *= 2 - Pm[0] * x;                                // p^-1 mod 2^64
-        const uint64_t inv64 = (uint64_t)0 - x;
+        uint64_t A[M], B[M], t[M + 2];
+        memcpy(A, a.l, sizeof A);
+        memcpy(B, b.l, sizeof B);
+        const HostConsts &hc = host_consts();
+        const uint64_t *Pm = hc.p;
+        const uint64_t inv64 = hc.inv64;
         for (int i = 0; i < M + 2; i++) t[i] = 0;
         for (int i = 0; i < M; i++) {
             unsigned __int128 cur;
@@ -230,12 +304,16 @@ struct Fe {
             t[M - 1] = (uint64_t)cur;
             t[M] = t[M + 1] + (uint64_t)(cur >> 64);
         }
-        Fe r;
+        // t < 2p and 2p < 2^(32N): t[M] == 0; one conditional subtraction
+        uint64_t s[M], borrow = 0;
         for (int i = 0; i < M; i++) {
-            r.l[2 * i] = (uint32_t)t[i];
-            r.l[2 * i + 1] = (uint32_t)(t[i] >> 32);
+            const unsigned __int128 d = (unsigned __int128)t[i] - Pm[i] - borrow;
+            s[i] = (uint64_t)d;
+            borrow = (uint64_t)(d >> 64) & 1;
         }
-        return reduce_once(r);  // t < 2p and 2p < 2^(32N): t[M] == 0
+        Fe r;
+        memcpy(r.l, borrow ? t : s, M * sizeof(uint64_t));
+        return r;
     }
     // the device algorithm (also compiled for the host so tests can check its carry logic)
     BZK_HD static Fe mul_evenodd(const Fe &a, const Fe &b) {

@@ -467,3 +467,64 @@ def _fr_inv_gpu(ctx, x):
             acc, out = out, acc
     ctx.synchronize()
     return acc.cpu().numpy().view(np.uint64).reshape(4)
+
+
+class PreparedVerifyingKey:
+    """bellman `PreparedVerifyingKey` held across verifications (bzk_groth16_pvk_*): e(alpha,beta) and the line
+    coefficients of gamma / delta are computed once.  `vk`: the 878+97n-byte bincode image or a dict of wire images."""
+
+    def __init__(self, vk):
+        from . import _lib
+        self._l = _lib.load()
+        blob = np.ascontiguousarray(vk_to_bincode(vk) if isinstance(vk, dict) else vk, dtype=np.uint8)
+        h = ct.c_void_p()
+        st = self._l.bzk_groth16_pvk_from_bytes(_host_ptr(blob), blob.size, ct.byref(h))
+        if st != 0:
+            raise _lib.BzkError(st, "groth16_pvk_from_bytes")
+        self._h = h
+
+    def free(self):
+        if self._h:
+            self._l.bzk_groth16_pvk_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def verify(self, public_inputs, proof387):
+        """one proof as its 387-byte `Groth16Proof` image"""
+        p = np.ascontiguousarray(proof387, dtype=np.uint8).reshape(387)
+        a, b, c = np.zeros(G1_BYTES, np.uint8), np.zeros(G2_BYTES, np.uint8), np.zeros(G1_BYTES, np.uint8)
+        a[:97], b[:193], c[:97] = p[:97], p[97:290], p[290:]
+        return self.verify_points(public_inputs, (a, b, c))
+
+    def verify_points(self, public_inputs, proof_points):
+        from . import _lib
+        pub = np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(-1, 4)
+        a, b, c = (np.ascontiguousarray(x, dtype=np.uint8) for x in proof_points)
+        st = self._l.bzk_groth16_verify_prepared(self._h, _host_ptr(pub), len(pub), _host_ptr(a), _host_ptr(b), _host_ptr(c))
+        if st < 0:
+            raise _lib.BzkError(st, "groth16_verify_prepared")
+        return bool(st)
+
+    def verify_batch(self, public_inputs, proofs387, seed=None, threads=0):
+        """public_inputs [m, n, 4] Montgomery, proofs387 [m, 387] -> (all_ok, ok_each[m]).  One final exponentiation for
+        the batch (random linear combination with 127-bit multipliers from `seed`, default os.urandom)."""
+        import os
+        from . import _lib
+        pub = np.ascontiguousarray(public_inputs, dtype=np.uint64)
+        proofs = np.ascontiguousarray(proofs387, dtype=np.uint8).reshape(-1, 387)
+        m = len(proofs)
+        if m == 0:
+            return True, np.zeros(0, dtype=bool)
+        pub = pub.reshape(m, -1, 4)
+        each = np.zeros(max(m, 1), dtype=np.uint8)
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little")
+        st = self._l.bzk_groth16_verify_batch(self._h, _host_ptr(pub), pub.shape[1], _host_ptr(proofs), m, seed, int(threads), _host_ptr(each))
+        if st < 0:
+            raise _lib.BzkError(st, "groth16_verify_batch")
+        return bool(st), each[:m].astype(bool)

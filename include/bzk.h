@@ -342,6 +342,25 @@ int32_t bzk_groth16_verify(const bzk_g1_affine *alpha_g1, const bzk_g2_affine *b
                            const bzk_fr *public_inputs, size_t n_inputs,
                            const bzk_g1_affine *proof_a, const bzk_g2_affine *proof_b, const bzk_g1_affine *proof_c);
 int32_t bzk_groth16_verify_bytes(const uint8_t *vk, size_t vk_len, const bzk_fr *public_inputs, size_t n_inputs, const uint8_t *proof387);
+/* Prepared verifying key — bellman `PreparedVerifyingKey`, which the reference rebuilds on every `groth16_verify` call
+ * (/root/reference/src/zk/groth16/mod.rs:97-108): e(alpha,beta) and the Miller-loop line coefficients of gamma and
+ * delta, computed once.  The plain entry points above keep the 8 most recently used prepared keys in an internal
+ * mutex-guarded cache; with an explicit handle there is no shared state. */
+typedef struct bzk_groth16_pvk bzk_groth16_pvk;
+int32_t bzk_groth16_pvk_create(const bzk_g1_affine *alpha_g1, const bzk_g2_affine *beta_g2, const bzk_g2_affine *gamma_g2,
+                               const bzk_g2_affine *delta_g2, const bzk_g1_affine *ic, size_t n_ic, bzk_groth16_pvk **out);
+int32_t bzk_groth16_pvk_from_bytes(const uint8_t *vk, size_t vk_len, bzk_groth16_pvk **out);
+int32_t bzk_groth16_pvk_free(bzk_groth16_pvk *pvk);
+int32_t bzk_groth16_verify_prepared(const bzk_groth16_pvk *pvk, const bzk_fr *public_inputs, size_t n_inputs,
+                                    const bzk_g1_affine *proof_a, const bzk_g2_affine *proof_b, const bzk_g1_affine *proof_c);
+/* Batch verification of m proofs under one key (a node syncing many blocks): random linear combination
+ *   prod_j e(r_j A_j, B_j) * e(-sum_j r_j acc_j, gamma) * e(-sum_j r_j C_j, delta) == e(alpha,beta)^(sum_j r_j)
+ * with 127-bit r_j derived from `seed` (draw a fresh random seed per batch), m + 2 Miller loops over `threads` host
+ * threads (<= 0: all) and ONE final exponentiation.  public_inputs: m rows of n_inputs Montgomery scalars; proofs387:
+ * m x 387 bytes.  Returns 1 if every proof verifies, else 0; ok_each (optional, m bytes) receives per-proof verdicts
+ * (on a failing batch the proofs are re-checked one by one). */
+int32_t bzk_groth16_verify_batch(const bzk_groth16_pvk *pvk, const bzk_fr *public_inputs, size_t n_inputs, const uint8_t *proofs387, size_t m,
+                                 uint64_t seed, int32_t threads, uint8_t *ok_each);
 /* Building blocks also used by the GPU-side trusted-setup helper (bellman `generate_parameters`):
  * CSR sparse matrix-vector product over Fr (out[row] = sum val*vec[col]) and fixed-base scalar
  * multiplication out[i] = [k_i] base written as wire images. */

@@ -36,7 +36,7 @@ def hostshim():
     import ctypes as ct
     src = os.path.join(ROOT, "tests", "hostshim", "shim.cpp")
     out = os.path.join(ROOT, "tests", "hostshim", "_shim.so")
-    deps = [src] + [os.path.join(ROOT, "bazuka_b200", "csrc", h) for h in ("ff.cuh", "ec.cuh", "ffu.cuh", "witness_core.cuh")]
+    deps = [src] + [os.path.join(ROOT, "bazuka_b200", "csrc", h) for h in ("ff.cuh", "ec.cuh", "witness_core.cuh", "pairing.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++",
                                "-I", os.path.join(ROOT, "bazuka_b200", "csrc"), src, "-o", out])

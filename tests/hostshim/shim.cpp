@@ -3,7 +3,6 @@
 // group law on the CPU so their logic is checked against the oracle without a GPU.
 #include <cstring>
 #include "ec.cuh"
-#include "ffu.cuh"
 #include "witness_core.cuh"
 #include <vector>
 using namespace bzk;
@@ -12,10 +11,12 @@ template <class T, int W> static void bin(const uint32_t *a, const uint32_t *b, 
         T x, y, z;
         memcpy(x.l, a + W * i, 4 * W); memcpy(y.l, b + W * i, 4 * W);
         switch (op) {
-            case 0: z = x + y; break;
-            case 1: z = x - y; break;
+            case 0: z = T::add_limbs32(x, y); break;   // the device text (explicit-carry build)
+            case 1: z = T::sub_limbs32(x, y); break;
             case 2: z = T::mul_evenodd(x, y); break;
-            default: z = x * y; break;  // host64 fast path
+            case 4: z = x + y; break;                  // host fast paths (64-bit limbs)
+            case 5: z = x - y; break;
+            default: z = x * y; break;
         }
         memcpy(r + W * i, z.l, 4 * W);
     }
@@ -33,15 +34,6 @@ void shim_fr_dot(const uint32_t *m, const uint32_t *s, size_t t, uint32_t *out) 
         Fr::wide_accumulate(acc, w);
     }
     Fr r = Fr::redc_wide(acc); memcpy(out, r.l, 32);
-}
-// carry-free 13x30-bit Fp (ffu.cuh): wire image -> internal -> op -> wire image
-void shim_fpu(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n, int op) {
-    for (size_t i = 0; i < n; i++) {
-        Fp x, y; memcpy(x.l, a + 12 * i, 48); memcpy(y.l, b + 12 * i, 48);
-        FpU u = FpU::from_fp(x), v = FpU::from_fp(y), w;
-        switch (op) { case 0: w = u + v; break; case 1: w = u - v; break; case 2: w = u * v; break; default: w = u; break; }
-        Fp z = w.to_fp(); memcpy(r + 12 * i, z.l, 48);
-    }
 }
 void shim_fr(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n, int op) { bin<Fr, 8>(a, b, r, n, op); }
 void shim_fp(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n, int op) { bin<Fp, 12>(a, b, r, n, op); }
@@ -91,5 +83,42 @@ void shim_witness_run(const int32_t *ops, uint32_t n_ops, const int32_t *lc_ptr,
     WitProgDev P{ops, lc_ptr, lc_slot, lc_coef, (const Fr *)coefs, n_ops, n_raw, n_ext};
     Fr d; memcpy(d.l, jj_d, 32);
     wit_run_slot(P, d, (const Fr *)raws, (const Fr *)ext, mem);
+}
+}
+
+// ---- csrc/pairing.cuh on the host: e(P,Q)^3 as 6 Fp2 coefficients (12 x 12 u32, Montgomery), and its pieces
+#include "pairing.cuh"
+extern "C" {
+static G1Affine shim_g1(const uint32_t *p) { G1Affine a; memcpy(a.x.l, p, 48); memcpy(a.y.l, p + 12, 48); return a; }
+static G2Affine shim_g2(const uint32_t *p) {
+    G2Affine a;
+    memcpy(a.x.c0.l, p, 48); memcpy(a.x.c1.l, p + 12, 48); memcpy(a.y.c0.l, p + 24, 48); memcpy(a.y.c1.l, p + 36, 48);
+    return a;
+}
+static void shim_f12_out(const pairing::Fp12 &f, uint32_t *out) {
+    for (int k = 0; k < 6; k++) { memcpy(out + 24 * k, f.c[k].c0.l, 48); memcpy(out + 24 * k + 12, f.c[k].c1.l, 48); }
+}
+static pairing::Fp12 shim_f12_in(const uint32_t *in) {
+    pairing::Fp12 f;
+    for (int k = 0; k < 6; k++) { memcpy(f.c[k].c0.l, in + 24 * k, 48); memcpy(f.c[k].c1.l, in + 24 * k + 12, 48); }
+    return f;
+}
+// g1: x|y (24 u32), g2: x.c0|x.c1|y.c0|y.c1 (48 u32), Montgomery; out: 144 u32
+void shim_pairing_cubed(const uint32_t *g1, const uint32_t *g2, uint32_t *out) {
+    pairing::G2Lines L;
+    pairing::compute_lines(shim_g2(g2), L);
+    pairing::MillerPair p{shim_g1(g1), &L};
+    shim_f12_out(pairing::final_exp(pairing::multi_miller(&p, 1)), out);
+}
+void shim_miller(const uint32_t *g1, const uint32_t *g2, uint32_t *out) {
+    pairing::G2Lines L;
+    pairing::compute_lines(shim_g2(g2), L);
+    pairing::MillerPair p{shim_g1(g1), &L};
+    shim_f12_out(pairing::multi_miller(&p, 1), out);
+}
+void shim_final_exp(const uint32_t *in, uint32_t *out) { shim_f12_out(pairing::final_exp(shim_f12_in(in)), out); }
+void shim_f12_inv_frob(const uint32_t *in, uint32_t *out_inv, uint32_t *out_frob) {
+    shim_f12_out(pairing::f12_inv(shim_f12_in(in)), out_inv);
+    shim_f12_out(pairing::f12_frob(shim_f12_in(in)), out_frob);
 }
 }

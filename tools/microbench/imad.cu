@@ -3,7 +3,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
-#include "../../bazuka_b200/csrc/ffu.cuh"
+#include "ffu.cuh"  // the measured-and-rejected carry-free prototype lives next to its microbenchmark
 using namespace bzk;
 
 #define ITERS 4096
