@@ -26,7 +26,9 @@ struct MsmPlan {
     uint32_t TB = 0;  // total buckets = G * NB
     uint32_t T = 1;   // table levels in use: level t holds [2^(c*G*t)] P (1 = plain bases)
     uint32_t G = 0;   // bucket groups = ceil(W / T): window j = t*G + g feeds group g from level t
+    uint32_t slice = 0, nbits = 0;  // bucket reduction: buckets per slice, bits of the slice index (host fold)
 };
+constexpr uint32_t kMaxWinPoints = 320;  // >= G * (1 + nbits) for every plan make_plan can produce
 
 struct NttTables {
     Fr *d_fwd = nullptr;  // omega^j, j < n/2

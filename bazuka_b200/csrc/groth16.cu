@@ -345,7 +345,7 @@ static int32_t groth16_prove_impl(bzk_ctx *ctx, const bzk_groth16_params *pk, co
         if (!ctx->aux_stream[k]) BZK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream[k], cudaStreamNonBlocking));
     for (int k = 0; k < 3; k++)
         if (!ctx->aux_ev[k]) BZK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->aux_ev[k], cudaEventDisableTiming));
-    constexpr size_t kWinBytes = 128 * sizeof(G2Xyzz);
+    constexpr size_t kWinBytes = kMaxWinPoints * sizeof(G2Xyzz);
     if (ctx->pinned_bytes < 5 * kWinBytes) {
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
         ctx->pinned = nullptr;

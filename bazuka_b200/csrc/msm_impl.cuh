@@ -361,23 +361,19 @@ __global__ void __launch_bounds__(256) k_fixup_long(const Xyzz<F> *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 // 6. bucket reduction: per window  sum_b (b+1) * B_b
 // ---------------------------------------------------------------------------------------------
-template <class F>
-__device__ __forceinline__ Xyzz<F> small_mul(const Xyzz<F> &p, uint32_t k) {
-    Xyzz<F> acc = Xyzz<F>::inf();
-    if (k == 0) return acc;
-    for (int i = 31 - __clz(k); i >= 0; i--) {
-        acc = acc.dbl();
-        if ((k >> i) & 1) acc.add(p);
-    }
-    return acc;
-}
-
+// A group's sum is  sum_b (b+1) B_b.  The buckets are cut into slices of `slice` consecutive buckets; slice s
+// (buckets lo = s*slice ...) contributes  acc_s + lo * run_s  with  run_s = sum B,  acc_s = sum (k+1) B_{lo+k}.
+// The dependent chain per thread is just the 2*slice running-sum additions: the [lo] multiple is NOT formed per
+// slice (a ~30-addition double-and-add that used to cost as much as the running sums) but through the bits of s,
+//     sum_s lo_s run_s = slice * sum_j 2^j T_j ,   T_j = sum over the slices whose index has bit j set of run_s ,
+// i.e. 1 + nbits independent tree sums per group (k_slice_combine, k_partial_sum) and a ~2 nbits-operation Horner
+// fold on the host.
 template <class F>
 __global__ void __launch_bounds__(128) k_bucket_slices(const Xyzz<F> *__restrict__ buckets, uint32_t NB, uint32_t slice, uint32_t nslices_total,
-                                                       Xyzz<F> *__restrict__ slice_out) {
+                                                       Xyzz<F> *__restrict__ acc_out, Xyzz<F> *__restrict__ run_out) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nslices_total) return;
-    const uint32_t per_win = (NB + slice - 1) / slice;  // the last slice of a window may be short
+    const uint32_t per_win = (NB + slice - 1) / slice;  // the last slice of a group may be short
     const uint32_t w = g / per_win, sidx = g % per_win;
     const uint32_t lo = sidx * slice;
     const uint32_t len = (lo + slice <= NB) ? slice : NB - lo;
@@ -387,18 +383,44 @@ __global__ void __launch_bounds__(128) k_bucket_slices(const Xyzz<F> *__restrict
         run.add(load_vec(B + lo + k));
         acc.add(run);
     }
-    if (lo) acc.add(small_mul(run, lo));
-    store_vec(slice_out + g, acc);
+    store_vec(acc_out + g, acc);
+    store_vec(run_out + g, run);
 }
 
-// one CTA per window: sum `per_win` slice results
+// grid (parts, 1 + nbits, G): CTA (p, j, g) tree-sums 256 consecutive slices of group g — acc_s for j = 0, run_s of
+// the slices with bit j-1 set for j >= 1 — into partial[(g*(1+nbits) + j) * parts + p]
+constexpr uint32_t kCombineThreads = 256;
 template <class F>
-__global__ void __launch_bounds__(1024) k_window_sum(const Xyzz<F> *__restrict__ slice_out, uint32_t per_win, Xyzz<F> *__restrict__ win_out) {
+__global__ void __launch_bounds__(kCombineThreads) k_slice_combine(const Xyzz<F> *__restrict__ acc_in, const Xyzz<F> *__restrict__ run_in, uint32_t per_win,
+                                                                  Xyzz<F> *__restrict__ partial) {
     extern __shared__ uint4 smem_raw[];
     Xyzz<F> *sh = (Xyzz<F> *)smem_raw;
-    const uint32_t w = blockIdx.x;
+    const uint32_t j = blockIdx.y, g = blockIdx.z, s = blockIdx.x * kCombineThreads + threadIdx.x;
+    Xyzz<F> v = Xyzz<F>::inf();
+    if (s < per_win) {
+        if (j == 0) v = load_vec(acc_in + (size_t)g * per_win + s);
+        else if ((s >> (j - 1)) & 1) v = load_vec(run_in + (size_t)g * per_win + s);
+    }
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (uint32_t o = kCombineThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            Xyzz<F> a = sh[threadIdx.x];
+            a.add(sh[threadIdx.x + o]);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) store_vec(partial + ((size_t)(g * gridDim.y + j)) * gridDim.x + blockIdx.x, sh[0]);
+}
+// one CTA per (j, g): sum of its `parts` partials
+template <class F>
+__global__ void __launch_bounds__(128) k_partial_sum(const Xyzz<F> *__restrict__ partial, uint32_t parts, Xyzz<F> *__restrict__ win_out) {
+    extern __shared__ uint4 smem_raw[];
+    Xyzz<F> *sh = (Xyzz<F> *)smem_raw;
+    const size_t row = blockIdx.x;
     Xyzz<F> acc = Xyzz<F>::inf();
-    for (uint32_t k = threadIdx.x; k < per_win; k += blockDim.x) acc.add(load_vec(slice_out + (size_t)w * per_win + k));
+    for (uint32_t k = threadIdx.x; k < parts; k += blockDim.x) acc.add(load_vec(partial + row * parts + k));
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (uint32_t o = blockDim.x / 2; o > 0; o >>= 1) {
@@ -409,7 +431,7 @@ __global__ void __launch_bounds__(1024) k_window_sum(const Xyzz<F> *__restrict__
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) store_vec(win_out + w, sh[0]);
+    if (threadIdx.x == 0) store_vec(win_out + row, sh[0]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -633,6 +655,15 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
     const uint32_t per_win = (pl.NB + slice - 1) / slice;
     const uint32_t nslices = per_win * pl.G;
     const uint32_t ntiles = div_up(pl.TB, kScanTile);
+    uint32_t nbits = 0;  // bits of the largest slice index
+    while (nbits < 32 && ((per_win - 1) >> nbits)) nbits++;
+    const uint32_t rows = pl.G * (1 + nbits);      // tree sums per MSM: A and T_0..T_{nbits-1} of every group
+    const uint32_t parts = div_up(per_win, kCombineThreads);
+    if (rows > kMaxWinPoints) return BZK_ERR_BAD_ARG;
+    MsmPlan full = pl;
+    full.slice = slice;
+    full.nbits = nbits;
+    *plan_out = full;
 
     // workspace
     size_t need = 0;
@@ -644,8 +675,9 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
         cv.take<Xyzz<F>>(pl.TB);
         cv.take<Xyzz<F>>(nslots); cv.take<int32_t>(nslots);
         cv.take<LongRun>(kLongQueueCap); cv.take<uint32_t>(4);
-        cv.take<Xyzz<F>>(nslices);
-        cv.take<Xyzz<F>>(pl.G);
+        cv.take<Xyzz<F>>(nslices); cv.take<Xyzz<F>>(nslices);
+        cv.take<Xyzz<F>>((size_t)rows * parts);
+        cv.take<Xyzz<F>>(rows);
         need = cv.used();
     }
     BZK_TRY(ensure_ws(ctx, ws, ws_bytes, need));
@@ -660,8 +692,9 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
     int32_t *part_bucket = cv.take<int32_t>(nslots);
     LongRun *long_queue = cv.take<LongRun>(kLongQueueCap);
     uint32_t *long_len = cv.take<uint32_t>(4);
-    Xyzz<F> *slice_out = cv.take<Xyzz<F>>(nslices);
-    Xyzz<F> *win_out = cv.take<Xyzz<F>>(pl.G);
+    Xyzz<F> *slice_acc = cv.take<Xyzz<F>>(nslices), *slice_run = cv.take<Xyzz<F>>(nslices);
+    Xyzz<F> *partial = cv.take<Xyzz<F>>((size_t)rows * parts);
+    Xyzz<F> *win_out = cv.take<Xyzz<F>>(rows);
 
     // stage marks: 0 clear+digits/histogram, 1 scan, 2 scatter, 3 accumulate, 4 fixup,
     //              5 bucket slices, 6 window sums (+ D2H of W points)
@@ -697,19 +730,24 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
         BZK_LAUNCHED(ctx);
     }
     timing_mark(ctx);
-    k_bucket_slices<F><<<div_up(nslices, 128), 128, 0, st>>>(buckets, pl.NB, slice, nslices, slice_out);
+    k_bucket_slices<F><<<div_up(nslices, 128), 128, 0, st>>>(buckets, pl.NB, slice, nslices, slice_acc, slice_run);
     BZK_LAUNCHED(ctx);
     timing_mark(ctx);
-    // one CTA per window; as many threads as 200 KB of shared memory holds accumulators for
-    uint32_t ws_threads = sizeof(Xyzz<F>) <= 192 ? 1024 : 512;
-    while (ws_threads > 32 && ws_threads / 2 >= per_win) ws_threads /= 2;
-    const size_t smem = (size_t)ws_threads * sizeof(Xyzz<F>);
-    BZK_CUDA(ctx, cudaFuncSetAttribute(k_window_sum<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_window_sum<F><<<pl.G, ws_threads, smem, st>>>(slice_out, per_win, win_out);
-    BZK_LAUNCHED(ctx);
+    {
+        const size_t smem = kCombineThreads * sizeof(Xyzz<F>);
+        BZK_CUDA(ctx, cudaFuncSetAttribute(k_slice_combine<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_slice_combine<F><<<dim3(parts, 1 + nbits, pl.G), kCombineThreads, smem, st>>>(slice_acc, slice_run, per_win, partial);
+        BZK_LAUNCHED(ctx);
+        uint32_t ps_threads = 128;
+        while (ps_threads > 32 && ps_threads / 2 >= parts) ps_threads /= 2;
+        const size_t smem2 = ps_threads * sizeof(Xyzz<F>);
+        BZK_CUDA(ctx, cudaFuncSetAttribute(k_partial_sum<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        k_partial_sum<F><<<rows, ps_threads, smem2, st>>>(partial, parts, win_out);
+        BZK_LAUNCHED(ctx);
+    }
 
-    // 7. the W window sums go to the host for the Horner chain (msm_host_finish)
-    BZK_CUDA(ctx, cudaMemcpyAsync(h_win, win_out, pl.G * sizeof(Xyzz<F>), cudaMemcpyDeviceToHost, st));
+    // 7. the (1 + nbits) sums of every group go to the host for the Horner folds (msm_host_finish)
+    BZK_CUDA(ctx, cudaMemcpyAsync(h_win, win_out, rows * sizeof(Xyzz<F>), cudaMemcpyDeviceToHost, st));
     timing_mark(ctx);
     ctx->timing = saved_timing;
     return BZK_OK;
@@ -718,11 +756,27 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
 template <class F>
 static void msm_host_finish(const MsmPlan &pl, const Xyzz<F> *h_win, typename Wire<F>::image *out) {
     if (pl.W == 0) { Wire<F>::to_image(out, Affine<F>::inf()); return; }
+    // group sum = A + slice * sum_j 2^j T_j  (see k_bucket_slices)
+    auto group_sum = [&](uint32_t g) {
+        const Xyzz<F> *row = h_win + (size_t)g * (1 + pl.nbits);
+        Xyzz<F> S = Xyzz<F>::inf();
+        for (int j = (int)pl.nbits - 1; j >= 0; j--) {
+            S = S.dbl();
+            S.add(row[1 + j]);
+        }
+        Xyzz<F> m = Xyzz<F>::inf();
+        for (int i = 31; i >= 0; i--) {
+            m = m.dbl();
+            if ((pl.slice >> i) & 1) m.add(S);
+        }
+        m.add(row[0]);
+        return m;
+    };
     // group g carries weight 2^(c*g) (the level factor 2^(c*G*t) is already in the table points)
-    Xyzz<F> acc = h_win[pl.G - 1];
+    Xyzz<F> acc = group_sum(pl.G - 1);
     for (int w = (int)pl.G - 2; w >= 0; w--) {
         for (uint32_t k = 0; k < pl.c; k++) acc = acc.dbl();
-        acc.add(h_win[w]);
+        acc.add(group_sum((uint32_t)w));
     }
     Wire<F>::to_image(out, acc.to_affine());
 }
@@ -730,7 +784,8 @@ static void msm_host_finish(const MsmPlan &pl, const Xyzz<F> *h_win, typename Wi
 template <class F>
 static int32_t msm_run(bzk_ctx *ctx, const BasesRef<F> &d_bases, const Fr *d_scalars, size_t n, typename Wire<F>::image *out) {
     if (!out) return BZK_ERR_BAD_ARG;
-    Xyzz<F> h_win[128];
+    static_assert(kMaxWinPoints * sizeof(Xyzz<F>) <= 160 * 1024, "h_win on the stack");
+    Xyzz<F> h_win[kMaxWinPoints];
     MsmPlan pl;
     BZK_TRY(msm_enqueue<F>(ctx, ctx->stream, &ctx->ws, &ctx->ws_bytes, true, d_bases, d_scalars, n, h_win, &pl));
     BZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
