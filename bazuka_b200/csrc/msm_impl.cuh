@@ -389,17 +389,22 @@ __global__ void __launch_bounds__(128) k_bucket_slices(const Xyzz<F> *__restrict
 
 // grid (parts, 1 + nbits, G): CTA (p, j, g) tree-sums 256 consecutive slices of group g — acc_s for j = 0, run_s of
 // the slices with bit j-1 set for j >= 1 — into partial[(g*(1+nbits) + j) * parts + p]
-constexpr uint32_t kCombineThreads = 256;
+// (a dependent addition costs ~9 us whatever the occupancy, so the shape is: kCombineSerial serial additions per
+// thread, then a 6-level shared-memory tree over 64 threads; the ~600 two-warp CTAs of a 2^19-bucket group are all
+// resident at once)
+constexpr uint32_t kCombineThreads = 64, kCombineSerial = 8, kCombineSpan = kCombineThreads * kCombineSerial;
 template <class F>
 __global__ void __launch_bounds__(kCombineThreads) k_slice_combine(const Xyzz<F> *__restrict__ acc_in, const Xyzz<F> *__restrict__ run_in, uint32_t per_win,
                                                                   Xyzz<F> *__restrict__ partial) {
     extern __shared__ uint4 smem_raw[];
     Xyzz<F> *sh = (Xyzz<F> *)smem_raw;
-    const uint32_t j = blockIdx.y, g = blockIdx.z, s = blockIdx.x * kCombineThreads + threadIdx.x;
+    const uint32_t j = blockIdx.y, g = blockIdx.z;
     Xyzz<F> v = Xyzz<F>::inf();
-    if (s < per_win) {
-        if (j == 0) v = load_vec(acc_in + (size_t)g * per_win + s);
-        else if ((s >> (j - 1)) & 1) v = load_vec(run_in + (size_t)g * per_win + s);
+    for (uint32_t k = 0; k < kCombineSerial; k++) {
+        const uint32_t s = blockIdx.x * kCombineSpan + k * kCombineThreads + threadIdx.x;
+        if (s >= per_win) break;
+        if (j == 0) v.add(load_vec(acc_in + (size_t)g * per_win + s));
+        else if ((s >> (j - 1)) & 1) v.add(load_vec(run_in + (size_t)g * per_win + s));
     }
     sh[threadIdx.x] = v;
     __syncthreads();
@@ -658,7 +663,7 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
     uint32_t nbits = 0;  // bits of the largest slice index
     while (nbits < 32 && ((per_win - 1) >> nbits)) nbits++;
     const uint32_t rows = pl.G * (1 + nbits);      // tree sums per MSM: A and T_0..T_{nbits-1} of every group
-    const uint32_t parts = div_up(per_win, kCombineThreads);
+    const uint32_t parts = div_up(per_win, kCombineSpan);
     if (rows > kMaxWinPoints) return BZK_ERR_BAD_ARG;
     MsmPlan full = pl;
     full.slice = slice;
