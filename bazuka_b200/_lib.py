@@ -99,6 +99,9 @@ SIGNATURES = {
     "bzk_mpn_circuit_shape": (_i32, [_vp, _vp]),
     "bzk_mpn_circuit_matrix": (_i32, [_vp, _u32, _vp, _vp, _vp]),
     "bzk_mpn_circuit_program": (_i32, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bzk_mpn_state_clone": (_i32, [_vp, ct.POINTER(_vp)]),
+    "bzk_mpn_state_info": (_i32, [_vp, _vp, ct.POINTER(_u64), ct.POINTER(_u64), ct.POINTER(_u64)]),
+    "bzk_mpn_state_commit_accounts": (_i32, [_vp]),
     "bzk_mpn_update_witness": (_i32, [_vp, _vp, _vp, _u64, _u32, _u64, _u64, _vp, _vp, _u32, _vp, _vp, _vp]),
     "bzk_witness_program_upload": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _vp, _u64, _u32, _u32, _vp, ct.POINTER(_vp)]),
     "bzk_witness_program_free": (_i32, [_vp, _vp]),

@@ -19,6 +19,7 @@
 namespace bzk {
 int32_t tree4_versioned_update(bzk_ctx *ctx, uint32_t depth, const uint32_t *d_tree_id, const uint64_t *d_idx, size_t n, Fr *d_vals,
                                const Fr *d_init_proofs, Fr *d_out_proofs);
+void witness_program_shape(const bzk_witness_program *p, uint64_t *n_ops, uint32_t *n_raw, uint32_t *n_ext);
 }
 using namespace bzk;
 
@@ -55,8 +56,15 @@ struct bzk_mpn_state {
     std::vector<Fr> defaults, tdefaults;                     // per level: state tree / token tree
     std::vector<std::unordered_map<uint64_t, Fr>> levels;    // sparse state tree, level 0 = leaves; defaults are not stored
     std::map<uint64_t, Account> accounts;
-    std::map<std::pair<FrKey, FrKey>, uint64_t> by_addr;      // first account holding an address
-    uint64_t next_free = 0;
+    // The chain's own tables, which the builders only READ (`get_mpn_account_indices`, `get_mpn_account_count`,
+    // /root/reference/src/mpn/update.rs:29,47-70): they change when a block is applied, not when a batch is built.
+    std::map<std::pair<FrKey, FrKey>, uint64_t> by_addr;      // address -> index of the first account holding it
+    uint64_t account_count = 0;
+    // `new_account_indices`: accounts created by the batches built so far on this fork (threaded through deposit ->
+    // withdraw -> update by `prepare_works`, /root/reference/src/mpn/mod.rs:330,353-414); bzk_mpn_state_commit_accounts
+    // moves them into the chain tables
+    std::map<std::pair<FrKey, FrKey>, uint64_t> pending;
+    uint64_t state_size = 0;  // ZkCompressedState::state_size = number of non-zero scalar leaves
     std::map<FrKey, Point> decompress_cache;
 
     Fr node(uint32_t lvl, uint64_t idx) const {
@@ -132,6 +140,7 @@ bool jj_decompress(bzk_mpn_state *s, const bzk_fr *x_canon, bool odd, Point *out
         Fr y;
         if (!fr_sqrt((Fr::one() + x2) * den.inv(), &y)) return false;  // a = -1
         p = Point{x, y};
+        if (s->decompress_cache.size() >= kDecompressCacheCap) s->decompress_cache.clear();
         s->decompress_cache[key_of(x)] = p;
     }
     const bool y_odd = (p.y.from_mont().l[0] & 1u) != 0;
@@ -139,6 +148,24 @@ bool jj_decompress(bzk_mpn_state *s, const bzk_fr *x_canon, bool odd, Point *out
     out->y = (y_odd != odd) ? p.y.neg() : p.y;
     return true;
 }
+
+// non-zero scalar leaves of one account (`set_data` counts a leaf when it becomes non-zero,
+// /root/reference/src/zk/state/mod.rs:327-341)
+uint64_t leaf_count(const Account &a) {
+    uint64_t n = (a.tx_nonce != 0) + (a.withdraw_nonce != 0) + !a.ax.is_zero() + !a.ay.is_zero();
+    for (auto &kv : a.tokens) n += !kv.second.token_id.is_zero() + (kv.second.amount != 0);
+    return n;
+}
+bool canonical(const bzk_fr &v) {
+    Fr a;
+    memcpy(a.l, &v, 32);
+    for (int i = 7; i >= 0; i--) {
+        if (a.l[i] < FrParams::p(i)) return true;
+        if (a.l[i] > FrParams::p(i)) return false;
+    }
+    return false;  // == r
+}
+constexpr size_t kDecompressCacheCap = 1u << 16;
 
 int find_token_index(const Account &a, uint32_t T, const Fr &token_id, bool empty_allowed) {
     for (auto &kv : a.tokens)
@@ -285,9 +312,12 @@ int32_t bzk_mpn_state_set_account(bzk_ctx *ctx, bzk_mpn_state *s, uint64_t index
     Account a;
     a.tx_nonce = tx_nonce; a.withdraw_nonce = withdraw_nonce;
     a.ax = fr_from_canon(addr_x); a.ay = fr_from_canon(addr_y);
+    if (!canonical(*addr_x) || !canonical(*addr_y)) return BZK_ERR_BAD_ARG;
     for (uint32_t k = 0; k < n_tokens; k++) {
-        if (token_index[k] >> (2 * s->T)) return BZK_ERR_BAD_ARG;
-        a.tokens[token_index[k]] = Money{fr_from_canon(token_id + k), token_amount[k]};
+        if (token_index[k] >> (2 * s->T) || !canonical(token_id[k])) return BZK_ERR_BAD_ARG;
+        const Fr id = fr_from_canon(token_id + k);
+        if (id.is_zero()) continue;  // `get_mpn_account` drops slots whose token id is zero (state/mod.rs:127-130)
+        a.tokens[token_index[k]] = Money{id, token_amount[k]};
     }
     Forest f;
     f.T = s->T;
@@ -302,9 +332,48 @@ int32_t bzk_mpn_state_set_account(bzk_ctx *ctx, bzk_mpn_state *s, uint64_t index
     BZK_TRY(tree_update_host(ctx, s->A, {0u}, {index}, vals, init, proofs));
     uint64_t node = index;
     for (uint32_t l = 0; l <= s->A; l++) { s->put(l, node, vals[l]); node >>= 2; }
+    auto old = s->accounts.find(index);
+    if (old != s->accounts.end()) {
+        s->state_size -= leaf_count(old->second);
+        // an overwritten account gives its address back if the table pointed at this slot
+        auto oit = s->by_addr.find(std::make_pair(key_of(old->second.ax), key_of(old->second.ay)));
+        if (oit != s->by_addr.end() && oit->second == index && !(old->second.ax == a.ax && old->second.ay == a.ay)) s->by_addr.erase(oit);
+    }
+    s->state_size += leaf_count(a);
     s->accounts[index] = a;
-    s->by_addr.emplace(std::make_pair(key_of(a.ax), key_of(a.ay)), index);
-    s->next_free = std::max(s->next_free, index + 1);
+    if (!(a.ax.is_zero() && a.ay.is_zero())) s->by_addr.emplace(std::make_pair(key_of(a.ax), key_of(a.ay)), index);
+    s->account_count = std::max(s->account_count, index + 1);
+    return BZK_OK;
+}
+
+/* An independent copy of the ledger (`db.fork_on_ram()`, /root/reference/src/mpn/mod.rs:313): build the batches of a
+ * block on the copy and keep it only if the block is accepted — bzk_mpn_update_build writes the ledger it is given. */
+int32_t bzk_mpn_state_clone(const bzk_mpn_state *s, bzk_mpn_state **out) {
+    if (!s || !out) return BZK_ERR_BAD_ARG;
+    auto *c = new (std::nothrow) bzk_mpn_state(*s);
+    if (!c) return BZK_ERR_OOM;
+    c->decompress_cache.clear();
+    *out = c;
+    return BZK_OK;
+}
+/* `ZkCompressedState { state_hash, state_size }` of the ledger (/root/reference/src/zk/mod.rs: state_size = non-zero scalar
+ * leaves) and the chain-side account count */
+int32_t bzk_mpn_state_info(const bzk_mpn_state *s, bzk_fr *state_hash, uint64_t *state_size, uint64_t *account_count, uint64_t *pending_accounts) {
+    if (!s) return BZK_ERR_BAD_ARG;
+    if (state_hash) fr_to_canon(state_hash, s->node(s->A, 0));
+    if (state_size) *state_size = s->state_size;
+    if (account_count) *account_count = s->account_count;
+    if (pending_accounts) *pending_accounts = s->pending.size();
+    return BZK_OK;
+}
+/* The block built on this fork was applied: its new accounts enter the chain's index table. */
+int32_t bzk_mpn_state_commit_accounts(bzk_mpn_state *s) {
+    if (!s) return BZK_ERR_BAD_ARG;
+    for (auto &kv : s->pending) {
+        s->by_addr.emplace(kv.first, kv.second);
+        s->account_count = std::max(s->account_count, kv.second + 1);
+    }
+    s->pending.clear();
     return BZK_OK;
 }
 
@@ -328,8 +397,15 @@ int32_t bzk_mpn_update_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_tx *t
         Fr src_bal_hash, dst_bal_hash;
     };
     std::map<uint64_t, Account> mirror;
-    auto by_addr = s->by_addr;
-    uint64_t next_free = s->next_free;
+    auto pending = s->pending;
+    auto index_of = [&](const Point &a, uint64_t *out) {
+        const auto key = std::make_pair(key_of(a.x), key_of(a.y));
+        auto it = s->by_addr.find(key);
+        if (it != s->by_addr.end()) { *out = it->second; return true; }
+        auto jt = pending.find(key);
+        if (jt != pending.end()) { *out = jt->second; return true; }
+        return false;
+    };
     auto get = [&](uint64_t i) -> Account {
         auto it = mirror.find(i);
         if (it != mirror.end()) return it->second;
@@ -344,16 +420,22 @@ int32_t bzk_mpn_update_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_tx *t
         if (accepted) accepted[k] = 0;
         if (plan.size() == cap) continue;
         const bzk_mpn_tx &tx = txs[k];
+        // malformed field elements cannot be put into a witness row: such a transaction is simply not eligible
+        if (!canonical(tx.src_pk_x) || !canonical(tx.dst_pk_x) || !canonical(tx.amount_token_id) || !canonical(tx.fee_token_id) ||
+            !canonical(tx.sig_rx) || !canonical(tx.sig_ry) || !canonical(tx.sig_s))
+            continue;
         const Fr fee_tok_id = fr_from_canon(&tx.fee_token_id), amt_tok_id = fr_from_canon(&tx.amount_token_id);
+        // the reference's pre-filter (update.rs:31-38): fee token and both keys decompressible; filtered, not an error
         if (!(fee_tok_id == fee_token)) continue;
         Point src_addr, dst_addr;
         if (!jj_decompress(s, &tx.src_pk_x, tx.src_pk_odd != 0, &src_addr) || !jj_decompress(s, &tx.dst_pk_x, tx.dst_pk_odd != 0, &dst_addr))
-            return BZK_ERR_NOT_ON_CURVE;
-        auto sit = by_addr.find(std::make_pair(key_of(src_addr.x), key_of(src_addr.y)));
-        if (sit == by_addr.end()) continue;
-        const uint64_t src_index = sit->second;
-        auto dit = by_addr.find(std::make_pair(key_of(dst_addr.x), key_of(dst_addr.y)));
-        const uint64_t dst_index = dit == by_addr.end() ? next_free : dit->second;
+            continue;
+        // update.rs:47-70: the chain's index table first, then the accounts created earlier on this fork; an unknown
+        // sender is rejected, an unknown receiver gets index  mpn_account_count + |new_account_indices|
+        uint64_t src_index = 0, dst_index = 0;
+        if (!index_of(src_addr, &src_index)) continue;
+        bool dst_new = false;
+        if (!index_of(dst_addr, &dst_index)) { dst_index = s->account_count + pending.size(); dst_new = true; }
         if (dst_index >> (2 * A)) continue;
         Account src_before = get(src_index), dst_before0 = get(dst_index);
         const int sti = find_token_index(src_before, T, amt_tok_id, false), dti = find_token_index(dst_before0, T, amt_tok_id, true),
@@ -383,8 +465,7 @@ int32_t bzk_mpn_update_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_tx *t
         if (!dst_after.tokens.count(dti)) dst_after.tokens[dti] = Money{amt_tok_id, 0};
         dst_after.tokens[dti].amount += tx.amount;
         mirror[dst_index] = dst_after;
-        by_addr.emplace(std::make_pair(key_of(dst_addr.x), key_of(dst_addr.y)), dst_index);
-        if (dst_index == next_free) next_free++;
+        if (dst_new) pending.emplace(std::make_pair(key_of(dst_addr.x), key_of(dst_addr.y)), dst_index);
         Plan p{};
         p.tx = k; p.src = src_index; p.dst = dst_index; p.sti = sti; p.sfi = sfi; p.dti = dti;
         p.src_before = src_before; p.src_mid = src_mid; p.src_after = src_after; p.dst_before = dst_before; p.dst_after = dst_after;
@@ -478,9 +559,13 @@ int32_t bzk_mpn_update_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_tx *t
         uint64_t node = s_idx[e];
         for (uint32_t l = 0; l <= A; l++) { s->put(l, node, s_vals[(size_t)l * ne + e]); node >>= 2; }
     }
-    for (uint64_t i : touched) s->accounts[i] = mirror[i];
-    s->by_addr = by_addr;
-    s->next_free = next_free;
+    for (uint64_t i : touched) {
+        auto it = s->accounts.find(i);
+        if (it != s->accounts.end()) s->state_size -= leaf_count(it->second);
+        s->state_size += leaf_count(mirror[i]);
+        s->accounts[i] = mirror[i];
+    }
+    s->pending = pending;
     std::vector<Fr> aux_in = {fee_token, fr_from_u64(fee_sum)}, aux_out;
     BZK_TRY(hash_rows(ctx, 2, aux_in, aux_out));
     fr_to_canon(public3 + 0, prev_root);
@@ -506,6 +591,13 @@ extern "C" int32_t bzk_mpn_update_witness(bzk_ctx *ctx, const bzk_witness_progra
                                           const bzk_fr *ext, uint32_t n_raw, const bzk_fr prologue[6], void *d_inputs, void *d_aux) {
     if (!ctx || !slot_prog || !epilogue_prog || !n_slots || !raws || !ext || !prologue || !d_inputs || !d_aux || n_raw < 16 + 3 * log4_token)
         return BZK_ERR_BAD_ARG;
+    {   // the rows must have the shape the two programs were compiled for (a mismatch would read / write out of bounds)
+        uint64_t s_ops = 0, e_ops = 0;
+        uint32_t s_raw = 0, s_ext = 0, e_raw = 0, e_ext = 0;
+        witness_program_shape(slot_prog, &s_ops, &s_raw, &s_ext);
+        witness_program_shape(epilogue_prog, &e_ops, &e_raw, &e_ext);
+        if (s_raw != n_raw || s_ext != 2 || s_ops != slot_vars || e_ext != 1 + n_slots || e_ops != epilogue_vars) return BZK_ERR_BAD_ARG;
+    }
     BZK_CUDA(ctx, cudaSetDevice(ctx->device));
     Fr head[12];  // 6 inputs, 6 prologue aux (Montgomery)
     const Fr commitment = fr_from_canon(prologue + 0), height = fr_from_canon(prologue + 1), state = fr_from_canon(prologue + 2),
@@ -526,7 +618,6 @@ extern "C" int32_t bzk_mpn_update_witness(bzk_ctx *ctx, const bzk_witness_progra
         epi_ext[1 + k] = row[0].l[0] ? row[15 + 3 * log4_token] : zero;
     }
     BZK_TRY(bzk_witness_run_dev(ctx, epilogue_prog, nullptr, epi_ext.data(), 1, z_aux + 6 + n_slots * slot_vars));
-    (void)epilogue_vars;
     return BZK_OK;
 }
 

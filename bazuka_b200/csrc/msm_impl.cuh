@@ -43,11 +43,17 @@ namespace bzk {
 // cost of a plan in "mixed additions": n*W bucket insertions + kReduceCost per bucket for the reduction
 // (calibrated on B200 at 2^20: two full additions per bucket in the running sums, the latency-bound
 // tree and the extra digit / scatter work of more windows)
-constexpr double kReduceCost = 6.0;
+// A narrow TOP window is expensive: scalars are < 2^255, so window W-1 holds only 255 - c*(W-1) meaningful bits; when
+// that is a handful (c = 19: 8 bits, c = 18 or 21: 3), a sixteenth of all entries lands in a few hundred buckets — the
+// histogram's REDs and the scatter's ATOMs serialise on those addresses and the runs go through the long-run path
+// (measured at 2^20: c = 19 costs 0.54 ms more than c = 20 in those three stages) — about 1.5 additions per term.
+constexpr double kReduceCost = 6.0, kNarrowTopCost = 1.5;
 static double plan_cost(size_t n, uint32_t c, uint32_t T) {
     const uint32_t W = (256 + c - 1) / c;
     const uint32_t Te = T < W ? T : W, G = (W + Te - 1) / Te;
-    return (double)n * W + kReduceCost * G * (double)(1u << (c - 1));
+    const int top_bits = 255 - (int)(c * (W - 1));
+    const double narrow = (W > 1 && top_bits < 10 && n >= 4096) ? kNarrowTopCost * (double)n : 0.0;
+    return (double)n * W + kReduceCost * G * (double)(1u << (c - 1)) + narrow;
 }
 // window plan for n terms over a base table of T levels built for window c_tab (0 = free choice)
 static MsmPlan make_plan(size_t n, uint32_t c_tab = 0, uint32_t T = 1, uint32_t G_tab = 0) {
@@ -74,7 +80,9 @@ static MsmPlan make_plan(size_t n, uint32_t c_tab = 0, uint32_t T = 1, uint32_t 
 static void choose_table(size_t n, uint32_t max_levels, uint32_t *c_out, uint32_t *T_out, uint32_t *G_out) {
     double best = 1e300;
     uint32_t bc = 16, bT = 1;
+    static const uint32_t force_c = std::getenv("BZK_TABLE_C") ? (uint32_t)atoi(std::getenv("BZK_TABLE_C")) : 0;  // tuning aid
     for (uint32_t c = 8; c <= 23; c++) {
+        if (force_c && c != force_c) continue;
         const uint32_t W = (256 + c - 1) / c;
         const uint32_t T = max_levels < W ? max_levels : W;
         if ((double)n * T >= 1073741824.0) continue;  // table index must fit 30 bits

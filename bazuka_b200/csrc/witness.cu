@@ -58,6 +58,13 @@ struct bzk_witness_program {
     uint64_t n_lc = 0, n_terms = 0, n_coefs = 0;
 };
 
+namespace bzk {
+// the shape a driver must match before it hands rows to the interpreter (csrc/mpn_host.cu)
+void witness_program_shape(const bzk_witness_program *p, uint64_t *n_ops, uint32_t *n_raw, uint32_t *n_ext) {
+    *n_ops = p->d.n_ops; *n_raw = p->d.n_raw; *n_ext = p->d.n_ext;
+}
+}  // namespace bzk
+
 extern "C" {
 
 int32_t bzk_witness_program_upload(bzk_ctx *ctx, const int32_t *ops, uint64_t n_ops, const int32_t *lc_ptr, uint64_t n_lc,
@@ -72,6 +79,8 @@ int32_t bzk_witness_program_upload(bzk_ctx *ctx, const int32_t *ops, uint64_t n_
         if (op[0] == W_RAW && (op[5] < 0 || (uint32_t)op[5] >= n_raw)) return BZK_ERR_BAD_ARG;
         if (op[0] == W_BIT && (op[5] < 0 || op[5] > 255)) return BZK_ERR_BAD_ARG;
         if (op[0] == W_JJ && (j + 1 >= n_ops || ops[(j + 1) * 6] != W_NOP)) return BZK_ERR_BAD_ARG;
+        // a NOP is only the second half of a JJ (which writes both variables); alone it would leave its variable unwritten
+        if (op[0] == W_NOP && (j == 0 || ops[(j - 1) * 6] != W_JJ)) return BZK_ERR_BAD_ARG;
         const int nlc = op[0] == W_JJ ? 4 : op[0] == W_SELECT ? 3 : op[0] == W_MUL ? 2 : (op[0] == W_RAW || op[0] == W_NOP) ? 0 : 1;
         for (int a = 0; a < nlc; a++) {
             const int32_t l = op[1 + a];

@@ -261,6 +261,16 @@ int32_t bzk_mpn_state_set_account(bzk_ctx *ctx, bzk_mpn_state *state, uint64_t i
                                   const bzk_fr *addr_x, const bzk_fr *addr_y, const uint32_t *token_index, const bzk_fr *token_id,
                                   const uint64_t *token_amount, uint32_t n_tokens);
 int32_t bzk_mpn_update_raw_width(uint32_t log4_tree, uint32_t log4_token, uint32_t *n_raw);
+/* Fork / introspection / block application for the ledger.  bzk_mpn_update_build WRITES the ledger it is given (state
+ * tree, accounts, the fork's new-account map) before any proof exists: build a block's batches on a clone
+ * (`db.fork_on_ram()`, /root/reference/src/mpn/mod.rs:313) and keep the clone only if the block is accepted; after a
+ * failed proof or a reorg, drop it.  `info`: the `ZkCompressedState {state_hash, state_size}` that goes into
+ * `MpnWork::new_root`, the chain's account count and the number of accounts created on this fork so far.
+ * `commit_accounts`: the block was applied — the fork's new accounts enter the chain's address index
+ * (`get_mpn_account_indices`), exactly what the builders consult first (/root/reference/src/mpn/update.rs:47-70). */
+int32_t bzk_mpn_state_clone(const bzk_mpn_state *state, bzk_mpn_state **out);
+int32_t bzk_mpn_state_info(const bzk_mpn_state *state, bzk_fr *state_hash, uint64_t *state_size, uint64_t *account_count, uint64_t *pending_accounts);
+int32_t bzk_mpn_state_commit_accounts(bzk_mpn_state *state);
 /* `PublicKey::decompress` (/root/reference/src/crypto/jubjub/curve.rs:78-88) on the host field arithmetic, no
  * context: y = sqrt((1 + x^2) / (1 - d x^2)) with the parity rule; canonical scalars. */
 int32_t bzk_jubjub_decompress(const bzk_fr *jubjub_d, const bzk_fr *x, int32_t y_is_odd, bzk_fr out_xy[2]);
