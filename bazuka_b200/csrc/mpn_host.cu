@@ -47,6 +47,7 @@ struct Account {
 };
 
 struct Point { Fr x, y; };
+constexpr size_t kDecompressCacheCap = 1u << 16;  // decompressed keys kept per ledger (cleared when full)
 
 }  // namespace
 
@@ -165,7 +166,6 @@ bool canonical(const bzk_fr &v) {
     }
     return false;  // == r
 }
-constexpr size_t kDecompressCacheCap = 1u << 16;
 
 int find_token_index(const Account &a, uint32_t T, const Fr &token_id, bool empty_allowed) {
     for (auto &kv : a.tokens)

@@ -71,10 +71,11 @@ def update_batched(hasher, state: MpnState, txs, log4_batch, fee_token=ZIESHA):
     prev_root = state.root
     # ------------------------------------------------------------------ phase 1: ledger logic on a mirror
     mirror = {}                                  # account index -> MpnAccount (current value)
-    by_addr = {}
-    for i, a in state.accounts.items():
-        by_addr.setdefault(a.address, i)
-    next_free = (max(state.accounts) + 1) if state.accounts else 0
+    pending = dict(state.new_account_indices)    # this fork's new accounts (update.rs:47-70), committed with the batch
+
+    def index_of(addr):
+        i = state.address_index.get(addr)
+        return i if i is not None else pending.get(addr)
 
     def get(i):
         if i not in mirror:
@@ -85,17 +86,21 @@ def update_batched(hasher, state: MpnState, txs, log4_batch, fee_token=ZIESHA):
     for tx in txs:
         if len(plan) == cap:
             break
-        if tx.fee.token_id != fee_token:
+        src_addr, dst_addr = N.jj_decompress_checked(tx.src_pub_key), N.jj_decompress_checked(tx.dst_pub_key)
+        if tx.fee.token_id != fee_token or src_addr is None or dst_addr is None:
             rejected.append(tx)
             continue
-        src_addr, dst_addr = N.jj_decompress(tx.src_pub_key), N.jj_decompress(tx.dst_pub_key)
-        src_index = by_addr.get(src_addr)
+        src_index = index_of(src_addr)
         if src_index is None:
             rejected.append(tx)
             continue
-        dst_index = by_addr.get(dst_addr)
-        if dst_index is None:
-            dst_index = next_free
+        dst_index = index_of(dst_addr)
+        dst_new = dst_index is None
+        if dst_new:
+            dst_index = state.account_count + len(pending)
+        if dst_index >> (2 * A):
+            rejected.append(tx)
+            continue
         src_before, dst_before0 = get(src_index), get(dst_index)
         sti = src_before.find_token_index(T, tx.amount.token_id, False)
         dti = dst_before0.find_token_index(T, tx.amount.token_id, True)
@@ -128,9 +133,8 @@ def update_batched(hasher, state: MpnState, txs, log4_batch, fee_token=ZIESHA):
         dst_after.address = dst_addr
         dst_after.tokens.setdefault(dti, Money(tx.amount.token_id, 0)).amount += tx.amount.amount
         mirror[dst_index] = dst_after.copy()
-        by_addr.setdefault(dst_addr, dst_index)
-        if dst_index == next_free:
-            next_free += 1
+        if dst_new:
+            pending[dst_addr] = dst_index
         plan.append(dict(tx=tx, src_index=src_index, dst_index=dst_index, sti=sti, sfi=sfi, dti=dti, src_before=src_before,
                          src_mid=src_mid, src_after=src_after, dst_before=dst_before, dst_after=dst_after,
                          src_token=Money(src_token.token_id, src_token.amount), src_fee_token=src_fee_token,
@@ -172,6 +176,7 @@ def update_batched(hasher, state: MpnState, txs, log4_batch, fee_token=ZIESHA):
         root = s_vals[A][3 * k + 2]
     # ------------------------------------------------------------------ commit: accounts + the nodes every write left behind
     _commit(state, mirror, touched, s_idx, s_vals)
+    state.new_account_indices = pending
     assert state.root == root
     public = {"state": prev_root, "aux_data": hasher.poseidon_batch([[fee_token, fee_sum]])[0], "next_state": root}
     return public, transitions, rejected
@@ -184,10 +189,15 @@ class _Ledger:
     """phase-1 mirror shared by the builders: touched accounts, address index, free-slot counter"""
 
     def __init__(self, state):
-        self.state, self.mirror, self.by_addr = state, {}, {}
-        for i, a in state.accounts.items():
-            self.by_addr.setdefault(a.address, i)
-        self.next_free = (max(state.accounts) + 1) if state.accounts else 0
+        self.state, self.mirror = state, {}
+        self.pending = dict(state.new_account_indices)
+
+    def index_of(self, addr):
+        i = self.state.address_index.get(addr)
+        return i if i is not None else self.pending.get(addr)
+
+    def new_index(self):
+        return self.state.account_count + len(self.pending)
 
     def get(self, i):
         if i not in self.mirror:
@@ -196,7 +206,6 @@ class _Ledger:
 
     def put(self, i, acc):
         self.mirror[i] = acc.copy()
-        self.by_addr.setdefault(acc.address, i)
 
 
 class _TokenForest:
@@ -240,6 +249,7 @@ def _commit(state, mirror, touched, s_idx, s_vals):
             state.tree._put(lvl, node, s_vals[lvl][e])
             node >>= 2
     for i in touched:
+        state.state_size += state.leaf_count(mirror[i]) - state.leaf_count(state.accounts.get(i))
         state.accounts[i] = mirror[i].copy()
 
 
@@ -258,10 +268,15 @@ def deposit_batched(hasher, state: MpnState, deposits, log4_batch):
     for d in deposits:
         if len(plan) == n:
             break
-        addr = N.jj_decompress(d.mpn_address)
-        idx = led.by_addr.get(addr)
-        if idx is None:
-            idx, led.next_free = led.next_free, led.next_free + 1
+        addr = N.jj_decompress_checked(d.mpn_address)
+        if addr is None:
+            continue
+        idx = led.index_of(addr)
+        is_new = idx is None
+        if is_new:
+            idx = led.new_index()
+        if idx >> (2 * state.A):
+            continue
         before = led.get(idx)
         ti = before.find_token_index(state.T, d.token_id, True)
         if ti is None or (N.jj_on_curve(before.address) and before.address != addr):
@@ -271,6 +286,8 @@ def deposit_batched(hasher, state: MpnState, deposits, log4_batch):
         after.address = addr
         after.tokens.setdefault(ti, Money(d.token_id, 0)).amount += d.amount
         led.put(idx, after)
+        if is_new:
+            led.pending[addr] = idx
         plan.append(dict(d=d, idx=idx, ti=ti, before=before, after=after, bal=Money(bal.token_id, bal.amount) if bal else Money(), addr=addr))
     touched = list(dict.fromkeys(p["idx"] for p in plan))
     forest = _TokenForest(state, touched)
@@ -290,6 +307,7 @@ def deposit_batched(hasher, state: MpnState, deposits, log4_batch):
         trans.append(DepositTransition(True, p["d"], p["before"], p["before_balances_hash"], p["bal"], s_proofs[k], p["idx"], p["ti"], p["bproof"], root))
         root = s_vals[state.A][k]
     _commit(state, led.mirror, touched, s_idx, s_vals)
+    state.new_account_indices = led.pending
     pk_hashes = hasher.poseidon_batch([[p["addr"][0], p["addr"][1]] for p in plan])
     rows = [[1, p["d"].token_id, p["d"].amount, pk_hashes[k]] for k, p in enumerate(plan)] + [[0, 0, 0, 0]] * (n - len(plan))
     return {"state": prev, "aux_data": _list_root(hasher, rows), "next_state": root}, trans
@@ -303,8 +321,8 @@ def withdraw_batched(hasher, state: MpnState, withdraws, log4_batch):
     for w in withdraws:
         if len(plan) == n:
             break
-        addr = N.jj_decompress(w.mpn_address)
-        idx = led.by_addr.get(addr)
+        addr = N.jj_decompress_checked(w.mpn_address)
+        idx = led.index_of(addr) if addr is not None else None
         if idx is None:
             continue
         before = led.get(idx)

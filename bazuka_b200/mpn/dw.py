@@ -76,14 +76,19 @@ def deposit(state: MpnState, deposits, log4_batch):
     """-> (public {state, aux_data, next_state}, transitions)."""
     prev, trans = state.root, []
     n = 1 << (2 * log4_batch)
-    next_free = (max(state.accounts) + 1) if state.accounts else 0
     for d in deposits:
         if len(trans) == n:
             break
-        addr = N.jj_decompress(d.mpn_address)
+        addr = N.jj_decompress_checked(d.mpn_address)
+        if addr is None:
+            continue
+        # deposit.rs:40-54: chain index table, then this fork's new accounts, else mpn_account_count + |new_account_indices|
         idx = state.index_of(addr)
-        if idx is None:
-            idx, next_free = next_free, next_free + 1
+        is_new = idx is None
+        if is_new:
+            idx = state.new_index()
+        if idx >> (2 * state.A):
+            continue
         before = state.get(idx)
         ti = before.find_token_index(state.T, d.token_id, True)
         if ti is None or (N.jj_on_curve(before.address) and before.address != addr):
@@ -94,7 +99,9 @@ def deposit(state: MpnState, deposits, log4_batch):
         after = before.copy()
         after.address = addr
         after.tokens.setdefault(ti, Money(d.token_id, 0)).amount += d.amount
-        state.set(idx, after)
+        state.write(idx, after)
+        if is_new:
+            state.new_account_indices[addr] = idx
         trans.append(DepositTransition(True, d, before, before.tokens_tree(state.T).root,
                                        Money(bal.token_id, bal.amount) if bal else Money(), proof, idx, ti, bproof, pre_root))
     rows = []
@@ -221,8 +228,8 @@ def withdraw(state: MpnState, withdraws, log4_batch):
     for w in withdraws:
         if len(trans) == n:
             break
-        addr = N.jj_decompress(w.mpn_address)
-        idx = state.index_of(addr)
+        addr = N.jj_decompress_checked(w.mpn_address)
+        idx = state.index_of(addr) if addr is not None else None
         if idx is None:
             continue
         before = state.get(idx)
@@ -237,16 +244,16 @@ def withdraw(state: MpnState, withdraws, log4_batch):
         tok = before.tokens[ti]
         after = before.copy()
         after.tokens[ti].amount -= w.amount.amount
-        state.set(idx, after)
+        state.write(idx, after)
         feeb = after.tokens[fi]
         if feeb.amount < w.fee.amount:
-            state.set(idx, before)
+            state.write(idx, before)
             continue
         fee_before = Money(feeb.token_id, feeb.amount)
         fproof = state.prove_token(idx, fi)
         after.tokens[fi].amount -= w.fee.amount
         after.withdraw_nonce += 1
-        state.set(idx, after)
+        state.write(idx, after)
         trans.append(WithdrawTransition(True, w, before, Money(tok.token_id, tok.amount), fee_before, proof, idx, ti, tproof,
                                         before.tokens_tree(state.T).root, fi, fproof, pre_root))
     rows = []

@@ -65,6 +65,29 @@ class NativeLedger:
         self.ctx._check(self.ctx._l.bzk_mpn_state_root(self._h, _host_ptr(out)))
         return _int(out)
 
+    def fork(self):
+        """`db.fork_on_ram()` (/root/reference/src/mpn/mod.rs:313): an independent copy to build a block's batches on;
+        drop it (free) when the block is not accepted — update_build writes the ledger it is called on."""
+        c = NativeLedger.__new__(NativeLedger)
+        c.ctx, c.A, c.T, c.n_raw = self.ctx, self.A, self.T, self.n_raw
+        h = ct.c_void_p()
+        self.ctx._check(self.ctx._l.bzk_mpn_state_clone(self._h, ct.byref(h)))
+        c._h = h
+        return c
+
+    def info(self):
+        """-> dict(state_hash, state_size, account_count, pending_accounts): `ZkCompressedState` for `MpnWork.new_root`,
+        the chain-side account count and the accounts created on this fork so far."""
+        from ..api import _host_ptr
+        root = np.zeros(4, dtype=np.uint64)
+        size, count, pend = ct.c_uint64(), ct.c_uint64(), ct.c_uint64()
+        self.ctx._check(self.ctx._l.bzk_mpn_state_info(self._h, _host_ptr(root), ct.byref(size), ct.byref(count), ct.byref(pend)))
+        return {"state_hash": _int(root), "state_size": size.value, "account_count": count.value, "pending_accounts": pend.value}
+
+    def commit_accounts(self):
+        """the block built on this fork was applied: its new accounts enter the chain's address index"""
+        self.ctx._check(self.ctx._l.bzk_mpn_state_commit_accounts(self._h))
+
     def set_account(self, index, acc: MpnAccount):
         from ..api import _host_ptr
         idx = np.array(sorted(acc.tokens), dtype=np.uint32)

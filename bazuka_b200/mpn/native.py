@@ -138,6 +138,23 @@ def jj_decompress(c):
     return (x, y)
 
 
+def jj_decompress_checked(c):
+    """`PublicKey::is_on_curve` (src/crypto/jubjub/mod.rs:71-73) as the builders use it: the decompressed point, or None
+    when x is not the abscissa of a curve point (the reference's `.sqrt().unwrap()` would panic there)."""
+    x, odd = c
+    if not 0 <= x < R:
+        return None
+    den = (1 - JJ_D * x * x) % R
+    if den == 0:
+        return None
+    y = fr_sqrt((1 - JJ_A * x * x) % R * pow(den, -1, R) % R)
+    if y is None:
+        return None
+    if (y & 1 == 1) != odd:
+        y = (-y) % R
+    return (x, y)
+
+
 def eddsa_keys(seed: bytes):
     """JubJub::generate_keys (mod.rs:112-125) -> (pk_affine, sk dict)."""
     randomness = hash_to_scalar(seed)

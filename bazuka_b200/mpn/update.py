@@ -67,17 +67,46 @@ class MpnState:
         self.A, self.T = log4_tree, log4_token
         self.accounts = {}
         self.tree = N.SparseTree4(log4_tree, MpnAccount().leaf_hash(log4_token))
+        # The CHAIN's tables, which the builders only read (`get_mpn_account_indices`, `get_mpn_account_count`,
+        # src/mpn/update.rs:29,47-70): they change when a block is applied (commit_accounts), not when a batch is built.
+        self.address_index = {}
+        self.account_count = 0
+        # `new_account_indices` (src/mpn/mod.rs:330): accounts created by the batches built so far on this fork, threaded
+        # through deposit -> withdraw -> update by prepare_works
+        self.new_account_indices = {}
+        self.state_size = 0            # ZkCompressedState.state_size: non-zero scalar leaves (src/zk/state/mod.rs:327-341)
 
     @property
     def root(self):
         return self.tree.root
 
+    @property
+    def compressed(self):
+        """`ZkCompressedState {state_hash, state_size}` — what goes into `MpnWork.new_root` (src/mpn/mod.rs:264-270)."""
+        return (self.tree.root, self.state_size)
+
     def get(self, idx):
         return self.accounts.get(idx, MpnAccount()).copy()
 
-    def set(self, idx, acc):
+    @staticmethod
+    def leaf_count(acc):
+        if acc is None:
+            return 0
+        return ((acc.tx_nonce != 0) + (acc.withdraw_nonce != 0) + (acc.address[0] != 0) + (acc.address[1] != 0)
+                + sum((m.token_id != 0) + (m.amount != 0) for m in acc.tokens.values()))
+
+    def write(self, idx, acc):
+        """`set_mpn_account` (src/zk/state/mod.rs:140-208): what the transition builders do to the state."""
+        self.state_size += self.leaf_count(acc) - self.leaf_count(self.accounts.get(idx))
         self.accounts[idx] = acc.copy()
         self.tree.set_leaf(idx, acc.leaf_hash(self.T))
+
+    def set(self, idx, acc):
+        """load an account as the chain knows it: state + the chain's address index and account count."""
+        self.write(idx, acc)
+        if acc.address != NULL_POINT:
+            self.address_index.setdefault(acc.address, idx)
+        self.account_count = max(self.account_count, idx + 1)
 
     def prove(self, idx):
         return self.tree.prove(idx)
@@ -86,10 +115,31 @@ class MpnState:
         return self.get(idx).tokens_tree(self.T).prove(token_index)
 
     def index_of(self, address):
-        for i, a in self.accounts.items():
-            if a.address == address:
-                return i
-        return None
+        """update.rs:47-70: the chain's index table first, then the accounts created earlier on this fork."""
+        i = self.address_index.get(address)
+        return i if i is not None else self.new_account_indices.get(address)
+
+    def new_index(self):
+        """update.rs:66: `mpn_account_count + new_account_indices.len()`"""
+        return self.account_count + len(self.new_account_indices)
+
+    def commit_accounts(self):
+        """the block built on this fork was applied: its new accounts enter the chain's address index."""
+        for addr, i in self.new_account_indices.items():
+            self.address_index.setdefault(addr, i)
+            self.account_count = max(self.account_count, i + 1)
+        self.new_account_indices = {}
+
+    def snapshot(self):
+        return (dict(self.accounts), _clone_tree(self.tree), self.state_size)
+
+    def restore(self, snap):
+        self.accounts, self.tree, self.state_size = snap
+
+    def fork(self):
+        """`db.fork_on_ram()` (src/mpn/mod.rs:313)"""
+        import copy
+        return copy.deepcopy(self)
 
 
 @dataclass
@@ -145,21 +195,28 @@ def update(state: MpnState, txs, log4_batch, fee_token=ZIESHA):
     A, T = state.A, state.T
     prev_root = state.root
     transitions, rejected, fee_sum = [], [], 0
-    next_free = (max(state.accounts) + 1) if state.accounts else 0
     for tx in txs:
         if len(transitions) == 1 << (2 * log4_batch):
             break
-        if tx.fee.token_id != fee_token:
+        # the reference's pre-filter (update.rs:31-38): fee token, and both keys must decompress to curve points
+        # (reported here with the rejected transactions; the reference drops them silently)
+        src_addr, dst_addr = N.jj_decompress_checked(tx.src_pub_key), N.jj_decompress_checked(tx.dst_pub_key)
+        if tx.fee.token_id != fee_token or src_addr is None or dst_addr is None:
             rejected.append(tx)
             continue
-        src_addr, dst_addr = N.jj_decompress(tx.src_pub_key), N.jj_decompress(tx.dst_pub_key)
+        # update.rs:47-70: chain index table, then this fork's new accounts; unknown sender -> rejected,
+        # unknown receiver -> index mpn_account_count + |new_account_indices|
         src_index = state.index_of(src_addr)
         if src_index is None:
             rejected.append(tx)
             continue
         dst_index = state.index_of(dst_addr)
-        if dst_index is None:
-            dst_index = next_free
+        dst_new = dst_index is None
+        if dst_new:
+            dst_index = state.new_index()
+        if dst_index >> (2 * A):
+            rejected.append(tx)
+            continue
         src_before, dst_before0 = state.get(src_index), state.get(dst_index)
         sti = src_before.find_token_index(T, tx.amount.token_id, False)
         dti = dst_before0.find_token_index(T, tx.amount.token_id, True)
@@ -175,23 +232,23 @@ def update(state: MpnState, txs, log4_batch, fee_token=ZIESHA):
                 or src_token.token_id != tx.amount.token_id or src_token.amount < tx.amount.amount):
             rejected.append(tx)
             continue
-        snap = (dict(state.accounts), _clone_tree(state.tree))
+        snap = state.snapshot()
         pre_root = state.root
         src_proof = state.prove(src_index)
         src_balance_proof = state.prove_token(src_index, sti)
         src_after = src_before.copy()
         src_after.tx_nonce += 1
         src_after.tokens[sti].amount -= tx.amount.amount
-        state.set(src_index, src_after)
+        state.write(src_index, src_after)
         src_fee_token = src_after.tokens.get(sfi)
         if src_fee_token is None or src_fee_token.token_id != tx.fee.token_id or src_fee_token.amount < tx.fee.amount:
-            state.accounts, state.tree = snap
+            state.restore(snap)
             rejected.append(tx)
             continue
         src_fee_token = Money(src_fee_token.token_id, src_fee_token.amount)
         src_fee_balance_proof = state.prove_token(src_index, sfi)
         src_after.tokens[sfi].amount -= tx.fee.amount
-        state.set(src_index, src_after)
+        state.write(src_index, src_after)
         dst_proof = state.prove(dst_index)
         dst_balance_proof = state.prove_token(dst_index, dti)
         dst_before = state.get(dst_index)
@@ -199,9 +256,9 @@ def update(state: MpnState, txs, log4_batch, fee_token=ZIESHA):
         dst_after = dst_before.copy()
         dst_after.address = dst_addr
         dst_after.tokens.setdefault(dti, Money(tx.amount.token_id, 0)).amount += tx.amount.amount
-        state.set(dst_index, dst_after)
-        if dst_index == next_free:
-            next_free += 1
+        state.write(dst_index, dst_after)
+        if dst_new:
+            state.new_account_indices[dst_addr] = dst_index
         transitions.append(UpdateTransition(
             True, tx, src_before, src_before.tokens_tree(T).root, Money(src_token.token_id, src_token.amount), src_fee_token,
             src_proof, src_index, sti, src_balance_proof, sfi, src_fee_balance_proof,

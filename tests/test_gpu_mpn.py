@@ -273,6 +273,7 @@ def test_witness_program_upload_rejects_malformed_programs(ctx):
     assert upload([[0, 0, 0, 0, 0, 0], [1, 1, 0, 0, 0, 0]]) == -1   # reads block variable 1 while defining it
     assert upload([[0, 0, 0, 0, 0, 5]]) == -1
     assert upload([[6, 0, 0, 0, 0, 0], [1, 0, 0, 0, 0, 0]]) == -1
+    assert upload([[0, 0, 0, 0, 0, 0], [7, 0, 0, 0, 0, 0]]) == -1   # a NOP that is not the second half of a JJ
 
 
 @pytest.mark.parametrize("kind", ["deposit", "withdraw"])
@@ -397,3 +398,92 @@ def test_worker_on_natively_compiled_circuit(ctx, cref):
         proofs.append(zk)
         worker.free(); led.free()
     assert (proofs[0] == proofs[1]).all()
+
+
+def test_native_ledger_follows_the_reference_rules_like_the_python_builder(ctx):
+    """csrc/mpn_host.cu against the Python restatement on the rules round 1 got wrong (/root/reference/src/mpn/update.rs):
+    keys that do not decompress are filtered instead of aborting the batch (:31-38); a new receiver gets index
+    `mpn_account_count + |new_account_indices|` and the map threads across batches on one fork (:47-70); `state_size`
+    is tracked (:29,256-266); a fork is independent of the ledger it was cloned from (`fork_on_ram`, mod.rs:313)."""
+    from bazuka_b200.mpn import native as N, update as U
+    from bazuka_b200.mpn.ledger import NativeLedger
+    from test_mpn_cpu import _off_curve_key
+    st, keys = make_state(3, 3, 3)
+    led = NativeLedger(ctx, 3, 3)
+    for i, a in st.accounts.items():
+        led.set_account(i, a)
+    # the chain has indexed ten accounts: load an empty-but-indexed slot 9 on both sides
+    st.account_count = 10
+    led.set_account(9, U.MpnAccount())
+    assert led.info() == {"state_hash": st.root, "state_size": st.state_size, "account_count": 10, "pending_accounts": 0}
+    new1, new2 = N.eddsa_keys(b"newcomer"), N.eddsa_keys(b"second")
+    keys += [new1, new2]
+    bad = transfer(keys, 0, 1, 1)
+    bad.dst_pub_key = _off_curve_key()
+    batch1 = [bad, transfer(keys, 0, 3, 1, amount=500), transfer(keys, 1, 4, 1, amount=7)]
+    fork = led.fork()
+    pub_py, trans, rej = U.update(st, batch1, 1)
+    raws, ext, acc, pub, n_acc = fork.update_build(batch1, 1)
+    assert acc.tolist() == [False, True, True] and n_acc == 2 and pub == pub_py and rej == [bad]
+    assert [t.dst_index for t in trans] == [10, 11]
+    assert fork.info() == {"state_hash": st.root, "state_size": st.state_size, "account_count": 10, "pending_accounts": 2}
+    assert led.info()["state_hash"] != st.root and led.info()["pending_accounts"] == 0       # the original did not move
+    # second batch on the same fork: the newcomer is a sender, a third new address continues the numbering
+    keys.append(N.eddsa_keys(b"third"))
+    batch2 = [transfer(keys, 3, 0, 1, amount=50, fee=1), transfer(keys, 0, 5, 2, amount=1)]
+    pub_py, trans, rej = U.update(st, batch2, 1)
+    raws, ext, acc, pub, n_acc = fork.update_build(batch2, 1)
+    assert acc.all() and pub == pub_py and [(t.src_index, t.dst_index) for t in trans] == [(10, 0), (0, 12)]
+    # a fork of the ORIGINAL never saw the map: the newcomer is an unknown sender there
+    other = led.fork()
+    _, _, acc_o, _, n_o = other.update_build(batch2[:1], 1)
+    assert n_o == 0 and not acc_o.any()
+    st.commit_accounts(); fork.commit_accounts()
+    assert fork.info() == {"state_hash": st.root, "state_size": st.state_size, "account_count": 13, "pending_accounts": 0}
+    batch3 = [transfer(keys, 4, 3, 1, amount=2, fee=1)]
+    pub_py, trans, _ = U.update(st, batch3, 1)
+    _, _, acc, pub, _ = fork.update_build(batch3, 1)
+    assert acc.all() and pub == pub_py and fork.info()["state_size"] == st.state_size
+    # set_account: a slot whose token id is zero is dropped; overwriting an account releases its address
+    z = NativeLedger(ctx, 3, 3)
+    a0 = U.MpnAccount(0, 0, keys[0][0], {0: U.Money(U.ZIESHA, 5), 1: U.Money(0, 9)})
+    z.set_account(0, a0)
+    ref = U.MpnState(3, 3)
+    ref.set(0, U.MpnAccount(0, 0, keys[0][0], {0: U.Money(U.ZIESHA, 5)}))
+    assert z.root == ref.root and z.info()["state_size"] == ref.state_size
+    z.set_account(0, U.MpnAccount(0, 0, keys[1][0], {0: U.Money(U.ZIESHA, 5)}))
+    _, _, acc, _, _ = z.update_build([transfer(keys, 0, 1, 1, amount=1)], 0)     # key 0 no longer owns an account
+    assert not acc.any()
+    for l in (led, fork, other, z):
+        l.free()
+
+
+def test_update_witness_rejects_rows_of_the_wrong_shape(ctx):
+    """bzk_mpn_update_witness checks its arguments against the uploaded programs (a program compiled for another (A, T, B)
+    would otherwise read and write out of bounds): wrong n_raw / slot_vars / slot count -> BZK_ERR_BAD_ARG."""
+    import ctypes as ct
+    import torch
+    from bazuka_b200.api import _dev_ptr, _host_ptr
+    from bazuka_b200.mpn import witness_program as W
+    from bazuka_b200.mpn.gpu_witness import UpdateWitnessGpu, upload_program, _canon_rows
+    gw = UpdateWitnessGpu(ctx, 3, 3)
+    p = gw.prog
+    ep = W.compile_update_epilogue(p, 1)
+    eh = upload_program(ctx, ep)
+    n = 4
+    raws, ext = np.zeros((n, p.n_raw, 4), np.uint64), np.zeros((n, 2, 4), np.uint64)
+    pro = _canon_rows([0, 0, 0, 1, 0, 0])
+    d_in = torch.empty((6, 4), dtype=torch.int64, device="cuda")
+    d_aux = torch.empty((p.p_aux + n * p.n_ops + ep.n_ops, 4), dtype=torch.int64, device="cuda")
+
+    def call(n_slots, slot_vars, epi_vars, n_raw):
+        return ctx._l.bzk_mpn_update_witness(ctx._h, gw._h, eh, n_slots, 3, slot_vars, epi_vars, _host_ptr(raws), _host_ptr(ext), n_raw,
+                                             _host_ptr(pro), _dev_ptr(d_in), _dev_ptr(d_aux))
+    assert call(n, p.n_ops, ep.n_ops, p.n_raw) == 0
+    assert call(n, p.n_ops, ep.n_ops, p.n_raw - 1) == -1
+    assert call(n, p.n_ops + 1, ep.n_ops, p.n_raw) == -1
+    assert call(n, p.n_ops, ep.n_ops + 1, p.n_raw) == -1
+    assert call(16, p.n_ops, ep.n_ops, p.n_raw) == -1          # the epilogue was compiled for 4 slots
+    ctx.synchronize()
+    ctx._l.bzk_witness_program_free(ctx._h, eh)
+    gw.free()

@@ -498,3 +498,89 @@ def test_reference_sum_hasher_membership_kat(monkeypatch):
         assert (idx[e] + sum(v for lvl in proofs[e] for v in lvl)) % N.R == 32640
     for e in range(256):  # during the first pass the proof sees exactly the leaves written so far
         assert sum(v for lvl in proofs[e] for v in lvl) % N.R == sum(range(e))
+
+
+# ------------------------------------------------------------------ the reference's ledger rules, pinned (update.rs:29-70,256-266)
+def _recount(st):
+    return sum(U.MpnState.leaf_count(a) for a in st.accounts.values())
+
+
+def _off_curve_key():
+    x = 2
+    while N.jj_decompress_checked((x, False)) is not None:
+        x += 1
+    return (x, False)
+
+
+def test_update_prefilter_drops_keys_that_do_not_decompress():
+    """update.rs:31-38: a transaction whose source or destination key is not on the curve is not eligible — the batch goes
+    on without it (round 1 aborted the whole batch)."""
+    from bazuka_b200.mpn import batch_update as BU
+    from oracle.py.state import HostTreeHasher
+    import copy
+    st, keys = make_state(3, 3, 3)
+    bad_dst = transfer(keys, 0, 1, 1)
+    bad_dst.dst_pub_key = _off_curve_key()
+    bad_src = transfer(keys, 1, 2, 1)
+    bad_src.src_pub_key = _off_curve_key()
+    txs = [bad_dst, transfer(keys, 0, 1, 1), bad_src, transfer(keys, 1, 2, 1, amount=5)]
+    st2 = copy.deepcopy(st)
+    pub, trans, rej = U.update(st, txs, 1)
+    assert [t.tx for t in trans] == [txs[1], txs[3]] and rej == [txs[0], txs[2]]
+    pub2, trans2, rej2 = BU.update_batched(HostTreeHasher(N.poseidon), st2, txs, 1)
+    assert pub2 == pub and rej2 == rej and st2.root == st.root
+
+
+def test_new_account_index_is_chain_count_plus_new_accounts_and_threads_across_batches():
+    """update.rs:47-70: the receiver of an unknown address gets index `mpn_account_count + new_account_indices.len()`;
+    the map is threaded across the batches built on one fork (mod.rs:330), so a later batch finds the newcomer as a
+    SENDER; a fresh fork that did not see the map rejects it; once the block is applied the chain table knows it."""
+    st, keys = make_state(3, 3, 3)
+    st.account_count = 10                       # the chain has indexed ten accounts (seven of them empty here)
+    new1, new2 = N.eddsa_keys(b"newcomer"), N.eddsa_keys(b"second")
+    keys += [new1, new2]
+    pub, trans, rej = U.update(st, [transfer(keys, 0, 3, 1, amount=500), transfer(keys, 1, 4, 1, amount=7)], 1)
+    assert [t.dst_index for t in trans] == [10, 11] and not rej
+    assert st.new_account_indices == {new1[0]: 10, new2[0]: 11} and st.account_count == 10
+    # next batch on the same fork: the newcomer spends; and a third new address continues the numbering
+    third = N.eddsa_keys(b"third")
+    keys.append(third)
+    fresh = st.fork()
+    fresh.new_account_indices = {}              # a fork that never saw the first batch's map
+    pub, trans, rej = U.update(st, [transfer(keys, 3, 0, 1, amount=50, fee=1), transfer(keys, 0, 5, 2, amount=1)], 1)
+    assert [(t.src_index, t.dst_index) for t in trans] == [(10, 0), (0, 12)] and not rej
+    _, trans_f, rej_f = U.update(fresh, [transfer(keys, 3, 0, 1, amount=50, fee=1)], 1)
+    assert not trans_f and len(rej_f) == 1
+    st.commit_accounts()
+    assert st.account_count == 13 and st.address_index[new1[0]] == 10 and not st.new_account_indices
+    pub, trans, rej = U.update(st, [transfer(keys, 4, 3, 1, amount=2, fee=1)], 1)
+    assert [(t.src_index, t.dst_index) for t in trans] == [(11, 10)]
+
+
+def test_state_size_counts_non_zero_leaves_through_every_builder():
+    """`ZkCompressedState.state_size` (update.rs:29,256-266; state/mod.rs:327-341): +1 when a scalar leaf becomes non-zero,
+    -1 when it returns to zero — through update, deposit, withdraw and their batched twins."""
+    import copy
+    from bazuka_b200.mpn import batch_update as BU, dw as D
+    from oracle.py.state import HostTreeHasher
+    st, keys = make_state(3, 3, 2, bal=1000)
+    assert st.state_size == _recount(st) == 2 * 4          # (pk.x, pk.y, token id, balance) per account; nonces are 0
+    keys.append(N.eddsa_keys(b"newcomer"))
+    st_b = copy.deepcopy(st)
+    txs = [transfer(keys, 0, 2, 1, amount=990, fee=10),     # empties account 0's balance: -1; creates 4 leaves at the newcomer; nonce +1
+           transfer(keys, 1, 0, 1, amount=5, fee=1)]
+    U.update(st, txs, 1)
+    assert st.state_size == _recount(st) == 8 + 4 + 1 - 1 + 1 + 1   # newcomer 4, nonce(0), balance(0) gone, nonce(1), balance(0) back
+    BU.update_batched(HostTreeHasher(N.poseidon), st_b, txs, 1)
+    assert st_b.state_size == st.state_size and st_b.compressed == st.compressed
+    dep = [D.MpnDeposit(N.jj_compress(N.eddsa_keys(b"dep-new")[0]), 77, 9), D.MpnDeposit(N.jj_compress(keys[0][0]), 77, 4)]
+    st_b = copy.deepcopy(st)
+    D.deposit(st, dep, 1)
+    BU.deposit_batched(HostTreeHasher(N.poseidon), st_b, dep, 1)
+    assert st.state_size == _recount(st) == st_b.state_size and st.root == st_b.root
+    w = D.MpnWithdraw(N.jj_compress(keys[1][0]), 1, amount=U.Money(U.ZIESHA, 100), fee=U.Money(U.ZIESHA, 2), fingerprint=4242)
+    w.sign(keys[1][1])
+    st_b = copy.deepcopy(st)
+    D.withdraw(st, [w], 1)
+    BU.withdraw_batched(HostTreeHasher(N.poseidon), st_b, [w], 1)
+    assert st.state_size == _recount(st) == st_b.state_size and st.root == st_b.root
