@@ -487,3 +487,55 @@ def test_update_witness_rejects_rows_of_the_wrong_shape(ctx):
     ctx.synchronize()
     ctx._l.bzk_witness_program_free(ctx._h, eh)
     gw.free()
+
+
+def test_worker_protocol_end_to_end_against_an_in_process_node(ctx, cref):
+    """a block's worth of traffic -> `prepare_works` (deposit, withdraw, update on one fork) -> bincode `GetMpnWorkResponse`
+    -> the worker proves every work from its WIRE image on the GPU -> bincode `PostMpnSolutionRequest` -> the node side runs
+    `MpnWork::verify` (commitment from (prover, reward) + check_proof) and counts the accepted proofs; a proof posted under
+    another prover address is refused (/root/reference/src/mpn/mod.rs:108-129,281-295; client/messages.rs:368-397)."""
+    from bazuka_b200.mpn import wire as Wr, works as Wk
+    from bazuka_b200.mpn.worker import MpnDepositWithdrawWorker, MpnUpdateWorker
+    from test_wire_cpu import _scenario
+    st, keys, deposits, withdraws, wpay, updates = _scenario()
+    A, T, B = 3, 3, 1
+    wu = MpnUpdateWorker(ctx, A, T, B, cref.fr_random(301, 5))
+    wd = MpnDepositWithdrawWorker(ctx, "deposit", A, T, B, cref.fr_random(302, 5))
+    ww = MpnDepositWithdrawWorker(ctx, "withdraw", A, T, B, cref.fr_random(303, 5))
+    config = {"log4_tree_size": A, "log4_token_tree_size": T, "log4_deposit_batch_size": B, "log4_withdraw_batch_size": B, "log4_update_batch_size": B,
+              "mpn_contract_id": 0x1234, "mpn_num_update_batches": 1, "mpn_num_deposit_batches": 1, "mpn_num_withdraw_batches": 1,
+              "deposit_vk": bytes(wd.vk_blob), "withdraw_vk": bytes(ww.vk_blob), "update_vk": bytes(wu.vk_blob)}
+    works, fork = Wk.prepare_works(config, st, deposits, withdraws, updates, {"deposit": 11, "withdraw": 22, "update": 33}, height=9,
+                                   withdraw_payments=wpay)
+    me, other = bytes(range(32)), bytes(range(1, 33))
+    served, accepted_log = [], []
+
+    def node(method, url, body):   # the three endpoints of /root/reference/src/node/mod.rs:393-413
+        served.append((method, url.rsplit("/", 1)[1]))
+        if url.endswith("/bincode/mpn/worker"):
+            return b"\x01"
+        if url.endswith("/bincode/mpn/work"):
+            assert Wr.dec_address(Wr.Reader(body)) == me
+            return Wr.get_mpn_work_response_to_bytes(works)
+        prover, proofs = Wr.post_mpn_solution_request_from_bytes(body)
+        ok = sum(1 for wid, p in proofs.items() if Wk.verify_work(works[wid], prover, np.frombuffer(p, dtype=np.uint8)))
+        accepted_log.append((prover, ok))
+        return (ok).to_bytes(8, "little")
+
+    prover = Wk.MpnProver(ctx)
+    prover.add_circuit("update", wu.prover, wu.pk, wu.witness)
+    prover.add_circuit("deposit", wd.prover, wd.pk, wd.witness)
+    prover.add_circuit("withdraw", ww.prover, ww.pk, ww.witness)
+    client = Wk.WorkerClient("127.0.0.1:8765", me, prover, opener=node)
+    assert client.register()
+    seeds = iter(range(400, 500))
+    n_works, n_ok = client.run_once(lambda: tuple(cref.fr_random(next(seeds), 2)))
+    assert (n_works, n_ok) == (3, 3) and served == [("POST", "worker"), ("GET", "work"), ("POST", "solution")]
+    # the commitment binds the proof to the prover: the same proof under another address is not accepted
+    r, s = cref.fr_random(77, 2)
+    p = prover.prove(works[2], me, r, s)
+    assert Wk.verify_work(works[2], me, np.frombuffer(p, dtype=np.uint8))
+    assert not Wk.verify_work(works[2], other, np.frombuffer(p, dtype=np.uint8))
+    assert not Wk.verify_work(dict(works[2], reward=34), me, np.frombuffer(p, dtype=np.uint8))
+    for w in (wu, wd, ww):
+        w.free()
