@@ -42,6 +42,9 @@ SIGNATURES = {
     "bzk_poseidon_load_params": (_i32, [_vp, _vp, _sz]),
     "bzk_poseidon_hash": (_i32, [_vp, _u32, _vp, _sz, _vp]),
     "bzk_poseidon_hash_dev": (_i32, [_vp, _u32, _vp, _sz, _vp]),
+    "bzk_poseidon_host_create": (_i32, [_vp, _sz, ct.POINTER(_vp)]),
+    "bzk_poseidon_host_free": (_i32, [_vp]),
+    "bzk_poseidon_host_hash": (_i32, [_vp, _u32, _vp, _sz, _vp]),
     "bzk_merkle4_build_dev": (_i32, [_vp, _vp, _u32]),
     "bzk_merkle4_prove_dev": (_i32, [_vp, _vp, _u32, _vp, _sz, _vp]),
     "bzk_merkle4_root_dev": (_i32, [_vp, _u32, _vp, _vp, _vp, _sz, _vp]),

@@ -315,3 +315,40 @@ class Context:
 
     def fp_mul_dev(self, d_a, d_b, d_out, n):
         self._check(self._l.bzk_fp_mul_dev(self._h, _dev_ptr(d_a), _dev_ptr(d_b), _dev_ptr(d_out), n))
+
+
+class HostPoseidon:
+    """`impl ZkHasher for PoseidonHasher` (/root/reference/src/zk/mod.rs:491-511) without a GPU round trip: single hashes on
+    the host field arithmetic of libbzk (bzk_poseidon_host_*).  inputs [n, arity, 4] or [arity, 4] Montgomery -> digests."""
+
+    def __init__(self):
+        self._l = _lib.load()
+        blob = open(_lib.PARAMS_PATH, "rb").read()
+        h = ct.c_void_p()
+        st = self._l.bzk_poseidon_host_create(blob, len(blob), ct.byref(h))
+        if st != 0:
+            raise BzkError(st, "poseidon_host_create")
+        self._h = h
+
+    def hash(self, inputs):
+        a = _as_fr(inputs)
+        single = a.ndim == 2
+        if single:
+            a = a[None]
+        n, arity, _ = a.shape
+        out = np.zeros((n, 4), dtype=np.uint64)
+        st = self._l.bzk_poseidon_host_hash(self._h, arity, _host_ptr(a), n, _host_ptr(out))
+        if st != 0:
+            raise BzkError(st, "poseidon_host_hash")
+        return out[0] if single else out
+
+    def free(self):
+        if self._h:
+            self._l.bzk_poseidon_host_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

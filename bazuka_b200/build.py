@@ -11,8 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 SO = os.path.join(HERE, "libbzk.so")
-SOURCES = ["msm_g2.cu", "msm_g1.cu", "groth16.cu", "poseidon.cu", "ntt.cu", "verify.cu", "witness.cu", "mpn_host.cu", "mpn_circuit.cu", "capi.cu"]
-HEADERS = ["ff.cuh", "ec.cuh", "common.cuh", "msm_impl.cuh", "witness_core.cuh", os.path.join("..", "..", "include", "bzk.h")]
+SOURCES = ["msm_g2.cu", "msm_g1.cu", "groth16.cu", "poseidon.cu", "poseidon_host.cu", "ntt.cu", "verify.cu", "witness.cu", "mpn_host.cu", "mpn_circuit.cu", "capi.cu"]
+HEADERS = ["ff.cuh", "ec.cuh", "common.cuh", "msm_impl.cuh", "witness_core.cuh", "pairing.cuh", os.path.join("..", "..", "include", "bzk.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -396,9 +396,3 @@ class UpdateCircuit:
             state_wit, fee_sum = self._tx_block(cs, tr, state_wit, accepted_fee_token, fee_sum)
         self._epilogue(cs, state_wit, accepted_fee_token, aux_wit, claimed, fee_sum)
         return cs
-
-
-def mpn_work_commitment(prover_bytes: bytes, reward_bytes: bytes) -> int:
-    """`MpnWork::verify`: commitment = ZkScalar::new(sha3(bincode((prover, reward))))
-    (/root/reference/src/mpn/mod.rs:281-285); callers pass the bincode pieces."""
-    return N.hash_to_scalar(prover_bytes + reward_bytes)

@@ -82,6 +82,15 @@ int32_t bzk_poseidon_hash(bzk_ctx *ctx, uint32_t arity, const bzk_fr *in, size_t
 /* device buffers (same layout), asynchronous on the ctx stream */
 int32_t bzk_poseidon_hash_dev(bzk_ctx *ctx, uint32_t arity, const void *d_in, size_t n, void *d_out);
 
+/* The same hash on the HOST, for the one-at-a-time calls of `impl ZkHasher for PoseidonHasher`
+ * (/root/reference/src/zk/mod.rs:491-511: every state-manager read path, transaction hash and calldata check makes single
+ * hashes behind a global mutex-guarded LRU): a kernel launch per hash would be slower than the CPU it replaces.
+ * `blob` = the same BZKPOSv1 table; the handle is immutable and thread-safe; in/out are Montgomery `ZkScalar` images. */
+typedef struct bzk_poseidon_host bzk_poseidon_host;
+int32_t bzk_poseidon_host_create(const uint8_t *blob, size_t len, bzk_poseidon_host **out);
+int32_t bzk_poseidon_host_free(bzk_poseidon_host *hasher);
+int32_t bzk_poseidon_host_hash(const bzk_poseidon_host *hasher, uint32_t arity, const bzk_fr *in, size_t n, bzk_fr *out);
+
 /* 4-ary Poseidon Merkle trees (dense) — the hash structure behind `KvStoreStateManager::{prove,
  * set_data}` (/root/reference/src/zk/state/mod.rs:218-264,310-420) and the merkle gadget
  * (/root/reference/src/zk/groth16/gadgets/merkle/mod.rs:21-65): node = Poseidon-4(children); a proof is,

@@ -246,3 +246,24 @@ def test_native_circuit_and_native_interpreter_satisfy_each_other(hostshim):
     rhs = sum(int.from_bytes(val[i].tobytes(), "little") * rinv % N.R * z[int(col[i])] for i in range(int(rp[j]), int(rp[j + 1]))) % N.R
     assert lhs != rhs
     nc.free()
+
+
+def test_host_poseidon_is_the_reference_hash(cref):
+    """bzk_poseidon_host_hash (the `ZkHasher` single-hash path, no GPU): the reference's 16 known answers
+    (/root/reference/src/zk/poseidon/mod.rs:116-133) and the C oracle on random inputs for every arity."""
+    import json, os, time
+    from bazuka_b200.api import HostPoseidon
+    from conftest import fr_arr, fr_ints
+    h = HostPoseidon()
+    kats = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "poseidon_kats.json")))["expected_decimal"]
+    for n, want in enumerate(kats, 1):
+        assert fr_ints(h.hash(fr_arr(list(range(n)))))[0] == int(want), n
+    for arity in range(1, 17):
+        inp = cref.fr_random(500 + arity, 40 * arity).reshape(40, arity, 4)
+        assert (h.hash(inp) == cref.poseidon(inp)).all(), arity
+    t0 = time.perf_counter()
+    one = cref.fr_random(9, 4)
+    for _ in range(200):
+        h.hash(one)
+    print(f"host Poseidon-4: {(time.perf_counter() - t0) / 200 * 1e6:.0f} us per hash (incl. ctypes)")
+    h.free()
