@@ -29,6 +29,7 @@
 // integer-ALU bound (≈ W * 10 Fp products per term), see DESIGN.md for both rooflines.
 #pragma once
 #include "common.cuh"
+#include "msm_affine.cuh"
 #include <cstdlib>
 #ifndef BZK_ACC_MIN_BLOCKS_G1
 #define BZK_ACC_MIN_BLOCKS_G1 4
@@ -227,7 +228,7 @@ template <class F> struct AccBlocks { static constexpr int value = 1; };
 template <> struct AccBlocks<Fp> { static constexpr int value = BZK_ACC_MIN_BLOCKS_G1; };
 
 template <class F>
-__global__ void __launch_bounds__(128, AccBlocks<F>::value) k_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
+__global__ void __launch_bounds__(128, AccBlocks<F>::value) k_accumulate(const Affine<F> *__restrict__ bases, const Affine<F> *__restrict__ scr, const uint32_t *__restrict__ sorted,
                                                     const uint32_t *__restrict__ offsets, uint32_t TB, uint32_t min_chunk,
                                                     Xyzz<F> *__restrict__ buckets, Xyzz<F> *__restrict__ part_pts,
                                                     int32_t *__restrict__ part_bucket) {
@@ -270,8 +271,14 @@ __global__ void __launch_bounds__(128, AccBlocks<F>::value) k_accumulate(const A
             run_from_bucket_start = true;
         }
         const uint32_t e = sorted[pos];
-        Affine<F> p = load_vec(bases + (e & 0x7fffffffu));
-        if (e >> 31) p.y = p.y.neg();
+        // scr != nullptr: the list went through affine rounds and bit 30 selects the pool of intermediate sums
+        Affine<F> p;
+        if (scr) {
+            p = load_ref(bases, scr, e);
+        } else {
+            p = load_vec(bases + (e & 0x7fffffffu));
+            if (e >> 31) p.y = p.y.neg();
+        }
         acc.madd(p);
     }
     // final run: complete only if it started at the bucket start and the bucket ends at `end`
@@ -654,6 +661,25 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
     const uint32_t acc_blocks = div_up(acc_threads, 128);
     const uint32_t nslots = 2 * acc_blocks * 128;
 
+    // batched-affine rounds before the XYZZ accumulation (msm_affine.cuh): worth it when buckets hold several entries
+    // and the point references fit 30 bits; R rounds leave 2^-R of the additions to the XYZZ kernel
+    static const int env_rounds = std::getenv("BZK_AFFINE_ROUNDS") ? atoi(std::getenv("BZK_AFFINE_ROUNDS")) : -1;
+    uint32_t R = 0;
+    if ((double)bases.n_tab * pl.T < 1073741824.0 && max_entries >= 8ull * pl.TB) {
+        R = env_rounds >= 0 ? (uint32_t)env_rounds : 2u;
+        while (R && (max_entries >> R) < 2ull * pl.TB) R--;   // stop when buckets are down to a couple of entries
+    }
+    if (R > 6) R = 6;
+    uint64_t cap[8];
+    cap[0] = max_entries;
+    uint64_t scr_points = 0;
+    for (uint32_t r = 0; r < R; r++) { cap[r + 1] = (cap[r] + pl.TB) / 2 + 1; scr_points += cap[r + 1]; }
+    if (scr_points >= (1ull << 30)) { R = 0; scr_points = 0; }
+    const uint32_t rnd_blocks = (uint32_t)ctx->sm_count * (sizeof(F) == sizeof(Fp) ? 4 : 2);
+    const uint32_t rnd_threads = rnd_blocks * kRoundThreads;
+    uint32_t mid_threads = 32;
+    while (mid_threads < rnd_blocks) mid_threads <<= 1;
+
     // slice length trades the serial running-sum (2*slice adds) against the [offset]*sum
     // double-and-add (~log2(NB/slice) doublings): short slices keep every SM busy
     // Slice length: the reduction is bound by the integer-multiply pipe, and its total work is
@@ -685,6 +711,14 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
         cv.take<uint32_t>(pl.TB + 1); cv.take<uint32_t>(pl.TB + 1); cv.take<uint32_t>(pl.TB + 1);
         cv.take<uint32_t>(ntiles + 1);
         cv.take<uint32_t>(max_entries);
+        if (R) {
+            cv.take<uint32_t>(cap[1]); cv.take<uint32_t>(cap[1]);
+            cv.take<uint32_t>(pl.TB + 2); cv.take<uint32_t>(pl.TB + 2);
+            cv.take<Affine<F>>(scr_points);
+            cv.take<F>(cap[1]);
+            cv.take<F>(rnd_threads); cv.take<F>(rnd_threads);
+            cv.take<F>(rnd_blocks); cv.take<F>(rnd_blocks); cv.take<F>(rnd_blocks); cv.take<F>(4);
+        }
         cv.take<Xyzz<F>>(pl.TB);
         cv.take<Xyzz<F>>(nslots); cv.take<int32_t>(nslots);
         cv.take<LongRun>(kLongQueueCap); cv.take<uint32_t>(4);
@@ -700,6 +734,17 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
     uint32_t *cursor = cv.take<uint32_t>(pl.TB + 1);
     uint32_t *tile_sums = cv.take<uint32_t>(ntiles + 1);
     uint32_t *sorted = cv.take<uint32_t>(max_entries);
+    uint32_t *rlist[2] = {nullptr, nullptr}, *roff[2] = {nullptr, nullptr};
+    Affine<F> *scr = nullptr;
+    F *rpre = nullptr, *thr_pre = nullptr, *thr_suf = nullptr, *blk_tot = nullptr, *blk_pre = nullptr, *blk_suf = nullptr, *inv_total = nullptr;
+    if (R) {
+        rlist[0] = cv.take<uint32_t>(cap[1]); rlist[1] = cv.take<uint32_t>(cap[1]);
+        roff[0] = cv.take<uint32_t>(pl.TB + 2); roff[1] = cv.take<uint32_t>(pl.TB + 2);
+        scr = cv.take<Affine<F>>(scr_points);
+        rpre = cv.take<F>(cap[1]);
+        thr_pre = cv.take<F>(rnd_threads); thr_suf = cv.take<F>(rnd_threads);
+        blk_tot = cv.take<F>(rnd_blocks); blk_pre = cv.take<F>(rnd_blocks); blk_suf = cv.take<F>(rnd_blocks); inv_total = cv.take<F>(4);
+    }
     Xyzz<F> *buckets = cv.take<Xyzz<F>>(pl.TB);
     Xyzz<F> *part_pts = cv.take<Xyzz<F>>(nslots);
     int32_t *part_bucket = cv.take<int32_t>(nslots);
@@ -730,11 +775,38 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
     k_digits<true><<<div_up(n, 256), 256, 0, st>>>(d_scalars, n, pl.c, pl.W, pl.NB, pl.G, (uint32_t)bases.n_tab, (uint32_t)bases.off, cursor, sorted);
     BZK_LAUNCHED(ctx);
     timing_mark(ctx);
-    k_accumulate<F><<<acc_blocks, 128, 0, st>>>(d_bases, sorted, offsets, pl.TB, 16u, buckets, part_pts, part_bucket);
+    const uint32_t *acc_list = sorted, *acc_off = offsets;
+    if (R) {
+        const size_t fsm = 2 * kRoundThreads * sizeof(F), msm_ = 2 * (size_t)mid_threads * sizeof(F);
+        BZK_CUDA(ctx, cudaFuncSetAttribute(k_round_mid<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm_));
+        uint32_t scr_base = 0;
+        for (uint32_t r = 0; r < R; r++) {
+            uint32_t *off1 = roff[r & 1], *list1 = rlist[r & 1];
+            k_round_counts<<<div_up(pl.TB + 1, 256), 256, 0, st>>>(acc_off, pl.TB, counts);
+            BZK_LAUNCHED(ctx);
+            k_scan_tile_sums<<<ntiles, kScanBlock, 0, st>>>(counts, pl.TB, tile_sums);
+            BZK_LAUNCHED(ctx);
+            k_scan_tiles<<<1, 1024, 0, st>>>(tile_sums, ntiles);
+            BZK_LAUNCHED(ctx);
+            k_scan_apply<<<ntiles, kScanBlock, 0, st>>>(counts, pl.TB, tile_sums, ntiles, off1, cursor);
+            BZK_LAUNCHED(ctx);
+            k_round_fwd<F><<<rnd_blocks, kRoundThreads, fsm, st>>>(d_bases, scr, acc_list, acc_off, off1, pl.TB, rpre, thr_pre, thr_suf, blk_tot);
+            BZK_LAUNCHED(ctx);
+            k_round_mid<F><<<1, mid_threads, msm_, st>>>(blk_tot, rnd_blocks, blk_pre, blk_suf, inv_total);
+            BZK_LAUNCHED(ctx);
+            k_round_bwd<F><<<rnd_blocks, kRoundThreads, 0, st>>>(d_bases, scr, scr_base, acc_list, acc_off, off1, pl.TB, rpre, thr_pre, thr_suf, blk_pre,
+                                                                 blk_suf, inv_total, list1);
+            BZK_LAUNCHED(ctx);
+            scr_base += (uint32_t)cap[r + 1];
+            acc_list = list1;
+            acc_off = off1;
+        }
+    }
+    k_accumulate<F><<<acc_blocks, 128, 0, st>>>(d_bases, R ? scr : nullptr, acc_list, acc_off, pl.TB, 16u, buckets, part_pts, part_bucket);
     BZK_LAUNCHED(ctx);
     timing_mark(ctx);
     BZK_CUDA(ctx, cudaMemsetAsync(long_len, 0, 16, st));
-    k_fixup<F><<<div_up(nslots, 128), 128, 0, st>>>(part_pts, part_bucket, nslots, offsets, pl.TB, acc_blocks * 128, 16u, buckets, long_queue, long_len);
+    k_fixup<F><<<div_up(nslots, 128), 128, 0, st>>>(part_pts, part_bucket, nslots, acc_off, pl.TB, acc_blocks * 128, 16u, buckets, long_queue, long_len);
     BZK_LAUNCHED(ctx);
     {
         const size_t fsmem = 256 * sizeof(Xyzz<F>);
