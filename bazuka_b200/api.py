@@ -135,6 +135,10 @@ class Context:
     def set_timing(self, on=True):
         self._check(self._l.bzk_ctx_set_timing(self._h, int(on)))
 
+    def set_msm_affine_rounds(self, g1=-1, g2=-1):
+        """batched-affine rounds before the XYZZ accumulation (speed knob; results unchanged); -1 = library default"""
+        self._check(self._l.bzk_ctx_set_msm_affine_rounds(self._h, int(g1), int(g2)))
+
     def stage_ms(self):
         """-> (runs, last_ms[16], sum_ms[16]) from the CUDA events the MSM driver records between kernels."""
         last = np.zeros(16, dtype=np.float32)

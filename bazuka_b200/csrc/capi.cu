@@ -164,6 +164,12 @@ int32_t bzk_ctx_set_timing(bzk_ctx *ctx, int32_t on) {
     for (int i = 0; i < bzk_ctx::kMaxStages; i++) { ctx->stage_ms[i] = 0; ctx->stage_ms_sum[i] = 0; }
     return BZK_OK;
 }
+int32_t bzk_ctx_set_msm_affine_rounds(bzk_ctx *ctx, int32_t g1_rounds, int32_t g2_rounds) {
+    if (!ctx || g1_rounds > 6 || g2_rounds > 6) return BZK_ERR_BAD_ARG;
+    ctx->affine_rounds[0] = g1_rounds;
+    ctx->affine_rounds[1] = g2_rounds;
+    return BZK_OK;
+}
 uint64_t bzk_ctx_stage_ms(const bzk_ctx *ctx, float *last_ms, double *sum_ms, uint32_t cap) {
     if (!ctx) return 0;
     for (uint32_t i = 0; i < cap && i < (uint32_t)bzk_ctx::kMaxStages; i++) {

@@ -56,6 +56,7 @@ struct bzk_ctx {
     bzk::NttTables ntt[29];
     bzk::Fr *d_gpow = nullptr;  // coset generator power tables, see ntt.cu
     int sm_count = bzk::kNumSMs;
+    int affine_rounds[2] = {-1, -1};  // batched-affine rounds for G1 / G2 sums (-1: BZK_AFFINE_ROUNDS[_G2] or the default 0)
     // side streams + arenas so that independent MSMs of one proof run concurrently (groth16.cu)
     cudaStream_t aux_stream[4] = {nullptr, nullptr, nullptr, nullptr};
     void *aux_ws[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -663,10 +663,17 @@ static int32_t msm_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_
 
     // batched-affine rounds before the XYZZ accumulation (msm_affine.cuh): worth it when buckets hold several entries
     // and the point references fit 30 bits; R rounds leave 2^-R of the additions to the XYZZ kernel
-    static const int env_rounds = std::getenv("BZK_AFFINE_ROUNDS") ? atoi(std::getenv("BZK_AFFINE_ROUNDS")) : -1;
+    // Measured on B200 at 2^20 / 13 windows (profiles/r02_msm_affine_rounds.txt): a G1 round costs 0.36 ns per addition
+    // (k_round_fwd is load-latency bound, k_round_bwd reaches 66 % of the multiplier peak, the inversion is a 0.7 ms
+    // single-thread chain) against 0.42 ns for the XYZZ kernel — R = 1 / 2 / 3 make the whole sum 0.45 / 0.83 / 1.4 ms
+    // SLOWER, so the default for G1 is 0 rounds; the knobs stay for G2 and for tuning.
+    static const int env_g1 = std::getenv("BZK_AFFINE_ROUNDS") ? atoi(std::getenv("BZK_AFFINE_ROUNDS")) : 0;
+    static const int env_g2 = std::getenv("BZK_AFFINE_ROUNDS_G2") ? atoi(std::getenv("BZK_AFFINE_ROUNDS_G2")) : 0;
+    const int ctx_rounds = ctx->affine_rounds[sizeof(F) == sizeof(Fp) ? 0 : 1];
+    const int env_rounds = ctx_rounds >= 0 ? ctx_rounds : (sizeof(F) == sizeof(Fp) ? env_g1 : env_g2);
     uint32_t R = 0;
-    if ((double)bases.n_tab * pl.T < 1073741824.0 && max_entries >= 8ull * pl.TB) {
-        R = env_rounds >= 0 ? (uint32_t)env_rounds : 2u;
+    if (env_rounds > 0 && (double)bases.n_tab * pl.T < 1073741824.0 && max_entries >= 8ull * pl.TB) {
+        R = (uint32_t)env_rounds;
         while (R && (max_entries >> R) < 2ull * pl.TB) R--;   // stop when buckets are down to a couple of entries
     }
     if (R > 6) R = 6;

@@ -68,6 +68,11 @@ int32_t bzk_ctx_synchronize(bzk_ctx *ctx);
  * (up to `cap` floats) and returns how many calls have been timed since timing was switched on. */
 int32_t bzk_ctx_set_timing(bzk_ctx *ctx, int32_t on);
 uint64_t bzk_ctx_stage_ms(const bzk_ctx *ctx, float *last_ms, double *sum_ms, uint32_t cap);
+/* Batched-affine rounds in front of the XYZZ bucket accumulation of G1 / G2 sums (csrc/msm_affine.cuh): each round
+ * replaces the entries of every bucket by their pairwise affine sums with one shared inversion.  Results are the same
+ * group elements for any value; it is a speed knob (0..6; negative = the library default, currently 0 for both groups —
+ * see DESIGN.md for the measurements). */
+int32_t bzk_ctx_set_msm_affine_rounds(bzk_ctx *ctx, int32_t g1_rounds, int32_t g2_rounds);
 /* kernels launched through this ctx since creation (bench.py's `gpu_launches`) */
 uint64_t bzk_ctx_launch_count(const bzk_ctx *ctx);
 
