@@ -17,7 +17,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
-]
+] + os.environ.get("BZK_NVCC_EXTRA", "").split()   # e.g. BZK_NVCC_EXTRA=-DBZK_MUL_NOINLINE for code-size experiments (use -f)
 
 
 def _stale(target, deps):

@@ -265,12 +265,17 @@ struct Fe {
     // E holds 64-bit partial products starting on even absolute columns, O those starting on odd
     // columns; row i adds a*b[i] and m_i*p and retires column i.
     BZK_HD friend Fe operator*(const Fe &a, const Fe &b) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(BZK_MUL_NOINLINE)
+        return mul_call(a, b);   // one out-of-line copy per translation unit: code-size experiment (instruction cache)
+#elif defined(__CUDA_ARCH__)
         return mul_evenodd(a, b);
 #else
         return mul_host64(a, b);
 #endif
     }
+#if defined(__CUDACC__)
+    __device__ __noinline__ static Fe mul_call(Fe a, Fe b) { return mul_evenodd(a, b); }
+#endif
     // host fast path: plain CIOS on 64-bit limbs (unsigned __int128 products); same result
     static inline Fe mul_host64(const Fe &a, const Fe &b) {
         constexpr int M = N / 2;
