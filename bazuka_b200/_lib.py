@@ -118,6 +118,7 @@ SIGNATURES = {
     "bzk_groth16_pvk_free": (_i32, [_vp]),
     "bzk_groth16_verify_prepared": (_i32, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "bzk_groth16_verify_batch": (_i32, [_vp, _vp, _sz, _vp, _sz, _u64, _i32, _vp]),
+    "bzk_groth16_verify_batch_dev": (_i32, [_vp, _vp, _vp, _sz, _vp, _sz, _u64, _vp]),
     "bzk_csr_spmv_dev": (_i32, [_vp, _vp, _vp, _vp, _u64, _vp, _vp]),
     "bzk_g1_fixed_base_mul_dev": (_i32, [_vp, _vp, _vp, _sz, _vp]),
     "bzk_g2_fixed_base_mul_dev": (_i32, [_vp, _vp, _vp, _sz, _vp]),

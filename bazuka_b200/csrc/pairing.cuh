@@ -28,30 +28,30 @@ struct Fp12 {
     Fp2 c[6];  // sum c[k] w^k, w^6 = xi = 1 + u
 };
 
-static inline Fp2 mul_xi(const Fp2 &a) { return Fp2{a.c0 - a.c1, a.c0 + a.c1}; }
-static inline Fp2 mul_fp(const Fp2 &a, const Fp &s) { return Fp2{a.c0 * s, a.c1 * s}; }
-static inline Fp2 conj2(const Fp2 &a) { return Fp2{a.c0, a.c1.neg()}; }
+BZK_HD Fp2 mul_xi(const Fp2 &a) { return Fp2{a.c0 - a.c1, a.c0 + a.c1}; }
+BZK_HD Fp2 mul_fp(const Fp2 &a, const Fp &s) { return Fp2{a.c0 * s, a.c1 * s}; }
+BZK_HD Fp2 conj2(const Fp2 &a) { return Fp2{a.c0, a.c1.neg()}; }
 
-static inline Fp12 f12_one() {
+BZK_HD Fp12 f12_one() {
     Fp12 r;
     for (int k = 0; k < 6; k++) r.c[k] = Fp2::zero();
     r.c[0] = Fp2::one();
     return r;
 }
-static inline Fp12 f12_fold(const Fp2 t[11]) {
+BZK_HD Fp12 f12_fold(const Fp2 t[11]) {
     Fp12 r;
     for (int k = 0; k < 5; k++) r.c[k] = t[k] + mul_xi(t[k + 6]);
     r.c[5] = t[5];
     return r;
 }
-static inline Fp12 f12_mul(const Fp12 &a, const Fp12 &b) {
+BZK_HD Fp12 f12_mul(const Fp12 &a, const Fp12 &b) {
     Fp2 t[11];
     for (int k = 0; k < 11; k++) t[k] = Fp2::zero();
     for (int i = 0; i < 6; i++)
         for (int j = 0; j < 6; j++) t[i + j] = t[i + j] + a.c[i] * b.c[j];
     return f12_fold(t);
 }
-static inline Fp12 f12_sqr(const Fp12 &a) {
+BZK_HD Fp12 f12_sqr(const Fp12 &a) {
     Fp2 t[11];
     for (int k = 0; k < 11; k++) t[k] = Fp2::zero();
     for (int i = 0; i < 6; i++) {
@@ -61,7 +61,7 @@ static inline Fp12 f12_sqr(const Fp12 &a) {
     return f12_fold(t);
 }
 // a * (l0 + l2 w^2 + l3 w^3)
-static inline Fp12 f12_mul_sparse(const Fp12 &a, const Fp2 &l0, const Fp2 &l2, const Fp2 &l3) {
+BZK_HD Fp12 f12_mul_sparse(const Fp12 &a, const Fp2 &l0, const Fp2 &l2, const Fp2 &l3) {
     Fp2 t[11];
     for (int k = 0; k < 11; k++) t[k] = Fp2::zero();
     for (int i = 0; i < 6; i++) {
@@ -71,12 +71,12 @@ static inline Fp12 f12_mul_sparse(const Fp12 &a, const Fp2 &l0, const Fp2 &l2, c
     }
     return f12_fold(t);
 }
-static inline Fp12 f12_conj(const Fp12 &a) {  // w -> -w: the p^6 Frobenius; the inverse on the cyclotomic subgroup
+BZK_HD Fp12 f12_conj(const Fp12 &a) {  // w -> -w: the p^6 Frobenius; the inverse on the cyclotomic subgroup
     Fp12 r = a;
     r.c[1] = a.c[1].neg(); r.c[3] = a.c[3].neg(); r.c[5] = a.c[5].neg();
     return r;
 }
-static inline bool f12_eq(const Fp12 &a, const Fp12 &b) {
+BZK_HD bool f12_eq(const Fp12 &a, const Fp12 &b) {
     for (int k = 0; k < 6; k++) if (a.c[k] != b.c[k]) return false;
     return true;
 }
@@ -131,7 +131,7 @@ static inline Fp12 f12_inv(const Fp12 &f) {
 }
 
 // ---- final exponentiation -----------------------------------------------------------------------------------------
-static const uint64_t kAbsX = 0xd201000000010000ULL;
+#define kAbsX 0xd201000000010000ULL   /* |x|, the BLS parameter (usable in host and device code) */
 static inline Fp12 pow_abs_x(const Fp12 &g) {
     Fp12 acc = g;
     for (int i = 62; i >= 0; i--) {
@@ -201,6 +201,43 @@ static inline void compute_lines(const Affine<Fp2> &Q, G2Lines &out) {
             Z = Z3;
         }
     }
+}
+
+// Miller loop of ONE pair with the G2 point walked on the fly and the G1 point in XYZZ form (x = X/ZZ, y = Y/ZZZ): every
+// line is additionally scaled by ZZ*ZZZ (an Fp factor the final exponentiation removes), so no inversion is needed to
+// feed a freshly scalar-multiplied point.  Same lines as compute_lines + multi_miller; no heap: usable in a kernel.
+BZK_HD Fp12 miller_one_xyzz(const Xyzz<Fp> &P, const Affine<Fp2> &Q) {
+    Fp12 f = f12_one();
+    if (P.is_inf() || Q.is_inf()) return f;
+    const Fp sx = P.X * P.ZZZ, sy = P.Y * P.ZZ, s0 = P.ZZ * P.ZZZ;   // (xP, yP, 1) * ZZ*ZZZ
+    Fp2 X = Q.x, Y = Q.y, Z = Fp2::one();
+    for (int i = 62; i >= 0; i--) {
+        f = f12_sqr(f);
+        {
+            const Fp2 A = X.sqr(), B = Y.sqr(), C = B.sqr(), ZZ = Z.sqr();
+            const Fp2 t = X + B;
+            const Fp2 D = (t.sqr() - A - C).dbl();
+            const Fp2 E = A.dbl() + A;
+            const Fp2 Z3 = (Y * Z).dbl();
+            f = f12_mul_sparse(f, mul_fp(E * X - B.dbl(), s0), mul_fp((E * ZZ).neg(), sx), mul_fp(Z3 * ZZ, sy));
+            const Fp2 X3 = E.sqr() - D.dbl();
+            Y = E * (D - X3) - C.dbl().dbl().dbl();
+            X = X3;
+            Z = Z3;
+        }
+        if ((kAbsX >> i) & 1) {
+            const Fp2 ZZ = Z.sqr();
+            const Fp2 H = Q.x * ZZ - X, Rr = Q.y * ZZ * Z - Y;
+            const Fp2 Z3 = Z * H;
+            f = f12_mul_sparse(f, mul_fp(Rr * Q.x - Q.y * Z3, s0), mul_fp(Rr.neg(), sx), mul_fp(Z3, sy));
+            const Fp2 HH = H.sqr(), HHH = HH * H, V = X * HH;
+            const Fp2 X3 = Rr.sqr() - HHH - V.dbl();
+            Y = Rr * (V - X3) - Y * HHH;
+            X = X3;
+            Z = Z3;
+        }
+    }
+    return f;
 }
 
 struct MillerPair {

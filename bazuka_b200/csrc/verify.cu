@@ -151,6 +151,72 @@ void derive_multipliers(uint64_t seed, size_t m, std::vector<Fr> &r) {
     }
 }
 
+// the part of a batch check that does not depend on the individual proofs' points:  given  f = prod_j miller(r_j A_j, B_j)
+// and  cs = sum_j r_j C_j,  test  f * miller(-sum_j r_j acc_j, gamma) * miller(-cs, delta) == e(alpha,beta)^(sum r_j)
+int32_t batch_tail(const bzk_groth16_pvk *k, const bzk_fr *public_inputs, size_t n_inputs, size_t m, const std::vector<Fr> &r, Fp12 f,
+                   const G1Xyzz &cs) {
+    // sum_j r_j acc_j = (sum r_j) ic_0 + sum_i (sum_j r_j x_ji) ic_i  — scalars combined in Fr first
+    std::vector<Fr> comb(n_inputs + 1, Fr::zero());
+    for (size_t j = 0; j < m; j++) {
+        const Fr rm = r[j].to_mont();
+        comb[0] = comb[0] + rm;
+        for (size_t i = 0; i < n_inputs; i++) {
+            Fr x;
+            memcpy(x.l, &public_inputs[j * n_inputs + i], 32);
+            comb[i + 1] = comb[i + 1] + rm * x;
+        }
+    }
+    std::vector<Fr> canon(n_inputs + 1);
+    for (size_t i = 0; i <= n_inputs; i++) canon[i] = comb[i].from_mont();
+    const G1Affine acc = small_msm(k->ic.data(), canon.data(), n_inputs + 1).to_affine();
+    const MillerPair tail[2] = {{acc.neg(), &k->gamma_lines}, {cs.to_affine().neg(), &k->delta_lines}};
+    f = f12_mul(f, multi_miller(tail, 2));
+    // e(alpha,beta)^(sum r_j): the cached value is already in the target group, raise it there
+    Fp12 rhs = f12_one();
+    const Fr e = canon[0];
+    for (int i = 254; i >= 0; i--) {
+        rhs = f12_sqr(rhs);
+        if ((e.l[i >> 5] >> (i & 31)) & 1) rhs = f12_mul(rhs, k->alpha_beta);
+    }
+    return f12_eq(final_exp(f), rhs) ? 1 : 0;
+}
+
+// one thread per proof: f_j = miller([r_j] A_j, B_j) with the G2 point walked on the fly, c_j = [r_j] C_j
+__global__ void __launch_bounds__(64) k_verify_miller(const uint8_t *__restrict__ proofs387, const Fr *__restrict__ r_canon, uint32_t m,
+                                                     Fp12 *__restrict__ out_f, G1Xyzz *__restrict__ out_c, uint8_t *__restrict__ malformed) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const uint8_t *p = proofs387 + (size_t)387 * j;
+    auto rd_fp = [&](const uint8_t *q) {
+        Fp v;
+        for (int i = 0; i < 12; i++) v.l[i] = (uint32_t)q[4 * i] | ((uint32_t)q[4 * i + 1] << 8) | ((uint32_t)q[4 * i + 2] << 16) | ((uint32_t)q[4 * i + 3] << 24);
+        return v;
+    };
+    G1Affine A = p[96] ? G1Affine::inf() : G1Affine{rd_fp(p), rd_fp(p + 48)};
+    G2Affine B = p[97 + 192] ? G2Affine::inf() : G2Affine{Fp2{rd_fp(p + 97), rd_fp(p + 145)}, Fp2{rd_fp(p + 193), rd_fp(p + 241)}};
+    G1Affine C = p[290 + 96] ? G1Affine::inf() : G1Affine{rd_fp(p + 290), rd_fp(p + 338)};
+    const Fp four = Fp::from_u32(4);
+    const bool okA = A.is_inf() || A.y.sqr() == A.x.sqr() * A.x + four, okC = C.is_inf() || C.y.sqr() == C.x.sqr() * C.x + four,
+               okB = B.is_inf() || B.y.sqr() == B.x.sqr() * B.x + Fp2{four, four};
+    malformed[j] = (okA && okB && okC) ? 0 : 1;
+    Fr r = load_vec(r_canon + j);
+    auto mul127 = [&](const G1Affine &P) {
+        G1Xyzz acc = G1Xyzz::inf();
+        for (int i = 126; i >= 0; i--) {
+            acc = acc.dbl();
+            if ((r.l[i >> 5] >> (i & 31)) & 1) acc.madd(P);
+        }
+        return acc;
+    };
+    if (malformed[j]) {
+        out_f[j] = f12_one();
+        out_c[j] = G1Xyzz::inf();
+        return;
+    }
+    out_f[j] = miller_one_xyzz(mul127(A), B);
+    out_c[j] = mul127(C);
+}
+
 }  // namespace
 
 extern "C" {
@@ -267,30 +333,7 @@ int32_t bzk_groth16_verify_batch(const bzk_groth16_pvk *k, const bzk_fr *public_
         Fp12 f = part[0];
         G1Xyzz cs = c_part[0];
         for (int t = 1; t < nt; t++) { f = f12_mul(f, part[t]); cs.add(c_part[t]); }
-        // sum_j r_j acc_j = (sum r_j) ic_0 + sum_i (sum_j r_j x_ji) ic_i  — scalars combined in Fr first
-        std::vector<Fr> comb(n_inputs + 1, Fr::zero());
-        for (size_t j = 0; j < m; j++) {
-            const Fr rm = r[j].to_mont();
-            comb[0] = comb[0] + rm;
-            for (size_t i = 0; i < n_inputs; i++) {
-                Fr x;
-                memcpy(x.l, &public_inputs[j * n_inputs + i], 32);
-                comb[i + 1] = comb[i + 1] + rm * x;
-            }
-        }
-        std::vector<Fr> canon(n_inputs + 1);
-        for (size_t i = 0; i <= n_inputs; i++) canon[i] = comb[i].from_mont();
-        const G1Affine acc = small_msm(k->ic.data(), canon.data(), n_inputs + 1).to_affine();
-        const MillerPair tail[2] = {{acc.neg(), &k->gamma_lines}, {cs.to_affine().neg(), &k->delta_lines}};
-        f = f12_mul(f, multi_miller(tail, 2));
-        // e(alpha,beta)^(sum r_j): the cached value is already in the target group, raise it there
-        Fp12 rhs = f12_one();
-        const Fr e = canon[0];
-        for (int i = 254; i >= 0; i--) {
-            rhs = f12_sqr(rhs);
-            if ((e.l[i >> 5] >> (i & 31)) & 1) rhs = f12_mul(rhs, k->alpha_beta);
-        }
-        all_ok = f12_eq(final_exp(f), rhs) ? 1 : 0;
+        all_ok = batch_tail(k, public_inputs, n_inputs, m, r, f, cs);
     }
     if (ok_each) {
         if (all_ok) {
@@ -305,6 +348,75 @@ int32_t bzk_groth16_verify_batch(const bzk_groth16_pvk *k, const bzk_fr *public_
             each(0);
             for (auto &x : th2) x.join();
         }
+    }
+    return all_ok;
+}
+
+
+/* The same batch check with the m proof-dependent Miller loops on the GPU (one thread per proof: [r_j]A_j, the walk of
+ * B_j on the twist and the 68 line evaluations, [r_j]C_j), the product of the m values and the two key-dependent loops +
+ * final exponentiation on the host.  Verdicts are identical to bzk_groth16_verify_batch's for the same seed. */
+int32_t bzk_groth16_verify_batch_dev(bzk_ctx *ctx, const bzk_groth16_pvk *k, const bzk_fr *public_inputs, size_t n_inputs,
+                                     const uint8_t *proofs387, size_t m, uint64_t seed, uint8_t *ok_each) {
+    if (!ctx || !k || (m && !proofs387) || k->ic.size() != n_inputs + 1 || (m && n_inputs && !public_inputs) || m >= (1u << 24)) return BZK_ERR_BAD_ARG;
+    if (m == 0) return 1;
+    BZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<Fr> r;
+    derive_multipliers(seed, m, r);
+    size_t need = 0;
+    {
+        Carver cv(nullptr);
+        cv.take<uint8_t>(387 * m); cv.take<Fr>(m); cv.take<Fp12>(m); cv.take<G1Xyzz>(m); cv.take<uint8_t>(m);
+        need = cv.used();
+    }
+    BZK_TRY(ensure_ws(ctx, &ctx->stage, &ctx->stage_bytes, need));
+    Carver cv(ctx->stage);
+    uint8_t *d_proofs = cv.take<uint8_t>(387 * m);
+    Fr *d_r = cv.take<Fr>(m);
+    Fp12 *d_f = cv.take<Fp12>(m);
+    G1Xyzz *d_c = cv.take<G1Xyzz>(m);
+    uint8_t *d_bad = cv.take<uint8_t>(m);
+    BZK_CUDA(ctx, cudaMemcpyAsync(d_proofs, proofs387, 387 * m, cudaMemcpyHostToDevice, ctx->stream));
+    BZK_CUDA(ctx, cudaMemcpyAsync(d_r, r.data(), m * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    k_verify_miller<<<div_up(m, 64), 64, 0, ctx->stream>>>(d_proofs, d_r, (uint32_t)m, d_f, d_c, d_bad);
+    BZK_LAUNCHED(ctx);
+    std::vector<Fp12> hf(m);
+    std::vector<G1Xyzz> hc(m);
+    std::vector<uint8_t> bad(m);
+    BZK_CUDA(ctx, cudaMemcpyAsync(hf.data(), d_f, m * sizeof(Fp12), cudaMemcpyDeviceToHost, ctx->stream));
+    BZK_CUDA(ctx, cudaMemcpyAsync(hc.data(), d_c, m * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, ctx->stream));
+    BZK_CUDA(ctx, cudaMemcpyAsync(bad.data(), d_bad, m, cudaMemcpyDeviceToHost, ctx->stream));
+    BZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bool well_formed = true;
+    for (size_t j = 0; j < m; j++) well_formed = well_formed && !bad[j];
+    int32_t all_ok = 0;
+    if (well_formed) {
+        // product tree over host threads
+        int nt = (int)std::thread::hardware_concurrency();
+        if (nt < 1) nt = 1;
+        if (nt > 16) nt = 16;
+        if ((size_t)nt > m) nt = (int)m;
+        std::vector<Fp12> part(nt, f12_one());
+        std::vector<G1Xyzz> cp(nt, G1Xyzz::inf());
+        auto work = [&](int t) {
+            Fp12 f = f12_one();
+            G1Xyzz cs = G1Xyzz::inf();
+            for (size_t j = m * t / nt; j < m * (t + 1) / nt; j++) { f = f12_mul(f, hf[j]); cs.add(hc[j]); }
+            part[t] = f;
+            cp[t] = cs;
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto &x : th) x.join();
+        Fp12 f = part[0];
+        G1Xyzz cs = cp[0];
+        for (int t = 1; t < nt; t++) { f = f12_mul(f, part[t]); cs.add(cp[t]); }
+        all_ok = batch_tail(k, public_inputs, n_inputs, m, r, f, cs);
+    }
+    if (ok_each) {
+        if (all_ok) memset(ok_each, 1, m);
+        else return bzk_groth16_verify_batch(k, public_inputs, n_inputs, proofs387, m, seed, 0, ok_each);  // locate the offenders on the host
     }
     return all_ok;
 }

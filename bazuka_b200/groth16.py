@@ -510,6 +510,23 @@ class PreparedVerifyingKey:
             raise _lib.BzkError(st, "groth16_verify_prepared")
         return bool(st)
 
+    def verify_batch_gpu(self, ctx, public_inputs, proofs387, seed=None):
+        """verify_batch with the per-proof Miller loops on the GPU (bzk_groth16_verify_batch_dev): same verdicts."""
+        import os
+        from . import _lib
+        proofs = np.ascontiguousarray(proofs387, dtype=np.uint8).reshape(-1, 387)
+        m = len(proofs)
+        if m == 0:
+            return True, np.zeros(0, dtype=bool)
+        pub = np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(m, -1, 4)
+        each = np.zeros(m, dtype=np.uint8)
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little")
+        st = self._l.bzk_groth16_verify_batch_dev(ctx._h, self._h, _host_ptr(pub), pub.shape[1], _host_ptr(proofs), m, seed, _host_ptr(each))
+        if st < 0:
+            raise _lib.BzkError(st, "groth16_verify_batch_dev")
+        return bool(st), each.astype(bool)
+
     def verify_batch(self, public_inputs, proofs387, seed=None, threads=0):
         """public_inputs [m, n, 4] Montgomery, proofs387 [m, 387] -> (all_ok, ok_each[m]).  One final exponentiation for
         the batch (random linear combination with 127-bit multipliers from `seed`, default os.urandom)."""

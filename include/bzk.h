@@ -385,6 +385,10 @@ int32_t bzk_groth16_verify_prepared(const bzk_groth16_pvk *pvk, const bzk_fr *pu
  * (on a failing batch the proofs are re-checked one by one). */
 int32_t bzk_groth16_verify_batch(const bzk_groth16_pvk *pvk, const bzk_fr *public_inputs, size_t n_inputs, const uint8_t *proofs387, size_t m,
                                  uint64_t seed, int32_t threads, uint8_t *ok_each);
+/* The same check with the m proof-dependent Miller loops on the GPU (one thread per proof); the key-dependent loops, the
+ * product and the single final exponentiation stay on the host.  Same verdicts as the host version for the same seed. */
+int32_t bzk_groth16_verify_batch_dev(bzk_ctx *ctx, const bzk_groth16_pvk *pvk, const bzk_fr *public_inputs, size_t n_inputs,
+                                     const uint8_t *proofs387, size_t m, uint64_t seed, uint8_t *ok_each);
 /* Building blocks also used by the GPU-side trusted-setup helper (bellman `generate_parameters`):
  * CSR sparse matrix-vector product over Fr (out[row] = sum val*vec[col]) and fixed-base scalar
  * multiplication out[i] = [k_i] base written as wire images. */

@@ -135,3 +135,39 @@ def test_base_sharded_partials_fold_to_the_same_proof(ctx, cref):
     one = pr.prove_partial(spk, d_in, d_aux)
     assert (BG.finalize(vk, one, r, s)[0] == want).all()
     spk.free(); pk.free(); pr.free()
+
+
+def test_batch_verifier_on_gpu_equals_host_batch_verifier(ctx, cref):
+    """bzk_groth16_verify_batch_dev (one thread per proof: [r_j]A_j, the Jacobian walk of B_j, 68 line evaluations; product,
+    key-dependent loops and the single final exponentiation on the host) against the host batch verifier and the oracle's
+    pairing check: all-valid batch accepted, a tampered C / a wrong input / a malformed point located."""
+    from bazuka_b200 import groth16 as BG, synth
+    from oracle import groth16_c as GC
+    ni, na, mats, inputs, aux = synth.build(4, 6, seed=3, ops=GC.CpuOps)
+    _, pr = _prover(ctx, ni, na, mats)
+    pk, vk = BG.setup_gpu(ctx, pr.r1cs, cref.fr_random(31, 5), cref.g1_generator(), cref.g2_generator())
+    m = 70
+    rs = cref.fr_random(32, 2 * m)
+    proofs, pts0 = [], None
+    for j in range(m):
+        blob, pts = pr.prove(pk, inputs, aux, rs[2 * j], rs[2 * j + 1], check_satisfied=(j == 0))
+        proofs.append(blob)
+        pts0 = pts0 or pts
+    proofs = np.stack(proofs)
+    assert GC.verify_py(vk, inputs[1:], pts0)
+    pubs = np.repeat(inputs[1:][None], m, axis=0)
+    pvk = BG.PreparedVerifyingKey(vk)
+    ok_h, each_h = pvk.verify_batch(pubs, proofs, seed=99)
+    ok_d, each_d = pvk.verify_batch_gpu(ctx, pubs, proofs, seed=99)
+    assert ok_h and ok_d and each_d.all()
+    bad = proofs.copy()
+    bad[3, 290:387] = proofs[4, 0:97]            # C replaced by another curve point
+    wrong = pubs.copy()
+    wrong[11, 0] = wrong[11, 1] if wrong.shape[1] > 1 else cref.fr_random(5, 1)[0]
+    bad2 = proofs.copy()
+    bad2[20, 7] ^= 1                              # not on the curve
+    for p_, pub_ in ((bad, pubs), (proofs, wrong), (bad2, pubs)):
+        ok_h, each_h = pvk.verify_batch(pub_, p_, seed=7)
+        ok_d, each_d = pvk.verify_batch_gpu(ctx, pub_, p_, seed=7)
+        assert not ok_h and not ok_d and (each_h == each_d).all() and each_d.sum() == m - 1
+    pvk.free(); pk.free(); pr.free()
