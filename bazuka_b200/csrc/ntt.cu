@@ -118,6 +118,51 @@ __global__ void __launch_bounds__(256) k_ntt_dif(Fr *__restrict__ a, const Fr *_
 }
 
 // ---------------------------------------------------------------------------------------------
+// DIT pass: stages s .. s+K-1 (butterfly distances 2^s .. 2^(s+K-1)) on 2^K register-resident elements per thread.
+// Takes its input in BIT-REVERSED order and leaves natural order after the last pass — what follows a DIF transform
+// whose reversal pass was skipped (the quotient pipeline: ifft -> coset_fft needs no permutation in between).
+// PRESCALE (first pass only): element at position p is first multiplied by c * g^rev(p) — the n^-1 of the ifft that
+// came before and the coset's distribute_powers(7) on the coefficient that sits at p.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ Fr gpow_at(const Fr *lo, const Fr *hi, size_t i);
+template <int K, bool PRESCALE>
+__global__ void __launch_bounds__(256) k_ntt_dit(Fr *__restrict__ a, const Fr *__restrict__ tw, uint32_t log_n, uint32_t s, Fr c,
+                                                 const Fr *__restrict__ glo, const Fr *__restrict__ ghi) {
+    const size_t n = (size_t)1 << log_n;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (n >> K)) return;
+    const size_t h0 = (size_t)1 << s;
+    const size_t low = t & (h0 - 1);
+    const size_t p0 = ((t >> s) << (s + K)) + low;
+    Fr x[1 << K];
+#pragma unroll
+    for (int m = 0; m < (1 << K); m++) {
+        const size_t p = p0 + (size_t)m * h0;
+        x[m] = load_vec(a + p);
+        if (PRESCALE) {
+            const size_t coeff = (size_t)(__brevll((unsigned long long)p) >> (64 - log_n));
+            x[m] = x[m] * (c * gpow_at(glo, ghi, coeff));
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+        const int d = 1 << q;
+        const uint32_t sh = log_n - 1 - s - q;  // log2(n / (2 h)), h = h0 * d
+#pragma unroll
+        for (int m = 0; m < (1 << K); m++) {
+            if (m & d) continue;
+            const size_t idx = (low + (size_t)(m & (d - 1)) * h0) << sh;
+            const Fr u = x[m];
+            const Fr v = (idx == 0) ? x[m + d] : x[m + d] * load_vec(tw + idx);
+            x[m] = u + v;
+            x[m + d] = u - v;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < (1 << K); m++) store_vec(a + p0 + (size_t)m * h0, x[m]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // bit-reversal permutation fused with the op's output scaling:
 //   mode 0: none     mode 1: * c (n^-1)     mode 2: * c * g^-i (icoset)   (i = natural output index)
 // pairs (i, rev i) are swapped by the thread owning the smaller index.
@@ -191,6 +236,31 @@ static int32_t run_dif(bzk_ctx *ctx, Fr *d, uint32_t log_n, const Fr *tw) {
     return BZK_OK;
 }
 
+// bit-reversed in, natural out; the first pass multiplies position p by c * g^rev(p)
+static int32_t run_dit_prescaled(bzk_ctx *ctx, Fr *d, uint32_t log_n, const Fr *tw, const Fr &c, const Fr *glo, const Fr *ghi) {
+    uint32_t s = 0;
+    bool first = true;
+    if (log_n == 0) {  // a single element: only the scaling (g^0 = 1)
+        k_scale_const<<<1, 256, 0, ctx->stream>>>(d, 1, c);
+        BZK_LAUNCHED(ctx);
+        return BZK_OK;
+    }
+    while (s < log_n) {
+        const uint32_t K = log_n - s >= 3 ? 3 : log_n - s;
+        const size_t threads = ((size_t)1 << log_n) >> K;
+        const uint32_t blocks = div_up(threads, 256);
+#define BZK_DIT(KK)                                                                                              \
+    if (first) k_ntt_dit<KK, true><<<blocks, 256, 0, ctx->stream>>>(d, tw, log_n, s, c, glo, ghi);                \
+    else k_ntt_dit<KK, false><<<blocks, 256, 0, ctx->stream>>>(d, tw, log_n, s, c, glo, ghi);
+        if (K == 3) { BZK_DIT(3) } else if (K == 2) { BZK_DIT(2) } else { BZK_DIT(1) }
+#undef BZK_DIT
+        BZK_LAUNCHED(ctx);
+        first = false;
+        s += K;
+    }
+    return BZK_OK;
+}
+
 int32_t ntt_launch(bzk_ctx *ctx, Fr *d, uint32_t log_n, int32_t op) {
     if (log_n > 28 || op < 0 || op > 3 || !d) return BZK_ERR_BAD_ARG;
     const size_t n = (size_t)1 << log_n;
@@ -237,9 +307,17 @@ int32_t groth16_h_launch(bzk_ctx *ctx, Fr *a, Fr *b, Fr *c, uint32_t log_n) {
     if (log_n > 28 || !a || !b || !c) return BZK_ERR_BAD_ARG;
     const size_t n = (size_t)1 << log_n;
     Fr *v[3] = {a, b, c};
+    // ifft then coset_fft of each evaluation vector WITHOUT the two permutation passes and the two scaling passes in
+    // between: the DIF transform leaves the coefficients bit-reversed, the DIT transform takes them that way, and
+    // its first pass applies n^-1 * 7^i to coefficient i on the way in (values identical to the four separate maps)
+    BZK_TRY(ensure_tables(ctx, log_n));
+    BZK_TRY(ensure_gpow(ctx));
+    const NttTables &tb = ctx->ntt[log_n];
+    uint32_t e[1] = {log_n};
+    const Fr ninv = Fr::from_u32(2).inv().pow(e, 1);
     for (int k = 0; k < 3; k++) {
-        BZK_TRY(ntt_launch(ctx, v[k], log_n, BZK_NTT_IFFT));
-        BZK_TRY(ntt_launch(ctx, v[k], log_n, BZK_NTT_COSET_FFT));
+        BZK_TRY(run_dif(ctx, v[k], log_n, tb.d_inv));
+        BZK_TRY(run_dit_prescaled(ctx, v[k], log_n, tb.d_fwd, ninv, ctx->d_gpow, ctx->d_gpow + kGpowN));
     }
     k_h_pointwise<<<div_up(n, 256), 256, 0, ctx->stream>>>(a, b, c, n, host_zinv(log_n));
     BZK_LAUNCHED(ctx);
