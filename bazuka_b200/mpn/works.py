@@ -81,6 +81,23 @@ def transitions_to_wire(kind, trans, payments=None):
     return out
 
 
+def _root_from_proof(index, leaf, proof):
+    """`calc_root_poseidon4` outside the circuit (/root/reference/src/zk/groth16/gadgets/merkle/mod.rs:53-65)"""
+    cur = leaf
+    for sib in proof:
+        vals = list(sib)
+        vals.insert(index & 3, cur)
+        cur = N.poseidon(vals)
+        index >>= 2
+    return cur
+
+
+def _entering_root(acc, balances_hash, index, proof):
+    """the state root a transition was built against — the builders' `pre_root` bookkeeping (the GPU witness path feeds it
+    to every slot), which does not travel: recomputed from the transition's own account, proof and index"""
+    return _root_from_proof(index, N.poseidon([acc.tx_nonce, acc.withdraw_nonce, acc.address[0], acc.address[1], balances_hash]), proof)
+
+
 def wire_to_transitions(kind, items):
     """wire dicts -> the builder dataclasses the circuits are synthesised from"""
     out = []
@@ -94,11 +111,15 @@ def wire_to_transitions(kind, items):
                 _money_b(t["src_before_fee_balance"]), t["src_proof"], t["src_index"], t["src_token_index"], t["src_balance_proof"],
                 t["src_fee_token_index"], t["src_fee_balance_proof"], _account_b(t["dst_before"]), t["dst_before_balances_hash"],
                 _money_b(t["dst_before_balance"]), t["dst_proof"], t["dst_index"], t["dst_token_index"], t["dst_balance_proof"]))
+            if t["enabled"]:
+                out[-1].pre_root = _entering_root(out[-1].src_before, t["src_before_balances_hash"], t["src_index"], t["src_proof"])
         elif kind == "deposit":
             p = t["tx"]["payment"]
             tx = D.MpnDeposit(tuple(t["tx"]["mpn_address"]), Wr.contract_id_scalar(p["amount"]["token_id"]), p["amount"]["amount"])
             out.append(D.DepositTransition(t["enabled"], tx, _account_b(t["before"]), t["before_balances_hash"], _money_b(t["before_balance"]),
                                            t["proof"], t["account_index"], t["token_index"], t["balance_proof"]))
+            if t["enabled"]:
+                out[-1].pre_root = _entering_root(out[-1].before, t["before_balances_hash"], t["account_index"], t["proof"])
         else:
             x, p = t["tx"], t["tx"]["payment"]
             tx = D.MpnWithdraw(tuple(x["mpn_address"]), x["mpn_withdraw_nonce"], {"r": tuple(x["mpn_sig"]["r"]), "s": x["mpn_sig"]["s"]},
@@ -106,6 +127,8 @@ def wire_to_transitions(kind, items):
             out.append(D.WithdrawTransition(t["enabled"], tx, _account_b(t["before"]), _money_b(t["before_token_balance"]),
                                             _money_b(t["before_fee_balance"]), t["proof"], t["account_index"], t["token_index"],
                                             t["token_balance_proof"], t["before_token_hash"], t["fee_token_index"], t["fee_balance_proof"]))
+            if t["enabled"]:
+                out[-1].pre_root = _entering_root(out[-1].before, t["before_token_hash"], t["account_index"], t["proof"])
     return out
 
 

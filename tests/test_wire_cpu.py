@@ -135,3 +135,17 @@ def test_several_batches_of_one_kind_continue_each_other():
     seq = make_state(3, 3, 3)[0]
     U.update(seq, updates, 2)
     assert fork.root == seq.root and fork.state_size == seq.state_size
+
+
+def test_entering_roots_are_recovered_from_the_wire():
+    """the builders' `pre_root` bookkeeping (what the GPU witness path feeds each slot) does not travel in an `MpnWork`; it
+    is recomputed from each transition's own account, Merkle proof and index — equal to the builders' values."""
+    st, keys, deposits, withdraws, wpay, updates = _scenario()
+    works, _ = Wk.prepare_works(_config(), st, deposits, withdraws, updates, {"deposit": 1, "withdraw": 2, "update": 3}, withdraw_payments=wpay)
+    f = st.fork()
+    _, dep = D.deposit(f, deposits, 1)
+    _, wd = D.withdraw(f, withdraws, 1)
+    _, up, _ = U.update(f, updates, 1)
+    for i, (kind, want) in enumerate((("deposit", dep), ("withdraw", wd), ("update", up))):
+        got = Wk.wire_to_transitions(kind, works[i]["data"][1])
+        assert [t.pre_root for t in got] == [t.pre_root for t in want] and all(t.pre_root for t in got)
