@@ -177,6 +177,40 @@ def prepare_works(config, state, deposits, withdraws, updates, rewards, height=0
     return dict(enumerate(works)), fork
 
 
+def final_delta(before, after):
+    """`MpnWorkPool.final_delta` (/root/reference/src/mpn/mod.rs:17-45,416-417): the scalar leaves the block's batches changed,
+    as `ZkDeltaPairs` = {locator: Some(value) | None}; a locator is [account, field] for the four account scalars and
+    [account, 4, token slot, 0 | 1] for a token's id / balance (`set_mpn_account`, src/zk/state/mod.rs:140-208); a leaf that
+    became zero is a `Remove` (None).  `before` / `after`: the ledger and the fork `prepare_works` returned."""
+    def leaves(acc):
+        out = {}
+        if acc is None:
+            return out
+        for f, v in enumerate((acc.tx_nonce, acc.withdraw_nonce, acc.address[0], acc.address[1])):
+            out[(f,)] = v
+        for slot, m in acc.tokens.items():
+            out[(4, slot, 0)] = m.token_id
+            out[(4, slot, 1)] = m.amount
+        return out
+
+    delta = {}
+    for idx in sorted(set(before.accounts) | set(after.accounts)):
+        old, new = leaves(before.accounts.get(idx)), leaves(after.accounts.get(idx))
+        for loc in sorted(set(old) | set(new)):
+            o, n = old.get(loc, 0), new.get(loc, 0)
+            if o != n:
+                delta[(idx,) + loc] = n if n != 0 else None
+    return delta
+
+
+def enc_delta(w, delta):
+    """bincode of `ZkDeltaPairs(HashMap<ZkDataLocator(Vec<u64>), Option<ZkScalar>>)`"""
+    w.u64(len(delta))
+    for loc, v in delta.items():
+        w.vec(list(loc), lambda w_, x: w_.u64(x))
+        w.option(v, lambda w_, x: w_.fr(x))
+
+
 def work_public_inputs(work, prover_address):
     """the five Groth16 inputs of `check_proof` for this work and prover (/root/reference/src/mpn/mod.rs:281-295)"""
     p = work["public_inputs"]

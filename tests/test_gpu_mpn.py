@@ -539,3 +539,20 @@ def test_worker_protocol_end_to_end_against_an_in_process_node(ctx, cref):
     assert not Wk.verify_work(dict(works[2], reward=34), me, np.frombuffer(p, dtype=np.uint8))
     for w in (wu, wd, ww):
         w.free()
+
+
+def test_prepare_works_with_the_batched_gpu_builders_equals_the_sequential_ones(ctx):
+    """`prepare_works` over batch_update.{deposit,withdraw,update}_batched (all hashing in batched GPU launches) produces the
+    same works, byte for byte, and the same final ledger as over the sequential builders."""
+    from bazuka_b200.mpn import batch_update as BU, wire as Wr, works as Wk
+    from test_wire_cpu import _scenario, _config
+    st, keys, deposits, withdraws, wpay, updates = _scenario()
+    h = BU.GpuTreeHasher(ctx)
+    rewards = {"deposit": 11, "withdraw": 22, "update": 33}
+    seq, fork_s = Wk.prepare_works(_config(), st, deposits, withdraws, updates, rewards, height=9, withdraw_payments=wpay)
+    gpu, fork_g = Wk.prepare_works(_config(), st, deposits, withdraws, updates, rewards, height=9, withdraw_payments=wpay,
+                                   builders=(lambda s, d, b: BU.deposit_batched(h, s, d, b), lambda s, w, b: BU.withdraw_batched(h, s, w, b),
+                                             lambda s, u, b: BU.update_batched(h, s, u, b)))
+    assert [Wr.work_to_bytes(gpu[i]) for i in range(3)] == [Wr.work_to_bytes(seq[i]) for i in range(3)]
+    assert fork_g.compressed == fork_s.compressed and fork_g.new_account_indices == fork_s.new_account_indices
+    assert Wk.final_delta(st, fork_g) == Wk.final_delta(st, fork_s)

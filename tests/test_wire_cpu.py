@@ -149,3 +149,35 @@ def test_entering_roots_are_recovered_from_the_wire():
     for i, (kind, want) in enumerate((("deposit", dep), ("withdraw", wd), ("update", up))):
         got = Wk.wire_to_transitions(kind, works[i]["data"][1])
         assert [t.pre_root for t in got] == [t.pre_root for t in want] and all(t.pre_root for t in got)
+
+
+def test_final_delta_lists_the_changed_leaves():
+    """mod.rs:17-45,416-417: what `prepare_works` hands the chain besides the works — every scalar leaf the batches changed."""
+    st, keys, deposits, withdraws, wpay, updates = _scenario()
+    _, fork = Wk.prepare_works(_config(), st, deposits, withdraws, updates, {"deposit": 1, "withdraw": 2, "update": 3}, withdraw_payments=wpay)
+    d = Wk.final_delta(st, fork)
+    # replaying the delta on the old leaves gives the new ledger's leaves
+    old = _leaves(st)
+    for loc, v in d.items():
+        if v is None:
+            old.pop(loc, None)
+        else:
+            old[loc] = v
+    assert {k: v for k, v in old.items() if v != 0} == {k: v for k, v in _leaves(fork).items() if v != 0}
+    assert fork.state_size == sum(1 for v in old.values() if v != 0)
+    assert (3, 2) in d and (3, 4, 0, 1) in d          # the depositor's new account: its key and its balance
+    assert all(len(loc) in (2, 4) for loc in d)
+    w = Wr.Writer()
+    Wk.enc_delta(w, d)
+    assert struct.unpack("<Q", bytes(w.b[:8]))[0] == len(d)
+
+
+def _leaves(state):
+    out = {}
+    for idx, acc in state.accounts.items():
+        for f, v in enumerate((acc.tx_nonce, acc.withdraw_nonce, acc.address[0], acc.address[1])):
+            out[(idx, f)] = v
+        for slot, m in acc.tokens.items():
+            out[(idx, 4, slot, 0)] = m.token_id
+            out[(idx, 4, slot, 1)] = m.amount
+    return out
