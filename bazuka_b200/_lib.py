@@ -96,6 +96,9 @@ SIGNATURES = {
     "bzk_jubjub_decompress": (_i32, [_vp, _vp, _i32, _vp]),
     "bzk_mpn_update_raw_width": (_i32, [_u32, _u32, _vp]),
     "bzk_mpn_update_build": (_i32, [_vp, _vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bzk_mpn_deposit_build": (_i32, [_vp, _vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bzk_mpn_withdraw_build": (_i32, [_vp, _vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bzk_mpn_dw_witness": (_i32, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     "bzk_mpn_update_circuit_compile": (_i32, [_u32, _u32, _u32, _vp, _sz, _vp, ct.POINTER(_vp)]),
     "bzk_mpn_dw_circuit_compile": (_i32, [_u32, _u32, _u32, _u32, _vp, _sz, _vp, ct.POINTER(_vp)]),
     "bzk_mpn_circuit_two_phase_info": (_i32, [_vp, _vp, _vp, _vp]),

@@ -247,6 +247,56 @@ struct Forest {
     }
 };
 
+
+// ---- JubJub on the host field arithmetic (projective twisted Edwards, a = -1): /root/reference/src/crypto/jubjub/curve.rs:90-160
+struct JJ { Fr x, y, z; };
+inline JJ jj_identity() { return JJ{Fr::zero(), Fr::one(), Fr::one()}; }
+inline JJ jj_add(const JJ &p, const JJ &q, const Fr &d) {   // unified addition (also doubles)
+    const Fr a = p.z * q.z, b = a * a, c = p.x * q.x, dd = p.y * q.y, e = d * c * dd, f = b - e, g = b + e;
+    return JJ{a * f * ((p.x + p.y) * (q.x + q.y) - c - dd), a * g * (dd + c), f * g};
+}
+inline JJ jj_mul(const Point &p, const Fr &k_canon, const Fr &d) {
+    const JJ base{p.x, p.y, Fr::one()};
+    JJ acc = jj_identity();
+    for (int i = 255; i >= 0; i--) {
+        acc = jj_add(acc, acc, d);
+        if ((k_canon.l[i >> 5] >> (i & 31)) & 1) acc = jj_add(acc, base, d);
+    }
+    return acc;
+}
+inline bool jj_equal(const JJ &p, const JJ &q) { return p.x * q.z == q.x * p.z && p.y * q.z == q.y * p.z; }
+inline Point jj_base() {   // BASE (curve.rs:146-164): x below, y = 18
+    Fr x;
+    const uint32_t l[8] = {0xec7beacau, 0x4df7b7ffu, 0xfd6c54edu, 0x2e3ebb21u, 0x0fd6cce6u, 0xf1fbf02du, 0x43ac65a6u, 0x3fd2814cu};
+    memcpy(x.l, l, 32);
+    return Point{x.to_mont(), Fr::from_u32(18)};
+}
+// `JubJub::verify` (/root/reference/src/crypto/jubjub/mod.rs:151-167) given h = Poseidon(R.x, R.y, A.x, A.y, msg) (Montgomery)
+inline bool eddsa_verify_with_h(const bzk_mpn_state *s, const Point &pk, const Point &sig_r, const Fr &sig_s_canon, const Fr &h_mont) {
+    if (!s->on_curve(pk.x, pk.y) || !s->on_curve(sig_r.x, sig_r.y)) return false;
+    const JJ lhs = jj_add(jj_mul(pk, h_mont.from_mont(), s->jj_d), JJ{sig_r.x, sig_r.y, Fr::one()}, s->jj_d);
+    return jj_equal(lhs, jj_mul(jj_base(), sig_s_canon, s->jj_d));
+}
+
+// root of `List<log4 B>(Struct[...])` over the batch's rows (deposit.rs:178-218, withdraw.rs:190-245): one hash per row,
+// then the 4-ary tree — every level one batched launch
+int32_t list_root(bzk_ctx *ctx, uint32_t arity, const std::vector<Fr> &rows, Fr *out) {
+    std::vector<Fr> cur;
+    BZK_TRY(hash_rows(ctx, arity, rows, cur));
+    while (cur.size() > 1) {
+        std::vector<Fr> nxt;
+        BZK_TRY(hash_rows(ctx, 4, cur, nxt));
+        cur.swap(nxt);
+    }
+    *out = cur[0];
+    return BZK_OK;
+}
+
+// shared tail of the deposit / withdraw builders: commit the mirror, public inputs
+struct DwCommon {
+    std::map<uint64_t, Account> mirror;
+    std::map<std::pair<FrKey, FrKey>, uint64_t> pending;
+};
 }  // namespace
 
 extern "C" {
@@ -575,6 +625,355 @@ int32_t bzk_mpn_update_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_tx *t
     return BZK_OK;
 }
 
+
+/* `mpn::deposit::deposit` (/root/reference/src/mpn/deposit.rs:11-233) without the L1 balance bookkeeping (chain state):
+ * up to 4^log4_batch eligible deposits, in order.  Outputs, one row per slot (null slots padded as DepositTransition::null):
+ *   raws1[slots][5]           phase-1 inputs  {enabled, token, amount, pk.x, pk.y}
+ *   raws2[slots][9+3T+3A]     phase-2 inputs  {account index, token index, account before (4), balances hash, balance before (2),
+ *                             balance proof, account proof}
+ *   roots[slots]              the state root entering each slot
+ *   reveal[slots][4]          the rows the circuit reveals {enabled, token, amount, H(pk)}; aux_data = their list root
+ *   public3                   {state, aux_data, next_state};   the ledger advances (build on a clone, see bzk_mpn_state_clone) */
+int32_t bzk_mpn_deposit_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_deposit *deps, uint64_t n_deps, uint32_t log4_batch, bzk_fr *raws1,
+                              bzk_fr *raws2, bzk_fr *roots, bzk_fr *reveal, uint8_t *accepted, bzk_fr public3[3], uint64_t *n_accepted) {
+    if (!ctx || !s || (n_deps && !deps) || !raws1 || !raws2 || !roots || !reveal || !public3 || !n_accepted || log4_batch > 8) return BZK_ERR_BAD_ARG;
+    BZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t A = s->A, T = s->T, w2 = 9 + 3 * T + 3 * A;
+    const uint64_t cap = 1ull << (2 * log4_batch);
+    const Fr prev_root = s->node(A, 0);
+    struct Plan { uint64_t k, idx; uint32_t ti; Account before, after; Money bal; Point addr; size_t e; Fr bal_hash; };
+    std::map<uint64_t, Account> mirror;
+    auto pending = s->pending;
+    auto get = [&](uint64_t i) -> Account {
+        auto it = mirror.find(i);
+        if (it != mirror.end()) return it->second;
+        auto jt = s->accounts.find(i);
+        return jt == s->accounts.end() ? Account() : jt->second;
+    };
+    std::vector<Plan> plan;
+    for (uint64_t k = 0; k < n_deps; k++) {
+        if (accepted) accepted[k] = 0;
+        if (plan.size() == cap) continue;
+        const bzk_mpn_deposit &d = deps[k];
+        if (!canonical(d.pk_x) || !canonical(d.token_id)) continue;
+        Point addr;
+        if (!jj_decompress(s, &d.pk_x, d.pk_odd != 0, &addr)) continue;
+        const auto key = std::make_pair(key_of(addr.x), key_of(addr.y));
+        uint64_t idx = 0;
+        bool is_new = false;
+        auto it = s->by_addr.find(key);
+        if (it != s->by_addr.end()) idx = it->second;
+        else {
+            auto jt = pending.find(key);
+            if (jt != pending.end()) idx = jt->second;
+            else { idx = s->account_count + pending.size(); is_new = true; }
+        }
+        if (idx >> (2 * A)) continue;
+        const Account before = get(idx);
+        const Fr tok = fr_from_canon(&d.token_id);
+        const int ti = find_token_index(before, T, tok, true);
+        if (ti < 0 || (s->on_curve(before.ax, before.ay) && (!(before.ax == addr.x) || !(before.ay == addr.y)))) continue;
+        Plan p{};
+        p.k = k; p.idx = idx; p.ti = (uint32_t)ti; p.before = before; p.addr = addr;
+        p.bal = before.tokens.count(ti) ? before.tokens.at(ti) : Money{Fr::zero(), 0};
+        p.after = before;
+        p.after.ax = addr.x; p.after.ay = addr.y;
+        if (!p.after.tokens.count(ti)) p.after.tokens[ti] = Money{tok, 0};
+        p.after.tokens[ti].amount += d.amount;
+        mirror[idx] = p.after;
+        if (is_new) pending.emplace(key, idx);
+        plan.push_back(std::move(p));
+        if (accepted) accepted[k] = 1;
+    }
+    Forest forest;
+    forest.T = T;
+    std::vector<uint64_t> touched;
+    for (auto &p : plan)
+        if (forest.tree_of.emplace(p.idx, (uint32_t)forest.tree_of.size()).second) touched.push_back(p.idx);
+    for (uint64_t acc : touched) {
+        auto it = s->accounts.find(acc);
+        if (it != s->accounts.end())
+            for (auto &kv : it->second.tokens) forest.write(acc, kv.first, kv.second);
+    }
+    forest.n_init = forest.idx.size();
+    for (auto &p : plan) p.e = forest.write(p.idx, p.ti, p.after.tokens[p.ti]);
+    BZK_TRY(forest.run(ctx, s->tdefaults));
+    std::vector<Fr> acct_rows, pk_rows;
+    for (auto &p : plan) {
+        p.bal_hash = forest.root(p.idx);
+        const Fr r = forest.applied(p.idx, p.e);
+        const Account &a = p.after;
+        acct_rows.push_back(fr_from_u64(a.tx_nonce)); acct_rows.push_back(fr_from_u64(a.withdraw_nonce));
+        acct_rows.push_back(a.ax); acct_rows.push_back(a.ay); acct_rows.push_back(r);
+        pk_rows.push_back(p.addr.x); pk_rows.push_back(p.addr.y);
+    }
+    std::vector<Fr> s_vals, s_proofs, pk_hash;
+    BZK_TRY(hash_rows(ctx, 5, acct_rows, s_vals));
+    BZK_TRY(hash_rows(ctx, 2, pk_rows, pk_hash));
+    std::vector<uint64_t> s_idx;
+    for (auto &p : plan) s_idx.push_back(p.idx);
+    const size_t ne = s_idx.size();
+    std::vector<Fr> init(ne * A * 3);
+    for (size_t e = 0; e < ne; e++) s->prove(s_idx[e], init.data() + e * A * 3);
+    BZK_TRY(tree_update_host(ctx, A, std::vector<uint32_t>(ne, 0u), s_idx, s_vals, init, s_proofs));
+    const Fr minus_one = Fr::one().neg();
+    Fr root = prev_root;
+    std::vector<Fr> rev_rows(cap * 4, Fr::zero());
+    for (uint64_t slot = 0; slot < cap; slot++) {
+        bzk_fr *r1 = raws1 + slot * 5, *r2 = raws2 + slot * w2, *rv = reveal + slot * 4;
+        memset(r1, 0, 5 * sizeof(bzk_fr)); memset(r2, 0, (size_t)w2 * sizeof(bzk_fr)); memset(rv, 0, 4 * sizeof(bzk_fr));
+        if (slot >= plan.size()) {
+            fr_to_canon(r1 + 4, minus_one);   // PublicKey::default().decompress() = (0, -1)
+            continue;
+        }
+        const Plan &p = plan[slot];
+        const bzk_mpn_deposit &d = deps[p.k];
+        fr_to_canon(roots + slot, root);
+        uint64_t one = 1;
+        memcpy(r1 + 0, &one, 8); r1[1] = d.token_id; memcpy(r1 + 2, &d.amount, 8); fr_to_canon(r1 + 3, p.addr.x); fr_to_canon(r1 + 4, p.addr.y);
+        size_t w = 0;
+        auto put_fr = [&](const Fr &v) { fr_to_canon(r2 + (w++), v); };
+        auto put_u = [&](uint64_t v) { memcpy(r2 + (w++), &v, 8); };
+        put_u(p.idx); put_u(p.ti); put_u(p.before.tx_nonce); put_u(p.before.withdraw_nonce); put_fr(p.before.ax); put_fr(p.before.ay);
+        put_fr(p.bal_hash); put_fr(p.bal.token_id); put_u(p.bal.amount);
+        for (uint32_t i = 0; i < T * 3; i++) put_fr(forest.proofs[p.e * T * 3 + i]);
+        for (uint32_t i = 0; i < A * 3; i++) put_fr(s_proofs[slot * A * 3 + i]);
+        if (w != w2) return BZK_ERR_BAD_ARG;
+        memcpy(rv + 0, &one, 8); rv[1] = d.token_id; memcpy(rv + 2, &d.amount, 8); fr_to_canon(rv + 3, pk_hash[slot]);
+        rev_rows[slot * 4 + 0] = Fr::one(); rev_rows[slot * 4 + 1] = fr_from_canon(&d.token_id); rev_rows[slot * 4 + 2] = fr_from_u64(d.amount);
+        rev_rows[slot * 4 + 3] = pk_hash[slot];
+        root = s_vals[(size_t)A * ne + slot];
+    }
+    for (uint64_t slot = plan.size(); slot < cap; slot++) fr_to_canon(roots + slot, root);
+    for (size_t e = 0; e < ne; e++) {
+        uint64_t node = s_idx[e];
+        for (uint32_t l = 0; l <= A; l++) { s->put(l, node, s_vals[(size_t)l * ne + e]); node >>= 2; }
+    }
+    for (uint64_t i : touched) {
+        auto it = s->accounts.find(i);
+        if (it != s->accounts.end()) s->state_size -= leaf_count(it->second);
+        s->state_size += leaf_count(mirror[i]);
+        s->accounts[i] = mirror[i];
+    }
+    s->pending = pending;
+    Fr aux;
+    BZK_TRY(list_root(ctx, 4, rev_rows, &aux));
+    fr_to_canon(public3 + 0, prev_root);
+    fr_to_canon(public3 + 1, aux);
+    fr_to_canon(public3 + 2, root);
+    *n_accepted = plan.size();
+    return BZK_OK;
+}
+
+/* `mpn::withdraw::withdraw` (/root/reference/src/mpn/withdraw.rs:10-259): nonce, balances and the EdDSA signature over
+ * Poseidon(fingerprint, nonce) are checked here (the hashes of a batch in two launches, the scalar multiplications on the
+ * host).  Rows: raws1[slots][12] {enabled, token, amount, fee token, fee, fingerprint, pk.x, pk.y, nonce, sig.r.x, sig.r.y, sig.s},
+ * raws2[slots][12+6T+3A] {account index, token index, fee token index, account before (4), token-tree hash, balance before (2),
+ * its proof, fee balance before (2), its proof, account proof}, reveal[slots][7] {enabled, token, amount, fee token, fee,
+ * fingerprint, calldata}. */
+int32_t bzk_mpn_withdraw_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_withdraw *wds, uint64_t n_wds, uint32_t log4_batch, bzk_fr *raws1,
+                               bzk_fr *raws2, bzk_fr *roots, bzk_fr *reveal, uint8_t *accepted, bzk_fr public3[3], uint64_t *n_accepted) {
+    if (!ctx || !s || (n_wds && !wds) || !raws1 || !raws2 || !roots || !reveal || !public3 || !n_accepted || log4_batch > 8) return BZK_ERR_BAD_ARG;
+    BZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t A = s->A, T = s->T, w2 = 12 + 6 * T + 3 * A;
+    const uint64_t cap = 1ull << (2 * log4_batch);
+    const Fr prev_root = s->node(A, 0);
+    // signature material of every candidate in two batched launches: msg = H(fingerprint, nonce), h = H(R.x, R.y, A.x, A.y, msg)
+    std::vector<Point> addr(n_wds);
+    std::vector<uint8_t> ok(n_wds, 0);
+    std::vector<Fr> msg_rows, h_rows, msgs, hs;
+    for (uint64_t k = 0; k < n_wds; k++) {
+        const bzk_mpn_withdraw &w = wds[k];
+        ok[k] = canonical(w.pk_x) && canonical(w.amount_token_id) && canonical(w.fee_token_id) && canonical(w.fingerprint) && canonical(w.sig_rx) &&
+                canonical(w.sig_ry) && canonical(w.sig_s) && jj_decompress(s, &w.pk_x, w.pk_odd != 0, &addr[k]);
+        msg_rows.push_back(ok[k] ? fr_from_canon(&w.fingerprint) : Fr::zero());
+        msg_rows.push_back(fr_from_u64(w.nonce));
+    }
+    BZK_TRY(hash_rows(ctx, 2, msg_rows, msgs));
+    for (uint64_t k = 0; k < n_wds; k++) {
+        const bzk_mpn_withdraw &w = wds[k];
+        h_rows.push_back(ok[k] ? fr_from_canon(&w.sig_rx) : Fr::zero()); h_rows.push_back(ok[k] ? fr_from_canon(&w.sig_ry) : Fr::zero());
+        h_rows.push_back(ok[k] ? addr[k].x : Fr::zero()); h_rows.push_back(ok[k] ? addr[k].y : Fr::zero()); h_rows.push_back(msgs[k]);
+    }
+    BZK_TRY(hash_rows(ctx, 5, h_rows, hs));
+    struct Plan { uint64_t k, idx; uint32_t ti, fi; Account before, mid, after; Money tok, fee_before; size_t e1, e2; Fr tok_hash; };
+    std::map<uint64_t, Account> mirror;
+    auto get = [&](uint64_t i) -> Account {
+        auto it = mirror.find(i);
+        if (it != mirror.end()) return it->second;
+        auto jt = s->accounts.find(i);
+        return jt == s->accounts.end() ? Account() : jt->second;
+    };
+    std::vector<Plan> plan;
+    for (uint64_t k = 0; k < n_wds; k++) {
+        if (accepted) accepted[k] = 0;
+        if (plan.size() == cap || !ok[k]) continue;
+        const bzk_mpn_withdraw &w = wds[k];
+        const auto key = std::make_pair(key_of(addr[k].x), key_of(addr[k].y));
+        uint64_t idx = 0;
+        auto it = s->by_addr.find(key);
+        if (it != s->by_addr.end()) idx = it->second;
+        else {
+            auto jt = s->pending.find(key);
+            if (jt == s->pending.end()) continue;
+            idx = jt->second;
+        }
+        const Account before = get(idx);
+        const Fr tok = fr_from_canon(&w.amount_token_id), ftok = fr_from_canon(&w.fee_token_id);
+        const int ti = find_token_index(before, T, tok, false), fi = find_token_index(before, T, ftok, false);
+        if (ti < 0 || fi < 0 || w.nonce != before.withdraw_nonce + 1) continue;
+        if (before.tokens.at(ti).amount < w.amount) continue;
+        Fr sig_s;
+        memcpy(sig_s.l, &w.sig_s, 32);
+        if (!eddsa_verify_with_h(s, addr[k], Point{fr_from_canon(&w.sig_rx), fr_from_canon(&w.sig_ry)}, sig_s, hs[k])) continue;
+        Plan p{};
+        p.k = k; p.idx = idx; p.ti = (uint32_t)ti; p.fi = (uint32_t)fi; p.before = before; p.tok = before.tokens.at(ti);
+        p.mid = before;
+        p.mid.tokens[ti].amount -= w.amount;
+        if (p.mid.tokens.at(fi).amount < w.fee) continue;
+        p.fee_before = p.mid.tokens.at(fi);
+        p.after = p.mid;
+        p.after.tokens[fi].amount -= w.fee;
+        p.after.withdraw_nonce += 1;
+        mirror[idx] = p.after;
+        plan.push_back(std::move(p));
+        if (accepted) accepted[k] = 1;
+    }
+    Forest forest;
+    forest.T = T;
+    std::vector<uint64_t> touched;
+    for (auto &p : plan)
+        if (forest.tree_of.emplace(p.idx, (uint32_t)forest.tree_of.size()).second) touched.push_back(p.idx);
+    for (uint64_t acc : touched) {
+        auto it = s->accounts.find(acc);
+        if (it != s->accounts.end())
+            for (auto &kv : it->second.tokens) forest.write(acc, kv.first, kv.second);
+    }
+    forest.n_init = forest.idx.size();
+    for (auto &p : plan) {
+        p.e1 = forest.write(p.idx, p.ti, p.mid.tokens[p.ti]);
+        p.e2 = forest.write(p.idx, p.fi, p.after.tokens[p.fi]);
+    }
+    BZK_TRY(forest.run(ctx, s->tdefaults));
+    std::vector<Fr> acct_rows, cd_rows;
+    auto push_acct = [&](const Account &a, const Fr &tok_root) {
+        acct_rows.push_back(fr_from_u64(a.tx_nonce)); acct_rows.push_back(fr_from_u64(a.withdraw_nonce));
+        acct_rows.push_back(a.ax); acct_rows.push_back(a.ay); acct_rows.push_back(tok_root);
+    };
+    for (auto &p : plan) {
+        p.tok_hash = forest.root(p.idx);
+        const Fr r1 = forest.applied(p.idx, p.e1), r2 = forest.applied(p.idx, p.e2);
+        push_acct(p.mid, r1); push_acct(p.after, r2);
+        const bzk_mpn_withdraw &w = wds[p.k];
+        cd_rows.push_back(addr[p.k].x); cd_rows.push_back(addr[p.k].y); cd_rows.push_back(fr_from_u64(w.nonce));
+        cd_rows.push_back(fr_from_canon(&w.sig_rx)); cd_rows.push_back(fr_from_canon(&w.sig_ry)); cd_rows.push_back(fr_from_canon(&w.sig_s));
+    }
+    std::vector<Fr> s_vals, s_proofs, cds;
+    BZK_TRY(hash_rows(ctx, 5, acct_rows, s_vals));
+    BZK_TRY(hash_rows(ctx, 6, cd_rows, cds));
+    std::vector<uint64_t> s_idx;
+    for (auto &p : plan) { s_idx.push_back(p.idx); s_idx.push_back(p.idx); }
+    const size_t ne = s_idx.size();
+    std::vector<Fr> init(ne * A * 3);
+    for (size_t e = 0; e < ne; e++) s->prove(s_idx[e], init.data() + e * A * 3);
+    BZK_TRY(tree_update_host(ctx, A, std::vector<uint32_t>(ne, 0u), s_idx, s_vals, init, s_proofs));
+    const Fr minus_one = Fr::one().neg();
+    Fr root = prev_root;
+    std::vector<Fr> rev_rows(cap * 7, Fr::zero());
+    for (uint64_t slot = 0; slot < cap; slot++) {
+        bzk_fr *r1 = raws1 + slot * 12, *r2 = raws2 + slot * w2, *rv = reveal + slot * 7;
+        memset(r1, 0, 12 * sizeof(bzk_fr)); memset(r2, 0, (size_t)w2 * sizeof(bzk_fr)); memset(rv, 0, 7 * sizeof(bzk_fr));
+        if (slot >= plan.size()) {
+            fr_to_canon(r1 + 7, minus_one);
+            continue;
+        }
+        const Plan &p = plan[slot];
+        const bzk_mpn_withdraw &w = wds[p.k];
+        fr_to_canon(roots + slot, root);
+        const uint64_t one = 1, nonce = w.nonce;
+        memcpy(r1 + 0, &one, 8); r1[1] = w.amount_token_id; memcpy(r1 + 2, &w.amount, 8); r1[3] = w.fee_token_id; memcpy(r1 + 4, &w.fee, 8);
+        r1[5] = w.fingerprint; fr_to_canon(r1 + 6, addr[p.k].x); fr_to_canon(r1 + 7, addr[p.k].y); memcpy(r1 + 8, &nonce, 8);
+        r1[9] = w.sig_rx; r1[10] = w.sig_ry; r1[11] = w.sig_s;
+        size_t q = 0;
+        auto put_fr = [&](const Fr &v) { fr_to_canon(r2 + (q++), v); };
+        auto put_u = [&](uint64_t v) { memcpy(r2 + (q++), &v, 8); };
+        put_u(p.idx); put_u(p.ti); put_u(p.fi); put_u(p.before.tx_nonce); put_u(p.before.withdraw_nonce); put_fr(p.before.ax); put_fr(p.before.ay);
+        put_fr(p.tok_hash); put_fr(p.tok.token_id); put_u(p.tok.amount);
+        for (uint32_t i = 0; i < T * 3; i++) put_fr(forest.proofs[p.e1 * T * 3 + i]);
+        put_fr(p.fee_before.token_id); put_u(p.fee_before.amount);
+        for (uint32_t i = 0; i < T * 3; i++) put_fr(forest.proofs[p.e2 * T * 3 + i]);
+        for (uint32_t i = 0; i < A * 3; i++) put_fr(s_proofs[(2 * slot) * A * 3 + i]);
+        if (q != w2) return BZK_ERR_BAD_ARG;
+        memcpy(rv + 0, &one, 8); rv[1] = w.amount_token_id; memcpy(rv + 2, &w.amount, 8); rv[3] = w.fee_token_id; memcpy(rv + 4, &w.fee, 8);
+        rv[5] = w.fingerprint; fr_to_canon(rv + 6, cds[slot]);
+        Fr *rr = rev_rows.data() + slot * 7;
+        rr[0] = Fr::one(); rr[1] = fr_from_canon(&w.amount_token_id); rr[2] = fr_from_u64(w.amount); rr[3] = fr_from_canon(&w.fee_token_id);
+        rr[4] = fr_from_u64(w.fee); rr[5] = fr_from_canon(&w.fingerprint); rr[6] = cds[slot];
+        root = s_vals[(size_t)A * ne + 2 * slot + 1];
+    }
+    for (uint64_t slot = plan.size(); slot < cap; slot++) fr_to_canon(roots + slot, root);
+    for (size_t e = 0; e < ne; e++) {
+        uint64_t node = s_idx[e];
+        for (uint32_t l = 0; l <= A; l++) { s->put(l, node, s_vals[(size_t)l * ne + e]); node >>= 2; }
+    }
+    for (uint64_t i : touched) {
+        auto it = s->accounts.find(i);
+        if (it != s->accounts.end()) s->state_size -= leaf_count(it->second);
+        s->state_size += leaf_count(mirror[i]);
+        s->accounts[i] = mirror[i];
+    }
+    Fr aux;
+    BZK_TRY(list_root(ctx, 7, rev_rows, &aux));
+    fr_to_canon(public3 + 0, prev_root);
+    fr_to_canon(public3 + 1, aux);
+    fr_to_canon(public3 + 2, root);
+    *n_accepted = plan.size();
+    return BZK_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// witness of a whole deposit / withdraw batch from the builder's rows: what `{Deposit,Withdraw}Circuit::synthesize`
+// assigns (/root/reference/src/mpn/circuits/deposit_circuit.rs:47-293, withdraw_circuit.rs:49-413), laid out as
+//   inputs = [1, commitment, height, state, aux_data, next_state]
+//   aux    = [the five public values] ++ phase-1 program x n_slots ++ reveal program ++ phase-2 program x n_slots
+// phase 2's externals per slot: ext_src[e] < 0 -> the state root entering the slot, else phase-1 raw ext_src[e] of the slot
+// (bzk_mpn_circuit_two_phase_info); the reveal program's externals are the builder's reveal rows, slot-major.
+// ---------------------------------------------------------------------------------------------
+extern "C" int32_t bzk_mpn_dw_witness(bzk_ctx *ctx, const bzk_witness_program *phase1, const bzk_witness_program *phase2,
+                                      const bzk_witness_program *reveal_prog, uint64_t n_slots, const bzk_fr *raws1, const bzk_fr *raws2,
+                                      const bzk_fr *roots, const int32_t *ext_src, uint32_t n_ext_src, const bzk_fr *reveal_rows,
+                                      const bzk_fr public5[5], void *d_inputs, void *d_aux) {
+    if (!ctx || !phase1 || !phase2 || !reveal_prog || !n_slots || !raws1 || !raws2 || !roots || (n_ext_src && !ext_src) || !reveal_rows || !public5 ||
+        !d_inputs || !d_aux)
+        return BZK_ERR_BAD_ARG;
+    uint64_t n1 = 0, n2 = 0, nr = 0;
+    uint32_t raw1 = 0, ext1 = 0, raw2 = 0, ext2 = 0, rawr = 0, extr = 0;
+    witness_program_shape(phase1, &n1, &raw1, &ext1);
+    witness_program_shape(phase2, &n2, &raw2, &ext2);
+    witness_program_shape(reveal_prog, &nr, &rawr, &extr);
+    if (ext1 != 0 || ext2 != n_ext_src || extr % n_slots != 0) return BZK_ERR_BAD_ARG;
+    for (uint32_t e = 0; e < n_ext_src; e++)
+        if (ext_src[e] >= (int32_t)raw1) return BZK_ERR_BAD_ARG;
+    BZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    Fr head[11];
+    head[0] = Fr::one();
+    for (int k = 0; k < 5; k++) { head[1 + k] = fr_from_canon(public5 + k); head[6 + k] = head[1 + k]; }
+    Fr *z_in = (Fr *)d_inputs, *z_aux = (Fr *)d_aux;
+    BZK_CUDA(ctx, cudaMemcpyAsync(z_in, head, 6 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    BZK_CUDA(ctx, cudaMemcpyAsync(z_aux, head + 6, 5 * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    BZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `head` is a stack buffer
+    BZK_TRY(bzk_witness_run_dev(ctx, phase1, raws1, nullptr, n_slots, z_aux + 5));
+    BZK_TRY(bzk_witness_run_dev(ctx, reveal_prog, nullptr, reveal_rows, 1, z_aux + 5 + n_slots * n1));
+    std::vector<bzk_fr> ext((size_t)n_slots * n_ext_src);
+    for (uint64_t k = 0; k < n_slots; k++)
+        for (uint32_t e = 0; e < n_ext_src; e++) ext[k * n_ext_src + e] = ext_src[e] < 0 ? roots[k] : raws1[k * raw1 + ext_src[e]];
+    BZK_TRY(bzk_witness_run_dev(ctx, phase2, raws2, ext.data(), n_slots, z_aux + 5 + n_slots * n1 + nr));
+    return BZK_OK;
+}
+
+extern "C" {
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------

@@ -302,9 +302,9 @@ def verify_bytes(vk_blob, public_inputs, proof387):
     """`check_proof` on the reference's byte images."""
     from . import _lib
     lib = _lib.load()
-    vk_blob = np.ascontiguousarray(vk_blob, dtype=np.uint8)
+    as_u8 = lambda b: np.frombuffer(bytes(b), dtype=np.uint8) if isinstance(b, (bytes, bytearray, memoryview)) else np.ascontiguousarray(b, dtype=np.uint8)
+    vk_blob, proof387 = as_u8(vk_blob), as_u8(proof387)
     pub = np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(-1, 4)
-    proof387 = np.ascontiguousarray(proof387, dtype=np.uint8)
     st = lib.bzk_groth16_verify_bytes(_host_ptr(vk_blob), vk_blob.size, _host_ptr(pub), len(pub), _host_ptr(proof387))
     if st < 0:
         raise _lib.BzkError(st, "groth16_verify_bytes")

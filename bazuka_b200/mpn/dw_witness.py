@@ -204,3 +204,38 @@ def compile_reveal_program(progs: TwoPhasePrograms, B):
     start = len(cs.aux)
     D.reveal_list_of_structs(cs, B, rows)
     return W.compile_block(cs.recipes[start:], start, ext)
+
+
+class NativeTwoPhaseWitness:
+    """the witness of a deposit / withdraw batch with no Python between the native builder's rows
+    (ledger.NativeLedger.{deposit,withdraw}_build) and z: the three programs of the native compiler
+    (native_circuit.NativeTwoPhaseCircuit: phase 1, phase 2, reveal) through bzk_mpn_dw_witness."""
+
+    def __init__(self, ctx, circuit):
+        from .gpu_witness import upload_program
+        self.ctx, self.circuit = ctx, circuit
+        self.progs = [circuit.program(k) for k in range(3)]
+        self._h = [upload_program(ctx, p) for p in self.progs]
+        self.ext_src = np.array([-1 if s[0] == "state" else s[1] for s in circuit.ext_src], dtype=np.int32)
+
+    def free(self):
+        for h in self._h:
+            self.ctx._l.bzk_witness_program_free(self.ctx._h, h)
+        self._h = []
+
+    def witness(self, rows, commitment, height):
+        """rows = the builder's dict -> (d_inputs [6,4], d_aux [na,4]) int64 CUDA tensors (Montgomery)"""
+        import torch
+        from ..api import _dev_ptr, _host_ptr
+        ctx, c = self.ctx, self.circuit
+        n = 1 << (2 * c.B)
+        pub = rows["public"]
+        head = _canon_rows([commitment, height, pub["state"], pub["aux_data"], pub["next_state"]])
+        dev = torch.device("cuda", ctx.device)
+        d_in = torch.empty((6, 4), dtype=torch.int64, device=dev)
+        d_aux = torch.empty((c.num_aux, 4), dtype=torch.int64, device=dev)
+        assert c.num_aux == 5 + n * (c.n1 + c.n2) + c.reveal_vars
+        ctx._check(ctx._l.bzk_mpn_dw_witness(ctx._h, self._h[0], self._h[1], self._h[2], n, _host_ptr(rows["raws1"]), _host_ptr(rows["raws2"]),
+                                             _host_ptr(rows["roots"]), _host_ptr(self.ext_src), len(self.ext_src), _host_ptr(rows["reveal"]),
+                                             _host_ptr(head), _dev_ptr(d_in), _dev_ptr(d_aux)))
+        return d_in, d_aux

@@ -20,6 +20,13 @@ _TX = np.dtype([("nonce", "<u8"), ("amount", "<u8"), ("fee", "<u8"), ("src_pk_od
 assert _TX.itemsize == 32 + 7 * 32
 
 
+_DEP = np.dtype([("pk_x", "<u8", 4), ("pk_odd", "u1"), ("pad", "u1", 7), ("token_id", "<u8", 4), ("amount", "<u8")])
+_WD = np.dtype([("pk_x", "<u8", 4), ("pk_odd", "u1"), ("pad", "u1", 3), ("nonce", "<u4"), ("sig_rx", "<u8", 4), ("sig_ry", "<u8", 4),
+                ("sig_s", "<u8", 4), ("amount_token_id", "<u8", 4), ("fee_token_id", "<u8", 4), ("fingerprint", "<u8", 4), ("amount", "<u8"),
+                ("fee", "<u8")])
+assert _DEP.itemsize == 80 and _WD.itemsize == 7 * 32 + 24
+
+
 def _canon(v):
     return np.frombuffer((v % R).to_bytes(32, "little"), dtype=np.uint64)
 
@@ -38,6 +45,27 @@ def pack_txs(txs):
         o["src_pk_x"], o["dst_pk_x"] = _canon(tx.src_pub_key[0]), _canon(tx.dst_pub_key[0])
         o["amount_token_id"], o["fee_token_id"] = _canon(tx.amount.token_id), _canon(tx.fee.token_id)
         o["sig_rx"], o["sig_ry"], o["sig_s"] = _canon(tx.sig["r"][0]), _canon(tx.sig["r"][1]), _canon(tx.sig["s"])
+    return out
+
+
+def pack_deposits(deps):
+    """list of dw.MpnDeposit -> array of bzk_mpn_deposit"""
+    out = np.zeros(len(deps), dtype=_DEP)
+    for k, d in enumerate(deps):
+        o = out[k]
+        o["pk_x"], o["pk_odd"], o["token_id"], o["amount"] = _canon(d.mpn_address[0]), int(d.mpn_address[1]), _canon(d.token_id), d.amount
+    return out
+
+
+def pack_withdraws(ws):
+    """list of dw.MpnWithdraw -> array of bzk_mpn_withdraw"""
+    out = np.zeros(len(ws), dtype=_WD)
+    for k, w in enumerate(ws):
+        o = out[k]
+        o["pk_x"], o["pk_odd"], o["nonce"] = _canon(w.mpn_address[0]), int(w.mpn_address[1]), w.mpn_withdraw_nonce
+        o["sig_rx"], o["sig_ry"], o["sig_s"] = _canon(w.mpn_sig["r"][0]), _canon(w.mpn_sig["r"][1]), _canon(w.mpn_sig["s"])
+        o["amount_token_id"], o["fee_token_id"], o["fingerprint"] = _canon(w.amount.token_id), _canon(w.fee.token_id), _canon(w.fingerprint)
+        o["amount"], o["fee"] = w.amount.amount, w.fee.amount
     return out
 
 
@@ -111,3 +139,29 @@ class NativeLedger:
                                                          _host_ptr(raws), _host_ptr(ext), _host_ptr(acc), _host_ptr(pub), ct.byref(n_acc)))
         public = {"state": _int(pub[0]), "aux_data": _int(pub[1]), "next_state": _int(pub[2])}
         return raws, ext, acc[:len(packed)].astype(bool), public, n_acc.value
+
+    def _dw_build(self, kind, packed, log4_batch):
+        from ..api import _host_ptr
+        A, T = self.A, self.T
+        w1, w2, wr = (5, 9 + 3 * T + 3 * A, 4) if kind == "deposit" else (12, 12 + 6 * T + 3 * A, 7)
+        slots = 1 << (2 * log4_batch)
+        raws1, raws2 = np.zeros((slots, w1, 4), dtype=np.uint64), np.zeros((slots, w2, 4), dtype=np.uint64)
+        roots, reveal = np.zeros((slots, 4), dtype=np.uint64), np.zeros((slots, wr, 4), dtype=np.uint64)
+        acc = np.zeros(max(len(packed), 1), dtype=np.uint8)
+        pub = np.zeros((3, 4), dtype=np.uint64)
+        n_acc = ct.c_uint64()
+        fn = self.ctx._l.bzk_mpn_deposit_build if kind == "deposit" else self.ctx._l.bzk_mpn_withdraw_build
+        self.ctx._check(fn(self.ctx._h, self._h, _host_ptr(packed), len(packed), log4_batch, _host_ptr(raws1), _host_ptr(raws2), _host_ptr(roots),
+                           _host_ptr(reveal), _host_ptr(acc), _host_ptr(pub), ct.byref(n_acc)))
+        public = {"state": _int(pub[0]), "aux_data": _int(pub[1]), "next_state": _int(pub[2])}
+        return {"raws1": raws1, "raws2": raws2, "roots": roots, "reveal": reveal, "accepted": acc[:len(packed)].astype(bool), "public": public,
+                "n_accepted": n_acc.value}
+
+    def deposit_build(self, deposits, log4_batch):
+        """`mpn::deposit::deposit` (/root/reference/src/mpn/deposit.rs:11-233) natively -> dict of the rows
+        bzk_mpn_dw_witness consumes (raws1, raws2, roots, reveal), the accepted mask and the three public values."""
+        return self._dw_build("deposit", deposits if isinstance(deposits, np.ndarray) else pack_deposits(deposits), log4_batch)
+
+    def withdraw_build(self, withdraws, log4_batch):
+        """`mpn::withdraw::withdraw` (/root/reference/src/mpn/withdraw.rs:10-259) natively, signature check included."""
+        return self._dw_build("withdraw", withdraws if isinstance(withdraws, np.ndarray) else pack_withdraws(withdraws), log4_batch)

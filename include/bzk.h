@@ -285,6 +285,37 @@ int32_t bzk_mpn_update_raw_width(uint32_t log4_tree, uint32_t log4_token, uint32
 int32_t bzk_mpn_state_clone(const bzk_mpn_state *state, bzk_mpn_state **out);
 int32_t bzk_mpn_state_info(const bzk_mpn_state *state, bzk_fr *state_hash, uint64_t *state_size, uint64_t *account_count, uint64_t *pending_accounts);
 int32_t bzk_mpn_state_commit_accounts(bzk_mpn_state *state);
+/* Deposit and withdraw batches natively (`mpn::deposit::deposit`, /root/reference/src/mpn/deposit.rs:11-233; `mpn::withdraw::withdraw`,
+ * /root/reference/src/mpn/withdraw.rs:10-259), next to the update builder: the same ledger, the same batched GPU hashing,
+ * rows of circuit inputs out.  `bzk_mpn_deposit` / `bzk_mpn_withdraw` carry what the circuits consume of `MpnDeposit` /
+ * `MpnWithdraw` (scalars canonical little-endian; `fingerprint` = `ContractWithdraw::fingerprint()` of the L1 payment).  The
+ * withdraw builder checks nonces, balances and the EdDSA signature; neither touches L1 balances (chain state).
+ *   raws1 / raws2   phase-1 / phase-2 inputs of every slot (widths 5 and 9+3T+3A for deposits, 12 and 12+6T+3A for withdrawals)
+ *   roots[slots]    the state root entering each slot (phase 2's external)
+ *   reveal          the rows the circuit reveals (4 / 7 per slot); public3 = {state, aux_data = their list root, next_state}
+ * bzk_mpn_dw_witness then runs the three programs of bzk_mpn_dw_circuit_compile (phase 1, reveal, phase 2) into z. */
+typedef struct {
+    bzk_fr pk_x;
+    uint8_t pk_odd, pad[7];
+    bzk_fr token_id;
+    uint64_t amount;
+} bzk_mpn_deposit;
+typedef struct {
+    bzk_fr pk_x;
+    uint8_t pk_odd, pad[3];
+    uint32_t nonce;
+    bzk_fr sig_rx, sig_ry, sig_s;
+    bzk_fr amount_token_id, fee_token_id, fingerprint;
+    uint64_t amount, fee;
+} bzk_mpn_withdraw;
+int32_t bzk_mpn_deposit_build(bzk_ctx *ctx, bzk_mpn_state *state, const bzk_mpn_deposit *deposits, uint64_t n, uint32_t log4_batch, bzk_fr *raws1,
+                              bzk_fr *raws2, bzk_fr *roots, bzk_fr *reveal, uint8_t *accepted, bzk_fr public3[3], uint64_t *n_accepted);
+int32_t bzk_mpn_withdraw_build(bzk_ctx *ctx, bzk_mpn_state *state, const bzk_mpn_withdraw *withdraws, uint64_t n, uint32_t log4_batch, bzk_fr *raws1,
+                               bzk_fr *raws2, bzk_fr *roots, bzk_fr *reveal, uint8_t *accepted, bzk_fr public3[3], uint64_t *n_accepted);
+typedef struct bzk_witness_program bzk_witness_program;
+int32_t bzk_mpn_dw_witness(bzk_ctx *ctx, const bzk_witness_program *phase1, const bzk_witness_program *phase2, const bzk_witness_program *reveal_prog,
+                           uint64_t n_slots, const bzk_fr *raws1, const bzk_fr *raws2, const bzk_fr *roots, const int32_t *ext_src, uint32_t n_ext_src,
+                           const bzk_fr *reveal_rows, const bzk_fr public5[5], void *d_inputs, void *d_aux);
 /* `PublicKey::decompress` (/root/reference/src/crypto/jubjub/curve.rs:78-88) on the host field arithmetic, no
  * context: y = sqrt((1 + x^2) / (1 - d x^2)) with the parity rule; canonical scalars. */
 int32_t bzk_jubjub_decompress(const bzk_fr *jubjub_d, const bzk_fr *x, int32_t y_is_odd, bzk_fr out_xy[2]);

@@ -215,6 +215,77 @@ def test_batched_deposit_withdraw_builders_on_gpu(ctx):
     _assert_same_transitions(tr1, tr2)
 
 
+@pytest.mark.parametrize("kind", ["deposit", "withdraw"])
+def test_native_deposit_withdraw_builders_and_witness(ctx, cref, kind):
+    """csrc/mpn_host.cu bzk_mpn_{deposit,withdraw}_build + bzk_mpn_dw_witness against the Python restatement: same
+    accepted set over two consecutive batches (new account, repeated account, bad signature / nonce / balance /
+    unknown key), rows equal to `deposit_raws` / `withdraw_raws` of the sequential builder's transitions, same entering
+    roots, reveal rows and public values; the resident witness equals `synthesize`'s and its proof verifies."""
+    import copy
+    from bazuka_b200 import groth16 as BG
+    from bazuka_b200.mpn import cs as C, dw as D, dw_witness as DW, native as N, update as U
+    from bazuka_b200.mpn.gpu_witness import _canon_rows
+    from bazuka_b200.mpn.ledger import NativeLedger
+    from bazuka_b200.mpn.native_circuit import NativeTwoPhaseCircuit
+    A = T = 3
+    B = 1
+    st, keys = make_state(A, T, 3)
+    led = NativeLedger(ctx, A, T)
+    for i, a in st.accounts.items():
+        led.set_account(i, a)
+    assert led.root == st.root
+    new1, new2 = N.eddsa_keys(b"dep-new")[0], N.eddsa_keys(b"dep-new-2")[0]
+    if kind == "deposit":
+        mk = lambda pk, tok, amt: D.MpnDeposit(N.jj_compress(pk), tok, amt)
+        batches = [[mk(keys[0][0], U.ZIESHA, 500), mk(new1, 77, 9), mk(keys[1][0], 77, 1), mk(keys[0][0], 77, 4), mk(new2, 5, 5)],
+                   [mk(new1, 78, 3), D.MpnDeposit((6, False), 77, 1), mk(new2, 5, 1)]]
+        seq, build, raws_of, w_rev = D.deposit, led.deposit_build, DW.deposit_raws, 4
+    else:
+        def mk(i, amt, nonce, fee=2, sk=None, tok=U.ZIESHA):
+            w = D.MpnWithdraw(N.jj_compress(keys[i][0]), nonce, amount=U.Money(tok, amt), fee=U.Money(U.ZIESHA, fee), fingerprint=1000 + amt)
+            w.sign(sk or keys[i][1])
+            return w
+        stranger = D.MpnWithdraw(N.jj_compress(new1), 1, amount=U.Money(U.ZIESHA, 1), fee=U.Money(U.ZIESHA, 0), fingerprint=1)
+        batches = [[mk(0, 100, 1), mk(1, 5, 1, sk=keys[0][1]), mk(1, 5, 1), mk(0, 30, 2), mk(2, 7, 2), stranger],
+                   [mk(2, 10**15, 1), mk(2, 7, 1, tok=12345), mk(0, 1, 3), mk(1, 1, 2, fee=10**15), mk(1, 1, 2)]]
+        seq, build, raws_of, w_rev = D.withdraw, led.withdraw_build, DW.withdraw_raws, 7
+    nc = NativeTwoPhaseCircuit(kind, A, T, B)
+    nw = DW.NativeTwoPhaseWitness(ctx, nc)
+    circ_cls = D.DepositCircuit if kind == "deposit" else D.WithdrawCircuit
+    last = None
+    for items in batches:
+        before = copy.deepcopy(st)
+        pub, trans = seq(st, items, B)
+        rows = build(items, B)
+        assert rows["public"] == pub and rows["n_accepted"] == len(trans) and led.root == st.root
+        assert [it for it, a in zip(items, rows["accepted"]) if a] == [t.tx for t in trans]
+        assert 0 < len(trans) < len(items)
+        circ = circ_cls(A, T, B, commitment=3, height=1, transitions=trans, **pub)
+        want = [raws_of(t, A, T) for t in circ.transitions]
+        assert (rows["raws1"].reshape(-1, 4) == _canon_rows([v for a, _ in want for v in a])).all()
+        assert (rows["raws2"].reshape(-1, 4) == _canon_rows([v for _, b in want for v in b])).all()
+        assert (rows["roots"] == _canon_rows(DW.slot_roots(circ))).all()
+        assert (rows["reveal"].reshape(-1, 4) == _canon_rows([v for r in DW.reveal_rows_native(kind, circ) for v in r])).all()
+        assert led.info()["state_size"] == st.state_size
+        ni, na, mats, inputs, aux = circ.synthesize(C.ConstraintSystem()).to_csr()
+        d_in, d_aux = nw.witness(rows, 3, 1)
+        got = d_aux.cpu().numpy().view(np.uint64)
+        assert got.shape == aux.shape
+        bad = np.nonzero((got != aux).any(axis=1))[0]
+        assert len(bad) == 0, (len(bad), bad[:8])
+        assert (d_in.cpu().numpy().view(np.uint64) == inputs).all()
+        last = (ni, na, mats, inputs, d_in, d_aux)
+    ni, na, mats, inputs, d_in, d_aux = last
+    n_ni, n_na, n_mats = nc.r1cs()
+    assert (n_ni, n_na) == (ni, na)
+    pr = BG.Prover(ctx, BG.R1CS(n_ni, n_na, *n_mats))
+    pk, vk = BG.setup_gpu(ctx, pr.r1cs, cref.fr_random(195, 5), cref.g1_generator(), cref.g2_generator())
+    r, s = cref.fr_random(196, 2)
+    blob, pts = pr.prove_dev(pk, d_in, d_aux, r, s)
+    assert BG.verify(vk, inputs[1:], pts)
+    nw.free(); nc.free(); led.free(); pk.free(); pr.free()
+
+
 def test_worker_object_end_to_end(ctx, cref):
     """MpnUpdateWorker: transactions -> batched builder -> GPU witness -> resident proof -> 391-byte ZkProof that the
     validator-side byte-image check accepts; byte-equal to the proof of the host-synthesised witness of the
