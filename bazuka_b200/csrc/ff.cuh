@@ -479,6 +479,83 @@ struct Fe {
         }
         return pow(e, N);
     }
+    // Inverse by the binary extended Euclid (0 -> 0): ~1.4*bits halvings and ~0.7*bits subtractions on N-limb integers,
+    // no multiplications until the two that restore the Montgomery form.  For a LONE thread (the witness interpreter's
+    // EdDSA ladders: one dependent affine addition after another) it is several times shorter than the 380 dependent
+    // products of the Fermat power; the throughput kernels batch their inversions and keep inv().
+    // Invariants: x1 * a = u, x2 * a = v (mod p); u, v odd after the halving loops; ends at u == 1 or v == 1.
+    BZK_HD_POW Fe inv_gcd() const {
+        if (is_zero()) return zero();
+        uint32_t u[N], v[N], x1[N], x2[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) { u[i] = l[i]; v[i] = P::p(i); x1[i] = 0; x2[i] = 0; }
+        x1[0] = 1;
+        auto is_one = [](const uint32_t *a) {
+            uint32_t t = a[0] ^ 1u;
+#pragma unroll
+            for (int i = 1; i < N; i++) t |= a[i];
+            return t == 0;
+        };
+        // a >>= 1 ; x = x / 2 mod p
+        auto halve = [](uint32_t *a, uint32_t *x) {
+#pragma unroll
+            for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+            a[N - 1] >>= 1;
+            uint32_t top = 0;
+            if (x[0] & 1u) {
+                CC cc{0};
+                x[0] = add_cc(x[0], P::p(0), cc);
+#pragma unroll
+                for (int i = 1; i < N; i++) x[i] = addc_cc(x[i], P::p(i), cc);
+                top = addc(0, 0, cc);
+            }
+#pragma unroll
+            for (int i = 0; i < N - 1; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+            x[N - 1] = (x[N - 1] >> 1) | (top << 31);
+        };
+        // x -= y mod p   (x, y < p)
+        auto sub_mod = [](uint32_t *x, const uint32_t *y) {
+            CC cc{0};
+            x[0] = sub_cc(x[0], y[0], cc);
+#pragma unroll
+            for (int i = 1; i < N; i++) x[i] = subc_cc(x[i], y[i], cc);
+            if (subc(0, 0, cc)) {
+                CC c2{0};
+                x[0] = add_cc(x[0], P::p(0), c2);
+#pragma unroll
+                for (int i = 1; i < N - 1; i++) x[i] = addc_cc(x[i], P::p(i), c2);
+                x[N - 1] = addc(x[N - 1], P::p(N - 1), c2);
+            }
+        };
+        while (!is_one(u) && !is_one(v)) {
+            while (!(u[0] & 1u)) halve(u, x1);
+            while (!(v[0] & 1u)) halve(v, x2);
+            uint32_t d[N];
+            CC cc{0};
+            d[0] = sub_cc(u[0], v[0], cc);
+#pragma unroll
+            for (int i = 1; i < N; i++) d[i] = subc_cc(u[i], v[i], cc);
+            if (!subc(0, 0, cc)) {  // u >= v
+#pragma unroll
+                for (int i = 0; i < N; i++) u[i] = d[i];
+                sub_mod(x1, x2);
+            } else {
+                CC c2{0};
+                v[0] = sub_cc(v[0], u[0], c2);
+#pragma unroll
+                for (int i = 1; i < N - 1; i++) v[i] = subc_cc(v[i], u[i], c2);
+                v[N - 1] = subc(v[N - 1], u[N - 1], c2);
+                sub_mod(x2, x1);
+            }
+        }
+        Fe r;
+        const bool first = is_one(u);
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = first ? x1[i] : x2[i];
+        // r = (aR)^-1 = a^-1 R^-1  ->  a^-1 R
+        const Fe rr = r2();
+        return (r * rr) * rr;
+    }
 };
 
 // ---------------------------------------------------------------------------------------------

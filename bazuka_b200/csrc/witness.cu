@@ -11,8 +11,16 @@
 // contiguous 1 KB run; the program stream (ops, LC pool, coefficients) is read at warp-uniform addresses
 // (broadcast).  The block's values are also written, slot-major -> tx-major, straight into the z vector the
 // prover consumes (aux_out[tx * n_ops + j]), so the witness never visits the host.
-// Bound: single-thread Fr latency (a slot is one dependent chain of ~10^6 limb-product rounds); batches
-// give the parallelism (256 / 1024 slots), not the slot.
+//
+// Round 2: ONE WARP PER SLOT, the program executed level by level.  At upload the host orders the ops by their depth in the
+// data-flow graph (level = 1 + the deepest operand); the ops of one level are independent, the lanes of the slot's warp take
+// them 32 at a time and a __syncwarp() separates levels.  A slot's critical path — the Merkle paths' Poseidon rounds, the two
+// 255-step EdDSA ladders — is ~5x shorter than its op count (a Poseidon state is t lanes wide, the ladders run side by side,
+// bit decompositions are flat), and the slot's variables are read straight out of its z segment (slot-major: no transposed
+// V array, no second store).  The one-thread-per-slot kernel stays for A/B runs (BZK_WITNESS_SERIAL=1).
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 #include "witness_core.cuh"
 
@@ -47,12 +55,62 @@ __global__ void __launch_bounds__(32) k_witness_run(WitProgDev P, Fr jj_d, const
     wit_run_slot(P, jj_d, raws + (size_t)tx * P.n_raw, ext + (size_t)tx * P.n_ext, mem);
 }
 
+// ---- level-parallel execution: a warp per slot -------------------------------------------------------------------
+struct WitSched {
+    const int32_t *sops;       // [n_exec][8]: code, lc0..lc3, imm, op index, unused — in (level, opcode) order, NOPs dropped
+    const int32_t *level_ptr;  // [n_levels + 1] into sops
+    uint32_t n_levels;
+};
+
+// the slot's variables live in its z segment; slots below block0 (ONE, externals) in a small side array
+struct WitMemSeg {
+    const Fr *pre;
+    Fr *z;
+    uint32_t block0;
+    __device__ __forceinline__ Fr load(int32_t slot) const {
+        const Fr *p = (uint32_t)slot < block0 ? pre + slot : z + ((uint32_t)slot - block0);
+        Fr r;
+        const uint4 *s = (const uint4 *)p;
+        uint4 a = s[0], b = s[1];
+        r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+        r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+        return r;
+    }
+    __device__ __forceinline__ void store(uint32_t slot, const Fr &v) const { store_vec(z + (slot - block0), v); }
+    __device__ __forceinline__ void out(uint32_t, const Fr &) const {}
+    __device__ __forceinline__ void prefetch(int32_t) const {}
+};
+
+__global__ void __launch_bounds__(32) k_witness_levels(WitProgDev P, WitSched S, Fr jj_d, const Fr *__restrict__ raws, const Fr *__restrict__ ext,
+                                                       uint32_t ntx, Fr *pre, Fr *aux_out) {
+    const uint32_t tx = blockIdx.x, lane = threadIdx.x, block0 = 1 + P.n_ext;
+    if (tx >= ntx) return;
+    Fr *mine = pre + (size_t)tx * block0;
+    if (lane == 0) store_vec(mine, Fr::one());
+    for (uint32_t k = lane; k < P.n_ext; k += 32) store_vec(mine + 1 + k, ext[(size_t)tx * P.n_ext + k].to_mont());
+    __syncwarp();
+    WitMemSeg mem{mine, aux_out + (size_t)tx * P.n_ops, block0};
+    const Fr *row = raws + (size_t)tx * P.n_raw;
+    int32_t lo = S.level_ptr[0];
+    for (uint32_t L = 0; L < S.n_levels; L++) {
+        const int32_t hi = S.level_ptr[L + 1];
+        for (int32_t i = lo + (int32_t)lane; i < hi; i += 32) {
+            const int4 *q = (const int4 *)(S.sops + (size_t)i * 8);
+            const int4 u = q[0], v = q[1];
+            wit_exec_op(P, jj_d, row, (uint32_t)v.z, u.x, u.y, u.z, u.w, v.x, v.y, mem);
+        }
+        lo = hi;
+        __syncwarp();  // orders this level's stores before the next level's loads (same warp, same SM)
+    }
+}
+
 }  // namespace bzk
 
 using namespace bzk;
 
 struct bzk_witness_program {
     WitProgDev d{};
+    WitSched sched{};
     Fr jj_d;
     void *blob = nullptr;
     uint64_t n_lc = 0, n_terms = 0, n_coefs = 0;
@@ -92,6 +150,37 @@ int32_t bzk_witness_program_upload(bzk_ctx *ctx, const int32_t *ops, uint64_t n_
             }
         }
     }
+    // schedule: depth of every variable in the data-flow graph, ops ordered by (depth, opcode)
+    std::vector<uint32_t> depth(kSlotBlock0 + n_ops, 0);
+    uint32_t n_levels = 0;
+    uint64_t n_exec = 0;
+    for (uint64_t j = 0; j < n_ops; j++) {
+        const int32_t *op = ops + j * 6;
+        if (op[0] == W_NOP) continue;   // its variable took the JJ's depth below
+        uint32_t d = 0;
+        const int nlc = wit_operands(op[0]);
+        for (int a = 0; a < nlc; a++)
+            for (int32_t k = lc_ptr[op[1 + a]]; k < lc_ptr[op[1 + a] + 1]; k++) d = std::max(d, depth[lc_slot[k]]);
+        depth[kSlotBlock0 + j] = d + 1;
+        if (op[0] == W_JJ) depth[kSlotBlock0 + j + 1] = d + 1;
+        n_levels = std::max(n_levels, d + 1);
+        n_exec++;
+    }
+    std::vector<int32_t> level_ptr(n_levels + 2, 0), sops(n_exec * 8 + 8, 0);
+    {
+        // counting sort on (level, opcode); levels are 1-based
+        std::vector<uint64_t> cnt((size_t)(n_levels + 1) * 8 + 1, 0);
+        for (uint64_t j = 0; j < n_ops; j++)
+            if (ops[j * 6] != W_NOP) cnt[(size_t)depth[kSlotBlock0 + j] * 8 + ops[j * 6] + 1]++;
+        for (size_t i = 1; i < cnt.size(); i++) cnt[i] += cnt[i - 1];
+        for (uint32_t L = 1; L <= n_levels + 1; L++) level_ptr[L - 1] = (int32_t)cnt[(size_t)L * 8];
+        for (uint64_t j = 0; j < n_ops; j++) {
+            const int32_t *op = ops + j * 6;
+            if (op[0] == W_NOP) continue;
+            int32_t *o = sops.data() + cnt[(size_t)depth[kSlotBlock0 + j] * 8 + op[0]]++ * 8;
+            o[0] = op[0]; o[1] = op[1]; o[2] = op[2]; o[3] = op[3]; o[4] = op[4]; o[5] = op[5]; o[6] = (int32_t)j;
+        }
+    }
     BZK_CUDA(ctx, cudaSetDevice(ctx->device));
     auto *p = new (std::nothrow) bzk_witness_program;
     if (!p) return BZK_ERR_OOM;
@@ -99,6 +188,7 @@ int32_t bzk_witness_program_upload(bzk_ctx *ctx, const int32_t *ops, uint64_t n_
     {
         Carver cv(nullptr);
         cv.take<int32_t>(n_ops * 6); cv.take<int32_t>(n_lc + 1); cv.take<int32_t>(n_terms + 1); cv.take<int32_t>(n_terms + 1); cv.take<Fr>(n_coefs);
+        cv.take<int32_t>(sops.size()); cv.take<int32_t>(level_ptr.size());
         need = cv.used();
     }
     if (cudaMalloc(&p->blob, need) != cudaSuccess) { delete p; cudaGetLastError(); return BZK_ERR_OOM; }
@@ -106,7 +196,10 @@ int32_t bzk_witness_program_upload(bzk_ctx *ctx, const int32_t *ops, uint64_t n_
     int32_t *d_ops = cv.take<int32_t>(n_ops * 6), *d_ptr = cv.take<int32_t>(n_lc + 1), *d_slot = cv.take<int32_t>(n_terms + 1),
             *d_coef = cv.take<int32_t>(n_terms + 1);
     Fr *d_coefs = cv.take<Fr>(n_coefs);
+    int32_t *d_sops = cv.take<int32_t>(sops.size()), *d_level_ptr = cv.take<int32_t>(level_ptr.size());
     cudaError_t e = cudaMemcpyAsync(d_ops, ops, n_ops * 6 * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_sops, sops.data(), sops.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_level_ptr, level_ptr.data(), level_ptr.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_ptr, lc_ptr, (n_lc + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && n_terms) e = cudaMemcpyAsync(d_slot, lc_slot, n_terms * 4, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && n_terms) e = cudaMemcpyAsync(d_coef, lc_coef, n_terms * 4, cudaMemcpyHostToDevice, ctx->stream);
@@ -114,6 +207,7 @@ int32_t bzk_witness_program_upload(bzk_ctx *ctx, const int32_t *ops, uint64_t n_
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { cudaFree(p->blob); delete p; BZK_CUDA(ctx, e); }
     p->d = WitProgDev{d_ops, d_ptr, d_slot, d_coef, d_coefs, (uint32_t)n_ops, n_raw, n_ext};
+    p->sched = WitSched{d_sops, d_level_ptr, n_levels};
     memcpy(&p->jj_d, jj_d, sizeof(Fr));
     p->n_lc = n_lc; p->n_terms = n_terms; p->n_coefs = n_coefs;
     *out = p;
@@ -131,19 +225,24 @@ int32_t bzk_witness_program_free(bzk_ctx *ctx, bzk_witness_program *p) {
 int32_t bzk_witness_run_dev(bzk_ctx *ctx, const bzk_witness_program *p, const bzk_fr *raws, const bzk_fr *ext, uint64_t ntx, void *d_aux_out) {
     if (!ctx || !p || (p->d.n_raw && !raws) || (p->d.n_ext && !ext) || !d_aux_out || !ntx || ntx > (1u << 24)) return BZK_ERR_BAD_ARG;
     BZK_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t n_slots = (size_t)1 + p->d.n_ext + p->d.n_ops;
+    static const bool serial = getenv("BZK_WITNESS_SERIAL") && atoi(getenv("BZK_WITNESS_SERIAL")) != 0;
+    // scratch: the serial kernel's transposed variable array, or the level kernel's {ONE, externals} rows
+    const size_t n_scratch = serial ? ((size_t)1 + p->d.n_ext + p->d.n_ops) * ntx : ((size_t)1 + p->d.n_ext) * ntx;
     size_t need;
     {
         Carver cv(nullptr);
-        cv.take<Fr>(n_slots * ntx); cv.take<Fr>((size_t)p->d.n_raw * ntx + 1); cv.take<Fr>((size_t)p->d.n_ext * ntx + 1);
+        cv.take<Fr>(n_scratch); cv.take<Fr>((size_t)p->d.n_raw * ntx + 1); cv.take<Fr>((size_t)p->d.n_ext * ntx + 1);
         need = cv.used();
     }
     BZK_TRY(ensure_ws(ctx, &ctx->ws, &ctx->ws_bytes, need));
     Carver cv(ctx->ws);
-    Fr *V = cv.take<Fr>(n_slots * ntx), *d_raws = cv.take<Fr>((size_t)p->d.n_raw * ntx + 1), *d_ext = cv.take<Fr>((size_t)p->d.n_ext * ntx + 1);
+    Fr *V = cv.take<Fr>(n_scratch), *d_raws = cv.take<Fr>((size_t)p->d.n_raw * ntx + 1), *d_ext = cv.take<Fr>((size_t)p->d.n_ext * ntx + 1);
     if (p->d.n_raw) BZK_CUDA(ctx, cudaMemcpyAsync(d_raws, raws, (size_t)p->d.n_raw * ntx * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
     if (p->d.n_ext) BZK_CUDA(ctx, cudaMemcpyAsync(d_ext, ext, (size_t)p->d.n_ext * ntx * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-    k_witness_run<<<(unsigned)div_up(ntx, 32), 32, 0, ctx->stream>>>(p->d, p->jj_d, d_raws, d_ext, (uint32_t)ntx, V, (Fr *)d_aux_out);
+    if (serial)
+        k_witness_run<<<(unsigned)div_up(ntx, 32), 32, 0, ctx->stream>>>(p->d, p->jj_d, d_raws, d_ext, (uint32_t)ntx, V, (Fr *)d_aux_out);
+    else
+        k_witness_levels<<<(unsigned)ntx, 32, 0, ctx->stream>>>(p->d, p->sched, p->jj_d, d_raws, d_ext, (uint32_t)ntx, V, (Fr *)d_aux_out);
     BZK_LAUNCHED(ctx);
     BZK_CUDA(ctx, cudaGetLastError());
     // the host buffers may be pageable: the copies above are complete for the caller only after this

@@ -47,16 +47,71 @@ BZK_HD bool jj_on_curve(const Fr &x, const Fr &y, const Fr &d) {
     return (y2 - x2) == (Fr::one() + d * x2 * y2);
 }
 
-// one slot: raws / ext are the slot's rows (canonical); slots: 0 = ONE, 1..n_ext externals, then block variables
+// op j of the program (any order that respects the data flow): code / a0..a3 / imm = its row of P.ops
+template <class Mem>
+BZK_HD void wit_exec_op(const WitProgDev &P, const Fr &jj_d, const Fr *raws, uint32_t j, int32_t code, int32_t a0, int32_t a1, int32_t a2, int32_t a3,
+                        int32_t imm, Mem &mem) {
+    const uint32_t block0 = 1 + P.n_ext;
+    Fr out = Fr::zero();
+    switch (code) {
+    case W_RAW: out = raws[imm].to_mont(); break;
+    case W_MUL: {
+        Fr a = wit_eval_lc(P, a0, mem);
+        out = (a1 == a0) ? a.sqr() : a * wit_eval_lc(P, a1, mem);
+        break;
+    }
+    case W_BIT: {
+        Fr c = wit_eval_lc(P, a0, mem).from_mont();
+        uint32_t w = 0;
+#pragma unroll
+        for (int i = 0; i < Fr::N; i++) w = (i == (imm >> 5)) ? c.l[i] : w;
+        out = ((w >> (imm & 31)) & 1u) ? Fr::one() : Fr::zero();
+        break;
+    }
+    case W_ISZERO: out = wit_eval_lc(P, a0, mem).is_zero() ? Fr::one() : Fr::zero(); break;
+    case W_INVZ: {
+        Fr a = wit_eval_lc(P, a0, mem);
+        out = a.inv_gcd();  // 0 -> 0
+        break;
+    }
+    case W_SELECT: {
+        Fr s = wit_eval_lc(P, a0, mem), a = wit_eval_lc(P, a1, mem), b = wit_eval_lc(P, a2, mem);
+        out = s.is_zero() ? a : b;
+        break;
+    }
+    case W_JJ: {
+        // twisted Edwards, a = -1 (/root/reference/src/crypto/jubjub/curve.rs:123-160; the gadget's hint
+        // /root/reference/src/zk/groth16/gadgets/eddsa/mod.rs:75-101 yields (0,0) for off-curve inputs)
+        Fr x1 = wit_eval_lc(P, a0, mem), y1 = wit_eval_lc(P, a1, mem);
+        Fr x2 = wit_eval_lc(P, a2, mem), y2 = wit_eval_lc(P, a3, mem);
+        Fr ox = Fr::zero(), oy = Fr::zero();
+        if (jj_on_curve(x1, y1, jj_d) && jj_on_curve(x2, y2, jj_d)) {
+            Fr x1x2 = x1 * x2, y1y2 = y1 * y2;
+            Fr k = jj_d * x1x2 * y1y2;
+            Fr dp = Fr::one() + k, dm = Fr::one() - k;
+            Fr inv = (dp * dm).inv_gcd();
+            ox = (x1 * y2 + y1 * x2) * dm * inv;
+            oy = (y1y2 + x1x2) * dp * inv;
+        }
+        out = ox;
+        mem.store(block0 + j + 1, oy);
+        mem.out(j + 1, oy);
+        break;
+    }
+    default: return;  // W_NOP: written by the preceding JJ
+    }
+    mem.store(block0 + j, out);
+    mem.out(j, out);
+}
+
+// one slot in program order: raws / ext are the slot's rows (canonical); slots: 0 = ONE, 1..n_ext externals, then block variables
 template <class Mem>
 BZK_HD void wit_run_slot(const WitProgDev &P, const Fr &jj_d, const Fr *raws, const Fr *ext, Mem &mem) {
-    const uint32_t block0 = 1 + P.n_ext;
     mem.store(0, Fr::one());
     for (uint32_t k = 0; k < P.n_ext; k++) mem.store(1 + k, ext[k].to_mont());
     for (uint32_t j = 0; j < P.n_ops; j++) {
         const int32_t *op = P.ops + (size_t)j * 6;
         const int32_t code = op[0], a0 = op[1], a1 = op[2], a2 = op[3], a3 = op[4], imm = op[5];
-        Fr out = Fr::zero();
         {
             // pull every operand towards L1 before the dependent evaluation starts (device: CCTL.E.PF1)
             const int nlc = wit_operands(code);
@@ -65,55 +120,7 @@ BZK_HD void wit_run_slot(const WitProgDev &P, const Fr &jj_d, const Fr *raws, co
             if (nlc > 2) wit_prefetch_lc(P, a2, mem);
             if (nlc > 3) wit_prefetch_lc(P, a3, mem);
         }
-        switch (code) {
-        case W_RAW: out = raws[imm].to_mont(); break;
-        case W_MUL: {
-            Fr a = wit_eval_lc(P, a0, mem);
-            out = (a1 == a0) ? a.sqr() : a * wit_eval_lc(P, a1, mem);
-            break;
-        }
-        case W_BIT: {
-            Fr c = wit_eval_lc(P, a0, mem).from_mont();
-            uint32_t w = 0;
-#pragma unroll
-            for (int i = 0; i < Fr::N; i++) w = (i == (imm >> 5)) ? c.l[i] : w;
-            out = ((w >> (imm & 31)) & 1u) ? Fr::one() : Fr::zero();
-            break;
-        }
-        case W_ISZERO: out = wit_eval_lc(P, a0, mem).is_zero() ? Fr::one() : Fr::zero(); break;
-        case W_INVZ: {
-            Fr a = wit_eval_lc(P, a0, mem);
-            out = a.is_zero() ? Fr::zero() : a.inv();
-            break;
-        }
-        case W_SELECT: {
-            Fr s = wit_eval_lc(P, a0, mem), a = wit_eval_lc(P, a1, mem), b = wit_eval_lc(P, a2, mem);
-            out = s.is_zero() ? a : b;
-            break;
-        }
-        case W_JJ: {
-            // twisted Edwards, a = -1 (/root/reference/src/crypto/jubjub/curve.rs:123-160; the gadget's hint
-            // /root/reference/src/zk/groth16/gadgets/eddsa/mod.rs:75-101 yields (0,0) for off-curve inputs)
-            Fr x1 = wit_eval_lc(P, a0, mem), y1 = wit_eval_lc(P, a1, mem);
-            Fr x2 = wit_eval_lc(P, a2, mem), y2 = wit_eval_lc(P, a3, mem);
-            Fr ox = Fr::zero(), oy = Fr::zero();
-            if (jj_on_curve(x1, y1, jj_d) && jj_on_curve(x2, y2, jj_d)) {
-                Fr x1x2 = x1 * x2, y1y2 = y1 * y2;
-                Fr k = jj_d * x1x2 * y1y2;
-                Fr dp = Fr::one() + k, dm = Fr::one() - k;
-                Fr inv = (dp * dm).inv();
-                ox = (x1 * y2 + y1 * x2) * dm * inv;
-                oy = (y1y2 + x1x2) * dp * inv;
-            }
-            out = ox;
-            mem.store(block0 + j + 1, oy);
-            mem.out(j + 1, oy);
-            break;
-        }
-        default: continue;  // W_NOP: written by the preceding JJ
-        }
-        mem.store(block0 + j, out);
-        mem.out(j, out);
+        wit_exec_op(P, jj_d, raws, j, code, a0, a1, a2, a3, imm, mem);
     }
 }
 

@@ -40,6 +40,12 @@ void shim_fp(const uint32_t *a, const uint32_t *b, uint32_t *r, size_t n, int op
 void shim_fr_inv(const uint32_t *a, uint32_t *r, size_t n) {
     for (size_t i = 0; i < n; i++) { Fr x; memcpy(x.l, a + 8 * i, 32); Fr z = x.inv(); memcpy(r + 8 * i, z.l, 32); }
 }
+void shim_fr_inv_gcd(const uint32_t *a, uint32_t *r, size_t n) {
+    for (size_t i = 0; i < n; i++) { Fr x; memcpy(x.l, a + 8 * i, 32); Fr z = x.inv_gcd(); memcpy(r + 8 * i, z.l, 32); }
+}
+void shim_fp_inv_gcd(const uint32_t *a, uint32_t *r, size_t n) {
+    for (size_t i = 0; i < n; i++) { Fp x; memcpy(x.l, a + 12 * i, 48); Fp z = x.inv_gcd(); memcpy(r + 12 * i, z.l, 48); }
+}
 void shim_fp_inv(const uint32_t *a, uint32_t *r, size_t n) {
     for (size_t i = 0; i < n; i++) { Fp x; memcpy(x.l, a + 12 * i, 48); Fp z = x.inv(); memcpy(r + 12 * i, z.l, 48); }
 }

@@ -66,6 +66,14 @@ def test_host_build_of_device_multiplier(hostshim, cref):
         assert (r == f(a, b)).all(), op
     hostshim.shim_fr_inv(a.ctypes.data_as(ct.c_void_p), r.ctypes.data_as(ct.c_void_p), ct.c_size_t(50))
     assert (r[:50] == cref.fr_inv(a[:50])).all()
+    # the Euclidean inverse the witness interpreter uses == the Fermat power, edge values included (0 -> 0)
+    edge = np.frombuffer(b"".join((v % Fd.R_MOD).to_bytes(32, "little") for v in (0, 1, 2, Fd.R_MOD - 1, Fd.R_MOD - 2, 1 << 254, (1 << 200) + 1)),
+                         dtype=np.uint64).reshape(-1, 4)
+    ae = np.concatenate([a[:400], edge])
+    r1, r2 = np.empty_like(ae), np.empty_like(ae)
+    hostshim.shim_fr_inv(ae.ctypes.data_as(ct.c_void_p), r1.ctypes.data_as(ct.c_void_p), ct.c_size_t(len(ae)))
+    hostshim.shim_fr_inv_gcd(ae.ctypes.data_as(ct.c_void_p), r2.ctypes.data_as(ct.c_void_p), ct.c_size_t(len(ae)))
+    assert (r1 == r2).all() and not r2[400].any()
     rnd = random.Random(1)
     vals = [rnd.randrange(Fd.P_MOD) for _ in range(n - 6)] + [0, 1, 2, Fd.P_MOD - 1, Fd.P_MOD - 2, (1 << 380)]
     x = np.frombuffer(b"".join(v.to_bytes(48, "little") for v in vals), dtype=np.uint64).reshape(-1, 6).copy()
@@ -76,6 +84,11 @@ def test_host_build_of_device_multiplier(hostshim, cref):
         assert (r == f(x, y)).all(), op
     hostshim.shim_fp_inv(x.ctypes.data_as(ct.c_void_p), r.ctypes.data_as(ct.c_void_p), ct.c_size_t(50))
     assert (r[:50] == cref.fp_inv(x[:50])).all()
+    xe = np.concatenate([x[:200], x[-6:]])
+    r1, r2 = np.empty_like(xe), np.empty_like(xe)
+    hostshim.shim_fp_inv(xe.ctypes.data_as(ct.c_void_p), r1.ctypes.data_as(ct.c_void_p), ct.c_size_t(len(xe)))
+    hostshim.shim_fp_inv_gcd(xe.ctypes.data_as(ct.c_void_p), r2.ctypes.data_as(ct.c_void_p), ct.c_size_t(len(xe)))
+    assert (r1 == r2).all()
 
 
 def test_host_build_of_lazy_inner_product(hostshim, cref):
