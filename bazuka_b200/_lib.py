@@ -87,6 +87,9 @@ SIGNATURES = {
     "bzk_g1_bases_levels": (ct.c_uint32, [_vp]),
     "bzk_g2_bases_levels": (ct.c_uint32, [_vp]),
     "bzk_groth16_params_set_shard": (_i32, [_vp, _u32, _u32]),
+    "bzk_groth16_shard_begin": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _u32, _vp]),
+    "bzk_groth16_h_combine_dev": (_i32, [_vp, _vp, _vp, _vp, _u32]),
+    "bzk_groth16_shard_finish": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bzk_groth16_prove_partial": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "bzk_groth16_finalize": (_i32, [_vp] * 14),
     "bzk_mpn_state_create": (_i32, [_vp, _u32, _u32, _vp, ct.POINTER(_vp)]),

@@ -20,6 +20,7 @@ int32_t merkle4_root(bzk_ctx *ctx, uint32_t log4, const uint64_t *d_idx, const F
 int32_t tree4_versioned_update(bzk_ctx *ctx, uint32_t depth, const uint32_t *d_tree_id, const uint64_t *d_idx, size_t n, Fr *d_vals,
                                const Fr *d_init_proofs, Fr *d_out_proofs);
 int32_t groth16_h_launch(bzk_ctx *ctx, Fr *a, Fr *b, Fr *c, uint32_t log_n);
+int32_t groth16_h_combine_launch(bzk_ctx *ctx, Fr *a, Fr *b, Fr *c, uint32_t log_n);
 
 __global__ void __launch_bounds__(256) k_fr_binop(int op, const Fr *__restrict__ a, const Fr *__restrict__ b, Fr *__restrict__ out, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,6 +290,10 @@ int32_t bzk_divide_by_z_on_coset_dev(bzk_ctx *ctx, void *d_data, uint32_t log_n)
 int32_t bzk_groth16_h_dev(bzk_ctx *ctx, void *d_a, void *d_b, void *d_c, uint32_t log_n) {
     BZK_ENTER(ctx);
     return groth16_h_launch(ctx, (Fr *)d_a, (Fr *)d_b, (Fr *)d_c, log_n);
+}
+int32_t bzk_groth16_h_combine_dev(bzk_ctx *ctx, void *d_a, void *d_b, void *d_c, uint32_t log_n) {
+    BZK_ENTER(ctx);
+    return groth16_h_combine_launch(ctx, (Fr *)d_a, (Fr *)d_b, (Fr *)d_c, log_n);
 }
 
 // ------------------------------------------------------------------ bases

@@ -75,6 +75,8 @@ struct bzk_ctx {
     cudaEvent_t g16_ev[8] = {nullptr};
     float g16_ms[8] = {0};
     bool g16_valid = false;
+    bzk::MsmPlan g16_plan[5];            // plans of the five sums of the proof in flight (kept across bzk_groth16_shard_begin / _finish)
+    bool split_open = false;        // a shard_begin is waiting for its shard_finish
 };
 
 // A resident base vector.  After bzk_g*_bases_precompute `d` holds tab_T levels of n points each: level t =

@@ -24,6 +24,7 @@ namespace bzk {
 int32_t precompute_g1(bzk_ctx *ctx, bzk_g1_bases *b, uint32_t max_levels);
 int32_t precompute_g2(bzk_ctx *ctx, bzk_g2_bases *b, uint32_t max_levels);
 int32_t groth16_h_launch(bzk_ctx *ctx, Fr *a, Fr *b, Fr *c, uint32_t log_n);
+int32_t groth16_to_coset_launch(bzk_ctx *ctx, Fr *v, uint32_t log_n);
 int32_t msm_g1_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_bytes, const BasesRef<Fp> &d_bases, const Fr *d_scalars, size_t n, void *h_win, MsmPlan *plan);
 int32_t msm_g2_enqueue(bzk_ctx *ctx, cudaStream_t st, void **ws, size_t *ws_bytes, const BasesRef<Fp2> &d_bases, const Fr *d_scalars, size_t n, void *h_win, MsmPlan *plan);
 void msm_g1_finish(const MsmPlan *plan, const void *h_win, bzk_g1_affine *out);
@@ -58,6 +59,15 @@ struct bzk_groth16_params {
 struct Groth16Partials {  // the four sums a proof is assembled from (wire images)
     bzk_g1_affine *a_sum, *b1_sum, *hl_sum;
     bzk_g2_affine *b2_sum;
+};
+
+// sharded schedule with the quotient split over the ranks: the call is cut in two around the exchange of polynomials
+struct Groth16Split {
+    int phase;              // 1 = begin (z, this rank's share of the evaluation vectors on the coset, the four witness sums enqueued)
+                            // 2 = finish (h sum over this rank's slice of the quotient, folds)
+    uint32_t poly_mask;     // begin: bit s set = this rank transforms evaluation vector s (a, b, c)
+    bzk::Fr *evals[3];      // begin: caller's device buffers (domain size) for those vectors
+    const bzk::Fr *h_shard; // finish: the rank's slice [lo, hi) of the quotient's coefficients (device)
 };
 
 namespace bzk {
@@ -271,10 +281,12 @@ int32_t bzk_groth16_params_free(bzk_ctx *ctx, bzk_groth16_params *p) {
 static int32_t groth16_prove_impl(bzk_ctx *ctx, const bzk_groth16_params *pk, const bzk_r1cs *cs, const bzk_fr *inputs, const bzk_fr *aux,
                                   cudaMemcpyKind witness_kind, const bzk_fr *r_mont, const bzk_fr *s_mont, int32_t check_satisfied,
                                   bzk_g1_affine *proof_a, bzk_g2_affine *proof_b, bzk_g1_affine *proof_c,
-                                  const Groth16Partials *partial = nullptr) {
-    if (!ctx || !pk || !cs || !inputs || (cs->num_aux && !aux)) return BZK_ERR_BAD_ARG;
-    if (!partial && (!r_mont || !s_mont || !proof_a || !proof_b || !proof_c)) return BZK_ERR_BAD_ARG;
-    if (!partial && pk->world != 1) return BZK_ERR_BAD_ARG;  // a shard can only produce partial sums
+                                  const Groth16Partials *partial = nullptr, const Groth16Split *split = nullptr) {
+    const int phase = split ? split->phase : 0;
+    if (!ctx || !pk || !cs || (phase != 2 && (!inputs || (cs->num_aux && !aux)))) return BZK_ERR_BAD_ARG;
+    if (!partial && phase != 1 && (!r_mont || !s_mont || !proof_a || !proof_b || !proof_c)) return BZK_ERR_BAD_ARG;
+    if (!partial && phase != 1 && pk->world != 1) return BZK_ERR_BAD_ARG;  // a shard can only produce partial sums
+    if (phase == 2 && (!partial || !ctx->split_open || (!split->h_shard && pk->h->n))) return BZK_ERR_BAD_ARG;
     BZK_CUDA(ctx, cudaSetDevice(ctx->device));
     // BZK_TRACE=1: host-side wall clock of the driver's phases on stderr (development aid)
     static const bool trace = std::getenv("BZK_TRACE") != nullptr;
@@ -311,21 +323,33 @@ static int32_t groth16_prove_impl(bzk_ctx *ctx, const bzk_groth16_params *pk, co
         if (!ctx->g16_ev[k]) cudaEventCreate(&ctx->g16_ev[k]);
         cudaEventRecord(ctx->g16_ev[k], s);
     };
+    MsmPlan *plan = ctx->g16_plan;
+    constexpr size_t kWinBytes = kMaxWinPoints * sizeof(G2Xyzz);
+    if (phase != 2) {
+    ctx->split_open = false;
     ctx->g16_valid = false;
     g16_mark(0, st);
     BZK_CUDA(ctx, cudaMemcpyAsync(z, inputs, ni * sizeof(Fr), witness_kind, st));
     if (na) BZK_CUDA(ctx, cudaMemcpyAsync(z + ni, aux, na * sizeof(Fr), witness_kind, st));
     // evaluations (rows >= ncons: the Input(i)*0=0 rows, then zero padding)
     Fr *ev[3] = {ea, eb, ec};
+    if (phase == 1) {
+        for (int s = 0; s < 3; s++) {
+            if (((split->poly_mask >> s) & 1) && !split->evals[s]) return BZK_ERR_BAD_ARG;
+            ev[s] = ((split->poly_mask >> s) & 1) ? split->evals[s] : nullptr;
+        }
+        ea = ev[0];
+    }
     for (int s = 0; s < 3; s++) {
+        if (!ev[s]) continue;
         BZK_CUDA(ctx, cudaMemsetAsync(ev[s] + cs->ncons, 0, (m - cs->ncons) * sizeof(Fr), st));
         if (cs->ncons) {
             k_csr_spmv<<<div_up(cs->ncons, 256), 256, 0, st>>>(cs->m[s].rowptr, cs->m[s].col, cs->m[s].val, cs->ncons, z, ev[s]);
             BZK_LAUNCHED(ctx);
         }
     }
-    BZK_CUDA(ctx, cudaMemcpyAsync(ea + cs->ncons, z, ni * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
-    if (check_satisfied && cs->ncons) {
+    if (ea) BZK_CUDA(ctx, cudaMemcpyAsync(ea + cs->ncons, z, ni * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    if (check_satisfied && cs->ncons && phase == 0) {
         BZK_CUDA(ctx, cudaMemsetAsync(d_bad, 0, 4, st));
         k_check_sat<<<div_up(cs->ncons, 256), 256, 0, st>>>(ea, eb, ec, cs->ncons, d_bad);
         BZK_LAUNCHED(ctx);
@@ -345,7 +369,6 @@ static int32_t groth16_prove_impl(bzk_ctx *ctx, const bzk_groth16_params *pk, co
         if (!ctx->aux_stream[k]) BZK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream[k], cudaStreamNonBlocking));
     for (int k = 0; k < 3; k++)
         if (!ctx->aux_ev[k]) BZK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->aux_ev[k], cudaEventDisableTiming));
-    constexpr size_t kWinBytes = kMaxWinPoints * sizeof(G2Xyzz);
     if (ctx->pinned_bytes < 5 * kWinBytes) {
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
         ctx->pinned = nullptr;
@@ -353,7 +376,6 @@ static int32_t groth16_prove_impl(bzk_ctx *ctx, const bzk_groth16_params *pk, co
         ctx->pinned_bytes = 5 * kWinBytes;
     }
     char *hw = (char *)ctx->pinned;
-    MsmPlan plan[5];
     lap("z + evaluations enqueued");
     cudaStream_t s_l = ctx->aux_stream[0], s_a = ctx->aux_stream[1], s_b1 = ctx->aux_stream[2], s_b2 = ctx->aux_stream[3];
     g16_mark(1, st);
@@ -373,9 +395,23 @@ static int32_t groth16_prove_impl(bzk_ctx *ctx, const bzk_groth16_params *pk, co
     BZK_CUDA(ctx, cudaStreamWaitEvent(s_b2, ctx->aux_ev[1], 0));
     BZK_TRY(msm_g1_enqueue(ctx, s_b1, &ctx->aux_ws[2], &ctx->aux_ws_bytes[2], bases_ref(pk->b1), gs_b + b_lo, b_n, hw + 3 * kWinBytes, &plan[3]));
     BZK_TRY(msm_g2_enqueue(ctx, s_b2, &ctx->aux_ws[3], &ctx->aux_ws_bytes[3], bases_ref(pk->b2), gs_b + b_lo, b_n, hw + 4 * kWinBytes, &plan[4]));
+    if (phase == 1) {
+        // this rank's evaluation vectors to the coset (ifft, then coset_fft); the pointwise step and the last transform
+        // happen on the rank that collects the three (bzk_groth16_h_combine_dev)
+        for (int s = 0; s < 3; s++)
+            if (ev[s]) BZK_TRY(groth16_to_coset_launch(ctx, ev[s], cs->log_m));
+        g16_mark(2, st);
+        BZK_CUDA(ctx, cudaStreamSynchronize(st));  // the caller hands the vectors to its transport next
+        ctx->split_open = true;
+        return BZK_OK;
+    }
     BZK_TRY(groth16_h_launch(ctx, ea, eb, ec, cs->log_m));  // ea <- h coefficients
     g16_mark(2, st);
-    BZK_TRY(msm_g1_enqueue(ctx, st, &ctx->ws, &ctx->ws_bytes, bases_ref(pk->h), ea + h_lo, h_n, hw, &plan[0]));
+    }  // phase != 2
+    char *hw = (char *)ctx->pinned;
+    const Fr *h_src = phase == 2 ? split->h_shard : ea + h_lo;
+    ctx->split_open = false;
+    BZK_TRY(msm_g1_enqueue(ctx, st, &ctx->ws, &ctx->ws_bytes, bases_ref(pk->h), h_src, h_n, hw, &plan[0]));
     g16_mark(3, st);
     for (int k = 0; k < 4; k++) g16_mark(4 + k, ctx->aux_stream[k]);
     lap("all kernels enqueued");
@@ -514,6 +550,26 @@ int32_t bzk_groth16_prove_partial(bzk_ctx *ctx, const bzk_groth16_params *pk, co
     return groth16_prove_impl(ctx, pk, cs, (const bzk_fr *)inputs, (const bzk_fr *)aux,
                               witness_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, nullptr, nullptr, check_satisfied,
                               nullptr, nullptr, nullptr, &part);
+}
+
+/* The sharded schedule with the quotient pipeline split over the ranks (include/bzk.h).  begin: z, the evaluation vectors in
+ * `poly_mask` (bit 0 = a, 1 = b, 2 = c) computed into the caller's buffers and taken to the coset, the l / a / b_g1 / b_g2
+ * partial sums enqueued on their streams (they keep running while the caller moves vectors between GPUs).  finish: the h sum
+ * over this rank's slice of the quotient coefficients, then the four partial sums as bzk_groth16_prove_partial returns them. */
+int32_t bzk_groth16_shard_begin(bzk_ctx *ctx, const bzk_groth16_params *pk, const bzk_r1cs *cs, const void *inputs, const void *aux,
+                                int32_t witness_on_device, uint32_t poly_mask, void *d_evals[3]) {
+    if (!d_evals || poly_mask > 7) return BZK_ERR_BAD_ARG;
+    const Groth16Split sp{1, poly_mask, {(Fr *)d_evals[0], (Fr *)d_evals[1], (Fr *)d_evals[2]}, nullptr};
+    return groth16_prove_impl(ctx, pk, cs, (const bzk_fr *)inputs, (const bzk_fr *)aux,
+                              witness_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                              nullptr, &sp);
+}
+int32_t bzk_groth16_shard_finish(bzk_ctx *ctx, const bzk_groth16_params *pk, const bzk_r1cs *cs, const void *d_h_shard,
+                                 bzk_g1_affine *a_sum, bzk_g1_affine *b1_sum, bzk_g2_affine *b2_sum, bzk_g1_affine *hl_sum) {
+    if (!a_sum || !b1_sum || !b2_sum || !hl_sum) return BZK_ERR_BAD_ARG;
+    const Groth16Partials part{a_sum, b1_sum, hl_sum, b2_sum};
+    const Groth16Split sp{2, 0, {nullptr, nullptr, nullptr}, (const Fr *)d_h_shard};
+    return groth16_prove_impl(ctx, pk, cs, nullptr, nullptr, cudaMemcpyDeviceToDevice, nullptr, nullptr, 0, nullptr, nullptr, nullptr, &part, &sp);
 }
 
 /* bellman `create_proof`'s last lines from the (summed) answers:

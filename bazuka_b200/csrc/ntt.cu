@@ -303,6 +303,27 @@ int32_t divide_by_z_launch(bzk_ctx *ctx, Fr *d, uint32_t log_n) {
     return BZK_OK;
 }
 
+// one evaluation vector to the coset: ifft then coset_fft, the first half of the quotient pipeline below
+int32_t groth16_to_coset_launch(bzk_ctx *ctx, Fr *v, uint32_t log_n) {
+    if (log_n > 28 || !v) return BZK_ERR_BAD_ARG;
+    BZK_TRY(ensure_tables(ctx, log_n));
+    BZK_TRY(ensure_gpow(ctx));
+    const NttTables &tb = ctx->ntt[log_n];
+    uint32_t e[1] = {log_n};
+    const Fr ninv = Fr::from_u32(2).inv().pow(e, 1);
+    BZK_TRY(run_dif(ctx, v, log_n, tb.d_inv));
+    return run_dit_prescaled(ctx, v, log_n, tb.d_fwd, ninv, ctx->d_gpow, ctx->d_gpow + kGpowN);
+}
+
+// the second half: a <- coefficients of (a*b - c) / Z from the three vectors on the coset
+int32_t groth16_h_combine_launch(bzk_ctx *ctx, Fr *a, Fr *b, Fr *c, uint32_t log_n) {
+    if (log_n > 28 || !a || !b || !c) return BZK_ERR_BAD_ARG;
+    const size_t n = (size_t)1 << log_n;
+    k_h_pointwise<<<div_up(n, 256), 256, 0, ctx->stream>>>(a, b, c, n, host_zinv(log_n));
+    BZK_LAUNCHED(ctx);
+    return ntt_launch(ctx, a, log_n, BZK_NTT_ICOSET_FFT);
+}
+
 int32_t groth16_h_launch(bzk_ctx *ctx, Fr *a, Fr *b, Fr *c, uint32_t log_n) {
     if (log_n > 28 || !a || !b || !c) return BZK_ERR_BAD_ARG;
     const size_t n = (size_t)1 << log_n;

@@ -201,6 +201,31 @@ class Prover:
                                                  _host_ptr(a_sum), _host_ptr(b1_sum), _host_ptr(b2_sum), _host_ptr(hl_sum)))
         return a_sum, b1_sum, b2_sum, hl_sum
 
+    def shard_begin(self, spk: ProvingKey, d_inputs, d_aux, evals):
+        """first half of the split sharded schedule: evals = [tensor | None] * 3 — the evaluation vectors (a, b, c) this rank owns,
+        as CUDA int64 tensors [2^log_m, 4] that receive them on the coset; the four witness sums start on their streams."""
+        import ctypes as ct
+        from .api import _dev_ptr
+        c = self.ctx
+        ptrs = (ct.c_void_p * 3)(*[_dev_ptr(e) if e is not None else None for e in evals])
+        mask = sum(1 << k for k, e in enumerate(evals) if e is not None)
+        c._check(c._l.bzk_groth16_shard_begin(c._h, spk._h, self._h, _dev_ptr(d_inputs), _dev_ptr(d_aux), 1, mask, ptrs))
+
+    def h_combine(self, d_a, d_b, d_c):
+        """(a*b - c)/Z from the three vectors on the coset, back to coefficients: d_a <- h"""
+        from .api import _dev_ptr
+        c = self.ctx
+        c._check(c._l.bzk_groth16_h_combine_dev(c._h, _dev_ptr(d_a), _dev_ptr(d_b), _dev_ptr(d_c), self.log_m))
+
+    def shard_finish(self, spk: ProvingKey, d_h_shard):
+        """second half: the h sum over this rank's slice of the quotient -> (a, b_g1, b_g2, h+l) partial sums"""
+        from .api import _dev_ptr
+        c = self.ctx
+        a_sum, b1_sum, hl_sum, b2_sum = np.zeros(G1_BYTES, np.uint8), np.zeros(G1_BYTES, np.uint8), np.zeros(G1_BYTES, np.uint8), np.zeros(G2_BYTES, np.uint8)
+        c._check(c._l.bzk_groth16_shard_finish(c._h, spk._h, self._h, _dev_ptr(d_h_shard) if d_h_shard is not None else None,
+                                                _host_ptr(a_sum), _host_ptr(b1_sum), _host_ptr(b2_sum), _host_ptr(hl_sum)))
+        return a_sum, b1_sum, b2_sum, hl_sum
+
     def prove_dev(self, pk: ProvingKey, d_inputs, d_aux, r, s, check_satisfied=True):
         """`prove` with the witness already resident: d_inputs [num_inputs,4], d_aux [num_aux,4] CUDA int64
         tensors of Montgomery images (e.g. written by mpn.gpu_witness)."""
@@ -270,6 +295,62 @@ def allgather_partials(partials, group=None, device="cpu"):
     dist.all_gather_into_tensor(gathered, mine, group=group)
     g = gathered.cpu().numpy().reshape(world, 512)
     return (fold(g[:, 0:104], "g1"), fold(g[:, 104:208], "g1"), fold(g[:, 312:512], "g2"), fold(g[:, 208:312], "g1"))
+
+
+class SplitShardedProver:
+    """Schedule (S) with the quotient pipeline split over the ranks (include/bzk.h, bzk_groth16_shard_begin): evaluation vector
+    s belongs to rank s mod world, rank 3 mod world combines them and deals the quotient's coefficients out in slices.  The
+    vectors move with NCCL point-to-point operations (torch.distributed); buffers are allocated once and reused."""
+
+    def __init__(self, prover, spk, rank, world, device, group=None):
+        import torch
+        from .dist import shard_range
+        self.pr, self.spk, self.rank, self.world, self.dev, self.group = prover, spk, rank, world, device, group
+        self.m = 1 << prover.log_m
+        self.owner = [s % world for s in range(3)]
+        self.comb = 3 % world
+        need = [self.owner[s] == rank or self.comb == rank for s in range(3)]
+        self.buf = [torch.empty((self.m, 4), dtype=torch.int64, device=device) if n else None for n in need]
+        self.ranges = [shard_range(self.m - 1, k, world) for k in range(world)]
+        lo, hi = self.ranges[rank]
+        self.h_mine = None if self.comb == rank else torch.empty((hi - lo, 4), dtype=torch.int64, device=device)
+
+    def partials(self, d_in, d_aux):
+        import torch
+        import torch.distributed as dist
+        pr, rank, comb = self.pr, self.rank, self.comb
+        pr.shard_begin(self.spk, d_in, d_aux, [self.buf[s] if self.owner[s] == rank else None for s in range(3)])
+        ops = []
+        for s in range(3):
+            if self.owner[s] == comb:
+                continue
+            if rank == self.owner[s]:
+                ops.append(dist.P2POp(dist.isend, self.buf[s], comb, self.group))
+            elif rank == comb:
+                ops.append(dist.P2POp(dist.irecv, self.buf[s], self.owner[s], self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        ops = []
+        if rank == comb:
+            torch.cuda.current_stream(self.dev).synchronize()      # the received vectors are complete
+            pr.h_combine(*self.buf)                                   # on the context's stream
+            pr.ctx.synchronize()
+            h = self.buf[0]
+            for k, (lo, hi) in enumerate(self.ranges):
+                if k != rank and hi > lo:
+                    ops.append(dist.P2POp(dist.isend, h[lo:hi], k, self.group))
+            lo, hi = self.ranges[rank]
+            mine = h[lo:hi]
+        else:
+            if self.h_mine.shape[0]:
+                ops.append(dist.P2POp(dist.irecv, self.h_mine, comb, self.group))
+            mine = self.h_mine
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        torch.cuda.current_stream(self.dev).synchronize()
+        return pr.shard_finish(self.spk, mine)
 
 
 def verify(vk, public_inputs, proof_points):

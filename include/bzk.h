@@ -243,6 +243,20 @@ int32_t bzk_groth16_params_set_shard(bzk_groth16_params *params, uint32_t rank, 
 int32_t bzk_groth16_prove_partial(bzk_ctx *ctx, const bzk_groth16_params *params, const bzk_r1cs *r1cs, const void *inputs, const void *aux,
                                   int32_t witness_on_device, int32_t check_satisfied,
                                   bzk_g1_affine *a_sum, bzk_g1_affine *b1_sum, bzk_g2_affine *b2_sum, bzk_g1_affine *hl_sum);
+/* The same schedule with the quotient pipeline split over the ranks as well (every rank would otherwise repeat the three
+ * SpMVs and seven NTTs, the part of a proof that does not shrink with `world`): evaluation vector s (0 = a, 1 = b, 2 = c) is
+ * owned by rank s mod world, which computes it from z and takes it to the coset (ifft, coset_fft); the owners send their
+ * vectors to rank 3 mod world, which forms (a*b - c)/Z and the quotient's coefficients (bzk_groth16_h_combine_dev: a <- h) and
+ * hands rank k the slice [(m-1)k/world, (m-1)(k+1)/world) of them.  The transport between GPUs is the caller's
+ * (bazuka_b200.groth16.prove_sharded_split uses NCCL point-to-point through torch.distributed).
+ *   bzk_groth16_shard_begin   z, the vectors in poly_mask into the caller's device buffers d_evals[s] (2^log_m scalars each),
+ *                             and the l / a / b_g1 / b_g2 partial sums enqueued — they keep the GPU busy during the exchange
+ *   bzk_groth16_shard_finish  the h partial sum over d_h_shard, then the four partial sums of bzk_groth16_prove_partial */
+int32_t bzk_groth16_shard_begin(bzk_ctx *ctx, const bzk_groth16_params *params, const bzk_r1cs *r1cs, const void *inputs, const void *aux,
+                                int32_t witness_on_device, uint32_t poly_mask, void *d_evals[3]);
+int32_t bzk_groth16_h_combine_dev(bzk_ctx *ctx, void *d_a, void *d_b, void *d_c, uint32_t log_n);
+int32_t bzk_groth16_shard_finish(bzk_ctx *ctx, const bzk_groth16_params *params, const bzk_r1cs *r1cs, const void *d_h_shard,
+                                 bzk_g1_affine *a_sum, bzk_g1_affine *b1_sum, bzk_g2_affine *b2_sum, bzk_g1_affine *hl_sum);
 int32_t bzk_groth16_finalize(const bzk_g1_affine *alpha_g1, const bzk_g1_affine *beta_g1, const bzk_g2_affine *beta_g2,
                              const bzk_g1_affine *delta_g1, const bzk_g2_affine *delta_g2,
                              const bzk_g1_affine *a_sum, const bzk_g1_affine *b1_sum, const bzk_g2_affine *b2_sum, const bzk_g1_affine *hl_sum,

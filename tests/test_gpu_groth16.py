@@ -137,6 +137,54 @@ def test_base_sharded_partials_fold_to_the_same_proof(ctx, cref):
     spk.free(); pk.free(); pr.free()
 
 
+def test_split_sharded_schedule_gives_the_same_proof(ctx, cref):
+    """bzk_groth16_shard_begin / _h_combine_dev / _shard_finish: three ranks emulated by three contexts on one GPU — rank s owns
+    evaluation vector s (computes it, takes it to the coset), rank 0 combines them into the quotient and deals out slices, every
+    rank sums its base shards — folded and finalised to the bytes of the unsharded proof; a finish without a begin is refused."""
+    import torch
+    import bazuka_b200 as B
+    from bazuka_b200 import groth16 as BG, synth, dist as bd
+    ni, na, mats, inputs, aux = synth.build(lanes=16, rounds=6, seed=31, ops=synth.GpuOps(ctx))
+    pr = BG.Prover(ctx, BG.R1CS(ni, na, *mats))
+    pk, vk = BG.setup_gpu(ctx, pr.r1cs, cref.fr_random(41, 5), cref.g1_generator(), cref.g2_generator())
+    r, s = cref.fr_random(42, 2)
+    want, _ = pr.prove(pk, inputs, aux, r, s)
+    d_in = torch.from_numpy(inputs.view(np.int64)).cuda()
+    d_aux = torch.from_numpy(aux.view(np.int64)).cuda()
+    world, m = 3, 1 << pr.log_m
+    ctxs = [B.Context(0) for _ in range(world)]
+    provers = [BG.Prover(c, BG.R1CS(ni, na, *mats)) for c in ctxs]
+    spks = [BG.shard_proving_key(c, pk, pr.log_m, k, world) for k, c in enumerate(ctxs)]
+    with pytest.raises(B.BzkError):
+        provers[1].shard_finish(spks[1], torch.zeros((1, 4), dtype=torch.int64, device="cuda"))
+    bufs = [torch.empty((m, 4), dtype=torch.int64, device="cuda") for _ in range(3)]
+    for k in range(world):
+        provers[k].shard_begin(spks[k], d_in, d_aux, [bufs[j] if j == k else None for j in range(3)])
+    provers[0].h_combine(*bufs)
+    ctxs[0].synchronize()
+    parts = []
+    for k in range(world):
+        lo, hi = bd.shard_range(m - 1, k, world)
+        parts.append(provers[k].shard_finish(spks[k], bufs[0][lo:hi].contiguous()))
+    sums = (bd.fold([p[0] for p in parts], "g1"), bd.fold([p[1] for p in parts], "g1"),
+            bd.fold([p[2] for p in parts], "g2"), bd.fold([p[3] for p in parts], "g1"))
+    blob, pts = BG.finalize(vk, sums, r, s)
+    assert (blob == want).all()
+    assert BG.verify(vk, inputs[1:], pts)
+    # one rank owning everything (world = 1) through the same entry points
+    spk1 = BG.shard_proving_key(ctx, pk, pr.log_m, 0, 1)
+    pr.shard_begin(spk1, d_in, d_aux, bufs)
+    pr.h_combine(*bufs)
+    ctx.synchronize()
+    one = pr.shard_finish(spk1, bufs[0][:m - 1].contiguous())
+    assert (BG.finalize(vk, one, r, s)[0] == want).all()
+    for x in spks + [spk1]:
+        x.free()
+    for x in provers:
+        x.free()
+    pk.free(); pr.free()
+
+
 def test_batch_verifier_on_gpu_equals_host_batch_verifier(ctx, cref):
     """bzk_groth16_verify_batch_dev (one thread per proof: [r_j]A_j, the Jacobian walk of B_j, 68 line evaluations; product,
     key-dependent loops and the single final exponentiation on the host) against the host batch verifier and the oracle's

@@ -166,6 +166,29 @@ def batch_section(ctx, A=15, T=3, B=4, steps=3, dist=None, rank=0, world=1, peak
                               "n_gpus": world, "ms_per_proof": min(ts) * 1e3, "ms_per_proof_median": float(np.median(ts)) * 1e3,
                               "single_gpu_ms_per_proof": t_one * 1e3, "speedup_vs_1gpu": t_one / min(ts),
                               "proof_bytes_equal_single_gpu": bool((blob_s == want).all())}
+            # (S') the same with the quotient pipeline split over the ranks too (bzk_groth16_shard_begin / _finish)
+            try:
+                sp = BG.SplitShardedProver(pr, spk, rank, world, dev)
+
+                def sharded_split():
+                    return BG.finalize(worker.vk, BG.allgather_partials(sp.partials(d_in, d_aux), device=dev), rnd[5], rnd[6])
+
+                blob_q, _ = sharded_split()
+                tq = []
+                for _ in range(reps):
+                    barrier()
+                    t0 = time.perf_counter()
+                    sharded_split()
+                    torch.cuda.synchronize()
+                    tq.append(max_over_ranks(time.perf_counter() - t0))
+                out["sharded"]["split_quotient"] = {
+                    "schedule": "S': S plus evaluation vector s owned by rank s mod world, combined on rank 3 mod world, quotient slices dealt "
+                                "out over NCCL point-to-point (2 x 512 MiB in, (world-1)/world x 512 MiB out at 2^24)",
+                    "ms_per_proof": min(tq) * 1e3, "ms_per_proof_median": float(np.median(tq)) * 1e3, "speedup_vs_1gpu": t_one / min(tq),
+                    "proof_bytes_equal_single_gpu": bool((blob_q == want).all())}
+                del sp
+            except Exception as e:
+                out["sharded"]["split_quotient"] = {"error": repr(e)}
             spk.free()
         except Exception as e:
             out["sharded"] = {"error": repr(e)}
