@@ -99,6 +99,7 @@ SIGNATURES = {
     "bzk_jubjub_decompress": (_i32, [_vp, _vp, _i32, _vp]),
     "bzk_mpn_update_raw_width": (_i32, [_u32, _u32, _vp]),
     "bzk_mpn_update_build": (_i32, [_vp, _vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bzk_jubjub_eddsa_verify": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "bzk_mpn_deposit_build": (_i32, [_vp, _vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bzk_mpn_withdraw_build": (_i32, [_vp, _vp, _vp, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bzk_mpn_dw_witness": (_i32, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),

@@ -321,6 +321,9 @@ class Context:
         self._check(self._l.bzk_fp_mul_dev(self._h, _dev_ptr(d_a), _dev_ptr(d_b), _dev_ptr(d_out), n))
 
 
+_FR_MODULUS = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+
 class HostPoseidon:
     """`impl ZkHasher for PoseidonHasher` (/root/reference/src/zk/mod.rs:491-511) without a GPU round trip: single hashes on
     the host field arithmetic of libbzk (bzk_poseidon_host_*).  inputs [n, arity, 4] or [arity, 4] Montgomery -> digests."""
@@ -345,6 +348,17 @@ class HostPoseidon:
         if st != 0:
             raise BzkError(st, "poseidon_host_hash")
         return out[0] if single else out
+
+    def eddsa_verify(self, jubjub_d, pk, message, sig_r, sig_s):
+        """`JubJub::verify` (/root/reference/src/crypto/jubjub/mod.rs:151-167) on the host: ints in, bool out"""
+        canon = lambda *v: np.frombuffer(b"".join((int(x) % _FR_MODULUS).to_bytes(32, "little") for x in v), dtype=np.uint64).reshape(-1, 4).copy()
+        d, a, m, r, s = canon(jubjub_d), canon(*pk), canon(message), canon(*sig_r), canon(sig_s)
+        if not all(0 <= int(x) < _FR_MODULUS for x in (*pk, message, *sig_r, sig_s)):
+            return False
+        st = self._l.bzk_jubjub_eddsa_verify(self._h, _host_ptr(d), _host_ptr(a), _host_ptr(m), _host_ptr(r), _host_ptr(s))
+        if st < 0:
+            raise BzkError(st, "jubjub_eddsa_verify")
+        return bool(st)
 
     def free(self):
         if self._h:

@@ -278,6 +278,29 @@ inline bool eddsa_verify_with_h(const bzk_mpn_state *s, const Point &pk, const P
     return jj_equal(lhs, jj_mul(jj_base(), sig_s_canon, s->jj_d));
 }
 
+}  // namespace
+
+// `JubJub::verify` (/root/reference/src/crypto/jubjub/mod.rs:151-167) as a stand-alone host call: the signature check the
+// withdraw builder applies (and a bank node applies to every MPN transaction before it enters the pool), on libbzk's host
+// field arithmetic and the host Poseidon.  All scalars canonical.  Returns 1 (valid), 0 (invalid) or a negative status.
+extern "C" int32_t bzk_jubjub_eddsa_verify(const bzk_poseidon_host *hasher, const bzk_fr *jubjub_d, const bzk_fr pk_xy[2], const bzk_fr *message,
+                                           const bzk_fr sig_r_xy[2], const bzk_fr *sig_s) {
+    if (!hasher || !jubjub_d || !pk_xy || !message || !sig_r_xy || !sig_s) return BZK_ERR_BAD_ARG;
+    if (!canonical(pk_xy[0]) || !canonical(pk_xy[1]) || !canonical(sig_r_xy[0]) || !canonical(sig_r_xy[1]) || !canonical(*sig_s) || !canonical(*message))
+        return 0;
+    bzk_mpn_state tmp;
+    tmp.jj_d = fr_from_canon(jubjub_d);
+    const Point pk{fr_from_canon(pk_xy + 0), fr_from_canon(pk_xy + 1)}, r{fr_from_canon(sig_r_xy + 0), fr_from_canon(sig_r_xy + 1)};
+    const Fr in[5] = {r.x, r.y, pk.x, pk.y, fr_from_canon(message)};
+    Fr h;
+    BZK_TRY(bzk_poseidon_host_hash(hasher, 5, (const bzk_fr *)in, 1, (bzk_fr *)&h));
+    Fr s_canon;
+    memcpy(s_canon.l, sig_s, 32);
+    return eddsa_verify_with_h(&tmp, pk, r, s_canon, h) ? 1 : 0;
+}
+
+namespace {
+
 // root of `List<log4 B>(Struct[...])` over the batch's rows (deposit.rs:178-218, withdraw.rs:190-245): one hash per row,
 // then the 4-ary tree — every level one batched launch
 int32_t list_root(bzk_ctx *ctx, uint32_t arity, const std::vector<Fr> &rows, Fr *out) {

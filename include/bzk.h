@@ -333,6 +333,10 @@ int32_t bzk_mpn_dw_witness(bzk_ctx *ctx, const bzk_witness_program *phase1, cons
 /* `PublicKey::decompress` (/root/reference/src/crypto/jubjub/curve.rs:78-88) on the host field arithmetic, no
  * context: y = sqrt((1 + x^2) / (1 - d x^2)) with the parity rule; canonical scalars. */
 int32_t bzk_jubjub_decompress(const bzk_fr *jubjub_d, const bzk_fr *x, int32_t y_is_odd, bzk_fr out_xy[2]);
+/* `JubJub::verify` (/root/reference/src/crypto/jubjub/mod.rs:151-167) on the host (no context): h = Poseidon(R.x, R.y, A.x, A.y,
+ * message), accept iff h*A + R == s*BASE and A, R are on the curve.  Canonical scalars; returns 1 / 0, negative on bad arguments. */
+int32_t bzk_jubjub_eddsa_verify(const bzk_poseidon_host *hasher, const bzk_fr *jubjub_d, const bzk_fr pk_xy[2], const bzk_fr *message,
+                                const bzk_fr sig_r_xy[2], const bzk_fr *sig_s);
 int32_t bzk_mpn_update_build(bzk_ctx *ctx, bzk_mpn_state *state, const bzk_mpn_tx *txs, uint64_t n_txs, uint32_t log4_batch,
                              const bzk_fr *fee_token, bzk_fr *raws, bzk_fr *ext, uint8_t *accepted, bzk_fr public3[3],
                              uint64_t *n_accepted);

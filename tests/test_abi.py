@@ -36,6 +36,33 @@ def test_struct_sizes_match_reference_images():
     assert len(C.g1_to_bytes(C.G1_GEN)) == 104 and len(C.g2_to_bytes(C.G2_GEN)) == 200
 
 
+def test_packed_transaction_structs_match_the_header(tmp_path):
+    """the numpy record layouts mpn/ledger.py packs (bzk_mpn_tx, bzk_mpn_deposit, bzk_mpn_withdraw) against the C compiler's view
+    of include/bzk.h: total size and every field offset."""
+    import subprocess
+    from bazuka_b200.mpn import ledger as L
+    fields = {"bzk_mpn_tx": (L._TX, ["nonce", "amount", "fee", "src_pk_odd", "dst_pk_odd", "src_pk_x", "dst_pk_x", "amount_token_id",
+                                     "fee_token_id", "sig_rx", "sig_ry", "sig_s"]),
+              "bzk_mpn_deposit": (L._DEP, ["pk_x", "pk_odd", "token_id", "amount"]),
+              "bzk_mpn_withdraw": (L._WD, ["pk_x", "pk_odd", "nonce", "sig_rx", "sig_ry", "sig_s", "amount_token_id", "fee_token_id",
+                                           "fingerprint", "amount", "fee"])}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "bzk.h"', 'int main(void) {']
+    for name, (_, fs) in fields.items():
+        src.append(f'printf("{name} %zu", sizeof({name}));')
+        src += [f'printf(" %zu", offsetof({name}, {f}));' for f in fs]
+        src.append('printf("\\n");')
+    src += ["return 0;", "}"]
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
+    for line in subprocess.check_output([str(exe)], text=True).splitlines():
+        name, size, *offs = line.split()
+        dt, fs = fields[name]
+        assert dt.itemsize == int(size), name
+        assert [dt.fields[f][1] for f in fs] == [int(o) for o in offs], name
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     import bazuka_b200 as B
@@ -280,3 +307,23 @@ def test_host_poseidon_is_the_reference_hash(cref):
         h.hash(one)
     print(f"host Poseidon-4: {(time.perf_counter() - t0) / 200 * 1e6:.0f} us per hash (incl. ctypes)")
     h.free()
+
+
+def test_host_eddsa_verify_is_the_reference_check():
+    """bzk_jubjub_eddsa_verify (host JubJub arithmetic + host Poseidon of libbzk) == the Python restatement of `JubJub::verify`
+    (/root/reference/src/crypto/jubjub/mod.rs:151-167) on valid signatures and on every kind of tampering the builders meet."""
+    from bazuka_b200.api import HostPoseidon
+    from bazuka_b200.mpn import native as N
+    hp = HostPoseidon()
+    for seed in (b"a", b"b", b"c"):
+        pk, sk = N.eddsa_keys(b"key-" + seed)
+        other, _ = N.eddsa_keys(b"other-" + seed)
+        msg = N.poseidon([int.from_bytes(seed, "big"), 7])
+        sig = N.eddsa_sign(sk, msg)
+        cases = [(pk, msg, sig["r"], sig["s"]), (pk, msg + 1, sig["r"], sig["s"]), (pk, msg, sig["r"], sig["s"] + 1), (other, msg, sig["r"], sig["s"]),
+                 (pk, msg, (sig["r"][0], sig["r"][1] + 1), sig["s"]), ((pk[0] + 1, pk[1]), msg, sig["r"], sig["s"]), (pk, msg, sig["r"], 0),
+                 (pk, msg, (0, 1), sig["s"]), (pk, msg, sig["r"], Fd.R_MOD + sig["s"])]
+        got = [hp.eddsa_verify(N.JJ_D, *c) for c in cases]
+        want = [N.eddsa_verify(c[0], c[1], {"r": c[2], "s": c[3]}) if all(0 <= v < Fd.R_MOD for v in (*c[0], c[1], *c[2], c[3])) else False for c in cases]
+        assert got == want and got[0] and not any(got[1:])
+    hp.free()
