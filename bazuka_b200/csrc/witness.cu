@@ -151,36 +151,8 @@ int32_t bzk_witness_program_upload(bzk_ctx *ctx, const int32_t *ops, uint64_t n_
         }
     }
     // schedule: depth of every variable in the data-flow graph, ops ordered by (depth, opcode)
-    std::vector<uint32_t> depth(kSlotBlock0 + n_ops, 0);
-    uint32_t n_levels = 0;
-    uint64_t n_exec = 0;
-    for (uint64_t j = 0; j < n_ops; j++) {
-        const int32_t *op = ops + j * 6;
-        if (op[0] == W_NOP) continue;   // its variable took the JJ's depth below
-        uint32_t d = 0;
-        const int nlc = wit_operands(op[0]);
-        for (int a = 0; a < nlc; a++)
-            for (int32_t k = lc_ptr[op[1 + a]]; k < lc_ptr[op[1 + a] + 1]; k++) d = std::max(d, depth[lc_slot[k]]);
-        depth[kSlotBlock0 + j] = d + 1;
-        if (op[0] == W_JJ) depth[kSlotBlock0 + j + 1] = d + 1;
-        n_levels = std::max(n_levels, d + 1);
-        n_exec++;
-    }
-    std::vector<int32_t> level_ptr(n_levels + 2, 0), sops(n_exec * 8 + 8, 0);
-    {
-        // counting sort on (level, opcode); levels are 1-based
-        std::vector<uint64_t> cnt((size_t)(n_levels + 1) * 8 + 1, 0);
-        for (uint64_t j = 0; j < n_ops; j++)
-            if (ops[j * 6] != W_NOP) cnt[(size_t)depth[kSlotBlock0 + j] * 8 + ops[j * 6] + 1]++;
-        for (size_t i = 1; i < cnt.size(); i++) cnt[i] += cnt[i - 1];
-        for (uint32_t L = 1; L <= n_levels + 1; L++) level_ptr[L - 1] = (int32_t)cnt[(size_t)L * 8];
-        for (uint64_t j = 0; j < n_ops; j++) {
-            const int32_t *op = ops + j * 6;
-            if (op[0] == W_NOP) continue;
-            int32_t *o = sops.data() + cnt[(size_t)depth[kSlotBlock0 + j] * 8 + op[0]]++ * 8;
-            o[0] = op[0]; o[1] = op[1]; o[2] = op[2]; o[3] = op[3]; o[4] = op[4]; o[5] = op[5]; o[6] = (int32_t)j;
-        }
-    }
+    std::vector<int32_t> level_ptr, sops;
+    const uint32_t n_levels = wit_build_schedule(ops, n_ops, lc_ptr, lc_slot, n_ext, sops, level_ptr);
     BZK_CUDA(ctx, cudaSetDevice(ctx->device));
     auto *p = new (std::nothrow) bzk_witness_program;
     if (!p) return BZK_ERR_OOM;

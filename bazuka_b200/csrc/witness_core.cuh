@@ -3,6 +3,9 @@
 // The memory policy is a template parameter: Mem::load(slot) / store(slot, v) address the slot's variable
 // array, Mem::out(j, v) additionally emits block variable j into z, Mem::prefetch(slot) is a hint.
 #pragma once
+#include <algorithm>
+#include <vector>
+
 #include "ff.cuh"
 
 namespace bzk {
@@ -122,6 +125,44 @@ BZK_HD void wit_run_slot(const WitProgDev &P, const Fr &jj_d, const Fr *raws, co
         }
         wit_exec_op(P, jj_d, raws, j, code, a0, a1, a2, a3, imm, mem);
     }
+}
+
+// Level schedule of a program (host): level of an op = 1 + the deepest of its operands (ONE, externals and raw inputs are at
+// depth 0), so the ops of one level are mutually independent.  sops[k][8] = {opcode, lc0..lc3, imm, op index, 0} ordered by
+// (level, opcode), NOPs dropped (a JJ writes both of its variables); level_ptr[L] .. level_ptr[L+1] delimit level L+1.
+inline uint32_t wit_build_schedule(const int32_t *ops, uint64_t n_ops, const int32_t *lc_ptr, const int32_t *lc_slot, uint32_t n_ext,
+                                   std::vector<int32_t> &sops, std::vector<int32_t> &level_ptr) {
+    const uint64_t block0 = 1 + (uint64_t)n_ext;
+    std::vector<uint32_t> depth(block0 + n_ops, 0);
+    uint32_t n_levels = 0;
+    uint64_t n_exec = 0;
+    for (uint64_t j = 0; j < n_ops; j++) {
+        const int32_t *op = ops + j * 6;
+        if (op[0] == W_NOP) continue;  // its variable took the JJ's depth below
+        uint32_t d = 0;
+        const int nlc = wit_operands(op[0]);
+        for (int a = 0; a < nlc; a++)
+            for (int32_t k = lc_ptr[op[1 + a]]; k < lc_ptr[op[1 + a] + 1]; k++) d = std::max(d, depth[lc_slot[k]]);
+        depth[block0 + j] = d + 1;
+        if (op[0] == W_JJ) depth[block0 + j + 1] = d + 1;
+        n_levels = std::max(n_levels, d + 1);
+        n_exec++;
+    }
+    level_ptr.assign(n_levels + 2, 0);
+    sops.assign(n_exec * 8 + 8, 0);
+    // counting sort on (level, opcode); levels are 1-based
+    std::vector<uint64_t> cnt((size_t)(n_levels + 1) * 8 + 1, 0);
+    for (uint64_t j = 0; j < n_ops; j++)
+        if (ops[j * 6] != W_NOP) cnt[(size_t)depth[block0 + j] * 8 + ops[j * 6] + 1]++;
+    for (size_t i = 1; i < cnt.size(); i++) cnt[i] += cnt[i - 1];
+    for (uint32_t L = 1; L <= n_levels + 1; L++) level_ptr[L - 1] = (int32_t)cnt[(size_t)L * 8];
+    for (uint64_t j = 0; j < n_ops; j++) {
+        const int32_t *op = ops + j * 6;
+        if (op[0] == W_NOP) continue;
+        int32_t *o = sops.data() + cnt[(size_t)depth[block0 + j] * 8 + op[0]]++ * 8;
+        o[0] = op[0]; o[1] = op[1]; o[2] = op[2]; o[3] = op[3]; o[4] = op[4]; o[5] = op[5]; o[6] = (int32_t)j;
+    }
+    return n_levels;
 }
 
 }  // namespace bzk

@@ -90,6 +90,44 @@ void shim_witness_run(const int32_t *ops, uint32_t n_ops, const int32_t *lc_ptr,
     Fr d; memcpy(d.l, jj_d, 32);
     wit_run_slot(P, d, (const Fr *)raws, (const Fr *)ext, mem);
 }
+
+// the same program in the order the GPU kernel runs it (witness.cu k_witness_levels): the schedule of wit_build_schedule, level
+// by level, the ops of a level BACKWARDS (any order inside a level must do); returns the level count, stats[0..3] =
+// executed ops, widest level, levels holding an inversion (JJ / INVZ)
+uint32_t shim_witness_run_levels(const int32_t *ops, uint32_t n_ops, const int32_t *lc_ptr, const int32_t *lc_slot, const int32_t *lc_coef,
+                                 const uint32_t *coefs, uint32_t n_raw, uint32_t n_ext, const uint32_t *jj_d, const uint32_t *raws,
+                                 const uint32_t *ext, uint32_t *aux_out, uint64_t *stats) {
+    struct Mem {   // the device layout: {ONE, externals} in a side array, block variables in the z segment
+        std::vector<Fr> pre;
+        Fr *z;
+        uint32_t block0;
+        Fr load(int32_t slot) const { return (uint32_t)slot < block0 ? pre[slot] : z[slot - block0]; }
+        void store(uint32_t slot, const Fr &v) { z[slot - block0] = v; }
+        void out(uint32_t, const Fr &) {}
+        void prefetch(int32_t) const {}
+    } mem;
+    mem.block0 = 1 + n_ext;
+    mem.pre.assign(mem.block0, Fr::one());
+    for (uint32_t k = 0; k < n_ext; k++) { Fr e; memcpy(e.l, ext + 8 * k, 32); mem.pre[1 + k] = e.to_mont(); }
+    mem.z = (Fr *)aux_out;
+    WitProgDev P{ops, lc_ptr, lc_slot, lc_coef, (const Fr *)coefs, n_ops, n_raw, n_ext};
+    Fr d; memcpy(d.l, jj_d, 32);
+    std::vector<int32_t> sops, level_ptr;
+    const uint32_t n_levels = wit_build_schedule(ops, n_ops, lc_ptr, lc_slot, n_ext, sops, level_ptr);
+    uint64_t widest = 0, heavy = 0;
+    for (uint32_t L = 0; L < n_levels; L++) {
+        bool inv = false;
+        for (int32_t i = level_ptr[L + 1] - 1; i >= level_ptr[L]; i--) {
+            const int32_t *o = sops.data() + (size_t)i * 8;
+            inv |= (o[0] == W_JJ || o[0] == W_INVZ);
+            wit_exec_op(P, d, (const Fr *)raws, (uint32_t)o[6], o[0], o[1], o[2], o[3], o[4], o[5], mem);
+        }
+        widest = std::max<uint64_t>(widest, (uint64_t)(level_ptr[L + 1] - level_ptr[L]));
+        heavy += inv;
+    }
+    if (stats) { stats[0] = (uint64_t)level_ptr[n_levels]; stats[1] = widest; stats[2] = heavy; }
+    return n_levels;
+}
 }
 
 // ---- csrc/pairing.cuh on the host: e(P,Q)^3 as 6 Fp2 coefficients (12 x 12 u32, Montgomery), and its pieces

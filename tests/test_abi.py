@@ -191,6 +191,16 @@ def test_host_build_of_witness_interpreter(hostshim):
                                   ct.c_uint32(prog.n_raw), ct.c_uint32(prog.n_ext), p(jj_d), p(raws), p(ext), p(out))
         want = C.to_mont(cs.aux[prog.p_aux + k * prog.n_ops: prog.p_aux + (k + 1) * prog.n_ops])
         assert (out == want).all(), (k, np.nonzero((out != want).any(axis=1))[0][:5])
+        # the order the GPU kernel uses: the upload-time level schedule (wit_build_schedule), a level's ops in any order,
+        # variables read from the slot's own output segment
+        out2 = np.zeros((prog.n_ops, 4), dtype=np.uint64)
+        stats = np.zeros(4, dtype=np.uint64)
+        hostshim.shim_witness_run_levels.restype = ct.c_uint32
+        n_levels = hostshim.shim_witness_run_levels(p(ops), ct.c_uint32(prog.n_ops), p(prog.lc_ptr), p(prog.lc_slot), p(prog.lc_coef), p(coefs),
+                                                    ct.c_uint32(prog.n_raw), ct.c_uint32(prog.n_ext), p(jj_d), p(raws), p(ext), p(out2), p(stats))
+        assert (out2 == want).all(), (k, np.nonzero((out2 != want).any(axis=1))[0][:5])
+        n_nop = int((ops[:, 0] == 7).sum())
+        assert int(stats[0]) == prog.n_ops - n_nop and 1000 < n_levels < prog.n_ops // 8 and int(stats[2]) <= 2 * n_nop
 
 
 @pytest.mark.parametrize("kind", ["deposit", "withdraw"])
