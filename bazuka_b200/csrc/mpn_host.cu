@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <map>
+#include <set>
 #include <unordered_map>
 #include <vector>
 
@@ -674,13 +675,15 @@ int32_t bzk_mpn_deposit_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_depo
         return jt == s->accounts.end() ? Account() : jt->second;
     };
     std::vector<Plan> plan;
+    std::set<uint64_t> rejected_srcs;   // deposit.rs:33 `rejected_pub_keys`: a rejected deposit takes its L1 source's later ones with it
     for (uint64_t k = 0; k < n_deps; k++) {
         if (accepted) accepted[k] = 0;
         if (plan.size() == cap) continue;
         const bzk_mpn_deposit &d = deps[k];
-        if (!canonical(d.pk_x) || !canonical(d.token_id)) continue;
+        auto reject = [&] { if (d.src_id) rejected_srcs.insert(d.src_id); };
+        if (!canonical(d.pk_x) || !canonical(d.token_id)) { reject(); continue; }
         Point addr;
-        if (!jj_decompress(s, &d.pk_x, d.pk_odd != 0, &addr)) continue;
+        if (!jj_decompress(s, &d.pk_x, d.pk_odd != 0, &addr)) { reject(); continue; }
         const auto key = std::make_pair(key_of(addr.x), key_of(addr.y));
         uint64_t idx = 0;
         bool is_new = false;
@@ -691,11 +694,15 @@ int32_t bzk_mpn_deposit_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_depo
             if (jt != pending.end()) idx = jt->second;
             else { idx = s->account_count + pending.size(); is_new = true; }
         }
-        if (idx >> (2 * A)) continue;
+        if (idx >> (2 * A)) { reject(); continue; }
         const Account before = get(idx);
         const Fr tok = fr_from_canon(&d.token_id);
         const int ti = find_token_index(before, T, tok, true);
-        if (ti < 0 || (s->on_curve(before.ax, before.ay) && (!(before.ax == addr.x) || !(before.ay == addr.y)))) continue;
+        if (ti < 0 || (d.src_id && rejected_srcs.count(d.src_id)) ||
+            (s->on_curve(before.ax, before.ay) && (!(before.ax == addr.x) || !(before.ay == addr.y)))) {
+            reject();
+            continue;
+        }
         Plan p{};
         p.k = k; p.idx = idx; p.ti = (uint32_t)ti; p.before = before; p.addr = addr;
         p.bal = before.tokens.count(ti) ? before.tokens.at(ti) : Money{Fr::zero(), 0};
@@ -819,6 +826,22 @@ int32_t bzk_mpn_withdraw_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_wit
         h_rows.push_back(ok[k] ? addr[k].x : Fr::zero()); h_rows.push_back(ok[k] ? addr[k].y : Fr::zero()); h_rows.push_back(msgs[k]);
     }
     BZK_TRY(hash_rows(ctx, 5, h_rows, hs));
+    // `verify_calldata` (src/core/transaction.rs:177-182, withdraw.rs:77) for the entries that carry the payment's calldata
+    bool any_calldata = false;
+    for (uint64_t k = 0; k < n_wds; k++) any_calldata |= wds[k].check_calldata != 0;
+    if (any_calldata) {
+        std::vector<Fr> rows, cd;
+        for (uint64_t k = 0; k < n_wds; k++) {
+            const bzk_mpn_withdraw &w = wds[k];
+            const bool on = ok[k] && w.check_calldata;
+            rows.push_back(on ? addr[k].x : Fr::zero()); rows.push_back(on ? addr[k].y : Fr::zero()); rows.push_back(fr_from_u64(w.nonce));
+            rows.push_back(on ? fr_from_canon(&w.sig_rx) : Fr::zero()); rows.push_back(on ? fr_from_canon(&w.sig_ry) : Fr::zero());
+            rows.push_back(on ? fr_from_canon(&w.sig_s) : Fr::zero());
+        }
+        BZK_TRY(hash_rows(ctx, 6, rows, cd));
+        for (uint64_t k = 0; k < n_wds; k++)
+            if (ok[k] && wds[k].check_calldata && (!canonical(wds[k].calldata) || !(cd[k] == fr_from_canon(&wds[k].calldata)))) ok[k] = 0;
+    }
     struct Plan { uint64_t k, idx; uint32_t ti, fi; Account before, mid, after; Money tok, fee_before; size_t e1, e2; Fr tok_hash; };
     std::map<uint64_t, Account> mirror;
     auto get = [&](uint64_t i) -> Account {

@@ -265,21 +265,31 @@ def deposit_batched(hasher, state: MpnState, deposits, log4_batch):
     from .dw import DepositTransition
     n, prev = 1 << (2 * log4_batch), state.root
     led, plan = _Ledger(state), []
+    rejected_srcs = set()                 # deposit.rs:33 `rejected_pub_keys`
+
+    def reject(d):
+        if d.src is not None:
+            rejected_srcs.add(d.src)
+
     for d in deposits:
         if len(plan) == n:
             break
         addr = N.jj_decompress_checked(d.mpn_address)
         if addr is None:
+            reject(d)
             continue
         idx = led.index_of(addr)
         is_new = idx is None
         if is_new:
             idx = led.new_index()
         if idx >> (2 * state.A):
+            reject(d)
             continue
         before = led.get(idx)
         ti = before.find_token_index(state.T, d.token_id, True)
-        if ti is None or (N.jj_on_curve(before.address) and before.address != addr):
+        if (ti is None or (d.src is not None and d.src in rejected_srcs)
+                or (N.jj_on_curve(before.address) and before.address != addr)):
+            reject(d)
             continue
         bal = before.tokens.get(ti)
         after = before.copy()
@@ -329,6 +339,8 @@ def withdraw_batched(hasher, state: MpnState, withdraws, log4_batch):
         ti = before.find_token_index(state.T, w.amount.token_id, False)
         fi = before.find_token_index(state.T, w.fee.token_id, False)
         if ti is None or fi is None or w.mpn_withdraw_nonce != before.withdraw_nonce + 1:
+            continue
+        if w.calldata is not None and w.calldata != w.expected_calldata():
             continue
         if before.tokens[ti].amount < w.amount.amount or not N.eddsa_verify(addr, w.message(), w.mpn_sig):
             continue

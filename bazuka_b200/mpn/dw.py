@@ -51,6 +51,8 @@ class MpnDeposit:
     mpn_address: tuple = (0, False)   # compressed public key
     token_id: int = 0
     amount: int = 0
+    src: object = None                # `payment.src`, the L1 account paying (any hashable id; None = not tracked): once one of its
+                                      # deposits is rejected, its later ones in the batch are too (deposit.rs:33,68-83)
 
 
 @dataclass
@@ -76,11 +78,18 @@ def deposit(state: MpnState, deposits, log4_batch):
     """-> (public {state, aux_data, next_state}, transitions)."""
     prev, trans = state.root, []
     n = 1 << (2 * log4_batch)
+    rejected_srcs = set()                 # deposit.rs:33 `rejected_pub_keys`
+
+    def reject(d):
+        if d.src is not None:
+            rejected_srcs.add(d.src)
+
     for d in deposits:
         if len(trans) == n:
             break
         addr = N.jj_decompress_checked(d.mpn_address)
         if addr is None:
+            reject(d)
             continue
         # deposit.rs:40-54: chain index table, then this fork's new accounts, else mpn_account_count + |new_account_indices|
         idx = state.index_of(addr)
@@ -88,10 +97,13 @@ def deposit(state: MpnState, deposits, log4_batch):
         if is_new:
             idx = state.new_index()
         if idx >> (2 * state.A):
+            reject(d)
             continue
         before = state.get(idx)
         ti = before.find_token_index(state.T, d.token_id, True)
-        if ti is None or (N.jj_on_curve(before.address) and before.address != addr):
+        if (ti is None or (d.src is not None and d.src in rejected_srcs)
+                or (N.jj_on_curve(before.address) and before.address != addr)):
+            reject(d)
             continue
         proof, bproof = state.prove(idx), state.prove_token(idx, ti)
         pre_root = state.root
@@ -192,6 +204,12 @@ class MpnWithdraw:
     amount: Money = field(default_factory=Money)
     fee: Money = field(default_factory=Money)
     fingerprint: int = 0           # `ContractWithdraw::fingerprint()` of the L1 payment (opaque here)
+    calldata: object = None        # `payment.calldata` when the caller has the L1 payment: must equal expected_calldata()
+                                   # (`verify_calldata`, src/core/transaction.rs:177-182; withdraw.rs:77); None = not checked
+
+    def expected_calldata(self):
+        a = N.jj_decompress(self.mpn_address)
+        return N.poseidon([a[0], a[1], self.mpn_withdraw_nonce, self.mpn_sig["r"][0], self.mpn_sig["r"][1], self.mpn_sig["s"]])
 
     def message(self):
         return N.poseidon([self.fingerprint, self.mpn_withdraw_nonce])
@@ -236,6 +254,8 @@ def withdraw(state: MpnState, withdraws, log4_batch):
         ti = before.find_token_index(state.T, w.amount.token_id, False)
         fi = before.find_token_index(state.T, w.fee.token_id, False)
         if ti is None or fi is None or w.mpn_withdraw_nonce != before.withdraw_nonce + 1:
+            continue
+        if w.calldata is not None and w.calldata != w.expected_calldata():
             continue
         if before.tokens[ti].amount < w.amount.amount or not N.eddsa_verify(addr, w.message(), w.mpn_sig):
             continue

@@ -20,11 +20,11 @@ _TX = np.dtype([("nonce", "<u8"), ("amount", "<u8"), ("fee", "<u8"), ("src_pk_od
 assert _TX.itemsize == 32 + 7 * 32
 
 
-_DEP = np.dtype([("pk_x", "<u8", 4), ("pk_odd", "u1"), ("pad", "u1", 7), ("token_id", "<u8", 4), ("amount", "<u8")])
-_WD = np.dtype([("pk_x", "<u8", 4), ("pk_odd", "u1"), ("pad", "u1", 3), ("nonce", "<u4"), ("sig_rx", "<u8", 4), ("sig_ry", "<u8", 4),
-                ("sig_s", "<u8", 4), ("amount_token_id", "<u8", 4), ("fee_token_id", "<u8", 4), ("fingerprint", "<u8", 4), ("amount", "<u8"),
-                ("fee", "<u8")])
-assert _DEP.itemsize == 80 and _WD.itemsize == 7 * 32 + 24
+_DEP = np.dtype([("pk_x", "<u8", 4), ("pk_odd", "u1"), ("pad", "u1", 7), ("token_id", "<u8", 4), ("amount", "<u8"), ("src_id", "<u8")])
+_WD = np.dtype([("pk_x", "<u8", 4), ("pk_odd", "u1"), ("check_calldata", "u1"), ("pad", "u1", 2), ("nonce", "<u4"), ("sig_rx", "<u8", 4),
+                ("sig_ry", "<u8", 4), ("sig_s", "<u8", 4), ("amount_token_id", "<u8", 4), ("fee_token_id", "<u8", 4), ("fingerprint", "<u8", 4),
+                ("amount", "<u8"), ("fee", "<u8"), ("calldata", "<u8", 4)])
+assert _DEP.itemsize == 88 and _WD.itemsize == 8 * 32 + 24
 
 
 def _canon(v):
@@ -51,9 +51,11 @@ def pack_txs(txs):
 def pack_deposits(deps):
     """list of dw.MpnDeposit -> array of bzk_mpn_deposit"""
     out = np.zeros(len(deps), dtype=_DEP)
+    src_ids = {}                                   # any hashable `src` -> a non-zero id (0 = not tracked)
     for k, d in enumerate(deps):
         o = out[k]
         o["pk_x"], o["pk_odd"], o["token_id"], o["amount"] = _canon(d.mpn_address[0]), int(d.mpn_address[1]), _canon(d.token_id), d.amount
+        o["src_id"] = 0 if d.src is None else src_ids.setdefault(d.src, len(src_ids) + 1)
     return out
 
 
@@ -66,6 +68,8 @@ def pack_withdraws(ws):
         o["sig_rx"], o["sig_ry"], o["sig_s"] = _canon(w.mpn_sig["r"][0]), _canon(w.mpn_sig["r"][1]), _canon(w.mpn_sig["s"])
         o["amount_token_id"], o["fee_token_id"], o["fingerprint"] = _canon(w.amount.token_id), _canon(w.fee.token_id), _canon(w.fingerprint)
         o["amount"], o["fee"] = w.amount.amount, w.fee.amount
+        if w.calldata is not None:
+            o["check_calldata"], o["calldata"] = 1, _canon(w.calldata)
     return out
 
 

@@ -142,6 +142,14 @@ def prepare_works(config, state, deposits, withdraws, updates, rewards, height=0
     dep_fn, wd_fn, up_fn = builders or (D.deposit, D.withdraw, U.update)
     fork = state.fork()
     works = []
+    # what the builders check of the L1 payments (deposit.rs:33,68-83 `rejected_pub_keys`; withdraw.rs:77 `verify_calldata`):
+    # entries that come with a payment and do not carry the field yet get it from the payment
+    for k, d in enumerate(deposits):
+        if d.src is None and k in (deposit_payments or {}):
+            d.src = bytes(deposit_payments[k]["src"])
+    for k, w in enumerate(withdraws):
+        if w.calldata is None and k in (withdraw_payments or {}):
+            w.calldata = withdraw_payments[k]["calldata"]
 
     def payments_of(trans, source, table, default):
         out = []

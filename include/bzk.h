@@ -313,14 +313,18 @@ typedef struct {
     uint8_t pk_odd, pad[7];
     bzk_fr token_id;
     uint64_t amount;
+    uint64_t src_id;   /* caller's id of `payment.src`, the paying L1 account (0 = not tracked): after one rejected deposit the
+                        * later deposits of the same source in the call are rejected too (deposit.rs:33,68-83) */
 } bzk_mpn_deposit;
 typedef struct {
     bzk_fr pk_x;
-    uint8_t pk_odd, pad[3];
+    uint8_t pk_odd, check_calldata, pad[2];   /* check_calldata: `calldata` below is the payment's and must equal
+                                               * Poseidon(pk.x, pk.y, nonce, sig.r.x, sig.r.y, sig.s) (`verify_calldata`) */
     uint32_t nonce;
     bzk_fr sig_rx, sig_ry, sig_s;
     bzk_fr amount_token_id, fee_token_id, fingerprint;
     uint64_t amount, fee;
+    bzk_fr calldata;
 } bzk_mpn_withdraw;
 int32_t bzk_mpn_deposit_build(bzk_ctx *ctx, bzk_mpn_state *state, const bzk_mpn_deposit *deposits, uint64_t n, uint32_t log4_batch, bzk_fr *raws1,
                               bzk_fr *raws2, bzk_fr *roots, bzk_fr *reveal, uint8_t *accepted, bzk_fr public3[3], uint64_t *n_accepted);

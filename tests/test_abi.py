@@ -43,9 +43,9 @@ def test_packed_transaction_structs_match_the_header(tmp_path):
     from bazuka_b200.mpn import ledger as L
     fields = {"bzk_mpn_tx": (L._TX, ["nonce", "amount", "fee", "src_pk_odd", "dst_pk_odd", "src_pk_x", "dst_pk_x", "amount_token_id",
                                      "fee_token_id", "sig_rx", "sig_ry", "sig_s"]),
-              "bzk_mpn_deposit": (L._DEP, ["pk_x", "pk_odd", "token_id", "amount"]),
-              "bzk_mpn_withdraw": (L._WD, ["pk_x", "pk_odd", "nonce", "sig_rx", "sig_ry", "sig_s", "amount_token_id", "fee_token_id",
-                                           "fingerprint", "amount", "fee"])}
+              "bzk_mpn_deposit": (L._DEP, ["pk_x", "pk_odd", "token_id", "amount", "src_id"]),
+              "bzk_mpn_withdraw": (L._WD, ["pk_x", "pk_odd", "check_calldata", "nonce", "sig_rx", "sig_ry", "sig_s", "amount_token_id",
+                                           "fee_token_id", "fingerprint", "amount", "fee", "calldata"])}
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "bzk.h"', 'int main(void) {']
     for name, (_, fs) in fields.items():
         src.append(f'printf("{name} %zu", sizeof({name}));')

@@ -197,18 +197,24 @@ def test_batched_deposit_withdraw_builders_on_gpu(ctx):
     h = BU.GpuTreeHasher(ctx)
     st1, keys = make_state(3, 3, 2)
     newpk, _ = N.eddsa_keys(b"dep-new")
-    deps = [D.MpnDeposit(N.jj_compress(keys[0][0]), U.ZIESHA, 500), D.MpnDeposit(N.jj_compress(newpk), 77, 9),
+    deps = [D.MpnDeposit(N.jj_compress(keys[0][0]), U.ZIESHA, 500), D.MpnDeposit((6, False), 77, 1, "carol"),
+            D.MpnDeposit(N.jj_compress(newpk), 77, 9), D.MpnDeposit(N.jj_compress(keys[1][0]), 77, 1, "carol"),
             D.MpnDeposit(N.jj_compress(keys[1][0]), 77, 1), D.MpnDeposit(N.jj_compress(keys[0][0]), 77, 4)]
     st2 = copy.deepcopy(st1)
     pub1, tr1 = D.deposit(st1, deps, 1)
     pub2, tr2 = BU.deposit_batched(h, st2, deps, 1)
-    assert pub1 == pub2 and st1.tree.levels == st2.tree.levels
+    assert pub1 == pub2 and st1.tree.levels == st2.tree.levels and len(tr1) == 4
     _assert_same_transitions(tr1, tr2)
     ws = []
     for i, amt, nonce in ((0, 100, 1), (1, 5, 1), (0, 30, 2)):
         w = D.MpnWithdraw(N.jj_compress(keys[i][0]), nonce, amount=U.Money(U.ZIESHA, amt), fee=U.Money(U.ZIESHA, 2), fingerprint=1000 + amt)
         w.sign(keys[i][1])
         ws.append(w)
+    ws[0].calldata = ws[0].expected_calldata()
+    bad = D.MpnWithdraw(N.jj_compress(keys[1][0]), 2, amount=U.Money(U.ZIESHA, 1), fee=U.Money(U.ZIESHA, 0), fingerprint=7)
+    bad.sign(keys[1][1])
+    bad.calldata = bad.expected_calldata() + 1
+    ws.insert(2, bad)
     pub1, tr1 = D.withdraw(st1, ws, 1)
     pub2, tr2 = BU.withdraw_batched(h, st2, ws, 1)
     assert pub1 == pub2 and st1.tree.levels == st2.tree.levels and len(tr1) == 3
@@ -236,9 +242,11 @@ def test_native_deposit_withdraw_builders_and_witness(ctx, cref, kind):
     assert led.root == st.root
     new1, new2 = N.eddsa_keys(b"dep-new")[0], N.eddsa_keys(b"dep-new-2")[0]
     if kind == "deposit":
-        mk = lambda pk, tok, amt: D.MpnDeposit(N.jj_compress(pk), tok, amt)
-        batches = [[mk(keys[0][0], U.ZIESHA, 500), mk(new1, 77, 9), mk(keys[1][0], 77, 1), mk(keys[0][0], 77, 4), mk(new2, 5, 5)],
-                   [mk(new1, 78, 3), D.MpnDeposit((6, False), 77, 1), mk(new2, 5, 1)]]
+        mk = lambda pk, tok, amt, src=None: D.MpnDeposit(N.jj_compress(pk), tok, amt, src)
+        # batch 2: a key that does not decompress puts its L1 source on the rejected list (deposit.rs:33,68-83), which takes the
+        # source's next deposit with it; another source's deposit to the same account goes through
+        batches = [[mk(keys[0][0], U.ZIESHA, 500, "a"), mk(new1, 77, 9), mk(keys[1][0], 77, 1, "b"), mk(keys[0][0], 77, 4, "a"), mk(new2, 5, 5)],
+                   [mk(new1, 78, 3), D.MpnDeposit((6, False), 77, 1, "carol"), mk(new2, 5, 1, "carol"), mk(new2, 5, 2, "dave")]]
         seq, build, raws_of, w_rev = D.deposit, led.deposit_build, DW.deposit_raws, 4
     else:
         def mk(i, amt, nonce, fee=2, sk=None, tok=U.ZIESHA):
@@ -246,7 +254,9 @@ def test_native_deposit_withdraw_builders_and_witness(ctx, cref, kind):
             w.sign(sk or keys[i][1])
             return w
         stranger = D.MpnWithdraw(N.jj_compress(new1), 1, amount=U.Money(U.ZIESHA, 1), fee=U.Money(U.ZIESHA, 0), fingerprint=1)
-        batches = [[mk(0, 100, 1), mk(1, 5, 1, sk=keys[0][1]), mk(1, 5, 1), mk(0, 30, 2), mk(2, 7, 2), stranger],
+        good_cd, bad_cd = mk(0, 100, 1), mk(2, 3, 1)         # `verify_calldata` (withdraw.rs:77): the payment's calldata is checked when given
+        good_cd.calldata, bad_cd.calldata = good_cd.expected_calldata(), bad_cd.expected_calldata() + 1
+        batches = [[good_cd, mk(1, 5, 1, sk=keys[0][1]), mk(1, 5, 1), mk(0, 30, 2), mk(2, 7, 2), stranger, bad_cd],
                    [mk(2, 10**15, 1), mk(2, 7, 1, tok=12345), mk(0, 1, 3), mk(1, 1, 2, fee=10**15), mk(1, 1, 2)]]
         seq, build, raws_of, w_rev = D.withdraw, led.withdraw_build, DW.withdraw_raws, 7
     nc = NativeTwoPhaseCircuit(kind, A, T, B)

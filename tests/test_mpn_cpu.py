@@ -331,7 +331,9 @@ def test_batched_deposit_and_withdraw_builders_equal_sequential():
     newpk, _ = N.eddsa_keys(b"dep-new")
     deps = [D.MpnDeposit(N.jj_compress(keys[0][0]), U.ZIESHA, 500), D.MpnDeposit(N.jj_compress(newpk), 77, 9),
             D.MpnDeposit(N.jj_compress(keys[1][0]), 77, 1), D.MpnDeposit(N.jj_compress(keys[0][0]), 77, 4),
-            D.MpnDeposit(N.jj_compress(newpk), 77, 1)]
+            D.MpnDeposit(N.jj_compress(newpk), 77, 1),
+            # a key that does not decompress lists its L1 source; the source's next deposit goes with it (deposit.rs:33,68-83)
+            D.MpnDeposit((6, False), 77, 1, "carol"), D.MpnDeposit(N.jj_compress(keys[1][0]), 77, 2, "carol")]
     st2 = copy.deepcopy(st1)
     pub1, tr1 = D.deposit(st1, deps, 2)
     pub2, tr2 = BU.deposit_batched(h, st2, deps, 2)
@@ -343,9 +345,14 @@ def test_batched_deposit_and_withdraw_builders_equal_sequential():
         w = D.MpnWithdraw(N.jj_compress(keys[i][0]), nonce, amount=U.Money(U.ZIESHA, amt), fee=U.Money(U.ZIESHA, 2), fingerprint=1000 + amt)
         w.sign(keys[i][1])
         ws.append(w)
+    ws[0].calldata = ws[0].expected_calldata()          # `verify_calldata` (withdraw.rs:77) when the payment's calldata is known
+    bad = D.MpnWithdraw(N.jj_compress(keys[1][0]), 2, amount=U.Money(U.ZIESHA, 1), fee=U.Money(U.ZIESHA, 0), fingerprint=7)
+    bad.sign(keys[1][1])
+    bad.calldata = bad.expected_calldata() + 1
+    ws.insert(2, bad)
     pub1, tr1 = D.withdraw(st1, ws, 1)
     pub2, tr2 = BU.withdraw_batched(h, st2, ws, 1)
-    assert len(tr1) == 3 and pub1 == pub2
+    assert len(tr1) == 3 and pub1 == pub2 and all(t.tx is not bad for t in tr1 + tr2)
     _assert_same_transitions(tr1, tr2)
     assert st1.root == st2.root and st1.tree.levels == st2.tree.levels
     assert {i: dataclasses_asdict(a) for i, a in st1.accounts.items()} == {i: dataclasses_asdict(a) for i, a in st2.accounts.items()}
@@ -584,3 +591,38 @@ def test_state_size_counts_non_zero_leaves_through_every_builder():
     D.withdraw(st, [w], 1)
     BU.withdraw_batched(HostTreeHasher(N.poseidon), st_b, [w], 1)
     assert st.state_size == _recount(st) == st_b.state_size and st.root == st_b.root
+
+
+def test_deposit_rejection_follows_the_l1_source_and_withdraw_checks_calldata():
+    """deposit.rs:33,68-83: a rejected deposit puts its L1 source (`payment.src`) on a list and the source's later deposits in
+    the call are rejected as well (their L1 nonces would no longer line up); withdraw.rs:77 / transaction.rs:177-182: a withdrawal
+    whose payment carries a calldata other than Poseidon(address, nonce, signature) is rejected.  Untracked entries (src None,
+    calldata None) behave as before."""
+    import copy
+    from bazuka_b200.mpn import dw as D
+    st, keys = make_state(3, 3, 2)
+    stranger = N.eddsa_keys(b"stranger")[0]
+    # account 0's token tree gets filled so that a deposit of a fifth token finds no slot: 2^(2*3) = 64 slots
+    full = st.get(0).copy()
+    for slot in range(1, 64):
+        full.tokens[slot] = U.Money(1000 + slot, 1)
+    st.set(0, full)
+    mk = lambda pk, tok, amt, src: D.MpnDeposit(N.jj_compress(pk), tok, amt, src)
+    deps = [mk(keys[1][0], 77, 5, "alice"),            # accepted
+            mk(keys[0][0], 9999, 1, "bob"),            # no free slot -> rejected, bob listed
+            mk(keys[1][0], 77, 6, "bob"),              # would be fine, but bob is listed
+            mk(stranger, 77, 7, "alice"),              # alice is still fine (new account)
+            mk(keys[0][0], 9998, 1, None),             # rejected, nobody listed
+            mk(keys[1][0], 77, 8, None)]               # accepted
+    pub, trans = D.deposit(copy.deepcopy(st), deps, 2)
+    assert [t.tx.amount for t in trans] == [5, 7, 8]
+    # withdrawals
+    st2, keys2 = make_state(3, 3, 2)
+    ws = []
+    for i, cd in ((0, "good"), (1, "bad"), (1, None)):
+        w = D.MpnWithdraw(N.jj_compress(keys2[i][0]), 1, amount=U.Money(U.ZIESHA, 10 + i), fee=U.Money(U.ZIESHA, 1), fingerprint=500 + i)
+        w.sign(keys2[i][1])
+        w.calldata = {"good": w.expected_calldata(), "bad": w.expected_calldata() + 1, None: None}[cd]
+        ws.append(w)
+    pub, trans = D.withdraw(st2, ws, 1)
+    assert [t.tx is w for t, w in zip(trans, (ws[0], ws[2]))] == [True, True] and len(trans) == 2

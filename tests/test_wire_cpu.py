@@ -71,8 +71,9 @@ def _scenario():
     w = D.MpnWithdraw(N.jj_compress(keys[1][0]), 1, amount=U.Money(U.ZIESHA, 100), fee=U.Money(U.ZIESHA, 2))
     payment = {"memo": "rent", "contract_id": 0x1234, "withdraw_circuit_id": 0, "calldata": 0, "dst": bytes(range(32)),
                "amount": {"token_id": "ziesha", "amount": 100}, "fee": {"token_id": "ziesha", "amount": 2}}
-    w.fingerprint = Wk.withdraw_fingerprint(payment)
+    w.fingerprint = Wk.withdraw_fingerprint(payment)        # of the payment with calldata zeroed, so it can be signed first
     w.sign(keys[1][1])
+    payment["calldata"] = w.expected_calldata()             # `verify_calldata`: Poseidon(address, nonce, signature)
     # the depositor's brand-new account (index account_count + 0) spends in the update batch of the same block
     updates = [transfer(keys, 3, 0, 1, amount=40, fee=1), transfer(keys, 0, 2, 1)]
     return st, keys, deposits, [w], {0: payment}, updates
@@ -181,3 +182,16 @@ def _leaves(state):
             out[(idx, 4, slot, 0)] = m.token_id
             out[(idx, 4, slot, 1)] = m.amount
     return out
+
+
+def test_prepare_works_rejects_a_withdrawal_whose_payment_calldata_is_wrong():
+    """withdraw.rs:77 through prepare_works: the calldata of the L1 payment that comes with a withdrawal is checked"""
+    st, keys, deposits, withdraws, wpay, updates = _scenario()
+    wpay[0]["calldata"] += 1
+    works, _ = Wk.prepare_works(_config(), st, deposits, withdraws, updates, {"deposit": 1, "withdraw": 2, "update": 3}, withdraw_payments=wpay)
+    kinds = {w["data"][0]: w for w in works.values()}
+    assert not any(t["enabled"] for t in kinds["withdraw"]["data"][1])
+    st, keys, deposits, withdraws, wpay, updates = _scenario()
+    works, _ = Wk.prepare_works(_config(), st, deposits, withdraws, updates, {"deposit": 1, "withdraw": 2, "update": 3}, withdraw_payments=wpay)
+    kinds = {w["data"][0]: w for w in works.values()}
+    assert sum(t["enabled"] for t in kinds["withdraw"]["data"][1]) == 1
