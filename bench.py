@@ -301,7 +301,7 @@ def run_ours(args, rank, local_rank, world):
             "traffic": ncu_traffic(), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": ALGO_BYTES_PER_TERM * n,
             "kernel_ms": acc_ms, "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
-            "note": "integer-ALU bound (about 16 windows x 10 Fp products per term); see DESIGN.md for the IMAD roofline",
+            "note": "integer-ALU bound (13 windows over the fixed-base table x ~11 Fp products per term); see DESIGN.md section 3.1-3.2 for the IMAD roofline",
         },
         "e2e": {"value": world * n / (e2e_step * 1e-3), "unit": UNIT, "ms_per_step": e2e_step,
                 "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 16 * 192 + 104,
