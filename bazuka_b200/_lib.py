@@ -114,6 +114,25 @@ SIGNATURES = {
     "bzk_mpn_state_info": (_i32, [_vp, _vp, ct.POINTER(_u64), ct.POINTER(_u64), ct.POINTER(_u64)]),
     "bzk_mpn_state_commit_accounts": (_i32, [_vp]),
     "bzk_mpn_update_witness": (_i32, [_vp, _vp, _vp, _u64, _u32, _u64, _u64, _vp, _vp, _u32, _vp, _vp, _vp]),
+    "bzk_mpn_work_decode": (_i32, [_vp, _sz, ct.POINTER(_vp), _vp]),
+    "bzk_mpn_work_free": (_i32, [_vp]),
+    "bzk_mpn_work_encode": (_i32, [_vp, _vp, _sz, ct.POINTER(_sz)]),
+    "bzk_mpn_work_get_info": (_i32, [_vp, _vp]),
+    "bzk_mpn_work_vk": (_i32, [_vp, ct.POINTER(_vp), ct.POINTER(_sz)]),
+    "bzk_mpn_commitment": (_i32, [_vp, _u64, _vp]),
+    "bzk_sha3_256": (_i32, [_vp, _sz, _vp]),
+    "bzk_mpn_work_public_inputs": (_i32, [_vp, _vp, _vp]),
+    "bzk_mpn_work_verify": (_i32, [_vp, _vp, _vp]),
+    "bzk_mpn_work_update_rows": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "bzk_mpn_work_dw_rows": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bzk_mpn_get_work_response_decode": (_i32, [_vp, _sz, _vp, _vp, _u64, ct.POINTER(_u64)]),
+    "bzk_mpn_get_work_request_encode": (_i32, [_vp, _vp]),
+    "bzk_mpn_post_solution_request_encode": (_i32, [_vp, _vp, _vp, _u64, _vp, _sz, ct.POINTER(_sz)]),
+    "bzk_mpn_post_solution_response_decode": (_i32, [_vp, _sz, ct.POINTER(_u64)]),
+    "bzk_mpn_circuit_kind": (_i32, [_vp, _vp]),
+    "bzk_mpn_prover_create": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, ct.POINTER(_vp)]),
+    "bzk_mpn_prover_free": (_i32, [_vp, _vp]),
+    "bzk_mpn_prover_prove_work": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _i32, _vp]),
     "bzk_witness_program_upload": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _vp, _u64, _u32, _u32, _vp, ct.POINTER(_vp)]),
     "bzk_witness_program_free": (_i32, [_vp, _vp]),
     "bzk_witness_run_dev": (_i32, [_vp, _vp, _vp, _vp, _u64, _vp]),

@@ -11,8 +11,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 SO = os.path.join(HERE, "libbzk.so")
-SOURCES = ["msm_g2.cu", "msm_g1.cu", "groth16.cu", "poseidon.cu", "poseidon_host.cu", "ntt.cu", "verify.cu", "witness.cu", "mpn_host.cu", "mpn_circuit.cu", "capi.cu"]
+SOURCES = ["msm_g2.cu", "msm_g1.cu", "groth16.cu", "poseidon.cu", "poseidon_host.cu", "ntt.cu", "verify.cu", "witness.cu", "mpn_host.cu", "mpn_wire.cu", "mpn_prover.cu", "mpn_circuit.cu", "capi.cu"]
 HEADERS = ["ff.cuh", "ec.cuh", "common.cuh", "msm_impl.cuh", "witness_core.cuh", "pairing.cuh", os.path.join("..", "..", "include", "bzk.h")]
+# headers only some sources include
+EXTRA_DEPS = {"mpn_wire.cu": ["mpn_wire.cuh"], "mpn_host.cu": ["mpn_wire.cuh"], "mpn_prover.cu": ["mpn_wire.cuh"]}
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -34,7 +36,7 @@ def build(force=False, verbose=False):
     for s in SOURCES:
         src = os.path.join(CSRC, s)
         obj = os.path.join(OBJ, s.replace(".cu", ".o"))
-        if force or _stale(obj, [src] + hdrs):
+        if force or _stale(obj, [src] + hdrs + [os.path.join(CSRC, h) for h in EXTRA_DEPS.get(s, [])]):
             jobs.append((src, obj))
 
     def compile_one(job):

@@ -882,6 +882,13 @@ int32_t bzk_mpn_circuit_shape(const bzk_mpn_circuit *c, uint64_t shape[12]) {
     return BZK_OK;
 }
 
+/* out[4] = {kind: 0 UpdateCircuit, 1 DepositCircuit, 2 WithdrawCircuit; log4_tree; log4_token; log4_batch} */
+int32_t bzk_mpn_circuit_kind(const bzk_mpn_circuit *c, uint32_t out[4]) {
+    if (!c || !out) return BZK_ERR_BAD_ARG;
+    out[0] = c->kind; out[1] = c->A; out[2] = c->T; out[3] = c->B;
+    return BZK_OK;
+}
+
 /* side = 0,1,2 (A,B,C): rowptr u64[ncons+1], col u32[nnz], val Fr[nnz] (Montgomery) — the arrays of bzk_r1cs_upload */
 int32_t bzk_mpn_circuit_matrix(const bzk_mpn_circuit *c, uint32_t side, uint64_t *rowptr, uint32_t *col, bzk_fr *val) {
     if (!c || side > 2 || !rowptr || !col || !val) return BZK_ERR_BAD_ARG;

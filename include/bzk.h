@@ -373,6 +373,8 @@ int32_t bzk_mpn_dw_circuit_compile(uint32_t kind, uint32_t log4_tree, uint32_t l
                                    size_t blob_len, const bzk_fr jubjub[3], bzk_mpn_circuit **out);
 int32_t bzk_mpn_circuit_two_phase_info(const bzk_mpn_circuit *circuit, uint64_t counts[2], int32_t *row_local, int32_t *ext_src);
 int32_t bzk_mpn_circuit_free(bzk_mpn_circuit *circuit);
+/* out[4] = {kind: 0 UpdateCircuit, 1 DepositCircuit, 2 WithdrawCircuit; log4_tree; log4_token; log4_batch} */
+int32_t bzk_mpn_circuit_kind(const bzk_mpn_circuit *circuit, uint32_t out[4]);
 /* shape = {num_inputs, num_aux, num_constraints, nnz_a, nnz_b, nnz_c, prologue_aux, slot_vars, state_out (slot-local),
  *          final_fee (slot-local), epilogue_vars, reveal_vars (two-phase circuits; 0 for the update circuit)} */
 int32_t bzk_mpn_circuit_shape(const bzk_mpn_circuit *circuit, uint64_t shape[12]);
@@ -404,6 +406,77 @@ int32_t bzk_witness_program_upload(bzk_ctx *ctx, const int32_t *ops, uint64_t n_
 int32_t bzk_witness_program_free(bzk_ctx *ctx, bzk_witness_program *prog);
 int32_t bzk_witness_run_dev(bzk_ctx *ctx, const bzk_witness_program *prog, const bzk_fr *raws, const bzk_fr *ext, uint64_t ntx,
                             void *d_aux_out);
+
+/* ------------------------------------------------------------------ worker protocol (bincode), host only
+ * What a node hands an MPN prover and takes back, in the reference's own wire format — `bincode::serialize` of
+ *   MpnWork {config, public_inputs, data, new_root, reward}      /root/reference/src/mpn/mod.rs:264-270
+ *   GetMpnWorkRequest / GetMpnWorkResponse {works: HashMap<usize, MpnWork>}
+ *   PostMpnSolutionRequest {prover, proofs: HashMap<usize, ZkProof>} / PostMpnSolutionResponse {accepted}
+ *                                                                  /root/reference/src/client/messages.rs:368-397
+ * (`BazukaClient::{get_mpn_works, post_mpn_proof}`, /root/reference/src/client/mod.rs:428-464) — so a Rust node or worker
+ * passes `&bincode::serialize(&work)?` across the FFI unconverted.  A decoded work re-encodes to the bytes it came from.
+ * Scalars of the info struct and of the row functions are CANONICAL (like the builders' rows); `public_inputs` are
+ * Montgomery images as the verifier takes them.  No GPU context: these run anywhere. */
+typedef struct bzk_mpn_work bzk_mpn_work;
+typedef struct {
+    uint32_t kind;                  /* MpnWorkData variant: 0 deposit, 1 withdraw, 2 update */
+    uint32_t log4_tree, log4_token; /* MpnConfig.log4_tree_size / log4_token_tree_size */
+    uint32_t log4_batch;            /* the config's batch size for this kind */
+    uint64_t n_transitions;
+    uint64_t height;                /* ZkPublicInputs */
+    bzk_fr state, aux_data, next_state;
+    bzk_fr new_root_hash;           /* ZkCompressedState {state_hash, state_size} */
+    uint64_t new_root_size;
+    uint64_t reward;
+} bzk_mpn_work_info;
+/* consumed == NULL: the buffer must hold exactly one work; otherwise *consumed = bytes read (works back to back) */
+int32_t bzk_mpn_work_decode(const uint8_t *bytes, size_t len, bzk_mpn_work **out, size_t *consumed);
+int32_t bzk_mpn_work_free(bzk_mpn_work *work);
+int32_t bzk_mpn_work_encode(const bzk_mpn_work *work, uint8_t *out, size_t cap, size_t *len);   /* out == NULL: size only */
+int32_t bzk_mpn_work_get_info(const bzk_mpn_work *work, bzk_mpn_work_info *out);
+/* `MpnWork::vk()`: the verifying-key image (878 + 97 n bytes, no enum tag) of the work's kind; valid while the work lives */
+int32_t bzk_mpn_work_vk(const bzk_mpn_work *work, const uint8_t **vk, size_t *len);
+/* `MpnWork::verify`'s commitment (/root/reference/src/mpn/mod.rs:283-285, chain side update_contract/mod.rs:29-32):
+ * ZkScalar::new(sha3_256(bincode((prover, reward)))) — canonical */
+int32_t bzk_mpn_commitment(const uint8_t prover[32], uint64_t reward, bzk_fr *out);
+int32_t bzk_sha3_256(const uint8_t *data, size_t len, uint8_t out[32]);   /* `Hasher::hash` (/root/reference/src/core/hash.rs:29) */
+/* [commitment, height, state, aux_data, next_state] for (work, prover): Montgomery, as bzk_groth16_verify_bytes takes them */
+int32_t bzk_mpn_work_public_inputs(const bzk_mpn_work *work, const uint8_t prover[32], bzk_fr out[5]);
+/* `MpnWork::verify(prover, proof)` (/root/reference/src/mpn/mod.rs:281-295): 1 accepted, 0 rejected, < 0 bad argument */
+int32_t bzk_mpn_work_verify(const bzk_mpn_work *work, const uint8_t prover[32], const uint8_t *proof387);
+/* A work's transitions as the rows the witness drivers consume — what the external prover does first with a work.  All 4^B
+ * slots of the work's batch size are written: a work carries only the transitions its builder made, the rest are padded like
+ * `{Update,Deposit,Withdraw}Transition::null` (/root/reference/src/mpn/mod.rs:440-537).
+ *   update:             raws[4^B][32 + 9T + 6A], ext[4^B][2] = {fee token, state root entering the slot}  -> bzk_mpn_update_witness
+ *   deposit / withdraw: raws1, raws2, roots[4^B], reveal (layouts of bzk_mpn_deposit_build / _withdraw_build) -> bzk_mpn_dw_witness
+ * The entering roots do not travel: they are recomputed from each transition's own account, proof and index with the host
+ * Poseidon.  BZK_ERR_NOT_ON_CURVE: a key of the work does not decompress; BZK_ERR_BAD_ARG: proofs of the wrong depth. */
+int32_t bzk_mpn_work_update_rows(const bzk_mpn_work *work, const bzk_poseidon_host *hasher, const bzk_fr *jubjub_d, const bzk_fr *fee_token,
+                                 bzk_fr *raws, bzk_fr *ext);
+int32_t bzk_mpn_work_dw_rows(const bzk_mpn_work *work, const bzk_poseidon_host *hasher, const bzk_fr *jubjub_d, bzk_fr *raws1, bzk_fr *raws2,
+                             bzk_fr *roots, bzk_fr *reveal);
+/* messages: up to `cap` works are decoded into ids[] / works[] (free each); *n = the number on the wire */
+int32_t bzk_mpn_get_work_response_decode(const uint8_t *bytes, size_t len, uint64_t *ids, bzk_mpn_work **works, uint64_t cap, uint64_t *n);
+int32_t bzk_mpn_get_work_request_encode(const uint8_t address[32], uint8_t out[40]);
+/* proofs387 = n x 387-byte Groth16Proof images (sent as 391-byte ZkProof::Groth16); out == NULL: size only */
+int32_t bzk_mpn_post_solution_request_encode(const uint8_t prover[32], const uint64_t *ids, const uint8_t *proofs387, uint64_t n, uint8_t *out,
+                                             size_t cap, size_t *len);
+int32_t bzk_mpn_post_solution_response_decode(const uint8_t *bytes, size_t len, uint64_t *accepted);
+
+/* ------------------------------------------------------------------ the external prover's job as one call
+ * `MpnWork` (bincode) in, `ZkProof::Groth16` (391 bytes, bincode) out — what the reference's workers do between
+ * `GET /bincode/mpn/work` and `POST /bincode/mpn/solution` (/root/reference/src/client/mod.rs:428-464; `MpnWork::verify` on the
+ * node side checks the result, /root/reference/src/mpn/mod.rs:281-295).  One prover per circuit (kind, A, T, B): it uploads the
+ * natively compiled circuit's witness programs and R1CS (bzk_mpn_{update,dw}_circuit_compile) and keeps z resident; `params` is
+ * that circuit's proving key (borrowed).  prove_work = bzk_mpn_work_decode -> bzk_mpn_work_{update,dw}_rows ->
+ * bzk_mpn_{update,dw}_witness -> bzk_groth16_prove_dev -> bzk_groth16_proof_bytes.  r, s: Montgomery images.
+ * BZK_ERR_BAD_ARG: malformed work, or a work of another kind / size than the prover's circuit. */
+typedef struct bzk_mpn_prover bzk_mpn_prover;
+int32_t bzk_mpn_prover_create(bzk_ctx *ctx, const bzk_mpn_circuit *circuit, const bzk_groth16_params *params, const uint8_t *poseidon_blob,
+                              size_t blob_len, const bzk_fr *jubjub_d, const bzk_fr *fee_token, bzk_mpn_prover **out);
+int32_t bzk_mpn_prover_free(bzk_ctx *ctx, bzk_mpn_prover *prover);
+int32_t bzk_mpn_prover_prove_work(bzk_ctx *ctx, bzk_mpn_prover *prover, const uint8_t *work_bytes, size_t work_len, const uint8_t prover_address[32],
+                                  const bzk_fr *r, const bzk_fr *s, int32_t check_satisfied, uint8_t zkproof391[391]);
 
 /* 387-byte bincode image of `Groth16Proof {a,b,c}` (/root/reference/src/zk/groth16/mod.rs:33-38);
  * prefix it with the u32 variant tag 0 for `ZkProof::Groth16` (391 B). */

@@ -67,14 +67,17 @@ def hostmpn():
     from bazuka_b200 import _lib
     d = os.path.join(ROOT, "tests", "hostshim")
     csrc = os.path.join(ROOT, "bazuka_b200", "csrc")
-    srcs = [os.path.join(csrc, f) for f in ("mpn_host.cu", "mpn_wire.cu", "poseidon_host.cu") if os.path.exists(os.path.join(csrc, f))]
+    srcs = [os.path.join(csrc, f) for f in ("mpn_host.cu", "mpn_wire.cu", "mpn_prover.cu", "mpn_circuit.cu", "poseidon_host.cu") if os.path.exists(os.path.join(csrc, f))]
     srcs.append(os.path.join(d, "mpn_shim.cpp"))
     out = os.path.join(d, "_mpn_shim.so")
     deps = srcs + [os.path.join(d, "fake_cuda_pre.h"), os.path.join(ROOT, "include", "bzk.h")] + \
-        [os.path.join(csrc, h) for h in ("ff.cuh", "ec.cuh", "common.cuh", "witness_core.cuh")]
+        [os.path.join(csrc, h) for h in ("ff.cuh", "ec.cuh", "common.cuh", "witness_core.cuh", "mpn_wire.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(x) > os.path.getmtime(out) for x in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-w", "-x", "c++", "-include", os.path.join(d, "fake_cuda_pre.h"),
-                               "-I", csrc, "-I", "/usr/local/cuda/include"] + srcs + ["-o", out])
+                               "-I", csrc, "-I", "/usr/local/cuda/include"] + srcs +
+                              # own definitions win (-Bsymbolic); what the host sources reach in OTHER host parts of the product (the
+                              # pairing verifier) comes from the real libbzk.so
+                              ["-x", "none", "-Wl,-Bsymbolic", _lib.SO_PATH, "-Wl,-rpath," + os.path.dirname(_lib.SO_PATH), "-o", out])
     lib = ct.CDLL(out)
     for name, (res, args) in _lib.SIGNATURES.items():
         fn = getattr(lib, name, None)

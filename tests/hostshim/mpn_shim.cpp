@@ -161,3 +161,69 @@ int32_t bzk_witness_run_dev(bzk_ctx *ctx, const bzk_witness_program *p, const bz
     return BZK_OK;
 }
 }
+
+// ---------------------------------------------------------------- the prover's resident R1CS and the prove call
+// bzk_mpn_prover_{create,prove_work} (csrc/mpn_prover.cu) end in bzk_r1cs_upload / bzk_groth16_prove_dev.  Here the "upload"
+// keeps the CSR on the host and the "prove" checks what the real call checks first — a(z) * b(z) == c(z) on every constraint of
+// the natively compiled circuit, for the z the native witness drivers just wrote — and returns the identity points: the CPU tier
+// proves the COMPOSITION (work bytes -> rows -> witness -> a satisfying assignment with the right public inputs); the MSM / NTT
+// half of the call is the GPU tier's.
+struct bzk_r1cs {
+    uint64_t ni = 0, na = 0, ncons = 0;
+    std::vector<uint64_t> rp[3];
+    std::vector<uint32_t> col[3];
+    std::vector<Fr> val[3];
+};
+static uint64_t g_last_unsat_row = ~0ull;
+extern "C" {
+int32_t bzk_r1cs_upload(bzk_ctx *ctx, uint64_t num_inputs, uint64_t num_aux, uint64_t num_constraints, const uint64_t *a_rowptr, const uint32_t *a_col,
+                        const bzk_fr *a_val, const uint64_t *b_rowptr, const uint32_t *b_col, const bzk_fr *b_val, const uint64_t *c_rowptr,
+                        const uint32_t *c_col, const bzk_fr *c_val, bzk_r1cs **out) {
+    if (!ctx || !out) return BZK_ERR_BAD_ARG;
+    auto *r = new bzk_r1cs;
+    r->ni = num_inputs; r->na = num_aux; r->ncons = num_constraints;
+    const uint64_t *rp[3] = {a_rowptr, b_rowptr, c_rowptr};
+    const uint32_t *col[3] = {a_col, b_col, c_col};
+    const bzk_fr *val[3] = {a_val, b_val, c_val};
+    for (int s = 0; s < 3; s++) {
+        r->rp[s].assign(rp[s], rp[s] + num_constraints + 1);
+        const uint64_t nnz = rp[s][num_constraints];
+        r->col[s].assign(col[s], col[s] + nnz);
+        r->val[s].resize(nnz);
+        memcpy(r->val[s].data(), val[s], nnz * sizeof(Fr));
+    }
+    *out = r;
+    return BZK_OK;
+}
+int32_t bzk_r1cs_free(bzk_ctx *, bzk_r1cs *r) {
+    delete r;
+    return BZK_OK;
+}
+int32_t bzk_groth16_prove_dev(bzk_ctx *ctx, const bzk_groth16_params *, const bzk_r1cs *r, const void *d_inputs, const void *d_aux, const bzk_fr *,
+                              const bzk_fr *, int32_t check_satisfied, bzk_g1_affine *pa, bzk_g2_affine *pb, bzk_g1_affine *pc) {
+    if (!ctx || !r || !d_inputs || !d_aux || !pa || !pb || !pc) return BZK_ERR_BAD_ARG;
+    const Fr *zi = (const Fr *)d_inputs, *za = (const Fr *)d_aux;
+    auto z = [&](uint32_t c) { return c < r->ni ? zi[c] : za[c - r->ni]; };
+    g_last_unsat_row = ~0ull;
+    if (!(zi[0] == Fr::one())) { g_last_unsat_row = 0; if (check_satisfied) return BZK_ERR_UNSAT; }
+    for (uint64_t row = 0; row < r->ncons; row++) {
+        Fr v[3];
+        for (int s = 0; s < 3; s++) {
+            Fr acc = Fr::zero();
+            for (uint64_t k = r->rp[s][row]; k < r->rp[s][row + 1]; k++) acc = acc + r->val[s][k] * z(r->col[s][k]);
+            v[s] = acc;
+        }
+        if (!(v[0] * v[1] == v[2])) {
+            g_last_unsat_row = row;
+            if (check_satisfied) return BZK_ERR_UNSAT;
+            break;
+        }
+    }
+    memset(pa, 0, sizeof *pa); memset(pb, 0, sizeof *pb); memset(pc, 0, sizeof *pc);
+    pa->infinity = pb->infinity = pc->infinity = 1;
+    return BZK_OK;
+}
+uint64_t shim_last_unsat_row() { return g_last_unsat_row; }
+// the z the last prover call left resident (the shim's "device" memory is host memory): copies n elements from a raw pointer
+void shim_peek(const void *p, void *out, size_t bytes) { memcpy(out, p, bytes); }
+}

@@ -1,0 +1,233 @@
+"""CPU tier: libbzk's native worker protocol (csrc/mpn_wire.cu, host code compiled unmodified into tests/hostshim/_mpn_shim.so)
+against the Python restatement (bazuka_b200/mpn/wire.py, works.py): sha3-256, the commitment, bincode of MpnWork and the
+messages byte for byte, and the rows a work's transitions feed the witness drivers."""
+import ctypes as ct
+import hashlib
+import struct
+
+import numpy as np
+import pytest
+
+from bazuka_b200.mpn import dw as D, dw_witness as DW, native as N, update as U, wire as Wr, witness_program as W, works as Wk
+from test_wire_cpu import _config, _scenario
+
+R = N.R
+
+
+def _ptr(a):
+    return ct.c_void_p(a.ctypes.data)
+
+
+def _canon(v):
+    return np.frombuffer((v % R).to_bytes(32, "little"), dtype=np.uint64).copy()
+
+
+def _canon_rows(values):
+    from bazuka_b200.mpn.gpu_witness import _canon_rows as f
+    return f(values)
+
+
+def _int(a):
+    return int.from_bytes(np.ascontiguousarray(a).tobytes(), "little")
+
+
+class _Work:
+    def __init__(self, lib, blob):
+        self.lib, self.h = lib, ct.c_void_p()
+        st = lib.bzk_mpn_work_decode(blob, len(blob), ct.byref(self.h), None)
+        if st != 0:
+            raise ValueError(st)
+
+    def encode(self):
+        n = ct.c_size_t()
+        assert self.lib.bzk_mpn_work_encode(self.h, None, 0, ct.byref(n)) == 0
+        buf = ct.create_string_buffer(n.value)
+        assert self.lib.bzk_mpn_work_encode(self.h, buf, n.value, ct.byref(n)) == 0
+        return buf.raw
+
+    def info(self):
+        dt = np.dtype([("kind", "<u4"), ("A", "<u4"), ("T", "<u4"), ("B", "<u4"), ("n", "<u8"), ("height", "<u8"), ("state", "<u8", 4), ("aux", "<u8", 4),
+                       ("next", "<u8", 4), ("root", "<u8", 4), ("size", "<u8"), ("reward", "<u8")])
+        out = np.zeros(1, dtype=dt)
+        assert self.lib.bzk_mpn_work_get_info(self.h, _ptr(out)) == 0
+        return out[0]
+
+    def free(self):
+        self.lib.bzk_mpn_work_free(self.h)
+
+
+@pytest.fixture(scope="module")
+def works():
+    st, keys, deposits, withdraws, wpay, updates = _scenario()
+    w, _ = Wk.prepare_works(_config(), st, deposits, withdraws, updates, {"deposit": 11, "withdraw": 22, "update": 33}, height=9, withdraw_payments=wpay)
+    return w
+
+
+@pytest.fixture(scope="module")
+def host_hasher(hostmpn):
+    from bazuka_b200 import _lib
+    blob = open(_lib.PARAMS_PATH, "rb").read()
+    h = ct.c_void_p()
+    assert hostmpn._l.bzk_poseidon_host_create(blob, len(blob), ct.byref(h)) == 0
+    return h
+
+
+def test_sha3_and_commitment(hostmpn):
+    lib = hostmpn._l
+    for n in (0, 1, 31, 135, 136, 137, 271, 272, 273, 1000):
+        data = bytes((7 * i + n) & 0xFF for i in range(n))
+        out = ct.create_string_buffer(32)
+        assert lib.bzk_sha3_256(data, n, out) == 0
+        assert out.raw == hashlib.sha3_256(data).digest(), n
+    for addr, reward in ((bytes(range(32)), 123_456_789), (bytes(32), 0), (bytes([255]) * 32, 2**64 - 1)):
+        out = np.zeros(4, np.uint64)
+        assert lib.bzk_mpn_commitment(addr, reward, _ptr(out)) == 0
+        assert _int(out) == Wr.commitment(addr, reward)
+
+
+def test_work_bincode_round_trips_byte_for_byte(hostmpn, works):
+    lib = hostmpn._l
+    for i, work in works.items():
+        blob = Wr.work_to_bytes(work)
+        w = _Work(lib, blob)
+        assert w.encode() == blob
+        info = w.info()
+        kind = ["deposit", "withdraw", "update"][info["kind"]]
+        assert kind == work["data"][0] and (info["A"], info["T"], info["B"]) == (3, 3, 1) and info["n"] == len(work["data"][1])
+        p = work["public_inputs"]
+        assert (info["height"], _int(info["state"]), _int(info["aux"]), _int(info["next"])) == (p["height"], p["state"], p["aux_data"], p["next_state"])
+        assert (_int(info["root"]), info["size"], info["reward"]) == (work["new_root"]["state_hash"], work["new_root"]["state_size"], work["reward"])
+        vk, n = ct.c_void_p(), ct.c_size_t()
+        assert lib.bzk_mpn_work_vk(w.h, ct.byref(vk), ct.byref(n)) == 0
+        assert ct.string_at(vk, n.value) == work["config"][kind + "_vk"]
+        pub = np.zeros((5, 4), np.uint64)
+        addr = bytes(range(32))
+        assert lib.bzk_mpn_work_public_inputs(w.h, addr, _ptr(pub)) == 0
+        from bazuka_b200.mpn.cs import to_mont
+        assert (pub == to_mont(Wk.work_public_inputs(work, addr))).all()
+        w.free()
+        # malformed images are refused, not mis-read
+        for bad in (blob[:-1], blob + b"\x00", blob[:5] + b"\x07" + blob[6:]):
+            with pytest.raises(ValueError):
+                _Work(lib, bad)
+    blob = Wr.work_to_bytes(works[2])
+    off = blob.index(((works[2]["public_inputs"]["state"] << 256) % R).to_bytes(32, "little"))
+    with pytest.raises(ValueError):                                    # scalar limbs must be reduced
+        _Work(lib, blob[:off] + R.to_bytes(32, "little") + blob[off + 32:])
+
+
+def test_message_envelopes(hostmpn, works):
+    lib = hostmpn._l
+    resp = Wr.get_mpn_work_response_to_bytes(works)
+    ids, hs, n = np.zeros(8, np.uint64), (ct.c_void_p * 8)(), ct.c_uint64()
+    assert lib.bzk_mpn_get_work_response_decode(resp, len(resp), _ptr(ids), hs, 8, ct.byref(n)) == 0
+    assert n.value == 3 and ids[:3].tolist() == [0, 1, 2]
+    for k in range(3):
+        ln = ct.c_size_t()
+        assert lib.bzk_mpn_work_encode(hs[k], None, 0, ct.byref(ln)) == 0 and ln.value == len(Wr.work_to_bytes(works[k]))
+        lib.bzk_mpn_work_free(hs[k])
+    assert lib.bzk_mpn_get_work_response_decode(resp[:-3], len(resp) - 3, _ptr(ids), hs, 8, ct.byref(n)) == -1
+    addr = bytes(range(32))
+    out = ct.create_string_buffer(40)
+    assert lib.bzk_mpn_get_work_request_encode(addr, out) == 0 and out.raw == Wr.get_mpn_work_request(addr)
+    proofs = {0: bytes(387), 2: bytes([1]) * 387}
+    want = Wr.post_mpn_solution_request(addr, proofs)
+    ln = ct.c_size_t()
+    pid, blob = np.array([0, 2], np.uint64), b"".join(proofs.values())
+    assert lib.bzk_mpn_post_solution_request_encode(addr, _ptr(pid), blob, 2, None, 0, ct.byref(ln)) == 0 and ln.value == len(want)
+    buf = ct.create_string_buffer(ln.value)
+    assert lib.bzk_mpn_post_solution_request_encode(addr, _ptr(pid), blob, 2, buf, ln.value, ct.byref(ln)) == 0 and buf.raw == want
+    acc = ct.c_uint64()
+    assert lib.bzk_mpn_post_solution_response_decode(struct.pack("<Q", 2), 8, ct.byref(acc)) == 0 and acc.value == 2
+
+
+def test_rows_of_a_work_equal_the_python_prover(hostmpn, works, host_hasher):
+    """what the external prover feeds the witness programs, derived natively from the WIRE image of each work: equal to
+    works.MpnProver's path (wire -> builder dataclasses -> raw_values / deposit_raws / withdraw_raws, entering roots recomputed
+    from each transition's own proof, revealed rows with their calldata hash, the withdraw fingerprint from the payment)."""
+    lib = hostmpn._l
+    A = T = 3
+    jj_d, fee = _canon(N.JJ_D), _canon(U.ZIESHA)
+    for i, work in works.items():
+        kind, items = work["data"]
+        trans = Wk.wire_to_transitions(kind, items)
+        p = work["public_inputs"]
+        w = _Work(lib, Wr.work_to_bytes(work))
+        n = 4                                            # 4^B slots: the work carries 2 transitions, the prover pads
+        if kind == "update":
+            circ = U.UpdateCircuit(A, T, 1, fee_token=U.ZIESHA, commitment=1, height=p["height"], state=p["state"], aux_data=p["aux_data"],
+                                   next_state=p["next_state"], transitions=trans)
+            n_raw = 32 + 9 * T + 6 * A
+            raws, ext = np.zeros((n, n_raw, 4), np.uint64), np.zeros((n, 2, 4), np.uint64)
+            assert lib.bzk_mpn_work_update_rows(w.h, host_hasher, _ptr(jj_d), _ptr(fee), _ptr(raws), _ptr(ext)) == 0
+            want_raws = np.stack([_canon_rows(W.raw_values(tr, A, T)) for tr in circ.transitions])
+            want_ext = np.stack([_canon_rows([circ.fee_token, r]) for r in W.slot_roots(circ)])
+            assert (raws == want_raws).all(), np.nonzero((raws != want_raws).any(axis=2))
+            assert (ext == want_ext).all()
+            # a deposit-shaped call on an update work is refused
+            assert lib.bzk_mpn_work_dw_rows(w.h, host_hasher, _ptr(jj_d), _ptr(raws), _ptr(raws), _ptr(raws), _ptr(raws)) == -1
+        else:
+            cls, raws_of, w1, w2, wr = ((D.DepositCircuit, DW.deposit_raws, 5, 9 + 3 * T + 3 * A, 4) if kind == "deposit" else
+                                        (D.WithdrawCircuit, DW.withdraw_raws, 12, 12 + 6 * T + 3 * A, 7))
+            circ = cls(A, T, 1, commitment=1, height=p["height"], state=p["state"], aux_data=p["aux_data"], next_state=p["next_state"], transitions=trans)
+            r1, r2 = np.zeros((n, w1, 4), np.uint64), np.zeros((n, w2, 4), np.uint64)
+            roots, rev = np.zeros((n, 4), np.uint64), np.zeros((n, wr, 4), np.uint64)
+            assert lib.bzk_mpn_work_dw_rows(w.h, host_hasher, _ptr(jj_d), _ptr(r1), _ptr(r2), _ptr(roots), _ptr(rev)) == 0
+            want = [raws_of(t, A, T) for t in circ.transitions]
+            assert (r1.reshape(-1, 4) == _canon_rows([v for a, _ in want for v in a])).all()
+            assert (r2.reshape(-1, 4) == _canon_rows([v for _, b in want for v in b])).all()
+            assert (roots == _canon_rows(DW.slot_roots(circ))).all()
+            assert (rev.reshape(-1, 4) == _canon_rows([v for r in DW.reveal_rows_native(kind, circ) for v in r])).all()
+            assert 0 < len(items) < n and all(t["enabled"] for t in items)                 # real slots and padded ones
+        w.free()
+
+
+def _compile(lib, kind, A, T, B):
+    from bazuka_b200 import _lib
+    blob = open(_lib.PARAMS_PATH, "rb").read()
+    jj = np.ascontiguousarray(np.stack([_canon(N.JJ_D), _canon(N.JJ_BASE_COFACTOR[0]), _canon(N.JJ_BASE_COFACTOR[1])]))
+    h = ct.c_void_p()
+    if kind == "update":
+        st = lib.bzk_mpn_update_circuit_compile(A, T, B, blob, len(blob), _ptr(jj), ct.byref(h))
+    else:
+        st = lib.bzk_mpn_dw_circuit_compile({"deposit": 1, "withdraw": 2}[kind], A, T, B, blob, len(blob), _ptr(jj), ct.byref(h))
+    assert st == 0
+    return h, blob
+
+
+def test_work_bytes_to_satisfying_witness_through_the_native_prover_object(hostmpn, works):
+    """bzk_mpn_prover_create / bzk_mpn_prover_prove_work (csrc/mpn_prover.cu) on the host build: the circuit compiled by C++, its
+    programs and R1CS "uploaded", then for the wire image of each work: rows -> witness drivers -> resident z -> the prove call,
+    which in this tier (tests/hostshim/mpn_shim.cpp) checks a(z) * b(z) = c(z) on every constraint of the compiled circuit.  So a
+    work that came off the wire yields a satisfying assignment; a tampered public input does not; a work of another kind is
+    refused.  (The MSM / NTT half of the prove call is the GPU tier's.)"""
+    lib = hostmpn._l
+    lib.shim_last_unsat_row.restype = ct.c_uint64
+    addr = bytes(range(32))
+    rs = np.zeros((2, 4), np.uint64)
+    provers = {}
+    for kind in ("deposit", "withdraw", "update"):
+        c, blob = _compile(lib, kind, 3, 3, 1)
+        k4 = np.zeros(4, np.uint32)
+        assert lib.bzk_mpn_circuit_kind(c, _ptr(k4)) == 0 and k4.tolist() == [{"update": 0, "deposit": 1, "withdraw": 2}[kind], 3, 3, 1]
+        p = ct.c_void_p()
+        jj_d, fee = _canon(N.JJ_D), _canon(U.ZIESHA)
+        hostmpn._check(lib.bzk_mpn_prover_create(hostmpn._h, c, ct.c_void_p(1), blob, len(blob), _ptr(jj_d), _ptr(fee), ct.byref(p)))
+        lib.bzk_mpn_circuit_free(c)                       # the prover keeps its own copies
+        provers[kind] = p
+    for i, work in works.items():
+        kind = work["data"][0]
+        blob = Wr.work_to_bytes(work)
+        out = ct.create_string_buffer(391)
+        st = lib.bzk_mpn_prover_prove_work(hostmpn._h, provers[kind], blob, len(blob), addr, _ptr(rs[0]), _ptr(rs[1]), 1, out)
+        assert st == 0, (kind, st, lib.shim_last_unsat_row())
+        assert out.raw[:4] == bytes(4) and len(out.raw) == 391
+        # the claimed end state is a public input the circuit ties to the transitions
+        bad = dict(work, public_inputs=dict(work["public_inputs"], next_state=work["public_inputs"]["next_state"] + 1))
+        bb = Wr.work_to_bytes(bad)
+        assert lib.bzk_mpn_prover_prove_work(hostmpn._h, provers[kind], bb, len(bb), addr, _ptr(rs[0]), _ptr(rs[1]), 1, out) == -7
+        other = provers["update" if kind != "update" else "deposit"]
+        assert lib.bzk_mpn_prover_prove_work(hostmpn._h, other, blob, len(blob), addr, _ptr(rs[0]), _ptr(rs[1]), 1, out) == -1
+        assert lib.bzk_mpn_prover_prove_work(hostmpn._h, provers[kind], blob[:-2], len(blob) - 2, addr, _ptr(rs[0]), _ptr(rs[1]), 1, out) == -1
+    for p in provers.values():
+        lib.bzk_mpn_prover_free(hostmpn._h, p)
