@@ -270,6 +270,54 @@ class MpnProver:
         return bytes(blob)
 
 
+class NativeMpnProver:
+    """the same job with nothing but libbzk between the wire and the proof: `prove(work_bytes, prover_address, r, s)` ->
+    391-byte `ZkProof::Groth16` image through bzk_mpn_prover_prove_work (csrc/mpn_prover.cu: bincode decode, rows, GPU witness,
+    resident proof).  One circuit per kind, compiled by the C++ definition (mpn/native_circuit.py); `pk` = groth16.ProvingKey of
+    that circuit's R1CS (the Python and the C++ definitions emit the same arrays, so a key made for either fits)."""
+
+    def __init__(self, ctx, fee_token=ZIESHA):
+        self.ctx, self.fee_token, self._p = ctx, fee_token, {}
+
+    def add_circuit(self, kind, native_circuit, pk):
+        import ctypes as ct
+        import os
+        import numpy as np
+        from .. import _lib
+        blob = open(_lib.PARAMS_PATH, "rb").read()
+        canon = lambda v: np.frombuffer((v % N.R).to_bytes(32, "little"), dtype=np.uint64).copy()
+        jj_d, fee = canon(N.JJ_D), canon(self.fee_token)
+        h = ct.c_void_p()
+        self.ctx._check(self.ctx._l.bzk_mpn_prover_create(self.ctx._h, native_circuit._h, pk._h, blob, len(blob), ct.c_void_p(jj_d.ctypes.data),
+                                                          ct.c_void_p(fee.ctypes.data), ct.byref(h)))
+        self._p[kind] = (h, pk)          # the key must outlive the prover
+
+    def prove(self, work_bytes, prover_address, r, s, check_satisfied=True):
+        import ctypes as ct
+        import numpy as np
+        kind = Wr._KINDS[self._kind_of(work_bytes)]
+        r, s = (np.ascontiguousarray(x, dtype=np.uint64) for x in (r, s))
+        out = ct.create_string_buffer(391)
+        self.ctx._check(self.ctx._l.bzk_mpn_prover_prove_work(self.ctx._h, self._p[kind][0], bytes(work_bytes), len(work_bytes), bytes(prover_address),
+                                                              ct.c_void_p(r.ctypes.data), ct.c_void_p(s.ctypes.data), 1 if check_satisfied else 0, out))
+        return out.raw
+
+    def _kind_of(self, work_bytes):
+        import ctypes as ct
+        import numpy as np
+        h = ct.c_void_p()
+        self.ctx._check(self.ctx._l.bzk_mpn_work_decode(bytes(work_bytes), len(work_bytes), ct.byref(h), None))
+        info = np.zeros(64, dtype=np.uint32)
+        self.ctx._l.bzk_mpn_work_get_info(h, ct.c_void_p(info.ctypes.data))
+        self.ctx._l.bzk_mpn_work_free(h)
+        return int(info[0])
+
+    def free(self):
+        for h, _ in self._p.values():
+            self.ctx._l.bzk_mpn_prover_free(self.ctx._h, h)
+        self._p = {}
+
+
 class WorkerClient:
     """the loop of an MPN worker against a node's HTTP API"""
 
