@@ -129,6 +129,9 @@ SIGNATURES = {
     "bzk_mpn_get_work_request_encode": (_i32, [_vp, _vp]),
     "bzk_mpn_post_solution_request_encode": (_i32, [_vp, _vp, _vp, _u64, _vp, _sz, ct.POINTER(_sz)]),
     "bzk_mpn_post_solution_response_decode": (_i32, [_vp, _sz, ct.POINTER(_u64)]),
+    "bzk_mpn_prepare_works": (_i32, [_vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _u64, _vp, ct.POINTER(_vp), ct.POINTER(_vp), ct.POINTER(_sz),
+                              ct.POINTER(_u64)]),
+    "bzk_buffer_free": (_i32, [_vp]),
     "bzk_mpn_circuit_kind": (_i32, [_vp, _vp]),
     "bzk_mpn_prover_create": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, ct.POINTER(_vp)]),
     "bzk_mpn_prover_free": (_i32, [_vp, _vp]),

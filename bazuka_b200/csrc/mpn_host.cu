@@ -11,6 +11,7 @@
 // operands, `bazuka_b200/mpn/witness_program.py::raw_values`), the state root entering every slot, and the three
 // state-dependent public inputs.  Scalars cross the ABI as canonical 32-byte little-endian integers.
 #include "common.cuh"
+#include "mpn_wire.cuh"
 #include <algorithm>
 #include <map>
 #include <set>
@@ -316,11 +317,21 @@ int32_t list_root(bzk_ctx *ctx, uint32_t arity, const std::vector<Fr> &rows, Fr 
     return BZK_OK;
 }
 
-// shared tail of the deposit / withdraw builders: commit the mirror, public inputs
-struct DwCommon {
-    std::map<uint64_t, Account> mirror;
-    std::map<std::pair<FrKey, FrKey>, uint64_t> pending;
-};
+// ---- the builders' plans as the reference's transition structs (`prepare_works` puts them on the wire)
+wire::Money wire_money(const Money &m) {
+    wire::Money w;
+    w.token = wire::ContractId::of_scalar(m.token_id);
+    w.amount = m.amount;
+    return w;
+}
+wire::Account wire_account(const Account &a) {
+    wire::Account w;
+    w.tx_nonce = (uint32_t)a.tx_nonce; w.withdraw_nonce = (uint32_t)a.withdraw_nonce;
+    w.address.x = a.ax; w.address.y = a.ay;
+    for (auto &kv : a.tokens) w.tokens.emplace_back((uint64_t)kv.first, wire_money(kv.second));   // ascending slot order
+    return w;
+}
+wire::Proof wire_proof(const Fr *p, uint32_t depth) { return wire::Proof(p, p + (size_t)depth * 3); }
 }  // namespace
 
 extern "C" {
@@ -454,6 +465,13 @@ int32_t bzk_mpn_state_commit_accounts(bzk_mpn_state *s) {
 int32_t bzk_mpn_update_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_tx *txs, uint64_t n_txs, uint32_t log4_batch,
                              const bzk_fr *fee_token_canon, bzk_fr *raws, bzk_fr *ext, uint8_t *accepted, bzk_fr public3[3],
                              uint64_t *n_accepted) {
+    return bzk::mpn_update_build_impl(ctx, s, txs, n_txs, log4_batch, fee_token_canon, raws, ext, accepted, public3, n_accepted, nullptr);
+}
+}  // extern "C"
+
+int32_t bzk::mpn_update_build_impl(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_tx *txs, uint64_t n_txs, uint32_t log4_batch,
+                                   const bzk_fr *fee_token_canon, bzk_fr *raws, bzk_fr *ext, uint8_t *accepted, bzk_fr public3[3],
+                                   uint64_t *n_accepted, bzk::UpdateSink *sink) {
     if (!ctx || !s || (n_txs && !txs) || !fee_token_canon || !raws || !ext || !public3 || !n_accepted || log4_batch > 8) return BZK_ERR_BAD_ARG;
     BZK_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint32_t A = s->A, T = s->T;
@@ -646,8 +664,28 @@ int32_t bzk_mpn_update_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_tx *t
     fr_to_canon(public3 + 1, aux_out[0]);
     fr_to_canon(public3 + 2, root);
     *n_accepted = plan.size();
+    if (sink) {   // `UpdateTransition` of every accepted transaction (/root/reference/src/mpn/update.rs:220-247)
+        sink->t.clear(); sink->from.clear();
+        for (size_t slot = 0; slot < plan.size(); slot++) {
+            const Plan &p = plan[slot];
+            wire::UpdateTransition t;
+            t.enabled = true;
+            t.src_before = wire_account(p.src_before); t.src_before_balances_hash = p.src_bal_hash;
+            t.src_before_balance = wire_money(p.src_token); t.src_before_fee_balance = wire_money(p.src_fee_token);
+            t.src_proof = wire_proof(s_proofs.data() + (3 * slot) * A * 3, A);
+            t.src_index = p.src; t.src_token_index = p.sti; t.src_balance_proof = wire_proof(forest.proofs.data() + p.e1 * T * 3, T);
+            t.src_fee_token_index = p.sfi; t.src_fee_balance_proof = wire_proof(forest.proofs.data() + p.e2 * T * 3, T);
+            t.dst_before = wire_account(p.dst_before); t.dst_before_balances_hash = p.dst_bal_hash; t.dst_before_balance = wire_money(p.dst_token);
+            t.dst_proof = wire_proof(s_proofs.data() + (3 * slot + 2) * A * 3, A);
+            t.dst_index = p.dst; t.dst_token_index = p.dti; t.dst_balance_proof = wire_proof(forest.proofs.data() + p.e3 * T * 3, T);
+            sink->t.push_back(std::move(t));
+            sink->from.push_back(p.tx);
+        }
+    }
     return BZK_OK;
 }
+
+extern "C" {
 
 
 /* `mpn::deposit::deposit` (/root/reference/src/mpn/deposit.rs:11-233) without the L1 balance bookkeeping (chain state):
@@ -660,6 +698,13 @@ int32_t bzk_mpn_update_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_tx *t
  *   public3                   {state, aux_data, next_state};   the ledger advances (build on a clone, see bzk_mpn_state_clone) */
 int32_t bzk_mpn_deposit_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_deposit *deps, uint64_t n_deps, uint32_t log4_batch, bzk_fr *raws1,
                               bzk_fr *raws2, bzk_fr *roots, bzk_fr *reveal, uint8_t *accepted, bzk_fr public3[3], uint64_t *n_accepted) {
+    return bzk::mpn_deposit_build_impl(ctx, s, deps, n_deps, log4_batch, raws1, raws2, roots, reveal, accepted, public3, n_accepted, nullptr);
+}
+}  // extern "C"
+
+int32_t bzk::mpn_deposit_build_impl(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_deposit *deps, uint64_t n_deps, uint32_t log4_batch, bzk_fr *raws1,
+                                    bzk_fr *raws2, bzk_fr *roots, bzk_fr *reveal, uint8_t *accepted, bzk_fr public3[3], uint64_t *n_accepted,
+                                    bzk::DepositSink *sink) {
     if (!ctx || !s || (n_deps && !deps) || !raws1 || !raws2 || !roots || !reveal || !public3 || !n_accepted || log4_batch > 8) return BZK_ERR_BAD_ARG;
     BZK_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint32_t A = s->A, T = s->T, w2 = 9 + 3 * T + 3 * A;
@@ -792,8 +837,23 @@ int32_t bzk_mpn_deposit_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_depo
     fr_to_canon(public3 + 1, aux);
     fr_to_canon(public3 + 2, root);
     *n_accepted = plan.size();
+    if (sink) {   // `DepositTransition` of every accepted deposit (/root/reference/src/mpn/deposit.rs:150-165)
+        sink->t.clear(); sink->from.clear();
+        for (size_t slot = 0; slot < plan.size(); slot++) {
+            const Plan &p = plan[slot];
+            wire::DepositTransition t;
+            t.enabled = true;
+            t.before = wire_account(p.before); t.before_balances_hash = p.bal_hash; t.before_balance = wire_money(p.bal);
+            t.proof = wire_proof(s_proofs.data() + slot * A * 3, A);
+            t.account_index = p.idx; t.token_index = p.ti; t.balance_proof = wire_proof(forest.proofs.data() + p.e * T * 3, T);
+            sink->t.push_back(std::move(t));
+            sink->from.push_back(p.k);
+        }
+    }
     return BZK_OK;
 }
+
+extern "C" {
 
 /* `mpn::withdraw::withdraw` (/root/reference/src/mpn/withdraw.rs:10-259): nonce, balances and the EdDSA signature over
  * Poseidon(fingerprint, nonce) are checked here (the hashes of a batch in two launches, the scalar multiplications on the
@@ -803,6 +863,13 @@ int32_t bzk_mpn_deposit_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_depo
  * fingerprint, calldata}. */
 int32_t bzk_mpn_withdraw_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_withdraw *wds, uint64_t n_wds, uint32_t log4_batch, bzk_fr *raws1,
                                bzk_fr *raws2, bzk_fr *roots, bzk_fr *reveal, uint8_t *accepted, bzk_fr public3[3], uint64_t *n_accepted) {
+    return bzk::mpn_withdraw_build_impl(ctx, s, wds, n_wds, log4_batch, raws1, raws2, roots, reveal, accepted, public3, n_accepted, nullptr);
+}
+}  // extern "C"
+
+int32_t bzk::mpn_withdraw_build_impl(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_withdraw *wds, uint64_t n_wds, uint32_t log4_batch, bzk_fr *raws1,
+                                     bzk_fr *raws2, bzk_fr *roots, bzk_fr *reveal, uint8_t *accepted, bzk_fr public3[3], uint64_t *n_accepted,
+                                     bzk::WithdrawSink *sink) {
     if (!ctx || !s || (n_wds && !wds) || !raws1 || !raws2 || !roots || !reveal || !public3 || !n_accepted || log4_batch > 8) return BZK_ERR_BAD_ARG;
     BZK_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint32_t A = s->A, T = s->T, w2 = 12 + 6 * T + 3 * A;
@@ -974,10 +1041,22 @@ int32_t bzk_mpn_withdraw_build(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_wit
     fr_to_canon(public3 + 1, aux);
     fr_to_canon(public3 + 2, root);
     *n_accepted = plan.size();
+    if (sink) {   // `WithdrawTransition` of every accepted withdrawal (/root/reference/src/mpn/withdraw.rs:160-178)
+        sink->t.clear(); sink->from.clear();
+        for (size_t slot = 0; slot < plan.size(); slot++) {
+            const Plan &p = plan[slot];
+            wire::WithdrawTransition t;
+            t.enabled = true;
+            t.before = wire_account(p.before); t.before_token_balance = wire_money(p.tok); t.before_fee_balance = wire_money(p.fee_before);
+            t.proof = wire_proof(s_proofs.data() + (2 * slot) * A * 3, A);
+            t.account_index = p.idx; t.token_index = p.ti; t.token_balance_proof = wire_proof(forest.proofs.data() + p.e1 * T * 3, T);
+            t.before_token_hash = p.tok_hash; t.fee_token_index = p.fi; t.fee_balance_proof = wire_proof(forest.proofs.data() + p.e2 * T * 3, T);
+            sink->t.push_back(std::move(t));
+            sink->from.push_back(p.k);
+        }
+    }
     return BZK_OK;
 }
-
-}  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
 // witness of a whole deposit / withdraw batch from the builder's rows: what `{Deposit,Withdraw}Circuit::synthesize`

@@ -6,6 +6,8 @@
 // checked byte for byte against the Python restatement (bazuka_b200/mpn/wire.py) in tests/test_wire_native_cpu.py.
 #include "mpn_wire.cuh"
 
+#include <map>
+
 namespace bzk {
 namespace wire {
 
@@ -265,6 +267,34 @@ bool dec_work(Reader &r, Work &k) {
     k.new_root_hash = r.fr(); k.new_root_size = r.u64();
     k.reward = r.u64();
     return r.ok;
+}
+
+bool dec_config_bytes(const uint8_t *b, size_t n, Config &c) {
+    Reader r(b, n);
+    dec_config(r, c);
+    return r.ok && r.o == n;
+}
+// `bincode::serialize(&Vec<T>)`: u64 count, then the elements
+bool dec_deposits(const uint8_t *b, size_t n, std::vector<MpnDeposit> &out) {
+    Reader r(b, n);
+    const uint64_t k = r.len(kMaxTransitions * 16);
+    out.clear();
+    for (uint64_t i = 0; r.ok && i < k; i++) { out.emplace_back(); dec_mpn_deposit(r, out.back()); }
+    return r.ok && r.o == n;
+}
+bool dec_withdraws(const uint8_t *b, size_t n, std::vector<MpnWithdraw> &out) {
+    Reader r(b, n);
+    const uint64_t k = r.len(kMaxTransitions * 16);
+    out.clear();
+    for (uint64_t i = 0; r.ok && i < k; i++) { out.emplace_back(); dec_mpn_withdraw(r, out.back()); }
+    return r.ok && r.o == n;
+}
+bool dec_txs(const uint8_t *b, size_t n, std::vector<MpnTx> &out) {
+    Reader r(b, n);
+    const uint64_t k = r.len(kMaxTransitions * 16);
+    out.clear();
+    for (uint64_t i = 0; r.ok && i < k; i++) { out.emplace_back(); dec_mpn_tx(r, out.back()); }
+    return r.ok && r.o == n;
 }
 
 }  // namespace wire
@@ -631,6 +661,163 @@ int32_t bzk_mpn_post_solution_request_encode(const uint8_t prover[32], const uin
 int32_t bzk_mpn_post_solution_response_decode(const uint8_t *bytes, size_t len, uint64_t *accepted) {
     if (!bytes || !accepted || len != 8) return BZK_ERR_BAD_ARG;
     memcpy(accepted, bytes, 8);
+    return BZK_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ prepare_works
+namespace {
+inline void canon_of(bzk_fr *out, const Fr &mont) { Fr c = mont.from_mont(); memcpy(out, c.l, 32); }
+}
+
+extern "C" {
+
+/* `mpn::prepare_works` (/root/reference/src/mpn/mod.rs:298-424) over the native ledger: on ONE fork of `state` (which is not
+ * modified), `mpn_num_deposit_batches` deposit batches, then the withdraw batches, then the update batches — every batch is
+ * offered the whole list again (what an earlier batch took is stale for the next), the accounts created on the way are found by
+ * the later batches (`new_account_indices`) — and every batch becomes an `MpnWork {config, public_inputs, data, new_root, reward}`.
+ * Inputs are the reference's own wire images: `bincode::serialize(&config)`, `&Vec<MpnDeposit>`, `&Vec<MpnWithdraw>`,
+ * `&Vec<MpnTransaction>`; rewards = {deposit, withdraw, update}.  What the builders check of the L1 side comes from the payments:
+ * a deposit's source (`rejected_pub_keys`), a withdrawal's calldata (`verify_calldata`) and fingerprint.  Output: the bincode of
+ * `HashMap<usize, MpnWork>` numbered in building order — the body of `GetMpnWorkResponse` — in a buffer to release with
+ * bzk_buffer_free, and the fork (bzk_mpn_state_free it, or bzk_mpn_state_commit_accounts + keep it when the block is applied).
+ * The validator's own reward deposit and the L1 balance bookkeeping of that function are chain state: the caller prepends that
+ * deposit to the list like the reference does (mod.rs:338-351). */
+int32_t bzk_mpn_prepare_works(bzk_ctx *ctx, const bzk_mpn_state *state, const uint8_t *config_bytes, size_t config_len, const uint8_t *deposits_bytes,
+                              size_t deposits_len, const uint8_t *withdraws_bytes, size_t withdraws_len, const uint8_t *updates_bytes, size_t updates_len,
+                              const uint64_t rewards[3], uint64_t height, const bzk_fr *fee_token, bzk_mpn_state **fork_out, uint8_t **works_bytes,
+                              size_t *works_len, uint64_t *n_works) {
+    if (!ctx || !state || !config_bytes || !rewards || !fee_token || !fork_out || !works_bytes || !works_len || !n_works) return BZK_ERR_BAD_ARG;
+    Config config;
+    std::vector<MpnDeposit> deposits;
+    std::vector<MpnWithdraw> withdraws;
+    std::vector<MpnTx> updates;
+    if (!dec_config_bytes(config_bytes, config_len, config)) return BZK_ERR_BAD_ARG;
+    if (deposits_bytes && !dec_deposits(deposits_bytes, deposits_len, deposits)) return BZK_ERR_BAD_ARG;
+    if (withdraws_bytes && !dec_withdraws(withdraws_bytes, withdraws_len, withdraws)) return BZK_ERR_BAD_ARG;
+    if (updates_bytes && !dec_txs(updates_bytes, updates_len, updates)) return BZK_ERR_BAD_ARG;
+    const uint32_t A = config.log4_tree, T = config.log4_token;
+    {
+        bzk_fr root;
+        uint64_t sz, cnt, pend;
+        BZK_TRY(bzk_mpn_state_info(state, &root, &sz, &cnt, &pend));
+        uint32_t w = 0;
+        // the ledger must have the config's shape (the row width is a function of (A, T))
+        if (A == 0 || A > 31 || T == 0 || T > 8 || config.log4_deposit_batch > 8 || config.log4_withdraw_batch > 8 || config.log4_update_batch > 8 ||
+            bzk_mpn_update_raw_width(A, T, &w) != BZK_OK)
+            return BZK_ERR_BAD_ARG;
+    }
+    // ---- the builders' flat inputs
+    std::vector<bzk_mpn_deposit> dep_in(deposits.size());
+    {
+        std::map<std::vector<uint8_t>, uint64_t> src_ids;   // L1 source -> non-zero id (deposit.rs:33 `rejected_pub_keys`)
+        for (size_t k = 0; k < deposits.size(); k++) {
+            const MpnDeposit &d = deposits[k];
+            bzk_mpn_deposit &o = dep_in[k];
+            memset(&o, 0, sizeof o);
+            canon_of(&o.pk_x, d.mpn_address.x); o.pk_odd = d.mpn_address.odd ? 1 : 0;
+            canon_of(&o.token_id, d.payment.amount.token.scalar()); o.amount = d.payment.amount.amount;
+            const std::vector<uint8_t> src(d.payment.src, d.payment.src + 32);
+            o.src_id = src_ids.emplace(src, src_ids.size() + 1).first->second;
+        }
+    }
+    std::vector<bzk_mpn_withdraw> wd_in(withdraws.size());
+    for (size_t k = 0; k < withdraws.size(); k++) {
+        const MpnWithdraw &w = withdraws[k];
+        bzk_mpn_withdraw &o = wd_in[k];
+        memset(&o, 0, sizeof o);
+        canon_of(&o.pk_x, w.mpn_address.x); o.pk_odd = w.mpn_address.odd ? 1 : 0; o.nonce = w.nonce;
+        canon_of(&o.sig_rx, w.sig.r.x); canon_of(&o.sig_ry, w.sig.r.y); canon_of(&o.sig_s, w.sig.s);
+        canon_of(&o.amount_token_id, w.payment.amount.token.scalar()); canon_of(&o.fee_token_id, w.payment.fee.token.scalar());
+        canon_of(&o.fingerprint, withdraw_fingerprint(w.payment));
+        o.amount = w.payment.amount.amount; o.fee = w.payment.fee.amount;
+        o.check_calldata = 1; canon_of(&o.calldata, w.payment.calldata);
+    }
+    std::vector<bzk_mpn_tx> up_in(updates.size());
+    for (size_t k = 0; k < updates.size(); k++) {
+        const MpnTx &t = updates[k];
+        bzk_mpn_tx &o = up_in[k];
+        memset(&o, 0, sizeof o);
+        o.nonce = t.nonce; o.amount = t.amount.amount; o.fee = t.fee.amount;
+        o.src_pk_odd = t.src.odd ? 1 : 0; o.dst_pk_odd = t.dst.odd ? 1 : 0;
+        canon_of(&o.src_pk_x, t.src.x); canon_of(&o.dst_pk_x, t.dst.x);
+        canon_of(&o.amount_token_id, t.amount.token.scalar()); canon_of(&o.fee_token_id, t.fee.token.scalar());
+        canon_of(&o.sig_rx, t.sig.r.x); canon_of(&o.sig_ry, t.sig.r.y); canon_of(&o.sig_s, t.sig.s);
+    }
+    // ---- the batches, on one fork
+    bzk_mpn_state *fork = nullptr;
+    BZK_TRY(bzk_mpn_state_clone(state, &fork));
+    std::vector<Work> works;
+    int32_t st = BZK_OK;
+    auto finish = [&](Work &w, const bzk_fr public3[3], uint32_t kind) {
+        w.config = config; w.height = height; w.kind = kind;
+        Fr v[3];
+        for (int i = 0; i < 3; i++) { memcpy(v[i].l, public3 + i, 32); v[i] = v[i].to_mont(); }
+        w.state = v[0]; w.aux_data = v[1]; w.next_state = v[2];
+        bzk_fr root;
+        uint64_t sz = 0;
+        bzk_mpn_state_info(fork, &root, &sz, nullptr, nullptr);
+        Fr rt;
+        memcpy(rt.l, &root, 32);
+        w.new_root_hash = rt.to_mont(); w.new_root_size = sz;
+        w.reward = rewards[kind];
+    };
+    for (uint64_t b = 0; st == BZK_OK && b < config.n_deposit_batches; b++) {
+        const uint64_t slots = 1ull << (2 * config.log4_deposit_batch);
+        std::vector<bzk_fr> r1(slots * 5), r2(slots * (9 + 3 * T + 3 * A)), roots(slots), rev(slots * 4);
+        bzk_fr pub[3];
+        uint64_t n_acc = 0;
+        DepositSink sink;
+        st = mpn_deposit_build_impl(ctx, fork, dep_in.data(), dep_in.size(), config.log4_deposit_batch, r1.data(), r2.data(), roots.data(), rev.data(), nullptr,
+                                    pub, &n_acc, &sink);
+        if (st != BZK_OK) break;
+        Work w;
+        for (size_t i = 0; i < sink.t.size(); i++) { sink.t[i].tx = deposits[sink.from[i]]; w.deposits.push_back(std::move(sink.t[i])); }
+        finish(w, pub, KIND_DEPOSIT);
+        works.push_back(std::move(w));
+    }
+    for (uint64_t b = 0; st == BZK_OK && b < config.n_withdraw_batches; b++) {
+        const uint64_t slots = 1ull << (2 * config.log4_withdraw_batch);
+        std::vector<bzk_fr> r1(slots * 12), r2(slots * (12 + 6 * T + 3 * A)), roots(slots), rev(slots * 7);
+        bzk_fr pub[3];
+        uint64_t n_acc = 0;
+        WithdrawSink sink;
+        st = mpn_withdraw_build_impl(ctx, fork, wd_in.data(), wd_in.size(), config.log4_withdraw_batch, r1.data(), r2.data(), roots.data(), rev.data(), nullptr,
+                                     pub, &n_acc, &sink);
+        if (st != BZK_OK) break;
+        Work w;
+        for (size_t i = 0; i < sink.t.size(); i++) { sink.t[i].tx = withdraws[sink.from[i]]; w.withdraws.push_back(std::move(sink.t[i])); }
+        finish(w, pub, KIND_WITHDRAW);
+        works.push_back(std::move(w));
+    }
+    for (uint64_t b = 0; st == BZK_OK && b < config.n_update_batches; b++) {
+        const uint64_t slots = 1ull << (2 * config.log4_update_batch);
+        std::vector<bzk_fr> raws(slots * (32 + 9 * T + 6 * A)), ext(slots * 2);
+        bzk_fr pub[3];
+        uint64_t n_acc = 0;
+        UpdateSink sink;
+        st = mpn_update_build_impl(ctx, fork, up_in.data(), up_in.size(), config.log4_update_batch, fee_token, raws.data(), ext.data(), nullptr, pub, &n_acc,
+                                   &sink);
+        if (st != BZK_OK) break;
+        Work w;
+        for (size_t i = 0; i < sink.t.size(); i++) { sink.t[i].tx = updates[sink.from[i]]; w.updates.push_back(std::move(sink.t[i])); }
+        finish(w, pub, KIND_UPDATE);
+        works.push_back(std::move(w));
+    }
+    if (st != BZK_OK) { bzk_mpn_state_free(fork); return st; }
+    Writer out;
+    out.u64(works.size());
+    for (size_t i = 0; i < works.size(); i++) { out.u64(i); enc_work(out, works[i]); }
+    uint8_t *buf = (uint8_t *)malloc(out.b.size() ? out.b.size() : 1);
+    if (!buf) { bzk_mpn_state_free(fork); return BZK_ERR_OOM; }
+    memcpy(buf, out.b.data(), out.b.size());
+    *works_bytes = buf; *works_len = out.b.size(); *n_works = works.size(); *fork_out = fork;
+    return BZK_OK;
+}
+
+int32_t bzk_buffer_free(uint8_t *buffer) {
+    free(buffer);
     return BZK_OK;
 }
 

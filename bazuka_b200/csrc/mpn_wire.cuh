@@ -189,4 +189,18 @@ Fr commitment(const uint8_t prover[32], uint64_t reward);
 Fr withdraw_fingerprint(const ContractWithdraw &p);
 
 }  // namespace wire
+
+// The transition builders of csrc/mpn_host.cu with an optional sink for the reference's transition structs (`tx` left empty:
+// `from[i]` = index of the input the i-th transition was made from) — what `prepare_works` puts on the wire.
+struct UpdateSink { std::vector<wire::UpdateTransition> t; std::vector<uint64_t> from; };
+struct DepositSink { std::vector<wire::DepositTransition> t; std::vector<uint64_t> from; };
+struct WithdrawSink { std::vector<wire::WithdrawTransition> t; std::vector<uint64_t> from; };
+int32_t mpn_update_build_impl(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_tx *txs, uint64_t n_txs, uint32_t log4_batch, const bzk_fr *fee_token_canon,
+                              bzk_fr *raws, bzk_fr *ext, uint8_t *accepted, bzk_fr public3[3], uint64_t *n_accepted, UpdateSink *sink);
+int32_t mpn_deposit_build_impl(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_deposit *deps, uint64_t n_deps, uint32_t log4_batch, bzk_fr *raws1,
+                               bzk_fr *raws2, bzk_fr *roots, bzk_fr *reveal, uint8_t *accepted, bzk_fr public3[3], uint64_t *n_accepted,
+                               DepositSink *sink);
+int32_t mpn_withdraw_build_impl(bzk_ctx *ctx, bzk_mpn_state *s, const bzk_mpn_withdraw *wds, uint64_t n_wds, uint32_t log4_batch, bzk_fr *raws1,
+                                bzk_fr *raws2, bzk_fr *roots, bzk_fr *reveal, uint8_t *accepted, bzk_fr public3[3], uint64_t *n_accepted,
+                                WithdrawSink *sink);
 }  // namespace bzk

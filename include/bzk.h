@@ -463,6 +463,22 @@ int32_t bzk_mpn_post_solution_request_encode(const uint8_t prover[32], const uin
                                              size_t cap, size_t *len);
 int32_t bzk_mpn_post_solution_response_decode(const uint8_t *bytes, size_t len, uint64_t *accepted);
 
+/* `mpn::prepare_works` (/root/reference/src/mpn/mod.rs:298-424) over the native ledger — the validator's side of the protocol.
+ * On ONE fork of `state` (not modified; `db.fork_on_ram()`): mpn_num_deposit_batches deposit batches, then the withdraw batches,
+ * then the update batches, every batch offered the whole list again, accounts created on the way visible to the later batches
+ * (`new_account_indices`); every batch becomes an MpnWork {config, public_inputs, data, new_root, reward}.  Inputs are the
+ * reference's wire images: `bincode::serialize` of the `MpnConfig`, of `&Vec<MpnDeposit>`, `&Vec<MpnWithdraw>` and
+ * `&Vec<MpnTransaction>` (NULL = none); rewards = {deposit, withdraw, update}; fee_token canonical (Ziesha = 1).  What the
+ * builders check of the L1 side is read from the payments (a deposit's source, a withdrawal's calldata and fingerprint).
+ * Outputs: *works_bytes = bincode of `HashMap<usize, MpnWork>` numbered in building order (the body of GetMpnWorkResponse;
+ * release with bzk_buffer_free), *fork_out = the ledger after all batches (bzk_mpn_state_free, or commit_accounts + keep).
+ * The validator's own reward deposit and the L1 balances are chain state: prepend that deposit like mod.rs:338-351 does. */
+int32_t bzk_mpn_prepare_works(bzk_ctx *ctx, const bzk_mpn_state *state, const uint8_t *config_bytes, size_t config_len, const uint8_t *deposits_bytes,
+                              size_t deposits_len, const uint8_t *withdraws_bytes, size_t withdraws_len, const uint8_t *updates_bytes, size_t updates_len,
+                              const uint64_t rewards[3], uint64_t height, const bzk_fr *fee_token, bzk_mpn_state **fork_out, uint8_t **works_bytes,
+                              size_t *works_len, uint64_t *n_works);
+int32_t bzk_buffer_free(uint8_t *buffer);
+
 /* ------------------------------------------------------------------ the external prover's job as one call
  * `MpnWork` (bincode) in, `ZkProof::Groth16` (391 bytes, bincode) out — what the reference's workers do between
  * `GET /bincode/mpn/work` and `POST /bincode/mpn/solution` (/root/reference/src/client/mod.rs:428-464; `MpnWork::verify` on the

@@ -58,3 +58,10 @@ def test_native_prover_turns_wire_works_into_accepted_proofs(ctx, cref):
     nat.free()
     for w in (wu, wd, ww):
         w.free()
+
+
+def test_native_prepare_works_on_the_gpu_builders(ctx):
+    """bzk_mpn_prepare_works over the real kernels (batched Poseidon, versioned tree update): the same block as the CPU tier's
+    case — GetMpnWorkResponse image equal to works.prepare_works' byte for byte, forks agree, several batches continue."""
+    from test_wire_native_cpu import prepare_works_case
+    prepare_works_case(ctx)

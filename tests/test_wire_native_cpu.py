@@ -231,3 +231,87 @@ def test_work_bytes_to_satisfying_witness_through_the_native_prover_object(hostm
         assert lib.bzk_mpn_prover_prove_work(hostmpn._h, provers[kind], blob[:-2], len(blob) - 2, addr, _ptr(rs[0]), _ptr(rs[1]), 1, out) == -1
     for p in provers.values():
         lib.bzk_mpn_prover_free(hostmpn._h, p)
+
+
+def _vec(items, enc):
+    w = Wr.Writer()
+    w.vec(items, enc)
+    return bytes(w.b)
+
+
+def test_native_prepare_works_equals_the_python_restatement_byte_for_byte(hostmpn):
+    prepare_works_case(hostmpn)
+
+
+def prepare_works_case(hostmpn):
+    """(shared with the GPU tier: `hostmpn` is any context-like object)  bzk_mpn_prepare_works (csrc/mpn_wire.cu over the three native builders) against works.prepare_works on the same block:
+    deposit -> withdraw -> update on one fork, the depositor's brand-new account spending in the update batch of the same block
+    (`new_account_indices`), a rejected withdrawal (wrong calldata) and a deposit rejected through its L1 source; the
+    GetMpnWorkResponse images are equal byte for byte, the forks agree, the original ledger did not move — and two update batches
+    continue each other."""
+    from test_native_host_cpu import _load
+    from test_mpn_cpu import make_state, transfer
+    lib = hostmpn._l
+    st, keys, deposits, withdraws, wpay, updates = _scenario()
+    # explicit L1 payments for every deposit; the third comes from the source of a deposit whose key does not decompress
+    deposits = deposits + [D.MpnDeposit((6, False), 77, 1), D.MpnDeposit(N.jj_compress(keys[1][0]), 77, 3)]
+    srcs = [bytes([1]) * 32, bytes([2]) * 32, bytes([3]) * 32, bytes([3]) * 32]
+    dpay = {k: {"memo": "d%d" % k, "contract_id": 0x1234, "deposit_circuit_id": 0, "calldata": 0, "src": srcs[k],
+                "amount": {"token_id": Wr.scalar_contract_id(d.token_id), "amount": d.amount}, "fee": {"token_id": "ziesha", "amount": 0}, "nonce": k + 1,
+                "sig": bytes([9]) * 64 if k == 1 else None} for k, d in enumerate(deposits)}
+    # a second withdrawal whose payment carries the wrong calldata
+    w2 = D.MpnWithdraw(N.jj_compress(keys[2][0]), 1, amount=U.Money(U.ZIESHA, 7), fee=U.Money(U.ZIESHA, 1))
+    pay2 = {"memo": "", "contract_id": None, "withdraw_circuit_id": 0, "calldata": 0, "dst": bytes(32), "amount": {"token_id": "ziesha", "amount": 7},
+            "fee": {"token_id": "ziesha", "amount": 1}}
+    w2.fingerprint = Wk.withdraw_fingerprint(pay2)
+    w2.sign(keys[2][1])
+    pay2["calldata"] = w2.expected_calldata() + 1
+    withdraws, wpay = withdraws + [w2], {**wpay, 1: pay2}
+    config = _config()
+    rewards = {"deposit": 11, "withdraw": 22, "update": 33}
+    led = _load(hostmpn, st, 3, 3)
+    root0 = led.root
+    want, fork_py = Wk.prepare_works(config, st, deposits, withdraws, updates, rewards, height=9, deposit_payments=dpay, withdraw_payments=wpay)
+    assert [len(want[i]["data"][1]) for i in range(3)] == [2, 1, 2]              # the bad key took its source's next deposit with it; one withdrawal was refused
+
+    def run(cfg, deps, wds, ups, state):
+        cw = Wr.Writer()
+        Wr.enc_config(cw, cfg)
+        cb = bytes(cw.b)
+        db = _vec([{"mpn_address": tuple(d.mpn_address), "payment": dpay[k]} for k, d in enumerate(deps)], Wr.enc_mpn_deposit)
+        wb = _vec([{"mpn_address": tuple(w.mpn_address), "mpn_withdraw_nonce": w.mpn_withdraw_nonce, "mpn_sig": {"r": tuple(w.mpn_sig["r"]), "s": w.mpn_sig["s"]},
+                    "payment": wpay[k]} for k, w in enumerate(wds)], Wr.enc_mpn_withdraw)
+        ub = _vec([{"nonce": t.nonce, "src_pub_key": tuple(t.src_pub_key), "dst_pub_key": tuple(t.dst_pub_key), "amount": Wk._money_w(t.amount),
+                    "fee": Wk._money_w(t.fee), "sig": {"r": tuple(t.sig["r"]), "s": t.sig["s"]}} for t in ups], Wr.enc_mpn_tx)
+        rw = np.array([11, 22, 33], np.uint64)
+        fee = _canon(U.ZIESHA)
+        fork, buf, ln, n = ct.c_void_p(), ct.c_void_p(), ct.c_size_t(), ct.c_uint64()
+        hostmpn._check(lib.bzk_mpn_prepare_works(hostmpn._h, state._h, cb, len(cb), db, len(db), wb, len(wb), ub, len(ub), _ptr(rw), 9, _ptr(fee),
+                                                 ct.byref(fork), ct.byref(buf), ct.byref(ln), ct.byref(n)))
+        out = ct.string_at(buf, ln.value)
+        lib.bzk_buffer_free(buf)
+        return out, fork, n.value
+
+    got, fork, n = run(config, deposits, withdraws, updates, led)
+    assert n == 3 and got == Wr.get_mpn_work_response_to_bytes(want)
+    assert led.root == root0 == st.root                                          # built on a fork
+    root, size, cnt, pend = np.zeros(4, np.uint64), ct.c_uint64(), ct.c_uint64(), ct.c_uint64()
+    assert lib.bzk_mpn_state_info(fork, _ptr(root), ct.byref(size), ct.byref(cnt), ct.byref(pend)) == 0
+    assert (_int(root), size.value, pend.value) == (fork_py.root, fork_py.state_size, len(fork_py.new_account_indices))
+    lib.bzk_mpn_state_free(fork)
+    # several batches of one kind continue each other (mod.rs:396-414)
+    st2, keys2 = make_state(3, 3, 3)
+    ups = [transfer(keys2, 0, 1, 1), transfer(keys2, 1, 2, 1), transfer(keys2, 2, 0, 1), transfer(keys2, 0, 2, 2), transfer(keys2, 1, 0, 2),
+           transfer(keys2, 2, 1, 2)]
+    led2 = _load(hostmpn, st2, 3, 3)
+    cfg2 = _config(num=(0, 0, 2))
+    want2, _ = Wk.prepare_works(cfg2, st2, [], [], ups, rewards, height=9)
+    got2, fork2, n2 = run(cfg2, [], [], ups, led2)
+    assert n2 == 2 and got2 == Wr.get_mpn_work_response_to_bytes(want2)
+    lib.bzk_mpn_state_free(fork2)
+    # malformed inputs are refused
+    fork, buf, ln, n = ct.c_void_p(), ct.c_void_p(), ct.c_size_t(), ct.c_uint64()
+    rw, fee = np.array([1, 2, 3], np.uint64), _canon(U.ZIESHA)
+    assert lib.bzk_mpn_prepare_works(hostmpn._h, led._h, b"\x03\x03", 2, None, 0, None, 0, None, 0, _ptr(rw), 0, _ptr(fee), ct.byref(fork), ct.byref(buf),
+                                     ct.byref(ln), ct.byref(n)) == -1
+    led.free(); led2.free()
