@@ -451,6 +451,62 @@ int32_t bzk_mpn_state_info(const bzk_mpn_state *s, bzk_fr *state_hash, uint64_t 
     if (pending_accounts) *pending_accounts = s->pending.size();
     return BZK_OK;
 }
+/* out[2] = {log4_tree, log4_token} the ledger was created with */
+int32_t bzk_mpn_state_shape(const bzk_mpn_state *s, uint32_t out[2]) {
+    if (!s || !out) return BZK_ERR_BAD_ARG;
+    out[0] = s->A; out[1] = s->T;
+    return BZK_OK;
+}
+/* `MpnWorkPool.final_delta` (/root/reference/src/mpn/mod.rs:17-45,416-417): every scalar leaf in which `after` (the fork
+ * prepare_works returned) differs from `before`, as the bincode of `ZkDeltaPairs(HashMap<ZkDataLocator(Vec<u64>), Option<ZkScalar>>)`:
+ * locator [account, field] for the four account scalars, [account, 4, token slot, 0 | 1] for a token's id / balance
+ * (`set_mpn_account`, /root/reference/src/zk/state/mod.rs:140-208); a leaf that became zero is a `Remove` (None).  Entries in
+ * ascending locator order.  Release the buffer with bzk_buffer_free. */
+int32_t bzk_mpn_state_delta(const bzk_mpn_state *before, const bzk_mpn_state *after, uint8_t **bytes, size_t *len, uint64_t *n_entries) {
+    if (!before || !after || !bytes || !len) return BZK_ERR_BAD_ARG;
+    using Loc = std::vector<uint64_t>;
+    auto leaves = [](const bzk_mpn_state *s, uint64_t idx, std::map<Loc, Fr> &out) {
+        auto it = s->accounts.find(idx);
+        if (it == s->accounts.end()) return;
+        const Account &a = it->second;
+        const Fr f[4] = {fr_from_u64(a.tx_nonce), fr_from_u64(a.withdraw_nonce), a.ax, a.ay};
+        for (uint64_t k = 0; k < 4; k++) out[Loc{idx, k}] = f[k];
+        for (auto &kv : a.tokens) {
+            out[Loc{idx, 4, kv.first, 0}] = kv.second.token_id;
+            out[Loc{idx, 4, kv.first, 1}] = fr_from_u64(kv.second.amount);
+        }
+    };
+    std::set<uint64_t> touched;
+    for (auto &kv : before->accounts) touched.insert(kv.first);
+    for (auto &kv : after->accounts) touched.insert(kv.first);
+    wire::Writer w;
+    uint64_t n = 0;
+    w.u64(0);
+    for (uint64_t idx : touched) {
+        std::map<Loc, Fr> o, a;
+        leaves(before, idx, o);
+        leaves(after, idx, a);
+        std::set<Loc> locs;
+        for (auto &kv : o) locs.insert(kv.first);
+        for (auto &kv : a) locs.insert(kv.first);
+        for (const Loc &l : locs) {
+            const Fr ov = o.count(l) ? o[l] : Fr::zero(), nv = a.count(l) ? a[l] : Fr::zero();
+            if (ov == nv) continue;
+            w.u64(l.size());
+            for (uint64_t x : l) w.u64(x);
+            if (nv.is_zero()) w.u8(0);
+            else { w.u8(1); w.fr(nv); }
+            n++;
+        }
+    }
+    memcpy(w.b.data(), &n, 8);
+    uint8_t *buf = (uint8_t *)malloc(w.b.size());
+    if (!buf) return BZK_ERR_OOM;
+    memcpy(buf, w.b.data(), w.b.size());
+    *bytes = buf; *len = w.b.size();
+    if (n_entries) *n_entries = n;
+    return BZK_OK;
+}
 /* The block built on this fork was applied: its new accounts enter the chain's index table. */
 int32_t bzk_mpn_state_commit_accounts(bzk_mpn_state *s) {
     if (!s) return BZK_ERR_BAD_ARG;

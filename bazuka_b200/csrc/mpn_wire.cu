@@ -702,10 +702,10 @@ int32_t bzk_mpn_prepare_works(bzk_ctx *ctx, const bzk_mpn_state *state, const ui
         bzk_fr root;
         uint64_t sz, cnt, pend;
         BZK_TRY(bzk_mpn_state_info(state, &root, &sz, &cnt, &pend));
-        uint32_t w = 0;
-        // the ledger must have the config's shape (the row width is a function of (A, T))
-        if (A == 0 || A > 31 || T == 0 || T > 8 || config.log4_deposit_batch > 8 || config.log4_withdraw_batch > 8 || config.log4_update_batch > 8 ||
-            bzk_mpn_update_raw_width(A, T, &w) != BZK_OK)
+        uint32_t shape[2] = {0, 0};
+        // the ledger must have the config's shape: the builders size their rows from the ledger's (A, T), the buffers below from the config's
+        if (bzk_mpn_state_shape(state, shape) != BZK_OK || shape[0] != A || shape[1] != T || config.log4_deposit_batch > 8 ||
+            config.log4_withdraw_batch > 8 || config.log4_update_batch > 8)
             return BZK_ERR_BAD_ARG;
     }
     // ---- the builders' flat inputs

@@ -299,6 +299,12 @@ int32_t bzk_mpn_update_raw_width(uint32_t log4_tree, uint32_t log4_token, uint32
 int32_t bzk_mpn_state_clone(const bzk_mpn_state *state, bzk_mpn_state **out);
 int32_t bzk_mpn_state_info(const bzk_mpn_state *state, bzk_fr *state_hash, uint64_t *state_size, uint64_t *account_count, uint64_t *pending_accounts);
 int32_t bzk_mpn_state_commit_accounts(bzk_mpn_state *state);
+int32_t bzk_mpn_state_shape(const bzk_mpn_state *state, uint32_t out[2]);   /* {log4_tree, log4_token} */
+/* `MpnWorkPool.final_delta` (/root/reference/src/mpn/mod.rs:17-45,416-417): the scalar leaves in which `after` (the fork
+ * bzk_mpn_prepare_works returned) differs from `before`, as the bincode of `ZkDeltaPairs` = HashMap<ZkDataLocator(Vec<u64>),
+ * Option<ZkScalar>>: [account, field] for the four account scalars, [account, 4, token slot, 0 | 1] for a token's id / balance;
+ * a leaf that became zero is None.  Ascending locator order; release with bzk_buffer_free. */
+int32_t bzk_mpn_state_delta(const bzk_mpn_state *before, const bzk_mpn_state *after, uint8_t **bytes, size_t *len, uint64_t *n_entries);
 /* Deposit and withdraw batches natively (`mpn::deposit::deposit`, /root/reference/src/mpn/deposit.rs:11-233; `mpn::withdraw::withdraw`,
  * /root/reference/src/mpn/withdraw.rs:10-259), next to the update builder: the same ledger, the same batched GPU hashing,
  * rows of circuit inputs out.  `bzk_mpn_deposit` / `bzk_mpn_withdraw` carry what the circuits consume of `MpnDeposit` /

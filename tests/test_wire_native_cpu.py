@@ -298,6 +298,14 @@ def prepare_works_case(hostmpn):
     root, size, cnt, pend = np.zeros(4, np.uint64), ct.c_uint64(), ct.c_uint64(), ct.c_uint64()
     assert lib.bzk_mpn_state_info(fork, _ptr(root), ct.byref(size), ct.byref(cnt), ct.byref(pend)) == 0
     assert (_int(root), size.value, pend.value) == (fork_py.root, fork_py.state_size, len(fork_py.new_account_indices))
+    # `final_delta`: the changed scalar leaves as ZkDeltaPairs, equal to the restatement's (same entries, same order, same bytes)
+    dbuf, dlen, dn = ct.c_void_p(), ct.c_size_t(), ct.c_uint64()
+    assert lib.bzk_mpn_state_delta(led._h, fork, ct.byref(dbuf), ct.byref(dlen), ct.byref(dn)) == 0
+    dw = Wr.Writer()
+    delta = Wk.final_delta(st, fork_py)
+    Wk.enc_delta(dw, delta)
+    assert dn.value == len(delta) > 10 and ct.string_at(dbuf, dlen.value) == bytes(dw.b)
+    lib.bzk_buffer_free(dbuf)
     lib.bzk_mpn_state_free(fork)
     # several batches of one kind continue each other (mod.rs:396-414)
     st2, keys2 = make_state(3, 3, 3)
@@ -314,4 +322,49 @@ def prepare_works_case(hostmpn):
     rw, fee = np.array([1, 2, 3], np.uint64), _canon(U.ZIESHA)
     assert lib.bzk_mpn_prepare_works(hostmpn._h, led._h, b"\x03\x03", 2, None, 0, None, 0, None, 0, _ptr(rw), 0, _ptr(fee), ct.byref(fork), ct.byref(buf),
                                      ct.byref(ln), ct.byref(n)) == -1
-    led.free(); led2.free()
+    # a ledger of another shape than the config's is refused before any row is written
+    from bazuka_b200.mpn.ledger import NativeLedger
+    odd = NativeLedger(hostmpn, 4, 2)
+    cw = Wr.Writer()
+    Wr.enc_config(cw, _config())
+    assert lib.bzk_mpn_prepare_works(hostmpn._h, odd._h, bytes(cw.b), len(cw.b), None, 0, None, 0, None, 0, _ptr(rw), 0, _ptr(fee), ct.byref(fork),
+                                     ct.byref(buf), ct.byref(ln), ct.byref(n)) == -1
+    led.free(); led2.free(); odd.free()
+
+
+def test_native_mpn_work_verify_with_a_real_proof(hostmpn, works, cref):
+    """`MpnWork::verify` natively (bzk_mpn_work_verify: commitment from (prover, reward), then check_proof against the work's
+    own verifying key).  The key and the proof come from the C oracle's setup / prover on a small circuit with the five public
+    inputs of an MPN proof, proved for the values this work and this prover address imply: accepted; another address, another
+    reward, or another work's inputs are not."""
+    from oracle import groth16_c as GC
+    from oracle.py import groth16 as G
+    from bazuka_b200 import groth16 as BG
+    from conftest import fr_arr
+    from test_groth16_cpu import to_csr
+    lib = hostmpn._l
+    cs = G.R1CS(num_inputs=6, num_aux=2)             # inputs 1..5 = commitment, height, state, aux_data, next_state
+    cs.enforce([(6, 1)], [(6, 1)], [(7, 1)])          # w * w = u
+    cs.enforce([(7, 1), (1, 1)], [(0, 1)], [(7, 1), (1, 1)])   # a row that reads a public input
+    mats = to_csr(cs)
+    pk = GC.setup(cs.num_inputs, cs.num_aux, mats, cref.fr_random(15, 5))
+    vk_blob = bytes(BG.vk_to_bincode(pk["vk"]))
+    me, other = bytes(range(32)), bytes(range(1, 33))
+    work = dict(works[2], config=dict(works[2]["config"], update_vk=vk_blob))
+    pub = Wk.work_public_inputs(work, me)
+    z = fr_arr([1] + pub + [3, 9])
+    r, s = cref.fr_random(16, 2)
+    proof = bytes(GC.proof_bytes(*GC.prove(cs.num_inputs, cs.num_aux, mats, pk, z[:6], z[6:], r, s)))
+    assert Wk.verify_work(work, me, np.frombuffer(proof, dtype=np.uint8))
+
+    def check(w, addr):
+        h = _Work(lib, Wr.work_to_bytes(w))
+        st = lib.bzk_mpn_work_verify(h.h, addr, proof)
+        h.free()
+        return st
+
+    assert check(work, me) == 1
+    assert check(work, other) == 0                                   # the commitment binds the proof to its prover
+    assert check(dict(work, reward=work["reward"] + 1), me) == 0     # ... and to the reward
+    assert check(dict(work, public_inputs=dict(work["public_inputs"], height=10)), me) == 0
+    assert check(works[2], me) == 0                                  # another key (here: not even valid points) never accepts
