@@ -196,3 +196,49 @@ def test_native_deposit_withdraw_builders_rows_and_witness(hostmpn, kind):
     for h in hs:
         hostmpn._l.bzk_witness_program_free(hostmpn._h, h)
     led.free()
+
+
+def test_native_update_builder_at_the_production_tree_shape(hostmpn):
+    """A = 15, T = 3 (/root/reference/src/config/blockchain.rs:22-26), accounts spread over the 2^30 leaves (indices above 2^16 and
+    2^29 - 1, so the newcomer lands in the upper half of the tree), one batch of four slots: rows, entering roots and public values equal `update()`'s, and the rows
+    recovered from the WIRE image of the resulting work (csrc/mpn_wire.cu) equal the builder's own."""
+    from bazuka_b200.mpn import native as N, update as U, wire as Wr, witness_program as W, works as Wk
+    from bazuka_b200._lib import PARAMS_PATH
+    from test_wire_cpu import _config
+    A, T, B = 15, 3, 1
+    st, keys = U.MpnState(A, T), []
+    spots = [0, 70_000, (1 << 29) - 1]
+    for i, idx in enumerate(spots):
+        pk, sk = N.eddsa_keys(b"acct%d" % i)
+        keys.append((pk, sk))
+        st.set(idx, U.MpnAccount(0, 0, pk, {0: U.Money(U.ZIESHA, 10 ** 9), 63: U.Money(77, 5)}))
+    st.account_count = 1 << 29
+    keys.append(N.eddsa_keys(b"newcomer"))
+    txs = [transfer(keys, 0, 1, 1), transfer(keys, 2, 0, 1, amount=9, fee=1), transfer(keys, 1, 3, 1, amount=3), transfer(keys, 0, 2, 7)]
+    led = _load(hostmpn, st, A, T)
+    assert led.info()["account_count"] == 1 << 29
+    pub, trans, rej = U.update(st, txs, B)
+    assert len(trans) == 3 and rej == [txs[3]] and trans[2].dst_index == 1 << 29
+    raws, ext, acc, public, n_acc = led.update_build(txs, B)
+    assert acc.tolist() == [True, True, True, False] and public == pub and led.root == st.root
+    circ = U.UpdateCircuit(A, T, B, commitment=5, height=1, transitions=trans, **pub)
+    want_raws = np.stack([_canon_rows(W.raw_values(tr, A, T)) for tr in circ.transitions])
+    want_ext = np.stack([_canon_rows([circ.fee_token, r]) for r in W.slot_roots(circ)])
+    assert (raws == want_raws).all() and (ext == want_ext).all()
+    # the same rows from the wire image of the work
+    cfg = dict(_config(), log4_tree_size=A, log4_token_tree_size=T, log4_update_batch_size=B)
+    work = {"config": cfg, "public_inputs": dict(pub, height=1), "data": ("update", Wk.transitions_to_wire("update", trans)),
+            "new_root": {"state_hash": st.root, "state_size": st.state_size}, "reward": 1}
+    blob = Wr.work_to_bytes(work)
+    lib = hostmpn._l
+    h, hasher = ct.c_void_p(), ct.c_void_p()
+    assert lib.bzk_mpn_work_decode(blob, len(blob), ct.byref(h), None) == 0
+    pb = open(PARAMS_PATH, "rb").read()
+    assert lib.bzk_poseidon_host_create(pb, len(pb), ct.byref(hasher)) == 0
+    raws2, ext2 = np.zeros_like(raws), np.zeros_like(ext)
+    canon = lambda v: np.frombuffer((v % N.R).to_bytes(32, "little"), dtype=np.uint64).copy()
+    jj_d, fee = canon(N.JJ_D), canon(U.ZIESHA)
+    assert lib.bzk_mpn_work_update_rows(h, hasher, _ptr(jj_d), _ptr(fee), _ptr(raws2), _ptr(ext2)) == 0
+    assert (raws2 == raws).all() and (ext2 == ext).all()
+    lib.bzk_mpn_work_free(h); lib.bzk_poseidon_host_free(hasher)
+    led.free()
