@@ -347,5 +347,8 @@ class WorkerClient:
         proofs = {}
         for wid, work in works.items():
             r, s = randomness()
-            proofs[wid] = self.prover.prove(work, self.address, r, s)
+            if isinstance(self.prover, NativeMpnProver):      # bincode in, 391 bytes out (a decoded work re-encodes to its bytes)
+                proofs[wid] = self.prover.prove(Wr.work_to_bytes(work), self.address, r, s)[4:]
+            else:
+                proofs[wid] = self.prover.prove(work, self.address, r, s)
         return len(works), (self.post_proofs(proofs) if proofs else 0)

@@ -368,3 +368,47 @@ def test_native_mpn_work_verify_with_a_real_proof(hostmpn, works, cref):
     assert check(dict(work, reward=work["reward"] + 1), me) == 0     # ... and to the reward
     assert check(dict(work, public_inputs=dict(work["public_inputs"], height=10)), me) == 0
     assert check(works[2], me) == 0                                  # another key (here: not even valid points) never accepts
+
+
+def test_worker_loop_over_the_native_prover_and_codec(hostmpn, works):
+    """`WorkerClient.run_once` with `NativeMpnProver` against an in-process node that speaks only through the NATIVE codec: the
+    node serves the GetMpnWorkResponse image, the worker proves each work from its bytes (here over the host build, whose prove
+    call checks satisfiability and returns identity points), posts a PostMpnSolutionRequest; the node decodes it, finds one
+    387-byte proof per work and runs `MpnWork::verify` on each (identity points are not a valid proof: 0 accepted)."""
+    import json, os
+    lib = hostmpn._l
+    me = bytes(range(32))
+    nat = Wk.NativeMpnProver(hostmpn)
+    # the node checks against a REAL key (a production MPN key, tests/golden/mpn_vks.json): the fixture's works carry placeholder
+    # key images whose "points" all have the infinity byte set — under such a key e(alpha, beta) = 1 and identity points verify
+    prod_vk = bytes.fromhex(next(iter(json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mpn_vks.json")))["vks"].values())))
+
+    class _Circ:            # what NativeMpnProver.add_circuit needs of mpn.native_circuit.Native*Circuit / groth16.ProvingKey
+        def __init__(self, h): self._h = h
+    for kind in ("deposit", "withdraw", "update"):
+        c, _ = _compile(lib, kind, 3, 3, 1)
+        nat.add_circuit(kind, _Circ(c), _Circ(ct.c_void_p(1)))
+        lib.bzk_mpn_circuit_free(c)
+    log = []
+
+    def node(method, url, body):
+        if url.endswith("/bincode/mpn/work"):
+            want = ct.create_string_buffer(40)
+            assert lib.bzk_mpn_get_work_request_encode(me, want) == 0 and body == want.raw
+            return Wr.get_mpn_work_response_to_bytes(works)
+        prover, proofs = Wr.post_mpn_solution_request_from_bytes(body)
+        ok = 0
+        for wid, p in proofs.items():
+            assert len(p) == 387
+            kind = works[wid]["data"][0]
+            h = _Work(lib, Wr.work_to_bytes(dict(works[wid], config=dict(works[wid]["config"], **{kind + "_vk": prod_vk}))))
+            ok += lib.bzk_mpn_work_verify(h.h, prover, p) == 1
+            h.free()
+        log.append((prover, sorted(proofs)))
+        return ok.to_bytes(8, "little")
+
+    client = Wk.WorkerClient("127.0.0.1:1", me, nat, opener=node)
+    zero = np.zeros(4, np.uint64)
+    assert client.run_once(lambda: (zero, zero)) == (3, 0)
+    assert log == [(me, [0, 1, 2])]
+    nat.free()
