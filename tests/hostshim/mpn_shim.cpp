@@ -175,6 +175,8 @@ struct bzk_r1cs {
     std::vector<Fr> val[3];
 };
 static uint64_t g_last_unsat_row = ~0ull;
+static const Fr *g_last_in = nullptr, *g_last_aux = nullptr;   // the z of the last prove call (still resident in its prover)
+static uint64_t g_last_ni = 0, g_last_na = 0;
 extern "C" {
 int32_t bzk_r1cs_upload(bzk_ctx *ctx, uint64_t num_inputs, uint64_t num_aux, uint64_t num_constraints, const uint64_t *a_rowptr, const uint32_t *a_col,
                         const bzk_fr *a_val, const uint64_t *b_rowptr, const uint32_t *b_col, const bzk_fr *b_val, const uint64_t *c_rowptr,
@@ -205,6 +207,7 @@ int32_t bzk_groth16_prove_dev(bzk_ctx *ctx, const bzk_groth16_params *, const bz
     const Fr *zi = (const Fr *)d_inputs, *za = (const Fr *)d_aux;
     auto z = [&](uint32_t c) { return c < r->ni ? zi[c] : za[c - r->ni]; };
     g_last_unsat_row = ~0ull;
+    g_last_in = zi; g_last_aux = za; g_last_ni = r->ni; g_last_na = r->na;
     if (!(zi[0] == Fr::one())) { g_last_unsat_row = 0; if (check_satisfied) return BZK_ERR_UNSAT; }
     for (uint64_t row = 0; row < r->ncons; row++) {
         Fr v[3];
@@ -224,6 +227,13 @@ int32_t bzk_groth16_prove_dev(bzk_ctx *ctx, const bzk_groth16_params *, const bz
     return BZK_OK;
 }
 uint64_t shim_last_unsat_row() { return g_last_unsat_row; }
+// copies the assignment the last prove call was given (valid while its prover lives): inputs[ni], aux[na], Montgomery
+int32_t shim_last_z(void *inputs, uint64_t ni, void *aux, uint64_t na) {
+    if (!g_last_in || ni != g_last_ni || na != g_last_na) return BZK_ERR_BAD_ARG;
+    memcpy(inputs, g_last_in, ni * sizeof(Fr));
+    memcpy(aux, g_last_aux, na * sizeof(Fr));
+    return BZK_OK;
+}
 // the z the last prover call left resident (the shim's "device" memory is host memory): copies n elements from a raw pointer
 void shim_peek(const void *p, void *out, size_t bytes) { memcpy(out, p, bytes); }
 }

@@ -412,3 +412,90 @@ def test_worker_loop_over_the_native_prover_and_codec(hostmpn, works):
     assert client.run_once(lambda: (zero, zero)) == (3, 0)
     assert log == [(me, [0, 1, 2])]
     nat.free()
+
+
+def test_transactions_to_accepted_proofs_through_the_native_path(hostmpn, cref):
+    """the whole protocol on the CPU tier with REAL proofs: keys from the C oracle's setup on the natively compiled circuits;
+    a block's traffic -> bzk_mpn_prepare_works (native builders) -> GetMpnWorkResponse bytes -> per work bzk_mpn_prover_prove_work
+    (native codec, rows, witness drivers; this tier's prove call checks satisfiability and keeps z) -> the C ORACLE's prover on
+    that z and key -> bzk_mpn_work_verify (`MpnWork::verify`, libbzk's host pairing) accepts the proof for the prover it was made
+    for and for no other.  What the GPU tier adds is the MSM / NTT half of the prove call, bit-exact against this same oracle."""
+    from oracle import groth16_c as GC
+    from bazuka_b200 import groth16 as BG
+    from test_native_host_cpu import _load
+    from test_mpn_cpu import make_state, transfer
+    lib = hostmpn._l
+    lib.shim_last_z.argtypes = [ct.c_void_p, ct.c_uint64, ct.c_void_p, ct.c_uint64]
+    A = T = 3
+    B = 0                                                        # one slot per batch keeps the oracle's setup to seconds
+    keys_c, provers, r1 = {}, {}, {}
+    jj_d, fee = _canon(N.JJ_D), _canon(U.ZIESHA)
+    for k, kind in enumerate(("deposit", "withdraw", "update")):
+        c, blob = _compile(lib, kind, A, T, B)
+        shape = np.zeros(12, np.uint64)
+        assert lib.bzk_mpn_circuit_shape(c, _ptr(shape)) == 0
+        ni, na, ncons = int(shape[0]), int(shape[1]), int(shape[2])
+        mats = []
+        for side in range(3):
+            nnz = int(shape[3 + side])
+            rp, col, val = np.zeros(ncons + 1, np.uint64), np.zeros(max(nnz, 1), np.uint32), np.zeros((max(nnz, 1), 4), np.uint64)
+            assert lib.bzk_mpn_circuit_matrix(c, side, _ptr(rp), _ptr(col), _ptr(val)) == 0
+            mats.append((rp, col[:nnz], val[:nnz]))
+        r1[kind] = (ni, na, mats)
+        keys_c[kind] = GC.setup(ni, na, mats, cref.fr_random(40 + k, 5))
+        p = ct.c_void_p()
+        hostmpn._check(lib.bzk_mpn_prover_create(hostmpn._h, c, ct.c_void_p(1), blob, len(blob), _ptr(jj_d), _ptr(fee), ct.byref(p)))
+        lib.bzk_mpn_circuit_free(c)
+        provers[kind] = p
+    cfg = dict(_config(), log4_deposit_batch_size=B, log4_withdraw_batch_size=B, log4_update_batch_size=B,
+               **{kind + "_vk": bytes(BG.vk_to_bincode(keys_c[kind]["vk"])) for kind in keys_c})
+    # the block: a newcomer deposits, an old account withdraws, the newcomer pays an old account — each batch one transaction
+    st, keys = make_state(A, T, 3)
+    keys.append(N.eddsa_keys(b"dep-new"))
+    dep = {"mpn_address": tuple(N.jj_compress(keys[3][0])),
+           "payment": {"memo": "hello", "contract_id": 0x1234, "deposit_circuit_id": 0, "calldata": 0, "src": bytes([7]) * 32,
+                       "amount": {"token_id": "ziesha", "amount": 5000}, "fee": {"token_id": "ziesha", "amount": 0}, "nonce": 1, "sig": None}}
+    w = D.MpnWithdraw(N.jj_compress(keys[1][0]), 1, amount=U.Money(U.ZIESHA, 100), fee=U.Money(U.ZIESHA, 2))
+    pay = {"memo": "rent", "contract_id": 0x1234, "withdraw_circuit_id": 0, "calldata": 0, "dst": bytes(range(32)),
+           "amount": {"token_id": "ziesha", "amount": 100}, "fee": {"token_id": "ziesha", "amount": 2}}
+    w.fingerprint = Wk.withdraw_fingerprint(pay)
+    w.sign(keys[1][1])
+    pay["calldata"] = w.expected_calldata()
+    wd = {"mpn_address": tuple(w.mpn_address), "mpn_withdraw_nonce": 1, "mpn_sig": {"r": tuple(w.mpn_sig["r"]), "s": w.mpn_sig["s"]}, "payment": pay}
+    t = transfer(keys, 3, 0, 1, amount=40, fee=1)
+    up = {"nonce": t.nonce, "src_pub_key": tuple(t.src_pub_key), "dst_pub_key": tuple(t.dst_pub_key), "amount": Wk._money_w(t.amount),
+          "fee": Wk._money_w(t.fee), "sig": {"r": tuple(t.sig["r"]), "s": t.sig["s"]}}
+    led = _load(hostmpn, st, A, T)
+    cw = Wr.Writer()
+    Wr.enc_config(cw, cfg)
+    cb, db, wb, ub = bytes(cw.b), _vec([dep], Wr.enc_mpn_deposit), _vec([wd], Wr.enc_mpn_withdraw), _vec([up], Wr.enc_mpn_tx)
+    rw = np.array([11, 22, 33], np.uint64)
+    fork, buf, ln, n = ct.c_void_p(), ct.c_void_p(), ct.c_size_t(), ct.c_uint64()
+    hostmpn._check(lib.bzk_mpn_prepare_works(hostmpn._h, led._h, cb, len(cb), db, len(db), wb, len(wb), ub, len(ub), _ptr(rw), 9, _ptr(fee), ct.byref(fork),
+                                             ct.byref(buf), ct.byref(ln), ct.byref(n)))
+    resp = ct.string_at(buf, ln.value)
+    lib.bzk_buffer_free(buf)
+    assert n.value == 3
+    served = Wr.get_mpn_work_response_from_bytes(resp)
+    assert [len(served[i]["data"][1]) for i in range(3)] == [1, 1, 1]           # every batch took its transaction
+    me, other = bytes(range(32)), bytes(range(1, 33))
+    for wid, work in served.items():
+        kind = work["data"][0]
+        blob = Wr.work_to_bytes(work)
+        out = ct.create_string_buffer(391)
+        r, s = cref.fr_random(60 + wid, 2)
+        assert lib.bzk_mpn_prover_prove_work(hostmpn._h, provers[kind], blob, len(blob), me, _ptr(r), _ptr(s), 1, out) == 0
+        ni, na, mats = r1[kind]
+        z_in, z_aux = np.zeros((ni, 4), np.uint64), np.zeros((na, 4), np.uint64)
+        assert lib.shim_last_z(_ptr(z_in), ni, _ptr(z_aux), na) == 0
+        from bazuka_b200.mpn.cs import to_mont
+        assert (z_in[1:] == to_mont(Wk.work_public_inputs(work, me))).all()     # the public inputs the node will check against
+        proof = bytes(GC.proof_bytes(*GC.prove(ni, na, mats, keys_c[kind], z_in, z_aux, r, s)))
+        h = _Work(lib, blob)
+        assert lib.bzk_mpn_work_verify(h.h, me, proof) == 1
+        assert lib.bzk_mpn_work_verify(h.h, other, proof) == 0
+        h.free()
+    for p in provers.values():
+        lib.bzk_mpn_prover_free(hostmpn._h, p)
+    lib.bzk_mpn_state_free(fork)
+    led.free()
