@@ -499,3 +499,52 @@ def test_transactions_to_accepted_proofs_through_the_native_path(hostmpn, cref):
         lib.bzk_mpn_prover_free(hostmpn._h, p)
     lib.bzk_mpn_state_free(fork)
     led.free()
+
+
+def test_decoder_survives_mutated_images(hostmpn, works, host_hasher):
+    """truncations, bit flips and spliced length prefixes of valid works: every image is either refused (BZK_ERR_BAD_ARG) or
+    decodes to something that re-encodes and whose rows can be asked for — never a crash or an out-of-bounds read (the length
+    prefixes of vectors, maps, strings and keys are all bounded before anything is allocated or copied)."""
+    import random
+    lib = hostmpn._l
+    rng = random.Random(20260923)
+    jj_d, fee = _canon(N.JJ_D), _canon(U.ZIESHA)
+    refused = accepted = 0
+    for work in works.values():
+        blob = Wr.work_to_bytes(work)
+        for trial in range(400):
+            b = bytearray(blob)
+            mode = trial % 4
+            if mode == 0:
+                b = b[:rng.randrange(len(b))]
+            elif mode == 1:
+                for _ in range(rng.randint(1, 4)):
+                    b[rng.randrange(len(b))] ^= 1 << rng.randrange(8)
+            elif mode == 2:                                   # a huge length prefix somewhere
+                o = rng.randrange(len(b) - 8)
+                b[o:o + 8] = struct.pack("<Q", rng.choice([2**63, 2**32, 10**6, 65]))
+            else:                                             # garbage tail after a valid head
+                cut = rng.randrange(len(b))
+                b = b[:cut] + bytes(rng.randrange(256) for _ in range(rng.randint(1, 64)))
+            h = ct.c_void_p()
+            st = lib.bzk_mpn_work_decode(bytes(b), len(b), ct.byref(h), None)
+            assert st in (0, -1)
+            if st != 0:
+                refused += 1
+                continue
+            accepted += 1
+            n = ct.c_size_t()
+            assert lib.bzk_mpn_work_encode(h, None, 0, ct.byref(n)) == 0 and n.value == len(b)    # canonical: same length back
+            info = np.zeros(64, np.uint32)
+            lib.bzk_mpn_work_get_info(h, _ptr(info))
+            kind, A, T, B = (int(x) for x in info[:4])
+            if (A, T, B) == (3, 3, 1):                        # buffers sized for the original shape
+                if kind == 2:
+                    raws, ext = np.zeros((4, 32 + 9 * T + 6 * A, 4), np.uint64), np.zeros((4, 2, 4), np.uint64)
+                    assert lib.bzk_mpn_work_update_rows(h, host_hasher, _ptr(jj_d), _ptr(fee), _ptr(raws), _ptr(ext)) in (0, -1, -4)
+                else:
+                    w1, w2, wr = (5, 9 + 3 * T + 3 * A, 4) if kind == 0 else (12, 12 + 6 * T + 3 * A, 7)
+                    r1, r2, ro, rv = (np.zeros((4, w, 4), np.uint64) for w in (w1, w2, 1, wr))
+                    assert lib.bzk_mpn_work_dw_rows(h, host_hasher, _ptr(jj_d), _ptr(r1), _ptr(r2), _ptr(ro), _ptr(rv)) in (0, -1, -4)
+            lib.bzk_mpn_work_free(h)
+    assert refused > 600 and accepted > 50, (refused, accepted)
