@@ -242,3 +242,45 @@ def test_native_update_builder_at_the_production_tree_shape(hostmpn):
     assert (raws2 == raws).all() and (ext2 == ext).all()
     lib.bzk_mpn_work_free(h); lib.bzk_poseidon_host_free(hasher)
     led.free()
+
+
+def test_reference_withdraw_scenario_at_the_production_config(hostmpn):
+    """the reference's own transition-builder test (/root/reference/src/mpn/withdraw.rs:270-353) on the native ledger: production
+    config (A = 15, T = 3, deposit / withdraw batches of 64), a fresh state, `TxBuilder::new("ABC")` deposits 10056 of token 123 into
+    its own MPN account (a new account: index 0), then withdraws 30 with a fee of 26 in the same token — one accepted transition
+    each, as the reference asserts; an empty withdraw batch builds too (`test_withdraw_empty`).  Rows, roots and public values
+    equal the Python restatement's."""
+    from bazuka_b200.mpn import dw as D, dw_witness as DW, native as N, update as U
+    from bazuka_b200.mpn.ledger import NativeLedger
+    A, T, B = 15, 3, 3
+    st = U.MpnState(A, T)
+    led = NativeLedger(hostmpn, A, T)
+    assert led.root == st.root
+    # test_withdraw_empty
+    pub0, tr0 = D.withdraw(st, [], B)
+    rows0 = led.withdraw_build([], B)
+    assert rows0["n_accepted"] == 0 == len(tr0) and rows0["public"] == pub0 and pub0["state"] == pub0["next_state"] == st.root
+    pk, sk = N.eddsa_keys(b"ABC")
+    dep = D.MpnDeposit(N.jj_compress(pk), 123, 10056, "abc-l1")
+    pub, trans = D.deposit(st, [dep], B)
+    rows = led.deposit_build([dep], B)
+    assert len(trans) == 1 == rows["n_accepted"] and rows["public"] == pub and led.root == st.root and trans[0].account_index == 0
+    circ = D.DepositCircuit(A, T, B, commitment=0, height=0, transitions=trans, **pub)
+    want = [DW.deposit_raws(t, A, T) for t in circ.transitions]
+    assert len(want) == 64
+    assert (rows["raws1"].reshape(-1, 4) == _canon_rows([v for a, _ in want for v in a])).all()
+    assert (rows["raws2"].reshape(-1, 4) == _canon_rows([v for _, b in want for v in b])).all()
+    assert (rows["roots"] == _canon_rows(DW.slot_roots(circ))).all()
+    w = D.MpnWithdraw(N.jj_compress(pk), 1, amount=U.Money(123, 30), fee=U.Money(123, 26), fingerprint=4242)
+    w.sign(sk)
+    pub, trans = D.withdraw(st, [w], B)
+    rows = led.withdraw_build([w], B)
+    assert len(trans) == 1 == rows["n_accepted"] and rows["public"] == pub and led.root == st.root
+    assert st.accounts[0].tokens[0].amount == 10056 - 30 - 26 and st.accounts[0].withdraw_nonce == 1
+    circ = D.WithdrawCircuit(A, T, B, commitment=0, height=0, transitions=trans, **pub)
+    want = [DW.withdraw_raws(t, A, T) for t in circ.transitions]
+    assert (rows["raws1"].reshape(-1, 4) == _canon_rows([v for a, _ in want for v in a])).all()
+    assert (rows["raws2"].reshape(-1, 4) == _canon_rows([v for _, b in want for v in b])).all()
+    assert (rows["reveal"].reshape(-1, 4) == _canon_rows([v for r in DW.reveal_rows_native("withdraw", circ) for v in r])).all()
+    assert led.info()["state_size"] == st.state_size
+    led.free()
