@@ -548,3 +548,50 @@ def test_decoder_survives_mutated_images(hostmpn, works, host_hasher):
                     assert lib.bzk_mpn_work_dw_rows(h, host_hasher, _ptr(jj_d), _ptr(r1), _ptr(r2), _ptr(ro), _ptr(rv)) in (0, -1, -4)
             lib.bzk_mpn_work_free(h)
     assert refused > 600 and accepted > 50, (refused, accepted)
+
+
+@pytest.mark.parametrize("kind", ["deposit", "withdraw", "update"])
+def test_reference_circuit_test_shape_all_null_batches(hostmpn, cref, kind):
+    """the reference's own circuit tests (/root/reference/src/mpn/circuits/test.rs:117-229): each MPN circuit at log4 sizes 3 / 3 / 1
+    with four NULL transitions -> setup -> prove -> verify.  Here on the native path: the circuit compiled by C++, an `MpnWork`
+    without transitions through bzk_mpn_prover_prove_work (all four slots padded like `..Transition::null`), setup and proof by
+    the C oracle on the resulting assignment, `MpnWork::verify` by libbzk's pairing — accepted; a wrong height is not."""
+    from oracle import groth16_c as GC
+    from bazuka_b200 import groth16 as BG
+    lib = hostmpn._l
+    lib.shim_last_z.argtypes = [ct.c_void_p, ct.c_uint64, ct.c_void_p, ct.c_uint64]
+    A, T, B = 3, 3, 1
+    st = U.MpnState(A, T)
+    pub = (D.deposit(st, [], B)[0] if kind == "deposit" else D.withdraw(st, [], B)[0] if kind == "withdraw" else U.update(st, [], B)[0])
+    c, blob = _compile(lib, kind, A, T, B)
+    shape = np.zeros(12, np.uint64)
+    lib.bzk_mpn_circuit_shape(c, _ptr(shape))
+    ni, na, ncons = int(shape[0]), int(shape[1]), int(shape[2])
+    mats = []
+    for side in range(3):
+        nnz = int(shape[3 + side])
+        rp, col, val = np.zeros(ncons + 1, np.uint64), np.zeros(max(nnz, 1), np.uint32), np.zeros((max(nnz, 1), 4), np.uint64)
+        lib.bzk_mpn_circuit_matrix(c, side, _ptr(rp), _ptr(col), _ptr(val))
+        mats.append((rp, col[:nnz], val[:nnz]))
+    key = GC.setup(ni, na, mats, cref.fr_random(90, 5))
+    jj_d, fee = _canon(N.JJ_D), _canon(U.ZIESHA)
+    p = ct.c_void_p()
+    hostmpn._check(lib.bzk_mpn_prover_create(hostmpn._h, c, ct.c_void_p(1), blob, len(blob), _ptr(jj_d), _ptr(fee), ct.byref(p)))
+    lib.bzk_mpn_circuit_free(c)
+    cfg = dict(_config(), **{kind + "_vk": bytes(BG.vk_to_bincode(key["vk"]))})
+    work = {"config": cfg, "public_inputs": dict(pub, height=3), "data": (kind, []), "new_root": {"state_hash": st.root, "state_size": 0}, "reward": 5}
+    wb = Wr.work_to_bytes(work)
+    me = bytes(range(32))
+    r, s = cref.fr_random(91, 2)
+    out = ct.create_string_buffer(391)
+    assert lib.bzk_mpn_prover_prove_work(hostmpn._h, p, wb, len(wb), me, _ptr(r), _ptr(s), 1, out) == 0
+    z_in, z_aux = np.zeros((ni, 4), np.uint64), np.zeros((na, 4), np.uint64)
+    assert lib.shim_last_z(_ptr(z_in), ni, _ptr(z_aux), na) == 0
+    proof = bytes(GC.proof_bytes(*GC.prove(ni, na, mats, key, z_in, z_aux, r, s)))
+    h = _Work(lib, wb)
+    assert lib.bzk_mpn_work_verify(h.h, me, proof) == 1
+    h.free()
+    h = _Work(lib, Wr.work_to_bytes(dict(work, public_inputs=dict(pub, height=4))))
+    assert lib.bzk_mpn_work_verify(h.h, me, proof) == 0
+    h.free()
+    lib.bzk_mpn_prover_free(hostmpn._h, p)
