@@ -595,3 +595,41 @@ def test_reference_circuit_test_shape_all_null_batches(hostmpn, cref, kind):
     assert lib.bzk_mpn_work_verify(h.h, me, proof) == 0
     h.free()
     lib.bzk_mpn_prover_free(hostmpn._h, p)
+
+
+def test_single_update_at_the_production_tree_shape_through_the_native_prover(hostmpn):
+    """BASELINE configs[0] — UpdateCircuit A = 15, T = 3, B = 0 (56 776 constraints), one signed transfer between two funded
+    accounts — from the wire image of its work through bzk_mpn_prover_prove_work on the host build: the natively compiled
+    circuit is satisfied by the assignment the native rows + witness driver produce (depth-15 Merkle paths, both EdDSA ladders)."""
+    from test_mpn_cpu import transfer
+    lib = hostmpn._l
+    lib.shim_last_unsat_row.restype = ct.c_uint64
+    A, T, B = 15, 3, 0
+    st, keys = U.MpnState(A, T), []
+    for i, seed in enumerate((b"ABC", b"DEF")):                      # SURVEY §8(d) config 1: seeds of `TxBuilder::new`
+        pk, sk = N.eddsa_keys(seed)
+        keys.append((pk, sk))
+        st.set(i, U.MpnAccount(0, 0, pk, {0: U.Money(U.ZIESHA, 10 ** 12)}))
+    pub, trans, rej = U.update(st, [transfer(keys, 0, 1, 1, amount=1000, fee=10)], B)
+    assert len(trans) == 1 and not rej
+    cfg = dict(_config(), log4_tree_size=A, log4_token_tree_size=T, log4_update_batch_size=B)
+    work = {"config": cfg, "public_inputs": dict(pub, height=1), "data": ("update", Wk.transitions_to_wire("update", trans)),
+            "new_root": {"state_hash": st.root, "state_size": st.state_size}, "reward": 7}
+    wb = Wr.work_to_bytes(work)
+    c, blob = _compile(lib, "update", A, T, B)
+    shape = np.zeros(12, np.uint64)
+    lib.bzk_mpn_circuit_shape(c, _ptr(shape))
+    assert int(shape[2]) == 56776                                     # SURVEY §8a: ≈ 56.8 k constraints for one transaction
+    jj_d, fee = _canon(N.JJ_D), _canon(U.ZIESHA)
+    p = ct.c_void_p()
+    hostmpn._check(lib.bzk_mpn_prover_create(hostmpn._h, c, ct.c_void_p(1), blob, len(blob), _ptr(jj_d), _ptr(fee), ct.byref(p)))
+    lib.bzk_mpn_circuit_free(c)
+    zero, out = np.zeros(4, np.uint64), ct.create_string_buffer(391)
+    st_ = lib.bzk_mpn_prover_prove_work(hostmpn._h, p, wb, len(wb), bytes(range(32)), _ptr(zero), _ptr(zero), 1, out)
+    assert st_ == 0, (st_, lib.shim_last_unsat_row())
+    # a forged signature is caught by the circuit, not proved
+    bad = Wk.transitions_to_wire("update", trans)
+    bad[0]["tx"]["sig"]["s"] = (bad[0]["tx"]["sig"]["s"] + 1) % N.R
+    bb = Wr.work_to_bytes(dict(work, data=("update", bad)))
+    assert lib.bzk_mpn_prover_prove_work(hostmpn._h, p, bb, len(bb), bytes(range(32)), _ptr(zero), _ptr(zero), 1, out) == -7
+    lib.bzk_mpn_prover_free(hostmpn._h, p)
