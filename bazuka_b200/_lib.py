@@ -135,7 +135,9 @@ SIGNATURES = {
                               ct.POINTER(_u64)]),
     "bzk_buffer_free": (_i32, [_vp]),
     "bzk_mpn_circuit_kind": (_i32, [_vp, _vp]),
-    "bzk_mpn_prover_create": (_i32, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, ct.POINTER(_vp)]),
+    "bzk_mpn_prover_create": (_i32, [_vp, _vp, _vp, _vp, _vp, ct.POINTER(_vp)]),
+    "bzk_mpn_work_update_rows_ctx": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "bzk_mpn_work_dw_rows_ctx": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bzk_mpn_prover_free": (_i32, [_vp, _vp]),
     "bzk_mpn_prover_prove_work": (_i32, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _i32, _vp]),
     "bzk_witness_program_upload": (_i32, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _u64, _vp, _u64, _u32, _u32, _vp, ct.POINTER(_vp)]),

@@ -4,7 +4,7 @@
 //
 //   bzk_mpn_prover_create     per circuit (kind, A, T, B): uploads the natively compiled circuit's witness programs and R1CS,
 //                             allocates the resident z = inputs ++ aux, borrows the proving key
-//   bzk_mpn_prover_prove_work work -> rows (mpn_wire.cu; entering roots, fingerprint and calldata hashes on the host Poseidon)
+//   bzk_mpn_prover_prove_work work -> rows (mpn_wire.cu; entering roots and calldata hashes in 2 + A batched launches)
 //                             -> witness on the GPU straight into z (bzk_mpn_update_witness / bzk_mpn_dw_witness)
 //                             -> bzk_groth16_prove_dev -> proof bytes
 // Nothing here is new arithmetic: it strings together calls that are each checked on their own; the composition is run in the
@@ -24,7 +24,6 @@ struct bzk_mpn_prover {
     std::vector<int32_t> ext_src;
     bzk_r1cs *r1cs = nullptr;
     const bzk_groth16_params *params = nullptr;
-    bzk_poseidon_host *hasher = nullptr;
     bzk_fr jj_d{}, fee_token{};
     void *d_z = nullptr;   // num_inputs + num_aux field elements
 };
@@ -49,17 +48,17 @@ int32_t bzk_mpn_prover_free(bzk_ctx *ctx, bzk_mpn_prover *p) {
     for (auto *w : p->prog)
         if (w) bzk_witness_program_free(ctx, w);
     if (p->r1cs) bzk_r1cs_free(ctx, p->r1cs);
-    if (p->hasher) bzk_poseidon_host_free(p->hasher);
     if (p->d_z) { cudaSetDevice(ctx->device); cudaFree(p->d_z); }
     delete p;
     return BZK_OK;
 }
 
 /* `params` must be the proving key of exactly this circuit (bzk_r1cs_shape of the circuit's R1CS gives the vector lengths) and
- * outlive the prover.  poseidon_blob: the BZKPOSv1 table; jubjub_d, fee_token (UpdateCircuit's `fee_token`, Ziesha = 1): canonical. */
-int32_t bzk_mpn_prover_create(bzk_ctx *ctx, const bzk_mpn_circuit *circuit, const bzk_groth16_params *params, const uint8_t *poseidon_blob,
-                              size_t blob_len, const bzk_fr *jubjub_d, const bzk_fr *fee_token, bzk_mpn_prover **out) {
-    if (!ctx || !circuit || !params || !poseidon_blob || !jubjub_d || !fee_token || !out) return BZK_ERR_BAD_ARG;
+ * outlive the prover; the context must have its Poseidon table loaded (bzk_poseidon_load_params: the rows' hashes are batched
+ * launches).  jubjub_d, fee_token (UpdateCircuit's `fee_token`, Ziesha = 1): canonical. */
+int32_t bzk_mpn_prover_create(bzk_ctx *ctx, const bzk_mpn_circuit *circuit, const bzk_groth16_params *params, const bzk_fr *jubjub_d,
+                              const bzk_fr *fee_token, bzk_mpn_prover **out) {
+    if (!ctx || !circuit || !params || !jubjub_d || !fee_token || !out) return BZK_ERR_BAD_ARG;
     std::unique_ptr<bzk_mpn_prover> p(new (std::nothrow) bzk_mpn_prover);
     if (!p) return BZK_ERR_OOM;
     uint32_t k4[4];
@@ -68,7 +67,7 @@ int32_t bzk_mpn_prover_create(bzk_ctx *ctx, const bzk_mpn_circuit *circuit, cons
     BZK_TRY(bzk_mpn_circuit_shape(circuit, p->shape));
     p->params = params;
     p->jj_d = *jubjub_d; p->fee_token = *fee_token;
-    int32_t st = bzk_poseidon_host_create(poseidon_blob, blob_len, &p->hasher);
+    int32_t st = BZK_OK;
     Fr d;
     memcpy(d.l, jubjub_d, 32);
     d = d.to_mont();
@@ -128,14 +127,14 @@ int32_t bzk_mpn_prover_prove_work(bzk_ctx *ctx, bzk_mpn_prover *p, const uint8_t
     if (p->kind == 0) {
         const uint32_t n_raw = 32 + 9 * p->T + 6 * p->A;
         std::vector<bzk_fr> raws(n * n_raw), ext(n * 2);
-        BZK_TRY(bzk_mpn_work_update_rows(work.get(), p->hasher, &p->jj_d, &p->fee_token, raws.data(), ext.data()));
+        BZK_TRY(bzk_mpn_work_update_rows_ctx(ctx, work.get(), &p->jj_d, &p->fee_token, raws.data(), ext.data()));
         const bzk_fr prologue[6] = {commitment, height, info.state, p->fee_token, info.aux_data, info.next_state};
         BZK_TRY(bzk_mpn_update_witness(ctx, p->prog[0], p->prog[1], n, p->T, p->shape[7], p->shape[10], raws.data(), ext.data(), n_raw, prologue, z_in,
                                        z_aux));
     } else {
         const uint32_t w1 = p->kind == 1 ? 5 : 12, w2 = p->kind == 1 ? 9 + 3 * p->T + 3 * p->A : 12 + 6 * p->T + 3 * p->A, wr = p->kind == 1 ? 4 : 7;
         std::vector<bzk_fr> raws1(n * w1), raws2(n * w2), roots(n), reveal(n * wr);
-        BZK_TRY(bzk_mpn_work_dw_rows(work.get(), p->hasher, &p->jj_d, raws1.data(), raws2.data(), roots.data(), reveal.data()));
+        BZK_TRY(bzk_mpn_work_dw_rows_ctx(ctx, work.get(), &p->jj_d, raws1.data(), raws2.data(), roots.data(), reveal.data()));
         const bzk_fr public5[5] = {commitment, height, info.state, info.aux_data, info.next_state};
         BZK_TRY(bzk_mpn_dw_witness(ctx, p->prog[0], p->prog[1], p->prog[2], n, raws1.data(), raws2.data(), roots.data(), p->ext_src.data(),
                                    (uint32_t)p->ext_src.size(), reveal.data(), public5, z_in, z_aux));

@@ -6,6 +6,7 @@
 // checked byte for byte against the Python restatement (bazuka_b200/mpn/wire.py) in tests/test_wire_native_cpu.py.
 #include "mpn_wire.cuh"
 
+#include <functional>
 #include <map>
 
 namespace bzk {
@@ -310,50 +311,69 @@ namespace {
 inline void canon_out(bzk_fr *out, const Fr &mont) { Fr c = mont.from_mont(); memcpy(out, c.l, 32); }
 inline void put_u(bzk_fr *out, uint64_t v) { memset(out, 0, 32); memcpy(out, &v, 8); }
 
+// batched Poseidon, in[n][arity] -> out[n] (Montgomery images): the host hasher, or a context's batched launch
+using HashBatch = std::function<int32_t(uint32_t arity, const Fr *in, size_t n, Fr *out)>;
+
+struct RootJob {   // one enabled transition: its account before, the balances hash in its leaf, its index and Merkle proof
+    const Account *account;
+    Fr balances_hash;
+    uint64_t index;
+    const Proof *proof;
+};
+
 struct RowCtx {
-    const bzk_poseidon_host *hasher;
+    HashBatch hash;
     const bzk_fr *jj_d;
-    int32_t hash(uint32_t arity, const Fr *in, Fr *out) const { return bzk_poseidon_host_hash(hasher, arity, (const bzk_fr *)in, 1, (bzk_fr *)out); }
     // PublicKey::decompress -> canonical affine point
     int32_t decompress(const PubKey &k, bzk_fr out[2]) const {
         bzk_fr x;
         canon_out(&x, k.x);
         return bzk_jubjub_decompress(jj_d, &x, k.odd ? 1 : 0, out);
     }
-    // `calc_root_poseidon4` outside the circuit (/root/reference/src/zk/groth16/gadgets/merkle/mod.rs:53-65)
-    int32_t root_from_proof(uint64_t index, Fr cur, const Proof &proof, Fr *out) const {
-        for (size_t l = 0; l < proof.size() / 3; l++) {
-            Fr v[4];
-            int w = 0;
-            for (uint64_t k = 0; k < 4; k++) v[k] = (k == (index & 3)) ? cur : proof[l * 3 + (w++)];
-            BZK_TRY(hash(4, v, &cur));
-            index >>= 2;
+    // The state root each job's transition was built against: leaf H(tx_nonce, withdraw_nonce, addr, balances hash), then
+    // `calc_root_poseidon4` (/root/reference/src/zk/groth16/gadgets/merkle/mod.rs:53-65) under the transition's own proof —
+    // level-synchronously over all jobs: one batch for the leaves, one per tree level (1 + depth launches for a whole batch
+    // instead of (1 + depth) dependent hashes per transaction).
+    int32_t entering_roots(const std::vector<RootJob> &jobs, uint32_t depth, std::vector<Fr> &out) const {
+        const size_t n = jobs.size();
+        out.assign(n, Fr::zero());
+        if (n == 0) return BZK_OK;
+        std::vector<Fr> in(n * 5), cur(n);
+        for (size_t j = 0; j < n; j++) {
+            const Account &a = *jobs[j].account;
+            Fr *row = in.data() + j * 5;
+            row[0] = Fr::from_u32(a.tx_nonce); row[1] = Fr::from_u32(a.withdraw_nonce); row[2] = a.address.x; row[3] = a.address.y;
+            row[4] = jobs[j].balances_hash;
         }
-        *out = cur;
+        BZK_TRY(hash(5, in.data(), n, cur.data()));
+        in.resize(n * 4);
+        for (uint32_t l = 0; l < depth; l++) {
+            for (size_t j = 0; j < n; j++) {
+                const uint64_t pos = (jobs[j].index >> (2 * l)) & 3;
+                const Fr *sib = jobs[j].proof->data() + (size_t)l * 3;
+                int w = 0;
+                for (uint64_t k = 0; k < 4; k++) in[j * 4 + k] = (k == pos) ? cur[j] : sib[w++];
+            }
+            BZK_TRY(hash(4, in.data(), n, cur.data()));
+        }
+        out = cur;
         return BZK_OK;
-    }
-    // the state root a transition was built against: leaf H(tx_nonce, withdraw_nonce, addr, balances hash) under its own proof
-    int32_t entering_root(const Account &a, const Fr &balances_hash, uint64_t index, const Proof &proof, Fr *out) const {
-        Fr in[5] = {Fr::from_u32(a.tx_nonce), Fr::from_u32(a.withdraw_nonce), a.address.x, a.address.y, balances_hash}, leaf;
-        BZK_TRY(hash(5, in, &leaf));
-        return root_from_proof(index, leaf, proof, out);
     }
 };
 
-// the state root entering every slot: an enabled transition's own; a disabled one takes the next enabled slot's, or — after the
-// last enabled slot — where the batch ends (`next_state`; `state` when nothing is enabled)
-template <class T, class F>
-int32_t slot_roots(const std::vector<T> &ts, const Fr &state, const Fr &next_state, F &&pre_root, std::vector<Fr> &out) {
+// the state root entering every slot: an enabled transition's own (roots[] of the enabled ones, in slot order); a disabled one
+// takes the next enabled slot's, or — after the last enabled slot — where the batch ends (`next_state`; `state` when nothing is
+// enabled)
+template <class T>
+void slot_roots(const std::vector<T> &ts, const Fr &state, const Fr &next_state, const std::vector<Fr> &enabled_roots, std::vector<Fr> &out) {
     const size_t n = ts.size();
     out.assign(n, Fr::zero());
-    bool any = false;
-    for (auto &t : ts) any |= t.enabled;
-    Fr carry = any ? next_state : state;
+    size_t e = enabled_roots.size();
+    Fr carry = e ? next_state : state;
     for (size_t k = n; k-- > 0;) {
-        if (ts[k].enabled) { BZK_TRY(pre_root(ts[k], &carry)); }
+        if (ts[k].enabled) carry = enabled_roots[--e];
         out[k] = carry;
     }
-    return BZK_OK;
 }
 bool proofs_shaped(const Proof &p, uint32_t levels) { return p.size() == (size_t)levels * 3; }
 
@@ -464,27 +484,30 @@ int32_t bzk_mpn_work_verify(const bzk_mpn_work *w, const uint8_t prover[32], con
     return bzk_groth16_verify_bytes(vk.data(), vk.size(), inputs, 5, proof387);
 }
 
-/* An update work's transitions as the rows bzk_mpn_update_witness consumes (the order of UpdateCircuit's allocations,
- * `bazuka_b200/mpn/witness_program.py::raw_values`): raws[4^B][32 + 9T + 6A], ext[4^B][2] = {fee token, state root entering the
- * slot} — the root is not on the wire: recomputed from the transition's own account, proof and index.  A work carries only the
- * transitions its builder made; the slots after them are padded as `UpdateTransition::null`.  Canonical scalars. */
-int32_t bzk_mpn_work_update_rows(const bzk_mpn_work *work, const bzk_poseidon_host *hasher, const bzk_fr *jubjub_d, const bzk_fr *fee_token,
-                                 bzk_fr *raws, bzk_fr *ext) {
-    if (!work || !hasher || !jubjub_d || !fee_token || !raws || !ext || work->w.kind != KIND_UPDATE) return BZK_ERR_BAD_ARG;
-    const Work &k = work->w;
+}  // extern "C"
+
+namespace {
+
+// An update work's transitions as the rows bzk_mpn_update_witness consumes (the order of UpdateCircuit's allocations,
+// `bazuka_b200/mpn/witness_program.py::raw_values`): raws[4^B][32 + 9T + 6A], ext[4^B][2] = {fee token, state root entering the
+// slot} — the root is not on the wire: recomputed from the transition's own account, proof and index.  A work carries only the
+// transitions its builder made; the slots after them are padded as `UpdateTransition::null`.  Canonical scalars.
+int32_t update_rows(const Work &k, const RowCtx &rc, const bzk_fr *fee_token, bzk_fr *raws, bzk_fr *ext) {
     const uint32_t A = k.config.log4_tree, T = k.config.log4_token, n_raw = 32 + 9 * T + 6 * A;
-    const RowCtx rc{hasher, jubjub_d};
-    std::vector<Fr> roots;
     std::vector<UpdateTransition> updates;
     if (!padded(k.updates, k.config.log4_update_batch, null_update(A, T), updates)) return BZK_ERR_BAD_ARG;
-    BZK_TRY(slot_roots(updates, k.state, k.next_state,
-                       [&](const UpdateTransition &t, Fr *out) { return rc.entering_root(t.src_before, t.src_before_balances_hash, t.src_index, t.src_proof, out); },
-                       roots));
-    for (size_t s = 0; s < updates.size(); s++) {
-        const UpdateTransition &t = updates[s];
+    std::vector<RootJob> jobs;
+    for (const UpdateTransition &t : updates) {
         if (!proofs_shaped(t.src_proof, A) || !proofs_shaped(t.dst_proof, A) || !proofs_shaped(t.src_balance_proof, T) ||
             !proofs_shaped(t.src_fee_balance_proof, T) || !proofs_shaped(t.dst_balance_proof, T))
             return BZK_ERR_BAD_ARG;
+        if (t.enabled) jobs.push_back(RootJob{&t.src_before, t.src_before_balances_hash, t.src_index, &t.src_proof});
+    }
+    std::vector<Fr> enabled_roots, roots;
+    BZK_TRY(rc.entering_roots(jobs, A, enabled_roots));
+    slot_roots(updates, k.state, k.next_state, enabled_roots, roots);
+    for (size_t s = 0; s < updates.size(); s++) {
+        const UpdateTransition &t = updates[s];
         bzk_fr *row = raws + s * n_raw;
         size_t w = 0;
         auto fr = [&](const Fr &v) { canon_out(row + (w++), v); };
@@ -515,30 +538,38 @@ int32_t bzk_mpn_work_update_rows(const bzk_mpn_work *work, const bzk_poseidon_ho
     return BZK_OK;
 }
 
-/* A deposit / withdraw work's transitions as the rows bzk_mpn_dw_witness consumes (layouts: bzk_mpn_deposit_build /
- * bzk_mpn_withdraw_build): raws1, raws2, the entering roots and the revealed rows, canonical scalars. */
-int32_t bzk_mpn_work_dw_rows(const bzk_mpn_work *work, const bzk_poseidon_host *hasher, const bzk_fr *jubjub_d, bzk_fr *raws1, bzk_fr *raws2,
-                             bzk_fr *roots_out, bzk_fr *reveal) {
-    if (!work || !hasher || !jubjub_d || !raws1 || !raws2 || !roots_out || !reveal || work->w.kind == KIND_UPDATE) return BZK_ERR_BAD_ARG;
-    const Work &k = work->w;
+// A deposit / withdraw work's transitions as the rows bzk_mpn_dw_witness consumes (layouts: bzk_mpn_deposit_build /
+// bzk_mpn_withdraw_build): raws1, raws2, the entering roots and the revealed rows, canonical scalars.  The calldata hash of
+// every enabled slot's revealed row in ONE batched hash.
+int32_t dw_rows(const Work &k, const RowCtx &rc, bzk_fr *raws1, bzk_fr *raws2, bzk_fr *roots_out, bzk_fr *reveal) {
     const uint32_t A = k.config.log4_tree, T = k.config.log4_token;
-    const RowCtx rc{hasher, jubjub_d};
-    std::vector<Fr> roots;
+    std::vector<Fr> enabled_roots, roots, cd_in, cd;
+    std::vector<RootJob> jobs;
+    auto mont_of = [](const bzk_fr &c) { Fr v; memcpy(v.l, &c, 32); return v.to_mont(); };
     if (k.kind == KIND_DEPOSIT) {
         const uint32_t w2 = 9 + 3 * T + 3 * A;
         std::vector<DepositTransition> deposits;
         if (!padded(k.deposits, k.config.log4_deposit_batch, null_deposit(A, T), deposits)) return BZK_ERR_BAD_ARG;
-        BZK_TRY(slot_roots(deposits, k.state, k.next_state,
-                           [&](const DepositTransition &t, Fr *out) { return rc.entering_root(t.before, t.before_balances_hash, t.account_index, t.proof, out); },
-                           roots));
+        std::vector<bzk_fr> pks(deposits.size() * 2);
         for (size_t s = 0; s < deposits.size(); s++) {
             const DepositTransition &t = deposits[s];
             if (!proofs_shaped(t.proof, A) || !proofs_shaped(t.balance_proof, T)) return BZK_ERR_BAD_ARG;
-            bzk_fr pk[2];
-            BZK_TRY(rc.decompress(t.tx.mpn_address, pk));
-            const Fr token = t.tx.payment.amount.token.scalar();
+            BZK_TRY(rc.decompress(t.tx.mpn_address, pks.data() + 2 * s));
+            if (!t.enabled) continue;
+            jobs.push_back(RootJob{&t.before, t.before_balances_hash, t.account_index, &t.proof});
+            cd_in.push_back(mont_of(pks[2 * s])); cd_in.push_back(mont_of(pks[2 * s + 1]));
+        }
+        BZK_TRY(rc.entering_roots(jobs, A, enabled_roots));
+        slot_roots(deposits, k.state, k.next_state, enabled_roots, roots);
+        cd.assign(jobs.size(), Fr::zero());
+        if (!jobs.empty()) BZK_TRY(rc.hash(2, cd_in.data(), jobs.size(), cd.data()));
+        size_t e = 0;
+        for (size_t s = 0; s < deposits.size(); s++) {
+            const DepositTransition &t = deposits[s];
+            const bzk_fr *pk = pks.data() + 2 * s;
             bzk_fr *r1 = raws1 + s * 5, *r2 = raws2 + s * w2, *rv = reveal + s * 4;
-            put_u(r1 + 0, t.enabled ? 1 : 0); canon_out(r1 + 1, token); put_u(r1 + 2, t.tx.payment.amount.amount); r1[3] = pk[0]; r1[4] = pk[1];
+            put_u(r1 + 0, t.enabled ? 1 : 0); canon_out(r1 + 1, t.tx.payment.amount.token.scalar()); put_u(r1 + 2, t.tx.payment.amount.amount);
+            r1[3] = pk[0]; r1[4] = pk[1];
             size_t w = 0;
             auto fr = [&](const Fr &v) { canon_out(r2 + (w++), v); };
             auto u = [&](uint64_t v) { put_u(r2 + (w++), v); };
@@ -548,14 +579,7 @@ int32_t bzk_mpn_work_dw_rows(const bzk_mpn_work *work, const bzk_poseidon_host *
             for (const Fr &v : t.proof) fr(v);
             if (w != w2) return BZK_ERR_BAD_ARG;
             // revealed row {enabled, token, amount, H(pk)} (deposit_circuit.rs: the calldata of a deposit is the hash of its MPN key)
-            Fr cd = Fr::zero();
-            if (t.enabled) {
-                Fr in[2];
-                memcpy(in[0].l, pk + 0, 32); memcpy(in[1].l, pk + 1, 32);
-                in[0] = in[0].to_mont(); in[1] = in[1].to_mont();
-                BZK_TRY(rc.hash(2, in, &cd));
-            }
-            rv[0] = r1[0]; rv[1] = r1[1]; rv[2] = r1[2]; canon_out(rv + 3, cd);
+            rv[0] = r1[0]; rv[1] = r1[1]; rv[2] = r1[2]; canon_out(rv + 3, t.enabled ? cd[e++] : Fr::zero());
             canon_out(roots_out + s, roots[s]);
         }
         return BZK_OK;
@@ -563,14 +587,25 @@ int32_t bzk_mpn_work_dw_rows(const bzk_mpn_work *work, const bzk_poseidon_host *
     const uint32_t w2 = 12 + 6 * T + 3 * A;
     std::vector<WithdrawTransition> withdraws;
     if (!padded(k.withdraws, k.config.log4_withdraw_batch, null_withdraw(A, T), withdraws)) return BZK_ERR_BAD_ARG;
-    BZK_TRY(slot_roots(withdraws, k.state, k.next_state,
-                       [&](const WithdrawTransition &t, Fr *out) { return rc.entering_root(t.before, t.before_token_hash, t.account_index, t.proof, out); },
-                       roots));
+    std::vector<bzk_fr> pks(withdraws.size() * 2);
     for (size_t s = 0; s < withdraws.size(); s++) {
         const WithdrawTransition &t = withdraws[s];
         if (!proofs_shaped(t.proof, A) || !proofs_shaped(t.token_balance_proof, T) || !proofs_shaped(t.fee_balance_proof, T)) return BZK_ERR_BAD_ARG;
-        bzk_fr pk[2];
-        BZK_TRY(rc.decompress(t.tx.mpn_address, pk));
+        BZK_TRY(rc.decompress(t.tx.mpn_address, pks.data() + 2 * s));
+        if (!t.enabled) continue;
+        jobs.push_back(RootJob{&t.before, t.before_token_hash, t.account_index, &t.proof});
+        // calldata = H(pk, nonce, sig) (`verify_calldata`, /root/reference/src/core/transaction.rs:177-182)
+        cd_in.push_back(mont_of(pks[2 * s])); cd_in.push_back(mont_of(pks[2 * s + 1])); cd_in.push_back(Fr::from_u32(t.tx.nonce));
+        cd_in.push_back(t.tx.sig.r.x); cd_in.push_back(t.tx.sig.r.y); cd_in.push_back(t.tx.sig.s);
+    }
+    BZK_TRY(rc.entering_roots(jobs, A, enabled_roots));
+    slot_roots(withdraws, k.state, k.next_state, enabled_roots, roots);
+    cd.assign(jobs.size(), Fr::zero());
+    if (!jobs.empty()) BZK_TRY(rc.hash(6, cd_in.data(), jobs.size(), cd.data()));
+    size_t e = 0;
+    for (size_t s = 0; s < withdraws.size(); s++) {
+        const WithdrawTransition &t = withdraws[s];
+        const bzk_fr *pk = pks.data() + 2 * s;
         const ContractWithdraw &p = t.tx.payment;
         bzk_fr *r1 = raws1 + s * 12, *r2 = raws2 + s * w2, *rv = reveal + s * 7;
         put_u(r1 + 0, t.enabled ? 1 : 0); canon_out(r1 + 1, p.amount.token.scalar()); put_u(r1 + 2, p.amount.amount);
@@ -589,20 +624,46 @@ int32_t bzk_mpn_work_dw_rows(const bzk_mpn_work *work, const bzk_poseidon_host *
         for (const Fr &v : t.fee_balance_proof) fr(v);
         for (const Fr &v : t.proof) fr(v);
         if (w != w2) return BZK_ERR_BAD_ARG;
-        // revealed row {enabled, token, amount, fee token, fee, fingerprint, calldata = H(pk, nonce, sig)} (`verify_calldata`)
-        Fr cd = Fr::zero();
-        if (t.enabled) {
-            Fr in[6];
-            memcpy(in[0].l, pk + 0, 32); memcpy(in[1].l, pk + 1, 32);
-            in[0] = in[0].to_mont(); in[1] = in[1].to_mont();
-            in[2] = Fr::from_u32(t.tx.nonce); in[3] = t.tx.sig.r.x; in[4] = t.tx.sig.r.y; in[5] = t.tx.sig.s;
-            BZK_TRY(rc.hash(6, in, &cd));
-        }
+        // revealed row {enabled, token, amount, fee token, fee, fingerprint, calldata}
         for (int i = 0; i < 6; i++) rv[i] = r1[i];
-        canon_out(rv + 6, cd);
+        canon_out(rv + 6, t.enabled ? cd[e++] : Fr::zero());
         canon_out(roots_out + s, roots[s]);
     }
     return BZK_OK;
+}
+
+RowCtx host_rows(const bzk_poseidon_host *hasher, const bzk_fr *jj_d) {
+    return RowCtx{[hasher](uint32_t arity, const Fr *in, size_t n, Fr *out) { return bzk_poseidon_host_hash(hasher, arity, (const bzk_fr *)in, n, (bzk_fr *)out); },
+                  jj_d};
+}
+RowCtx ctx_rows(bzk_ctx *ctx, const bzk_fr *jj_d) {
+    return RowCtx{[ctx](uint32_t arity, const Fr *in, size_t n, Fr *out) { return bzk_poseidon_hash(ctx, arity, (const bzk_fr *)in, n, (bzk_fr *)out); }, jj_d};
+}
+}  // namespace
+
+extern "C" {
+
+/* host variants: the hashes on the host Poseidon (no GPU context; a node that only wants to LOOK at a work) */
+int32_t bzk_mpn_work_update_rows(const bzk_mpn_work *work, const bzk_poseidon_host *hasher, const bzk_fr *jubjub_d, const bzk_fr *fee_token,
+                                 bzk_fr *raws, bzk_fr *ext) {
+    if (!work || !hasher || !jubjub_d || !fee_token || !raws || !ext || work->w.kind != KIND_UPDATE) return BZK_ERR_BAD_ARG;
+    return update_rows(work->w, host_rows(hasher, jubjub_d), fee_token, raws, ext);
+}
+int32_t bzk_mpn_work_dw_rows(const bzk_mpn_work *work, const bzk_poseidon_host *hasher, const bzk_fr *jubjub_d, bzk_fr *raws1, bzk_fr *raws2,
+                             bzk_fr *roots_out, bzk_fr *reveal) {
+    if (!work || !hasher || !jubjub_d || !raws1 || !raws2 || !roots_out || !reveal || work->w.kind == KIND_UPDATE) return BZK_ERR_BAD_ARG;
+    return dw_rows(work->w, host_rows(hasher, jubjub_d), raws1, raws2, roots_out, reveal);
+}
+/* the prover's variants: the same rows with every hash in batched launches on the context (1 + A launches for the entering roots
+ * of a whole batch, one for the calldata hashes) — what bzk_mpn_prover_prove_work uses */
+int32_t bzk_mpn_work_update_rows_ctx(bzk_ctx *ctx, const bzk_mpn_work *work, const bzk_fr *jubjub_d, const bzk_fr *fee_token, bzk_fr *raws, bzk_fr *ext) {
+    if (!ctx || !work || !jubjub_d || !fee_token || !raws || !ext || work->w.kind != KIND_UPDATE) return BZK_ERR_BAD_ARG;
+    return update_rows(work->w, ctx_rows(ctx, jubjub_d), fee_token, raws, ext);
+}
+int32_t bzk_mpn_work_dw_rows_ctx(bzk_ctx *ctx, const bzk_mpn_work *work, const bzk_fr *jubjub_d, bzk_fr *raws1, bzk_fr *raws2, bzk_fr *roots_out,
+                                 bzk_fr *reveal) {
+    if (!ctx || !work || !jubjub_d || !raws1 || !raws2 || !roots_out || !reveal || work->w.kind == KIND_UPDATE) return BZK_ERR_BAD_ARG;
+    return dw_rows(work->w, ctx_rows(ctx, jubjub_d), raws1, raws2, roots_out, reveal);
 }
 
 /* `GetMpnWorkResponse { works: HashMap<usize, MpnWork> }` (/root/reference/src/client/messages.rs:371-376): up to `cap` works

@@ -284,11 +284,10 @@ class NativeMpnProver:
         import os
         import numpy as np
         from .. import _lib
-        blob = open(_lib.PARAMS_PATH, "rb").read()
         canon = lambda v: np.frombuffer((v % N.R).to_bytes(32, "little"), dtype=np.uint64).copy()
         jj_d, fee = canon(N.JJ_D), canon(self.fee_token)
         h = ct.c_void_p()
-        self.ctx._check(self.ctx._l.bzk_mpn_prover_create(self.ctx._h, native_circuit._h, pk._h, blob, len(blob), ct.c_void_p(jj_d.ctypes.data),
+        self.ctx._check(self.ctx._l.bzk_mpn_prover_create(self.ctx._h, native_circuit._h, pk._h, ct.c_void_p(jj_d.ctypes.data),
                                                           ct.c_void_p(fee.ctypes.data), ct.byref(h)))
         self._p[kind] = (h, pk)          # the key must outlive the prover
 

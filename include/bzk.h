@@ -461,6 +461,11 @@ int32_t bzk_mpn_work_update_rows(const bzk_mpn_work *work, const bzk_poseidon_ho
                                  bzk_fr *raws, bzk_fr *ext);
 int32_t bzk_mpn_work_dw_rows(const bzk_mpn_work *work, const bzk_poseidon_host *hasher, const bzk_fr *jubjub_d, bzk_fr *raws1, bzk_fr *raws2,
                              bzk_fr *roots, bzk_fr *reveal);
+/* the same rows with every hash in batched launches on a context (1 + A launches for the entering roots of the whole batch, one
+ * for the calldata hashes) instead of (1 + A) dependent host hashes per transaction — what bzk_mpn_prover_prove_work uses */
+int32_t bzk_mpn_work_update_rows_ctx(bzk_ctx *ctx, const bzk_mpn_work *work, const bzk_fr *jubjub_d, const bzk_fr *fee_token, bzk_fr *raws, bzk_fr *ext);
+int32_t bzk_mpn_work_dw_rows_ctx(bzk_ctx *ctx, const bzk_mpn_work *work, const bzk_fr *jubjub_d, bzk_fr *raws1, bzk_fr *raws2, bzk_fr *roots,
+                                 bzk_fr *reveal);
 /* messages: up to `cap` works are decoded into ids[] / works[] (free each); *n = the number on the wire */
 int32_t bzk_mpn_get_work_response_decode(const uint8_t *bytes, size_t len, uint64_t *ids, bzk_mpn_work **works, uint64_t cap, uint64_t *n);
 int32_t bzk_mpn_get_work_request_encode(const uint8_t address[32], uint8_t out[40]);
@@ -490,12 +495,12 @@ int32_t bzk_buffer_free(uint8_t *buffer);
  * `GET /bincode/mpn/work` and `POST /bincode/mpn/solution` (/root/reference/src/client/mod.rs:428-464; `MpnWork::verify` on the
  * node side checks the result, /root/reference/src/mpn/mod.rs:281-295).  One prover per circuit (kind, A, T, B): it uploads the
  * natively compiled circuit's witness programs and R1CS (bzk_mpn_{update,dw}_circuit_compile) and keeps z resident; `params` is
- * that circuit's proving key (borrowed).  prove_work = bzk_mpn_work_decode -> bzk_mpn_work_{update,dw}_rows ->
+ * that circuit's proving key (borrowed).  prove_work = bzk_mpn_work_decode -> bzk_mpn_work_{update,dw}_rows_ctx ->
  * bzk_mpn_{update,dw}_witness -> bzk_groth16_prove_dev -> bzk_groth16_proof_bytes.  r, s: Montgomery images.
  * BZK_ERR_BAD_ARG: malformed work, or a work of another kind / size than the prover's circuit. */
 typedef struct bzk_mpn_prover bzk_mpn_prover;
-int32_t bzk_mpn_prover_create(bzk_ctx *ctx, const bzk_mpn_circuit *circuit, const bzk_groth16_params *params, const uint8_t *poseidon_blob,
-                              size_t blob_len, const bzk_fr *jubjub_d, const bzk_fr *fee_token, bzk_mpn_prover **out);
+int32_t bzk_mpn_prover_create(bzk_ctx *ctx, const bzk_mpn_circuit *circuit, const bzk_groth16_params *params, const bzk_fr *jubjub_d,
+                              const bzk_fr *fee_token, bzk_mpn_prover **out);
 int32_t bzk_mpn_prover_free(bzk_ctx *ctx, bzk_mpn_prover *prover);
 int32_t bzk_mpn_prover_prove_work(bzk_ctx *ctx, bzk_mpn_prover *prover, const uint8_t *work_bytes, size_t work_len, const uint8_t prover_address[32],
                                   const bzk_fr *r, const bzk_fr *s, int32_t check_satisfied, uint8_t zkproof391[391]);

@@ -212,7 +212,7 @@ def test_work_bytes_to_satisfying_witness_through_the_native_prover_object(hostm
         assert lib.bzk_mpn_circuit_kind(c, _ptr(k4)) == 0 and k4.tolist() == [{"update": 0, "deposit": 1, "withdraw": 2}[kind], 3, 3, 1]
         p = ct.c_void_p()
         jj_d, fee = _canon(N.JJ_D), _canon(U.ZIESHA)
-        hostmpn._check(lib.bzk_mpn_prover_create(hostmpn._h, c, ct.c_void_p(1), blob, len(blob), _ptr(jj_d), _ptr(fee), ct.byref(p)))
+        hostmpn._check(lib.bzk_mpn_prover_create(hostmpn._h, c, ct.c_void_p(1), _ptr(jj_d), _ptr(fee), ct.byref(p)))
         lib.bzk_mpn_circuit_free(c)                       # the prover keeps its own copies
         provers[kind] = p
     for i, work in works.items():
@@ -444,7 +444,7 @@ def test_transactions_to_accepted_proofs_through_the_native_path(hostmpn, cref):
         r1[kind] = (ni, na, mats)
         keys_c[kind] = GC.setup(ni, na, mats, cref.fr_random(40 + k, 5))
         p = ct.c_void_p()
-        hostmpn._check(lib.bzk_mpn_prover_create(hostmpn._h, c, ct.c_void_p(1), blob, len(blob), _ptr(jj_d), _ptr(fee), ct.byref(p)))
+        hostmpn._check(lib.bzk_mpn_prover_create(hostmpn._h, c, ct.c_void_p(1), _ptr(jj_d), _ptr(fee), ct.byref(p)))
         lib.bzk_mpn_circuit_free(c)
         provers[kind] = p
     cfg = dict(_config(), log4_deposit_batch_size=B, log4_withdraw_batch_size=B, log4_update_batch_size=B,
@@ -576,7 +576,7 @@ def test_reference_circuit_test_shape_all_null_batches(hostmpn, cref, kind):
     key = GC.setup(ni, na, mats, cref.fr_random(90, 5))
     jj_d, fee = _canon(N.JJ_D), _canon(U.ZIESHA)
     p = ct.c_void_p()
-    hostmpn._check(lib.bzk_mpn_prover_create(hostmpn._h, c, ct.c_void_p(1), blob, len(blob), _ptr(jj_d), _ptr(fee), ct.byref(p)))
+    hostmpn._check(lib.bzk_mpn_prover_create(hostmpn._h, c, ct.c_void_p(1), _ptr(jj_d), _ptr(fee), ct.byref(p)))
     lib.bzk_mpn_circuit_free(c)
     cfg = dict(_config(), **{kind + "_vk": bytes(BG.vk_to_bincode(key["vk"]))})
     work = {"config": cfg, "public_inputs": dict(pub, height=3), "data": (kind, []), "new_root": {"state_hash": st.root, "state_size": 0}, "reward": 5}
@@ -622,7 +622,7 @@ def test_single_update_at_the_production_tree_shape_through_the_native_prover(ho
     assert int(shape[2]) == 56776                                     # ≈ 56.8 k constraints for one transaction
     jj_d, fee = _canon(N.JJ_D), _canon(U.ZIESHA)
     p = ct.c_void_p()
-    hostmpn._check(lib.bzk_mpn_prover_create(hostmpn._h, c, ct.c_void_p(1), blob, len(blob), _ptr(jj_d), _ptr(fee), ct.byref(p)))
+    hostmpn._check(lib.bzk_mpn_prover_create(hostmpn._h, c, ct.c_void_p(1), _ptr(jj_d), _ptr(fee), ct.byref(p)))
     lib.bzk_mpn_circuit_free(c)
     zero, out = np.zeros(4, np.uint64), ct.create_string_buffer(391)
     st_ = lib.bzk_mpn_prover_prove_work(hostmpn._h, p, wb, len(wb), bytes(range(32)), _ptr(zero), _ptr(zero), 1, out)
