@@ -8,7 +8,7 @@
 //                             -> witness on the GPU straight into z (bzk_mpn_update_witness / bzk_mpn_dw_witness)
 //                             -> bzk_groth16_prove_dev -> proof bytes
 // Nothing here is new arithmetic: it strings together calls that are each checked on their own; the composition is run in the
-// CPU tier over the host stand-ins (tests/test_wire_native_cpu.py) and on the GPU in tests/test_gpu_mpn.py.
+// CPU tier over the host stand-ins (tests/test_wire_native_cpu.py) and on the GPU in tests/test_gpu_zz_native_worker.py.
 #include <memory>
 
 #include "mpn_wire.cuh"
