@@ -284,3 +284,133 @@ def test_reference_withdraw_scenario_at_the_production_config(hostmpn):
     assert (rows["reveal"].reshape(-1, 4) == _canon_rows([v for r in DW.reveal_rows_native("withdraw", circ) for v in r])).all()
     assert led.info()["state_size"] == st.state_size
     led.free()
+
+
+def test_randomised_differential_of_the_update_ledger_rules(hostmpn):
+    """random transfer traffic on a SMALL state (A = 2: sixteen accounts, T = 1: four token slots per account) so that every rule
+    fires many times — unknown and undecompressible keys, wrong nonces, overdrafts, fee tokens that are not the accepted one or not
+    held, transfers to oneself, new receivers until the account tree is full, token trees that fill up, tokens whose slot was
+    chosen by the first free index: over consecutive batches on one ledger the C++ builder and the Python restatement of
+    `update()` must accept the same transactions, produce the same rows / roots / public values and end in the same state."""
+    import random
+    from bazuka_b200.mpn import native as N, update as U, witness_program as W
+    from bazuka_b200.mpn.ledger import NativeLedger
+    A, T, B = 2, 1, 1
+    rng = random.Random(77)
+    keys = [N.eddsa_keys(b"rk%d" % i) for i in range(24)]
+    tokens = [U.ZIESHA, 5, 6, 7, 8, 9]
+    st = U.MpnState(A, T)
+    for i in range(5):
+        st.set(i, U.MpnAccount(0, 0, keys[i][0], {0: U.Money(U.ZIESHA, 10 ** 6), 1: U.Money(tokens[1 + i % 3], 500)}))
+    led = NativeLedger(hostmpn, A, T)
+    for i, a in st.accounts.items():
+        led.set_account(i, a)
+    assert led.root == st.root
+    known = list(range(5))                          # key numbers that own an account
+    nonces = {i: 0 for i in known}
+    total_acc = total = 0
+    for batch_no in range(40):
+        txs = []
+        for _ in range(rng.randint(1, 7)):
+            s = rng.choice(known) if rng.random() < 0.85 else rng.randrange(len(keys))
+            d = rng.randrange(len(keys)) if rng.random() < 0.4 else rng.choice(known)
+            tok = rng.choice(tokens) if rng.random() < 0.5 else U.ZIESHA
+            amount = rng.choice([0, 1, 3, 50, 499, 10 ** 5, 10 ** 7])
+            fee_tok = U.ZIESHA if rng.random() < 0.9 else rng.choice(tokens)
+            nonce = nonces.get(s, 0) + 1 + (1 if rng.random() < 0.1 else 0)
+            tx = U.MpnTransaction(nonce, N.jj_compress(keys[s][0]), N.jj_compress(keys[d][0]), U.Money(tok, amount), U.Money(fee_tok, rng.choice([0, 1, 7])))
+            tx.sign(keys[s][1])
+            if rng.random() < 0.05:
+                tx.dst_pub_key = _off_curve_key()        # (after signing: the message hash decompresses the key)
+            txs.append(tx)
+        pub, trans, rej = U.update(st, txs, B)
+        raws, ext, acc, public, n_acc = led.update_build(txs, B)
+        got = [t for t, a in zip(txs, acc) if a]
+        assert got == [t.tx for t in trans], (batch_no, [txs.index(t) for t in got], [txs.index(t.tx) for t in trans])
+        assert public == pub and led.root == st.root and led.info()["state_size"] == st.state_size, batch_no
+        circ = U.UpdateCircuit(A, T, B, commitment=1, height=1, transitions=trans, **pub)
+        want = np.stack([_canon_rows(W.raw_values(tr, A, T)) for tr in circ.transitions])
+        assert (raws == want).all(), batch_no
+        assert (ext == np.stack([_canon_rows([circ.fee_token, r]) for r in W.slot_roots(circ)])).all(), batch_no
+        for t in trans:                               # bookkeeping for the generator
+            s = next(i for i, k in enumerate(keys) if N.jj_compress(k[0]) == t.tx.src_pub_key)
+            nonces[s] = t.tx.nonce
+            d = next((i for i, k in enumerate(keys) if N.jj_compress(k[0]) == t.tx.dst_pub_key), None)
+            if d is not None and d not in known:
+                known.append(d)
+                nonces.setdefault(d, 0)
+        total += len(txs)
+        total_acc += len(trans)
+        if batch_no % 10 == 9:                        # a block boundary: the new accounts enter the chain's index table
+            st.commit_accounts(); led.commit_accounts()
+    assert total_acc > 30 and total - total_acc > 30, (total, total_acc)
+    assert len(st.accounts) >= 12                     # the tree filled up with newcomers
+    led.free()
+
+
+def test_randomised_differential_of_the_deposit_and_withdraw_rules(hostmpn):
+    """the same for `deposit()` / `withdraw()`: random deposits (new accounts until the tree is full, tokens until an account's four
+    slots are full, keys that do not decompress, L1 sources whose earlier deposit was rejected) alternating with random withdrawals
+    (wrong nonce, wrong signer, unknown key, overdraft of the token or of the fee, fee in a token the account does not hold, wrong
+    calldata) on one small ledger: same accepted sets, rows, roots, revealed rows, public values and `state_size` throughout."""
+    import random
+    from bazuka_b200.mpn import dw as D, dw_witness as DW, native as N, update as U
+    from bazuka_b200.mpn.ledger import NativeLedger
+    A, T, B = 2, 1, 1
+    rng = random.Random(4242)
+    keys = [N.eddsa_keys(b"dk%d" % i) for i in range(22)]
+    tokens = [U.ZIESHA, 5, 6, 7, 8, 9]
+    st = U.MpnState(A, T)
+    led = NativeLedger(hostmpn, A, T)
+    wn = {}                                          # key number -> withdraw nonce
+    n_dep = n_wd = n_dep_acc = n_wd_acc = 0
+    for round_no in range(30):
+        deps = []
+        for _ in range(rng.randint(1, 6)):
+            k = rng.randrange(len(keys))
+            addr = (6, False) if rng.random() < 0.08 else N.jj_compress(keys[k][0])
+            deps.append(D.MpnDeposit(addr, rng.choice(tokens), rng.choice([1, 40, 1000]), rng.choice(["a", "b", "c", None])))
+        pub, trans = D.deposit(st, deps, B)
+        rows = led.deposit_build(deps, B)
+        assert [d for d, a in zip(deps, rows["accepted"]) if a] == [t.tx for t in trans], round_no
+        assert rows["public"] == pub and led.root == st.root and led.info()["state_size"] == st.state_size, round_no
+        circ = D.DepositCircuit(A, T, B, commitment=0, height=0, transitions=trans, **pub)
+        want = [DW.deposit_raws(t, A, T) for t in circ.transitions]
+        assert (rows["raws1"].reshape(-1, 4) == _canon_rows([v for a, _ in want for v in a])).all(), round_no
+        assert (rows["raws2"].reshape(-1, 4) == _canon_rows([v for _, b in want for v in b])).all(), round_no
+        assert (rows["roots"] == _canon_rows(DW.slot_roots(circ))).all(), round_no
+        assert (rows["reveal"].reshape(-1, 4) == _canon_rows([v for r in DW.reveal_rows_native("deposit", circ) for v in r])).all(), round_no
+        n_dep += len(deps); n_dep_acc += len(trans)
+        owners = {tuple(a.address): i for i, a in st.accounts.items()}
+        wds = []
+        for _ in range(rng.randint(1, 6)):
+            k = rng.randrange(len(keys))
+            acc = st.accounts.get(owners.get(tuple(keys[k][0])))
+            held = [m.token_id for m in acc.tokens.values()] if acc else tokens
+            tok = rng.choice(held) if rng.random() < 0.8 else rng.choice(tokens)
+            ftok = rng.choice(held) if rng.random() < 0.8 else rng.choice(tokens)
+            nonce = wn.get(k, 0) + 1 + (1 if rng.random() < 0.1 else 0)
+            w = D.MpnWithdraw(N.jj_compress(keys[k][0]), nonce, amount=U.Money(tok, rng.choice([0, 1, 30, 5000])), fee=U.Money(ftok, rng.choice([0, 1, 2000])),
+                              fingerprint=rng.randrange(1, 10 ** 9))
+            w.sign(keys[rng.randrange(len(keys))][1] if rng.random() < 0.1 else keys[k][1])
+            if rng.random() < 0.3:
+                w.calldata = w.expected_calldata() + (1 if rng.random() < 0.3 else 0)
+            wds.append(w)
+        pub, trans = D.withdraw(st, wds, B)
+        rows = led.withdraw_build(wds, B)
+        assert [x for x, a in zip(wds, rows["accepted"]) if a] == [t.tx for t in trans], round_no
+        assert rows["public"] == pub and led.root == st.root and led.info()["state_size"] == st.state_size, round_no
+        circ = D.WithdrawCircuit(A, T, B, commitment=0, height=0, transitions=trans, **pub)
+        want = [DW.withdraw_raws(t, A, T) for t in circ.transitions]
+        assert (rows["raws1"].reshape(-1, 4) == _canon_rows([v for a, _ in want for v in a])).all(), round_no
+        assert (rows["raws2"].reshape(-1, 4) == _canon_rows([v for _, b in want for v in b])).all(), round_no
+        assert (rows["roots"] == _canon_rows(DW.slot_roots(circ))).all(), round_no
+        assert (rows["reveal"].reshape(-1, 4) == _canon_rows([v for r in DW.reveal_rows_native("withdraw", circ) for v in r])).all(), round_no
+        for t in trans:
+            k = next(i for i, kk in enumerate(keys) if N.jj_compress(kk[0]) == t.tx.mpn_address)
+            wn[k] = t.tx.mpn_withdraw_nonce
+        n_wd += len(wds); n_wd_acc += len(trans)
+        if round_no % 7 == 6:
+            st.commit_accounts(); led.commit_accounts()
+    assert n_dep_acc > 25 and n_dep - n_dep_acc > 10 and n_wd_acc > 15 and n_wd - n_wd_acc > 25, (n_dep, n_dep_acc, n_wd, n_wd_acc)
+    led.free()
