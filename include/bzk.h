@@ -483,7 +483,8 @@ int32_t bzk_mpn_post_solution_response_decode(const uint8_t *bytes, size_t len, 
  * builders check of the L1 side is read from the payments (a deposit's source, a withdrawal's calldata and fingerprint).
  * Outputs: *works_bytes = bincode of `HashMap<usize, MpnWork>` numbered in building order (the body of GetMpnWorkResponse;
  * release with bzk_buffer_free), *fork_out = the ledger after all batches (bzk_mpn_state_free, or commit_accounts + keep).
- * The validator's own reward deposit and the L1 balances are chain state: prepend that deposit like mod.rs:338-351 does. */
+ * The validator's own reward deposit and the L1 balances are chain state: prepend that deposit like mod.rs:338-351 does, and offer only
+ * deposits whose L1 source can pay amount and fee (`check_balance`, /root/reference/src/mpn/deposit.rs:85-107 reads `db.get_balance`). */
 int32_t bzk_mpn_prepare_works(bzk_ctx *ctx, const bzk_mpn_state *state, const uint8_t *config_bytes, size_t config_len, const uint8_t *deposits_bytes,
                               size_t deposits_len, const uint8_t *withdraws_bytes, size_t withdraws_len, const uint8_t *updates_bytes, size_t updates_len,
                               const uint64_t rewards[3], uint64_t height, const bzk_fr *fee_token, bzk_mpn_state **fork_out, uint8_t **works_bytes,
