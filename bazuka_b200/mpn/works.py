@@ -270,6 +270,14 @@ class MpnProver:
         return bytes(blob)
 
 
+def work_info_dtype():
+    """numpy image of `bzk_mpn_work_info` (include/bzk.h); tests/test_abi.py checks it against the C compiler's layout"""
+    import numpy as np
+    return np.dtype([("kind", "<u4"), ("log4_tree", "<u4"), ("log4_token", "<u4"), ("log4_batch", "<u4"), ("n_transitions", "<u8"), ("height", "<u8"),
+                     ("state", "<u8", 4), ("aux_data", "<u8", 4), ("next_state", "<u8", 4), ("new_root_hash", "<u8", 4), ("new_root_size", "<u8"),
+                     ("reward", "<u8")])
+
+
 class NativeMpnProver:
     """the same job with nothing but libbzk between the wire and the proof: `prove(work_bytes, prover_address, r, s)` ->
     391-byte `ZkProof::Groth16` image through bzk_mpn_prover_prove_work (csrc/mpn_prover.cu: bincode decode, rows, GPU witness,
@@ -306,10 +314,10 @@ class NativeMpnProver:
         import numpy as np
         h = ct.c_void_p()
         self.ctx._check(self.ctx._l.bzk_mpn_work_decode(bytes(work_bytes), len(work_bytes), ct.byref(h), None))
-        info = np.zeros(64, dtype=np.uint32)
+        info = np.zeros(1, dtype=work_info_dtype())
         self.ctx._l.bzk_mpn_work_get_info(h, ct.c_void_p(info.ctypes.data))
         self.ctx._l.bzk_mpn_work_free(h)
-        return int(info[0])
+        return int(info[0]["kind"])
 
     def free(self):
         for h, _ in self._p.values():

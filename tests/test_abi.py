@@ -40,8 +40,10 @@ def test_packed_transaction_structs_match_the_header(tmp_path):
     """the numpy record layouts mpn/ledger.py packs (bzk_mpn_tx, bzk_mpn_deposit, bzk_mpn_withdraw) against the C compiler's view
     of include/bzk.h: total size and every field offset."""
     import subprocess
-    from bazuka_b200.mpn import ledger as L
-    fields = {"bzk_mpn_tx": (L._TX, ["nonce", "amount", "fee", "src_pk_odd", "dst_pk_odd", "src_pk_x", "dst_pk_x", "amount_token_id",
+    from bazuka_b200.mpn import ledger as L, works as Wk
+    fields = {"bzk_mpn_work_info": (Wk.work_info_dtype(), ["kind", "log4_tree", "log4_token", "log4_batch", "n_transitions", "height", "state", "aux_data",
+                                                           "next_state", "new_root_hash", "new_root_size", "reward"]),
+              "bzk_mpn_tx": (L._TX, ["nonce", "amount", "fee", "src_pk_odd", "dst_pk_odd", "src_pk_x", "dst_pk_x", "amount_token_id",
                                      "fee_token_id", "sig_rx", "sig_ry", "sig_s"]),
               "bzk_mpn_deposit": (L._DEP, ["pk_x", "pk_odd", "token_id", "amount", "src_id"]),
               "bzk_mpn_withdraw": (L._WD, ["pk_x", "pk_odd", "check_calldata", "nonce", "sig_rx", "sig_ry", "sig_s", "amount_token_id",
