@@ -95,38 +95,37 @@ struct bzk_mpn_state {
 
 namespace {
 
-// Fr square root (Tonelli-Shanks, r - 1 = 2^32 * odd, 7 = non-residue); false when none exists
+// Fr square root (Tonelli-Shanks, r - 1 = 2^32 * q with q odd, 7 = non-residue); false when none exists.  One 223-bit power:
+// w = a^((q-1)/2) gives both x = a*w = a^((q+1)/2) and t = x*w = a^q; the loop then corrects x by powers of c = 7^q (computed
+// once); a non-residue is recognised at the end (x^2 != a) instead of by a separate Legendre power.
 bool fr_sqrt(const Fr &a, Fr *out) {
     if (a.is_zero()) { *out = a; return true; }
-    // q = (r - 1) >> 32, as 32-bit words (224 bits)
-    uint32_t q[8] = {0}, rm1[8];
+    // q = (r - 1) >> 32, as 32-bit words (224 bits); e = (q - 1) / 2
+    uint32_t q[8] = {0}, rm1[8], e[8];
     for (int i = 0; i < 8; i++) rm1[i] = FrParams::p(i);
     rm1[0] -= 1;
     for (int i = 0; i < 7; i++) q[i] = rm1[i + 1];
-    uint32_t half[8];  // (r - 1) / 2
-    for (int i = 0; i < 8; i++) half[i] = (rm1[i] >> 1) | (i < 7 ? rm1[i + 1] << 31 : 0);
-    if (!(a.pow(half, 8) == Fr::one())) return false;
-    uint32_t q1[8];  // (q + 1) / 2
-    {
-        uint64_t c = 1;
-        uint32_t t[8];
-        for (int i = 0; i < 8; i++) { c += q[i]; t[i] = (uint32_t)c; c >>= 32; }
-        for (int i = 0; i < 8; i++) q1[i] = (t[i] >> 1) | (i < 7 ? t[i + 1] << 31 : 0);
-    }
+    for (int i = 0; i < 8; i++) e[i] = (q[i] >> 1) | (i < 7 ? q[i + 1] << 31 : 0);   // q is odd: (q - 1) / 2 = q >> 1
+    static const Fr c0 = Fr::from_u32(7).pow(q, 8);   // generator of the 2^32-torsion
+    const Fr w = a.pow(e, 8);
+    Fr x = a * w, t = x * w, c = c0;
     uint32_t m = 32;
-    Fr c = Fr::from_u32(7).pow(q, 8), t = a.pow(q, 8), r = a.pow(q1, 8);
     while (!(t == Fr::one())) {
         uint32_t i = 0;
         Fr t2 = t;
-        while (!(t2 == Fr::one())) { t2 = t2 * t2; i++; }
+        while (!(t2 == Fr::one())) {
+            t2 = t2 * t2;
+            if (++i == m) return false;   // t has order 2^m: a is not a square
+        }
         Fr b = c;
         for (uint32_t k = 0; k + i + 1 < m; k++) b = b * b;
         m = i;
         c = b * b;
         t = t * c;
-        r = r * b;
+        x = x * b;
     }
-    *out = r;
+    if (!(x * x == a)) return false;
+    *out = x;
     return true;
 }
 
@@ -141,7 +140,7 @@ bool jj_decompress(bzk_mpn_state *s, const bzk_fr *x_canon, bool odd, Point *out
         Fr den = Fr::one() - s->jj_d * x2;
         if (den.is_zero()) return false;
         Fr y;
-        if (!fr_sqrt((Fr::one() + x2) * den.inv(), &y)) return false;  // a = -1
+        if (!fr_sqrt((Fr::one() + x2) * den.inv_gcd(), &y)) return false;  // a = -1
         p = Point{x, y};
         if (s->decompress_cache.size() >= kDecompressCacheCap) s->decompress_cache.clear();
         s->decompress_cache[key_of(x)] = p;
