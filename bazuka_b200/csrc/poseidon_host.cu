@@ -20,6 +20,78 @@ struct bzk_poseidon_host {
 
 using namespace bzk;
 
+namespace {
+// One MDS row on 64-bit limbs with ONE Montgomery reduction: sum_k m[k] * s[k] is accumulated unreduced (t <= 17 products of two
+// values < r: < 2^515, nine limbs), reduced once, and brought below r by conditional subtractions — the same value, bit for bit,
+// as reducing every product (the device kernels do the same with 32-bit limbs: Fe::mul_wide / redc_wide in csrc/poseidon.cu).
+inline Fr mds_row_dot(const Fr *m, const Fr *s, uint32_t t) {
+    // product scanning (Comba): column k collects every a_i * b_j with i + j = k of every term in a three-word accumulator;
+    // no data-dependent branches
+    uint64_t acc[9];
+    uint64_t c0 = 0, c1 = 0, c2 = 0;
+    const uint64_t *A = (const uint64_t *)m, *B = (const uint64_t *)s;   // Fr = 8 x u32 = 4 x u64 on a little-endian host
+    for (int col = 0; col < 7; col++) {
+        const int lo = col < 4 ? 0 : col - 3, hi = col < 4 ? col : 3;
+        for (uint32_t k = 0; k < t; k++) {
+            const uint64_t *a = A + 4 * k, *b = B + 4 * k;
+            for (int i = lo; i <= hi; i++) {
+                const unsigned __int128 pr = (unsigned __int128)a[i] * b[col - i];
+                const unsigned __int128 s0 = (unsigned __int128)c0 + (uint64_t)pr;
+                c0 = (uint64_t)s0;
+                const unsigned __int128 s1 = (unsigned __int128)c1 + (uint64_t)(pr >> 64) + (uint64_t)(s0 >> 64);
+                c1 = (uint64_t)s1;
+                c2 += (uint64_t)(s1 >> 64);
+            }
+        }
+        acc[col] = c0;
+        c0 = c1; c1 = c2; c2 = 0;
+    }
+    acc[7] = c0; acc[8] = c1;
+    uint64_t p[4];
+    for (int i = 0; i < 4; i++) p[i] = (uint64_t)FrParams::p(2 * i) | ((uint64_t)FrParams::p(2 * i + 1) << 32);
+    uint64_t inv = (uint64_t)(0u - FrParams::inv());   // p^-1 mod 2^32 ...
+    inv *= 2 - p[0] * inv;                             // ... one Newton step: mod 2^64
+    inv = (uint64_t)0 - inv;                           // -p^-1 mod 2^64
+    uint64_t top = 0;                                  // limb 9
+    for (int i = 0; i < 4; i++) {                      // Montgomery reduction by 2^256, limb by limb
+        const uint64_t q = acc[i] * inv;
+        unsigned __int128 c = 0;
+        for (int j = 0; j < 4; j++) {
+            c += (unsigned __int128)q * p[j] + acc[i + j];
+            acc[i + j] = (uint64_t)c;
+            c >>= 64;
+        }
+        for (int j = i + 4; j < 9; j++) {
+            c += acc[j];
+            acc[j] = (uint64_t)c;
+            c >>= 64;
+        }
+        top += (uint64_t)c;
+    }
+    // acc[4..8] (+ top) < (17 r^2 + 2^256 r) / 2^256 < 9 r: a few conditional subtractions
+    uint64_t r[6] = {acc[4], acc[5], acc[6], acc[7], acc[8], top};
+    for (;;) {
+        bool ge = r[4] != 0 || r[5] != 0;
+        if (!ge) {
+            ge = true;
+            for (int i = 3; i >= 0; i--) {
+                if (r[i] != p[i]) { ge = r[i] > p[i]; break; }
+            }
+        }
+        if (!ge) break;
+        uint64_t br = 0;
+        for (int i = 0; i < 6; i++) {
+            const unsigned __int128 d = (unsigned __int128)r[i] - (i < 4 ? p[i] : 0) - br;
+            r[i] = (uint64_t)d;
+            br = (uint64_t)(d >> 64) & 1;
+        }
+    }
+    Fr out;
+    memcpy(out.l, r, 32);
+    return out;
+}
+}  // namespace
+
 extern "C" {
 
 int32_t bzk_poseidon_host_create(const uint8_t *blob, size_t len, bzk_poseidon_host **out) {
@@ -80,11 +152,7 @@ int32_t bzk_poseidon_host_hash(const bzk_poseidon_host *h, uint32_t arity, const
                 const Fr x2 = s[k] * s[k];
                 s[k] = x2 * x2 * s[k];
             }
-            for (uint32_t j = 0; j < t; j++) {
-                Fr acc = W.mds[(size_t)j * t] * s[0];
-                for (uint32_t k = 1; k < t; k++) acc = acc + W.mds[(size_t)j * t + k] * s[k];
-                nx[j] = acc;
-            }
+            for (uint32_t j = 0; j < t; j++) nx[j] = mds_row_dot(W.mds.data() + (size_t)j * t, s, t);
             for (uint32_t k = 0; k < t; k++) s[k] = nx[k];
         }
         memcpy(&out[i], s[1].l, 32);
